@@ -1,0 +1,440 @@
+// seqik_core.cuh -- per-lane solver core of the sequential leg-IK path.
+//
+// One "stage solve" of SeqIKPy (reference: seqikpy/leg_inverse_kinematics.py:259-282,
+// ikpy Chain.inverse_kinematics -> scipy.optimize.least_squares, method "trf") is a
+// bounded nonlinear least-squares problem with 3 residuals and at most TWO variables
+// that move the end point: every other chain slot (Base link,
+// frozen links, the last link) has an identically-zero Jacobian column.
+//
+// This header restates scipy's Trust-Region-Reflective iteration
+// (scipy/optimize/_lsq/trf.py:206-413, common.py) on that active pair, in the pivot
+// frame of the stage, so that the whole solve is closed-form scalar arithmetic that
+// lives in registers:
+//   * the SVD of the augmented Jacobian becomes the eigen-decomposition of a 2x2 matrix;
+//   * the inert slots enter only through `null_sq` (their squared norm: initial trust
+//     radius trf.py:236 and the xtol test common.py:705-718) and `max_nfev = 100 n`;
+//   * m = 3 < n always, so solve_lsq_trust_region (common.py:57-168) always takes its
+//     rank-deficient branch -- restated literally, including the final rescale of the
+//     step to the trust radius and the Levenberg parameter that may end negative.
+//
+// FP32 specifics (none change the FP64 instantiation's results beyond rounding):
+//   * distances to the bounds (dl, du) are carried as separate scalars and updated
+//     incrementally, so Coleman-Li scaling near an active bound keeps full relative
+//     accuracy (scipy iterates sit 1e-14 inside the bounds);
+//   * a trial point is evaluated through the angle-addition form (sin/cos of the STEP),
+//     which yields the change of the end point, hence the actual cost reduction, with
+//     relative accuracy ~1e-6 even when it is 1e-9 of the cost (ftol = 1e-8).
+//
+// The same header is compiled by nvcc for the kernels and by g++ for the host-side
+// test harness in tests/hostsim (test infrastructure; never loaded by the product).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SK_HD __host__ __device__ __forceinline__
+#else
+#define SK_HD inline
+#endif
+
+namespace seqik {
+
+// ---------------------------------------------------------------------------------
+// scalar helpers
+// ---------------------------------------------------------------------------------
+template <typename R> struct Num;
+template <> struct Num<float> {
+    static SK_HD float sqrt_(float x) { return sqrtf(x); }
+    static SK_HD float abs_(float x) { return fabsf(x); }
+    static SK_HD float max_(float a, float b) { return fmaxf(a, b); }
+    static SK_HD float min_(float a, float b) { return fminf(a, b); }
+    static SK_HD float copysign_(float a, float b) { return copysignf(a, b); }
+    static SK_HD void sincos_(float x, float* s, float* c) {
+#if defined(__CUDA_ARCH__)
+        sincosf(x, s, c);
+#else
+        *s = sinf(x); *c = cosf(x);
+#endif
+    }
+    static SK_HD float inf() { return INFINITY; }
+    static SK_HD float tiny() { return 1.17549435e-38f; }     // stands in for nextafter(0, .)
+    static SK_HD float eps_in() { return 2.220446e-16f; }     // fp64 ulp: strict-feasibility gap
+};
+template <> struct Num<double> {
+    static SK_HD double sqrt_(double x) { return sqrt(x); }
+    static SK_HD double abs_(double x) { return fabs(x); }
+    static SK_HD double max_(double a, double b) { return fmax(a, b); }
+    static SK_HD double min_(double a, double b) { return fmin(a, b); }
+    static SK_HD double copysign_(double a, double b) { return copysign(a, b); }
+    static SK_HD void sincos_(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
+    static SK_HD double inf() { return (double)INFINITY; }
+    static SK_HD double tiny() { return 4.9406564584124654e-324; }
+    static SK_HD double eps_in() { return 2.220446049250313e-16; }
+};
+
+enum : int { KIND_XY = 0, KIND_ZY = 1 };   // Rx(a)Ry(b) (stage 1)  |  Rz(a)Ry(b) (stages 2-4)
+
+enum : int {
+    ST_MAXFEV = 0, ST_GTOL = 1, ST_FTOL = 2, ST_XTOL = 3, ST_BOTH = 4, ST_RUNNING = -1
+};
+
+template <typename R> struct Vec3 { R x, y, z; };
+template <typename R> SK_HD R dot(const Vec3<R>& a, const Vec3<R>& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+
+// End point of the solved segment in the pivot frame, w = Rot_a Ry(b) (0,0,-L), and its
+// two Jacobian columns.  `has_a` = 0 turns variable a into an inert slot (stage 4).
+template <typename R>
+SK_HD void stage_point(int kind, R L, R has_a, R sa, R ca, R sb, R cb,
+                       Vec3<R>& w, Vec3<R>& ja, Vec3<R>& jb) {
+    const R Lsb = L * sb, Lcb = L * cb;
+    if (kind == KIND_XY) {
+        w = {-Lsb, Lcb * sa, -Lcb * ca};
+        ja = {R(0), Lcb * ca, Lcb * sa};
+        jb = {-Lcb, -Lsb * sa, Lsb * ca};
+    } else {
+        w = {-Lsb * ca, -Lsb * sa, -Lcb};
+        ja = {has_a * Lsb * sa, -has_a * Lsb * ca, R(0)};
+        jb = {-Lcb * ca, -Lcb * sa, Lsb};
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// One stage solve: state + one evaluation per trip()
+// ---------------------------------------------------------------------------------
+template <typename R>
+struct StageSolve {
+    // problem
+    int kind; R L, has_a; Vec3<R> q; R span0, span1;   // span = ub - lb (inf if unbounded)
+    bool fin_lb0, fin_ub0, fin_lb1, fin_ub1;
+    R null_sq; int max_nfev;
+    // iterate
+    R x0, x1, dl0, dl1, du0, du1;      // angles and distances to the bounds
+    R sa, ca, sb, cb;                   // sin/cos of the iterate
+    Vec3<R> f, ja, jb; R cost, g0, g1;
+    R Delta, alpha; int nfev, status; bool fresh;
+    // outer-iteration quantities (valid while !fresh)
+    R d0, d1, dh0, dh1, gh0, gh1, lam0, lam1, ex, ey, suf0, suf1, theta;
+    Vec3<R> jh0, jh1;
+
+    typedef Num<R> N;
+
+    SK_HD void cl_scaling(R& v0, R& v1, R& dv0, R& dv1) const {
+        v0 = R(1); dv0 = R(0); v1 = R(1); dv1 = R(0);
+        if (g0 < R(0) && fin_ub0) { v0 = du0; dv0 = R(-1); } else if (g0 > R(0) && fin_lb0) { v0 = dl0; dv0 = R(1); }
+        if (g1 < R(0) && fin_ub1) { v1 = du1; dv1 = R(-1); } else if (g1 > R(0) && fin_lb1) { v1 = dl1; dv1 = R(1); }
+    }
+
+    // least_squares prologue: x0 made strictly feasible (rstep 1e-10), f, J, g, Delta0
+    SK_HD void init(int kind_, R L_, R has_a_, const Vec3<R>& q_, R a, R b,
+                    R lb0, R ub0, R lb1, R ub1, R null_sq_, int n_full) {
+        kind = kind_; L = L_; has_a = has_a_; q = q_; null_sq = null_sq_; max_nfev = 100 * n_full;
+        fin_lb0 = lb0 > -N::inf(); fin_ub0 = ub0 < N::inf(); fin_lb1 = lb1 > -N::inf(); fin_ub1 = ub1 < N::inf();
+        span0 = ub0 - lb0; span1 = ub1 - lb1;
+        x0 = a; x1 = b;
+        dl0 = a - lb0; du0 = ub0 - a; dl1 = b - lb1; du1 = ub1 - b;
+        const R rs = R(1e-10);
+        if (dl0 <= R(0)) { dl0 = rs * N::max_(R(1), N::abs_(lb0)); x0 = lb0 + dl0; du0 = span0 - dl0; }
+        if (du0 <= R(0)) { du0 = rs * N::max_(R(1), N::abs_(ub0)); x0 = ub0 - du0; dl0 = span0 - du0; }
+        if (dl1 <= R(0)) { dl1 = rs * N::max_(R(1), N::abs_(lb1)); x1 = lb1 + dl1; du1 = span1 - dl1; }
+        if (du1 <= R(0)) { du1 = rs * N::max_(R(1), N::abs_(ub1)); x1 = ub1 - du1; dl1 = span1 - du1; }
+        N::sincos_(x0, &sa, &ca); N::sincos_(x1, &sb, &cb);
+        Vec3<R> w; stage_point(kind, L, has_a, sa, ca, sb, cb, w, ja, jb);
+        f = {w.x - q.x, w.y - q.y, w.z - q.z};
+        cost = R(0.5) * dot(f, f);
+        g0 = dot(ja, f); g1 = dot(jb, f);
+        R v0, v1, dv0, dv1; cl_scaling(v0, v1, dv0, dv1);
+        Delta = N::sqrt_(null_sq + x0 * x0 / v0 + x1 * x1 / v1);
+        if (Delta == R(0)) Delta = R(1);
+        alpha = R(0); nfev = 1; status = ST_RUNNING; fresh = true;
+    }
+
+    SK_HD bool done() const { return status != ST_RUNNING; }
+
+    // value of the hat-space quadratic model at s (evaluate_quadratic, common.py)
+    SK_HD R model(R s0, R s1) const {
+        const R jx = jh0.x * s0 + jh1.x * s1, jy = jh0.y * s0 + jh1.y * s1, jz = jh0.z * s0 + jh1.z * s1;
+        return R(0.5) * (jx * jx + jy * jy + jz * jz + s0 * dh0 * s0 + s1 * dh1 * s1) + s0 * gh0 + s1 * gh1;
+    }
+
+    // step_size_to_bound from distances (dl, du) along p; hit flags
+    static SK_HD R to_bound(R dl0_, R du0_, R dl1_, R du1_, R p0, R p1, bool& h0, bool& h1) {
+        R s0 = N::inf(), s1 = N::inf();
+        if (p0 != R(0)) s0 = N::max_(-dl0_ / p0, du0_ / p0);
+        if (p1 != R(0)) s1 = N::max_(-dl1_ / p1, du1_ / p1);
+        const R m = N::min_(s0, s1);
+        h0 = (p0 != R(0)) && (s0 == m); h1 = (p1 != R(0)) && (s1 == m);
+        return m;
+    }
+
+    // minimize_quadratic_1d(a, b, lo, hi, c)
+    static SK_HD void minq(R a, R b, R lo, R hi, R c, R& t_best, R& y_best) {
+        t_best = lo; y_best = lo * (a * lo + b) + c;
+        const R yh = hi * (a * hi + b) + c;
+        if (yh < y_best) { y_best = yh; t_best = hi; }
+        if (a != R(0)) {
+            const R e = R(-0.5) * b / a;
+            if (lo < e && e < hi) {
+                const R ye = e * (a * e + b) + c;
+                if (ye < y_best) { y_best = ye; t_best = e; }
+            }
+        }
+    }
+
+    // select_step (trf.py:129-203) restricted to the active pair
+    SK_HD void select_step(R p0, R p1, R ph0, R ph1, R& st0, R& st1, R& sh0, R& sh1, R& pred) const {
+        const bool inb = (dl0 + p0 >= R(0)) && (du0 - p0 >= R(0)) && (dl1 + p1 >= R(0)) && (du1 - p1 >= R(0));
+        if (inb) { st0 = p0; st1 = p1; sh0 = ph0; sh1 = ph1; pred = -model(ph0, ph1); return; }
+        bool h0, h1;
+        const R p_stride = to_bound(dl0, du0, dl1, du1, p0, p1, h0, h1);
+        R rh0 = h0 ? -ph0 : ph0, rh1 = h1 ? -ph1 : ph1;
+        R r0 = d0 * rh0, r1 = d1 * rh1;
+        p0 *= p_stride; p1 *= p_stride; ph0 *= p_stride; ph1 *= p_stride;
+        // intersect_trust_region(ph, rh, Delta): positive root
+        R to_tr;
+        {
+            const R a = rh0 * rh0 + rh1 * rh1, b = ph0 * rh0 + ph1 * rh1;
+            const R c = N::min_(ph0 * ph0 + ph1 * ph1 - Delta * Delta, R(0));
+            const R disc = N::sqrt_(N::max_(b * b - a * c, R(0)));
+            const R qq = -(b + N::copysign_(disc, b));
+            R t1 = R(0), t2 = R(0);
+            if (qq != R(0)) { t1 = qq / a; t2 = c / qq; }
+            to_tr = N::max_(t1, t2);
+        }
+        bool u0, u1;
+        const R to_bd = to_bound(dl0 + p0, du0 - p0, dl1 + p1, du1 - p1, r0, r1, u0, u1);
+        const R r_stride = N::min_(to_bd, to_tr);
+        R r_l, r_u;
+        if (r_stride > R(0)) {
+            r_l = (R(1) - theta) * p_stride / r_stride;
+            r_u = (r_stride == to_bd) ? theta * to_bd : to_tr;
+        } else { r_l = R(0); r_u = R(-1); }
+        R r_value = N::inf();
+        if (r_l <= r_u) {
+            // build_quadratic_1d(Jh, gh, rh, s0=ph, diag=dh)
+            const R vx = jh0.x * rh0 + jh1.x * rh1, vy = jh0.y * rh0 + jh1.y * rh1, vz = jh0.z * rh0 + jh1.z * rh1;
+            const R ux = jh0.x * ph0 + jh1.x * ph1, uy = jh0.y * ph0 + jh1.y * ph1, uz = jh0.z * ph0 + jh1.z * ph1;
+            const R a = R(0.5) * (vx * vx + vy * vy + vz * vz + rh0 * dh0 * rh0 + rh1 * dh1 * rh1);
+            const R b = gh0 * rh0 + gh1 * rh1 + (ux * vx + uy * vy + uz * vz) + ph0 * dh0 * rh0 + ph1 * dh1 * rh1;
+            const R c = R(0.5) * (ux * ux + uy * uy + uz * uz) + gh0 * ph0 + gh1 * ph1
+                        + R(0.5) * (ph0 * dh0 * ph0 + ph1 * dh1 * ph1);
+            R rs; minq(a, b, r_l, r_u, c, rs, r_value);
+            rh0 = rh0 * rs + ph0; rh1 = rh1 * rs + ph1;
+            r0 = rh0 * d0; r1 = rh1 * d1;
+        }
+        // strictly interior truncated step
+        p0 *= theta; p1 *= theta; ph0 *= theta; ph1 *= theta;
+        const R p_value = model(ph0, ph1);
+        // scaled anti-gradient
+        R ah0 = -gh0, ah1 = -gh1;
+        R a0 = d0 * ah0, a1 = d1 * ah1;
+        const R to_tr2 = Delta / N::sqrt_(ah0 * ah0 + ah1 * ah1);
+        const R to_bd2 = to_bound(dl0, du0, dl1, du1, a0, a1, u0, u1);
+        const R ag_hi = (to_bd2 < to_tr2) ? theta * to_bd2 : to_tr2;
+        R ag_value, ags;
+        {
+            const R vx = jh0.x * ah0 + jh1.x * ah1, vy = jh0.y * ah0 + jh1.y * ah1, vz = jh0.z * ah0 + jh1.z * ah1;
+            const R a = R(0.5) * (vx * vx + vy * vy + vz * vz + ah0 * dh0 * ah0 + ah1 * dh1 * ah1);
+            const R b = gh0 * ah0 + gh1 * ah1;
+            minq(a, b, R(0), ag_hi, R(0), ags, ag_value);
+        }
+        if (p_value < r_value && p_value < ag_value) { st0 = p0; st1 = p1; sh0 = ph0; sh1 = ph1; pred = -p_value; }
+        else if (r_value < p_value && r_value < ag_value) { st0 = r0; st1 = r1; sh0 = rh0; sh1 = rh1; pred = -r_value; }
+        else { st0 = a0 * ags; st1 = a1 * ags; sh0 = ah0 * ags; sh1 = ah1 * ags; pred = -ag_value; }
+    }
+
+    // One function evaluation (one pass of the inner `while actual_reduction <= 0` loop,
+    // preceded by the outer-iteration head when the previous step was accepted).
+    SK_HD void trip() {
+        const R gtol = R(1e-8), ftol = R(1e-8), xtol = R(1e-8);
+        if (fresh) {
+            R v0, v1, dv0, dv1; cl_scaling(v0, v1, dv0, dv1);
+            const R g_norm = N::max_(N::abs_(g0 * v0), N::abs_(g1 * v1));
+            if (g_norm < gtol) { status = ST_GTOL; return; }
+            if (nfev >= max_nfev) { status = ST_MAXFEV; return; }
+            d0 = N::sqrt_(v0); d1 = N::sqrt_(v1);
+            dh0 = g0 * dv0; dh1 = g1 * dv1;
+            gh0 = d0 * g0; gh1 = d1 * g1;
+            jh0 = {ja.x * d0, ja.y * d0, ja.z * d0};
+            jh1 = {jb.x * d1, jb.y * d1, jb.z * d1};
+            // B = Jh^T Jh + diag(dh); eigen-decomposition (== SVD of [Jh; sqrt(dh)])
+            const R b00 = dot(jh0, jh0) + dh0, b01 = dot(jh0, jh1), b11 = dot(jh1, jh1) + dh1;
+            const R tr = R(0.5) * (b00 + b11), df = R(0.5) * (b00 - b11);
+            const R rad = N::sqrt_(df * df + b01 * b01);
+            lam0 = tr + rad;
+            lam1 = (lam0 != R(0)) ? N::max_((b00 * b11 - b01 * b01) / lam0, R(0)) : R(0);
+            R vx, vy;
+            if (df >= R(0)) { vx = df + rad; vy = b01; } else { vx = b01; vy = rad - df; }
+            const R nrm = N::sqrt_(vx * vx + vy * vy);
+            if (nrm == R(0)) { ex = R(1); ey = R(0); } else { ex = vx / nrm; ey = vy / nrm; }
+            // suf = V^T gh with V = [[ex, -ey], [ey, ex]]
+            suf0 = ex * gh0 + ey * gh1; suf1 = -ey * gh0 + ex * gh1;
+            theta = N::max_(R(0.995), R(1) - g_norm);
+            fresh = false;
+        }
+        // ---- solve_lsq_trust_region, rank-deficient branch
+        R t0, t1;
+        {
+            R a_up = N::sqrt_(suf0 * suf0 + suf1 * suf1) / Delta, a_lo = R(0);
+            if (alpha == R(0)) alpha = R(0.001) * a_up;
+            for (int it = 0; it < 10; ++it) {
+                if (alpha < a_lo || alpha > a_up) alpha = N::max_(R(0.001) * a_up, N::sqrt_(a_lo * a_up));
+                const R e0 = lam0 + alpha, e1 = lam1 + alpha;
+                t0 = (e0 != R(0)) ? suf0 / e0 : R(0); t1 = (e1 != R(0)) ? suf1 / e1 : R(0);
+                const R pn = N::sqrt_(t0 * t0 + t1 * t1);
+                const R phi = pn - Delta;
+                R dd = R(0);
+                if (e0 != R(0)) dd += t0 * t0 / e0;
+                if (e1 != R(0)) dd += t1 * t1 / e1;
+                const R dphi = -dd / pn;
+                if (phi < R(0)) a_up = alpha;
+                const R ratio = phi / dphi;
+                a_lo = N::max_(a_lo, alpha - ratio);
+                alpha -= (phi + Delta) * ratio / Delta;
+                if (N::abs_(phi) < R(0.01) * Delta) break;
+            }
+            const R e0 = lam0 + alpha, e1 = lam1 + alpha;
+            t0 = (e0 != R(0)) ? suf0 / e0 : R(0); t1 = (e1 != R(0)) ? suf1 / e1 : R(0);
+        }
+        R ph0 = -(ex * t0 - ey * t1), ph1 = -(ey * t0 + ex * t1);
+        {
+            const R sc = Delta / N::sqrt_(ph0 * ph0 + ph1 * ph1);
+            ph0 *= sc; ph1 *= sc;
+        }
+        R st0, st1, sh0, sh1, pred;
+        select_step(d0 * ph0, d1 * ph1, ph0, ph1, st0, st1, sh0, sh1, pred);
+
+        // ---- trial point: strictly feasible, evaluated through the step's sin/cos
+        R nx0 = x0 + st0, nx1 = x1 + st1;
+        R ndl0 = dl0 + st0, ndu0 = du0 - st0, ndl1 = dl1 + st1, ndu1 = du1 - st1;
+        R e0 = st0, e1 = st1;   // applied step
+        if (ndl0 <= R(0)) { const R gap = inner_gap(nx0 - ndl0); e0 = gap - dl0; ndl0 = gap; ndu0 = span0 - gap; nx0 = x0 + e0; }
+        if (ndu0 <= R(0)) { const R gap = inner_gap(nx0 + ndu0); e0 = du0 - gap; ndu0 = gap; ndl0 = span0 - gap; nx0 = x0 + e0; }
+        if (ndl1 <= R(0)) { const R gap = inner_gap(nx1 - ndl1); e1 = gap - dl1; ndl1 = gap; ndu1 = span1 - gap; nx1 = x1 + e1; }
+        if (ndu1 <= R(0)) { const R gap = inner_gap(nx1 + ndu1); e1 = du1 - gap; ndu1 = gap; ndl1 = span1 - gap; nx1 = x1 + e1; }
+        R sda, cda, sdb, cdb;
+        N::sincos_(e0, &sda, &cda); N::sincos_(e1, &sdb, &cdb);
+        const R va = (cda > R(0)) ? sda * sda / (R(1) + cda) : R(1) - cda;   // 1 - cos(step)
+        const R vb = (cdb > R(0)) ? sdb * sdb / (R(1) + cdb) : R(1) - cdb;
+        const R dsa = ca * sda - sa * va, dca = -sa * sda - ca * va;
+        const R dsb = cb * sdb - sb * vb, dcb = -sb * sdb - cb * vb;
+        const R nsa = sa + dsa, nca = ca + dca, nsb = sb + dsb, ncb = cb + dcb;
+        Vec3<R> dw;
+        if (kind == KIND_XY) {
+            dw = {-L * dsb, L * (dcb * nsa + cb * dsa), -L * (dcb * nca + cb * dca)};
+        } else {
+            dw = {-L * (dsb * nca + sb * dca), -L * (dsb * nsa + sb * dsa), -L * dcb};
+        }
+        nfev += 1;
+        const R actual = -(dot(f, dw) + R(0.5) * dot(dw, dw));
+        const R step_h_norm = N::sqrt_(sh0 * sh0 + sh1 * sh1);
+        // update_tr_radius
+        R ratio;
+        if (pred > R(0)) ratio = actual / pred; else if (pred == R(0) && actual == R(0)) ratio = R(1); else ratio = R(0);
+        R Delta_new = Delta;
+        if (ratio < R(0.25)) Delta_new = R(0.25) * step_h_norm;
+        else if (ratio > R(0.75) && step_h_norm > R(0.95) * Delta) Delta_new = R(2) * Delta;
+        // check_termination
+        const R step_norm = N::sqrt_(st0 * st0 + st1 * st1);
+        const R x_norm = N::sqrt_(null_sq + x0 * x0 + x1 * x1);
+        const bool ft = (actual < ftol * cost) && (ratio > R(0.25));
+        const bool xt = step_norm < xtol * (xtol + x_norm);
+        int term = ST_RUNNING;
+        if (ft && xt) term = ST_BOTH; else if (ft) term = ST_FTOL; else if (xt) term = ST_XTOL;
+        if (term == ST_RUNNING) { alpha *= Delta / Delta_new; Delta = Delta_new; }
+        if (actual > R(0)) {
+            x0 = nx0; x1 = nx1; dl0 = ndl0; du0 = ndu0; dl1 = ndl1; du1 = ndu1;
+            sa = nsa; ca = nca; sb = nsb; cb = ncb;
+            f = {f.x + dw.x, f.y + dw.y, f.z + dw.z};
+            cost = cost - actual;
+            Vec3<R> w; stage_point(kind, L, has_a, sa, ca, sb, cb, w, ja, jb);
+            g0 = dot(ja, f); g1 = dot(jb, f);
+            fresh = true;
+        }
+        if (term != ST_RUNNING) status = term;
+        else if (!(actual > R(0)) && nfev >= max_nfev) status = ST_MAXFEV;
+    }
+
+    // make_strictly_feasible(x, lb, ub, rstep=0): one fp64 ulp inside the bound `b`
+    static SK_HD R inner_gap(R b) {
+        const R ab = N::abs_(b);
+        return (ab > R(0)) ? N::eps_in() * ab : N::tiny();
+    }
+};
+
+// ---------------------------------------------------------------------------------
+// 3x3 frame algebra for the stage hand-off
+// ---------------------------------------------------------------------------------
+template <typename R> struct Mat3 { Vec3<R> c0, c1, c2; };   // columns
+
+template <typename R> SK_HD Vec3<R> mulT(const Mat3<R>& A, const Vec3<R>& v) {   // A^T v
+    return {dot(A.c0, v), dot(A.c1, v), dot(A.c2, v)};
+}
+template <typename R> SK_HD Vec3<R> mul(const Mat3<R>& A, const Vec3<R>& v) {    // A v
+    return {A.c0.x * v.x + A.c1.x * v.y + A.c2.x * v.z,
+            A.c0.y * v.x + A.c1.y * v.y + A.c2.y * v.z,
+            A.c0.z * v.x + A.c1.z * v.y + A.c2.z * v.z};
+}
+template <typename R> SK_HD Vec3<R> lin(const Vec3<R>& a, R s, const Vec3<R>& b, R t) {
+    return {a.x * s + b.x * t, a.y * s + b.y * t, a.z * s + b.z * t};
+}
+// A <- A * Rot_a(a) * Ry(b), Rot_a = Rx (KIND_XY) or Rz (KIND_ZY)
+template <typename R> SK_HD Mat3<R> advance(const Mat3<R>& A, int kind, R sa, R ca, R sb, R cb) {
+    Mat3<R> B;
+    if (kind == KIND_XY) { B.c0 = A.c0; B.c1 = lin(A.c1, ca, A.c2, sa); B.c2 = lin(A.c1, -sa, A.c2, ca); }
+    else { B.c0 = lin(A.c0, ca, A.c1, sa); B.c1 = lin(A.c0, -sa, A.c1, ca); B.c2 = A.c2; }
+    Mat3<R> C;
+    C.c0 = lin(B.c0, cb, B.c2, -sb); C.c1 = B.c1; C.c2 = lin(B.c0, sb, B.c2, cb);
+    return C;
+}
+
+// Per-chain constants (one leg of one trial)
+template <typename R> struct ChainParams {
+    R seg[4];        // Coxa, Femur, Tibia, Tarsus lengths
+    R lb[7], ub[7];  // DOF order: ThC_yaw, ThC_pitch, ThC_roll, CTr_pitch, CTr_roll, FTi_pitch, TiTa_pitch
+    R null_sq[4];    // squared norm of the inert seed slots of stages 1-4
+};
+
+struct FrameStats { int nfev[4]; int status[4]; };
+
+// Reference (serial) composition of the four stage solves of one frame; the kernels use
+// the same pieces but interleave them across lanes.  `ang` in/out: previous frame's
+// angles (warm start, leg_inverse_kinematics.py:272) -> this frame's.
+// `kp`: 5 key points (row 0 = ThC origin).  `fk`: 9x3 output rows (may be null).
+template <typename R>
+SK_HD void solve_frame(const ChainParams<R>& P, const R* kp, R* ang, R* fk, FrameStats* fs, int stage_mask = 0xF) {
+    const int n_full[4] = {4, 6, 8, 9};
+    const Vec3<R> o = {kp[0], kp[1], kp[2]};
+    Mat3<R> A = {{R(1), R(0), R(0)}, {R(0), R(1), R(0)}, {R(0), R(0), R(1)}};
+    Vec3<R> piv = {R(0), R(0), R(0)};
+    Vec3<R> joint[4];
+    for (int s = 0; s < 4; ++s) {
+        const Vec3<R> tgt = {kp[3 * (s + 1)] - o.x, kp[3 * (s + 1) + 1] - o.y, kp[3 * (s + 1) + 2] - o.z};
+        const Vec3<R> rel = {tgt.x - piv.x, tgt.y - piv.y, tgt.z - piv.z};
+        const Vec3<R> q = mulT(A, rel);
+        const int kind = (s == 0) ? KIND_XY : KIND_ZY;
+        const int ia = (s == 3) ? -1 : 2 * s, ib = (s == 3) ? 6 : 2 * s + 1;
+        StageSolve<R> S;
+        const R inf = Num<R>::inf();
+        if (s == 3) S.init(kind, P.seg[s], R(0), q, R(0), ang[ib], -inf, inf, P.lb[ib], P.ub[ib], P.null_sq[s], n_full[s]);
+        else S.init(kind, P.seg[s], R(1), q, ang[ia], ang[ib], P.lb[ia], P.ub[ia], P.lb[ib], P.ub[ib], P.null_sq[s], n_full[s]);
+        if (stage_mask & (1 << s)) { while (!S.done()) S.trip(); }
+        if (s != 3) ang[ia] = S.x0;
+        ang[ib] = S.x1;
+        if (fs) { fs->nfev[s] = S.nfev; fs->status[s] = S.status; }
+        // next pivot = pivot + A w = target + A f
+        const Vec3<R> Af = mul(A, S.f);
+        piv = {tgt.x + Af.x, tgt.y + Af.y, tgt.z + Af.z};
+        joint[s] = piv;
+        A = advance(A, kind, S.sa, S.ca, S.sb, S.cb);
+    }
+    if (fk) {
+        for (int r = 0; r < 4; ++r) { fk[3 * r] = o.x; fk[3 * r + 1] = o.y; fk[3 * r + 2] = o.z; }
+        const int row[5] = {4, 5, 6, 7, 8};
+        const int src[5] = {0, 0, 1, 2, 3};
+        for (int k = 0; k < 5; ++k) {
+            fk[3 * row[k]] = joint[src[k]].x + o.x; fk[3 * row[k] + 1] = joint[src[k]].y + o.y; fk[3 * row[k] + 2] = joint[src[k]].z + o.z;
+        }
+    }
+}
+
+}  // namespace seqik

@@ -1,0 +1,47 @@
+"""Builds and loads tests/hostsim (the g++ build of csrc/seqik_core.cuh).  TEST INFRASTRUCTURE."""
+import ctypes
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+CSRC = ROOT / "sequential-inverse-kinematics_b200" / "csrc"
+SRC = Path(__file__).resolve().parent / "hostsim" / "hostsim.cpp"
+OUT = Path(__file__).resolve().parent / "hostsim" / "libhostsim.so"
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    deps = [SRC, CSRC / "seqik_core.cuh"]
+    if not OUT.exists() or any(d.stat().st_mtime > OUT.stat().st_mtime for d in deps):
+        # -ffp-contract=off: no FMA contraction, so the f64 build tracks the Python model closely
+        cmd = ["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-std=c++17", "-x", "c++", str(SRC),
+               "-I", str(CSRC), "-o", str(OUT)]
+        subprocess.run(cmd, check=True)
+    _lib = ctypes.CDLL(os.fspath(OUT))
+    return _lib
+
+
+def solve_chain(pose, seg, lb, ub, null_sq, seed, dtype=np.float32, stage_mask=0xF):
+    """pose (N,5,3) -> angles (N,7), fk (N,9,3), nfev (N,4), status (N,4) computed by the host build."""
+    lib = load()
+    fn = lib.hostsim_chain_f32 if dtype == np.float32 else lib.hostsim_chain_f64
+    pose = np.ascontiguousarray(pose, dtype=dtype)
+    n = pose.shape[0]
+    args = [np.ascontiguousarray(a, dtype=dtype) for a in (seg, lb, ub, null_sq, seed)]
+    angles = np.zeros((n, 7), dtype=dtype)
+    fk = np.zeros((n, 9, 3), dtype=dtype)
+    nfev = np.zeros((n, 4), dtype=np.int32)
+    status = np.zeros((n, 4), dtype=np.int32)
+    P = ctypes.c_void_p
+    fn.argtypes = [P, ctypes.c_int64, P, P, P, P, P, P, P, P, P, ctypes.c_int]
+    fn.restype = None
+    fn(pose.ctypes.data, n, *(a.ctypes.data for a in args), angles.ctypes.data, fk.ctypes.data,
+       nfev.ctypes.data, status.ctypes.data, stage_mask)
+    return angles, fk, nfev, status
