@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""Headline benchmark: leg-frames/s of the 4-stage sequential leg IK (+FK) on synthetic pose data.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--trials T] [--frames F] [--impl ours|reference]
+
+One "step" = one pass of the hot path (stages 1-4 + 9-row FK) over T trials x 6 legs x F frames per GPU
+(default T = 1000, F = 1000: BASELINE.json config "synthetic 1k trials x 1000 frames x 6 legs on 1 B200").
+Under torchrun every rank owns its own T trials (weak scaling; no collective on the data path) -- N = 8 with
+--trials 1250 is exactly the 10k-trial configuration sharded over 8 GPUs.
+
+Prints ONE JSON line (rank 0).  `value` times the kernel with the pose already resident in HBM; `e2e` times
+the public batched call with HOST pinned buffers (H2D of the pose, solve, D2H of angles + FK in the timed
+region).  `roofline` describes the solver kernel; `cpu_baseline` is the CPU oracle (the reference's
+algorithm: restated ikpy glue + scipy TRF) timed on this box's host cores on a bounded sample.
+
+--impl reference times that CPU implementation alone, with every host core, on bounded samples of the same
+workload (the reference's own per-frame chain rebuild needs ikpy/sympy, which is not
+installable offline; the oracle is its arithmetic without that overhead, i.e. a faster stand-in).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+os.environ.setdefault("OMP_NUM_THREADS", "1")
+
+import numpy as np  # noqa: E402
+
+METRIC = "leg-frames/sec, 4-stage seq IK"
+UNIT = "leg-frames/s"
+ALG_BYTES_PER_LEG_FRAME = 60 + 28 + 108          # pose in + angles out + FK out, fp32 (SURVEY.md 8d / DESIGN.md)
+ALG_FLOP_PER_LEG_FRAME = 14.5e3                   # nominal full-chain model of SURVEY.md 8d
+
+
+# --------------------------------------------------------------------------------------------- CPU oracle legs
+def _oracle_job(job):
+    """One (trial, leg) chain through the CPU oracle; returns leg-frames solved."""
+    from oracle import seqik_oracle as O
+    from seqikpy_b200 import synthetic as S
+    trial, li, n_frame = job
+    size, bounds, init = S.chain_constants()
+    leg = S.LEGS[li]
+    pose = S.make_trial(trial, 1000)[:n_frame, li]
+    O.run_ik_and_fk({f"{leg}_leg": pose}, size, bounds, init)
+    return n_frame
+
+
+def oracle_throughput(n_trial, n_frame, procs, repeats=1):
+    """leg-frames/s of the CPU oracle over n_trial x 6 chains with `procs` worker processes
+    (process-level parallelism over legs like examples/example_leg_inv_kinematics_parallel.py:186-189)."""
+    from multiprocessing import get_context
+    jobs = [(tr, li, n_frame) for tr in range(n_trial) for li in range(6)]
+    ctx = get_context("fork")
+    with ctx.Pool(procs) as pool:
+        pool.map(_oracle_job, [(0, 0, 2)] * procs)          # import + first-call costs out of the timed region
+        times = []
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            done = sum(pool.map(_oracle_job, jobs, chunksize=1))
+            times.append(time.perf_counter() - t0)
+    return done, times
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    procs = max(1, min(cores, 64))
+    n_trial = max(1, (procs + 5) // 6)                      # enough chains to occupy every worker
+    n_frame = args.ref_frames
+    per_step = n_trial * 6 * n_frame
+    from multiprocessing import get_context
+    jobs = [(tr, li, n_frame) for tr in range(n_trial) for li in range(6)]
+    with get_context("fork").Pool(procs) as pool:
+        pool.map(_oracle_job, [(0, 0, 2)] * procs)
+        for _ in range(args.warmup):
+            pool.map(_oracle_job, jobs, chunksize=1)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_oracle_job, jobs, chunksize=1)
+        dt = time.perf_counter() - t0
+    value = per_step * args.steps / dt
+    sample = f"{n_trial} trial(s) x 6 legs x first {n_frame} frames per step, {procs} worker processes (one chain each)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, note="CPU oracle on a bounded sample of this workload"),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- helpers
+def workload_config(args, note=None):
+    cfg = {
+        "workload": f"synthetic {args.trials} trials x {args.frames} frames x 6 legs per GPU, 4-stage seq IK + FK "
+                    f"(BASELINE config 'synthetic 1k trials x 1000 frames x 6 legs on 1 B200' at the defaults)",
+        "trials_per_gpu": args.trials, "frames": args.frames, "legs": 6,
+        "chains_per_gpu": args.trials * 6, "parallelism": f"trial shards x{args.gpus}, no collective",
+        "l2": "inputs+outputs per step (1.18 GB at the defaults) exceed the 126 MB L2; no explicit flush",
+    }
+    if note:
+        cfg["note"] = note
+    return cfg
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks/throttle reasons of one GPU while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def physical_gpu_index(local_rank):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        ids = [v for v in vis.split(",") if v.strip()]
+        if local_rank < len(ids) and ids[local_rank].strip().isdigit():
+            return int(ids[local_rank])
+    return local_rank
+
+
+# --------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from seqikpy_b200 import _native, synthetic as S
+    from seqikpy_b200.batch import BatchedLegIK
+    from seqikpy_b200.kinematic_chain import KinematicChainSeq
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: a CUDA device is required (there is no CPU fallback for the product path)")
+    _native.load_library()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if world != args.gpus and rank == 0:
+        print(f"bench.py: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
+
+    T, F = args.trials, args.frames
+    size, bounds, init = S.chain_constants()
+    chain = KinematicChainSeq(bounds, list(S.LEGS), size)
+    sess = BatchedLegIK(chain, init, S.LEGS, T, F, device=dev, schedule=args.schedule)
+
+    # synthetic pose of this rank's trials, chain-major, in pinned host memory
+    t_gen = time.perf_counter()
+    host_pose = torch.empty((T, 6, F, 5, 3), dtype=torch.float32, pin_memory=True)
+    hp = host_pose.numpy()
+    for i in range(T):
+        hp[i] = S.make_trial(rank * T + i, F).astype(np.float32).transpose(1, 0, 2, 3)
+    t_gen = time.perf_counter() - t_gen
+    sess.d_pose.copy_(host_pose.reshape(sess.n_chain, F, 5, 3))
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """K steps bracketed by barrier + synchronize; CUDA events on the launching stream; max over ranks (ms)."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item())
+
+    # ---- kernel-only (inputs resident in HBM)
+    for _ in range(max(args.warmup, 3)):
+        sess.solve_device()
+    sampler = ClockSampler(physical_gpu_index(local_rank)) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_total = timed(lambda: sess.solve_device(want_stats=False), args.steps)
+    ms_step = ms_total / args.steps
+    # ---- end to end through the public batched call with host buffers
+    for _ in range(2):
+        sess.solve_host(host_pose)
+    ms_e2e = timed(lambda: sess.solve_host(host_pose, synchronize=False), args.steps) / args.steps
+    clocks = sampler.stop() if sampler else None
+
+    sess.solve_device()
+    torch.cuda.synchronize()
+    nfev = sess.nfev.to(torch.float64).sum(0)                     # evaluations per stage, this rank
+    fk_err = torch.tensor([sess.mean_fk_error()], dtype=torch.float64, device=dev)
+    maxfev = (sess.status == 0).sum().to(torch.float64).reshape(1)
+    if world > 1:
+        dist.all_reduce(nfev); dist.all_reduce(fk_err); dist.all_reduce(maxfev)
+    leg_frames_rank = sess.leg_frames
+    leg_frames = leg_frames_rank * world
+    nfev_per_lf = (nfev / leg_frames).tolist()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+        fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12           # TFLOP/s at max clock
+        ach_gbs = leg_frames_rank * ALG_BYTES_PER_LEG_FRAME / (ms_step * 1e-3) / 1e9
+        ach_tf = leg_frames_rank * ALG_FLOP_PER_LEG_FRAME / (ms_step * 1e-3) / 1e12
+        traffic = None
+        try:
+            traffic = json.loads((ROOT / "profiles" / "solver_traffic.json").read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        cpu = None
+        if not args.no_cpu_baseline:
+            procs = max(1, min(6, host_cores()))
+            n_fr = args.cpu_frames
+            # fresh interpreter: no fork of a process that holds a CUDA context
+            out = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--cpu-baseline-only", "--cpu-frames", str(n_fr),
+                                  "--cpu-procs", str(procs)], capture_output=True, text=True, check=True).stdout
+            res = json.loads(out.strip().splitlines()[-1])
+            cpu = {"value": res["leg_frames"] / res["seconds"], "unit": UNIT, "cores": procs, "kind": "port",
+                   "sample": f"trial 0 x 6 legs x first {n_fr} frames of this workload, CPU oracle (restated ikpy glue + scipy TRF), "
+                             f"{procs} processes over legs like the reference's Pool(6) example"}
+        line = {
+            "metric": METRIC, "value": leg_frames / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+            "e2e": {"value": leg_frames / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": leg_frames_rank * 60, "d2h_bytes_per_step": leg_frames_rank * (28 + 108),
+                    "bytes_are": "per GPU"},
+            "gpu_launches": args.steps,
+            "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                         "traffic": traffic, "kernel": "leg_solve", "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback",
+                         "note": "the solver is FP32-latency bound, not HBM bound; see fp32",
+                         "fp32": {"achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_tf / fp32_peak,
+                                  "flop_model": "nominal 14.5 kFLOP per leg-frame (SURVEY.md 8d)",
+                                  "nfev_per_leg_frame_by_stage": nfev_per_lf}},
+            "cpu_baseline": cpu,
+            "mean_fk_error_mm": float(fk_err.item()) / world, "chains_at_max_nfev": int(maxfev.item()),
+            "clocks": clocks, "data_gen_s": t_gen, "schedule": args.schedule,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--trials", type=int, default=1000, help="trials per GPU")
+    ap.add_argument("--frames", type=int, default=1000)
+    ap.add_argument("--schedule", type=int, default=0, help="kernel schedule (0 auto, 1 lane per chain, 2 stage pipeline)")
+    ap.add_argument("--cpu-frames", type=int, default=200, help="frames per leg of the cpu_baseline sample")
+    ap.add_argument("--ref-frames", type=int, default=100, help="frames per chain and step of --impl reference")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline-only", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-procs", type=int, default=6, help=argparse.SUPPRESS)
+    args = ap.parse_args()
+    if args.cpu_baseline_only:
+        done, times = oracle_throughput(1, args.cpu_frames, args.cpu_procs)
+        print(json.dumps({"leg_frames": done, "seconds": times[0]}))
+        return
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,157 @@
+/* seqik.h -- C ABI of libseqik_sm100.so, the B200 (sm_100a) implementation of SeqIKPy's
+ * leg inverse-kinematics hot path.
+ *
+ * The reference (NeLy-EPFL/sequential-inverse-kinematics, pure Python) has no FFI seam;
+ * its seam is the Python class API.  Each entry point below states which reference
+ * function(s) it replaces (paths relative to the reference repository root).  The
+ * binding a maintainer of the reference would add is a ctypes stub: see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch tensors:
+ *     tensor.data_ptr()); the library allocates nothing that outlives a call;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = the
+ *     legacy default stream) of the calling thread's current device;
+ *   - return value: 0 ok, SEQIK_EINVAL bad argument, SEQIK_ECUDA CUDA error; the message
+ *     is available (per host thread) from seqik_last_error();
+ *   - strides are in ELEMENTS (floats), not bytes; the innermost key-point block
+ *     ([5][3], [9][3], [7]) is always contiguous;
+ *   - a "chain" is one leg of one trial; frames of a chain are solved serially (warm
+ *     start), chains are independent.  DOF order everywhere: ThC_yaw, ThC_pitch, ThC_roll,
+ *     CTr_pitch, CTr_roll, FTi_pitch, TiTa_pitch (the insertion order of the reference's
+ *     joint_angles_dict, seqikpy/leg_inverse_kinematics.py:285-320).
+ */
+#ifndef SEQIK_H_
+#define SEQIK_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEQIK_ABI_VERSION 2
+#define SEQIK_OK 0
+#define SEQIK_EINVAL (-1)
+#define SEQIK_ECUDA (-3)
+
+/* flags of seqik_leg_solve_f32 */
+#define SEQIK_FLAG_GN_STAGE(s) (1u << (s))   /* s = 0..3: stage s+1 takes the Gauss-Newton step when it fits the
+                                                trust region (what scipy's TRF does on the longer chains) */
+#define SEQIK_FLAG_DEFAULT (SEQIK_FLAG_GN_STAGE(1) | SEQIK_FLAG_GN_STAGE(2))
+#define SEQIK_FLAG_SCHED_SHIFT 8             /* bits 8..11: kernel schedule, 0 = automatic,
+                                                1 = one lane per chain, 2 = one lane per (chain, stage) pipeline */
+#define SEQIK_FLAG_SCHED_MASK (0xFu << SEQIK_FLAG_SCHED_SHIFT)
+
+int seqik_abi_version(void);
+const char* seqik_last_error(void);
+
+/* Per-chain constants of seqik_leg_solve_f32 / seqik_fk_f32: one row of 32 floats per chain.
+ *   [0..3]   segment lengths Coxa, Femur, Tibia, Tarsus (KinematicChainSeq.body_size,
+ *            seqikpy/kinematic_chain.py:170-421; utils.calculate_body_size utils.py:89-123)
+ *   [4..10]  lower bounds, [11..17] upper bounds of the 7 DOFs (bounds_dof)
+ *   [18..24] seeds of the 7 DOFs = the ACTIVE slots of INITIAL_ANGLES[leg]["stage_k"]
+ *            (seqikpy/data.py:4-22; leg_inverse_kinematics.py:272,376)
+ *   [25..28] squared norm of the INERT slots (Base link, frozen links, last link) of the four
+ *            stage seed vectors: they enter scipy's initial trust radius and xtol test
+ *   [29..31] reserved (0)
+ */
+#define SEQIK_CHAIN_PARAM_FLOATS 32
+
+/* 4-stage sequential leg IK + stage-4 forward kinematics.
+ * Replaces LegInvKinSeq.run_ik_and_fk / calculate_ik_stage
+ * (seqikpy/leg_inverse_kinematics.py:200-403) together with what they call:
+ * KinematicChainSeq.create_leg_chain (seqikpy/kinematic_chain.py:99-421),
+ * ikpy Chain.inverse_kinematics / forward_kinematics and scipy.optimize.least_squares.
+ *
+ *   pose    [n_chain][n_frame][5][3] key points (row 0 = Thorax-Coxa origin, row s = target of
+ *           stage s), addressed as pose + c*pose_chain_stride + t*pose_frame_stride
+ *   affine  NULL, or [n_chain][8] = (fixed_coxa xyz, scale, template_coxa xyz, 0): the
+ *           AlignPose.align_leg map (seqikpy/alignment.py:471-485) applied on load
+ *   params  [n_chain][32] (layout above)
+ *   angles  [n_chain][n_frame][7] out.  When stage_mask does not start at stage 1 it is also an
+ *           INPUT: the DOFs of the earlier stages are read from it per frame and frozen -- the
+ *           `angles=self.joint_angles_dict, t=t` of kinematic_chain.py:99-150
+ *   fk      NULL, or [n_chain][n_frame][9][3] out (rows 0-3 origin, 4-5 Coxa-Femur joint,
+ *           6 Femur-Tibia, 7 Tibia-Tarsus, 8 Claw: leg_inverse_kinematics.py:71-77,279-282);
+ *           rows of stages after the last solved one are left untouched
+ *   status  NULL, or [n_chain] out: 0 if some solve hit max_nfev, else 1
+ *   nfev    NULL, or [n_chain][4] out: function evaluations summed over frames, per stage
+ *   stage_mask  bit s set = solve stage s+1; the set bits must be contiguous
+ *           (stages=[a..b] of run_ik_and_fk, leg_inverse_kinematics.py:350-353)
+ */
+int seqik_leg_solve_f32(const float* pose, int64_t pose_chain_stride, int64_t pose_frame_stride,
+                        const float* affine, const float* params,
+                        float* angles, int64_t ang_chain_stride, int64_t ang_frame_stride,
+                        float* fk, int64_t fk_chain_stride, int64_t fk_frame_stride,
+                        int32_t* status, uint32_t* nfev,
+                        int64_t n_chain, int64_t n_frame, uint32_t stage_mask, uint32_t flags, void* stream);
+
+/* Forward kinematics only: angles -> 9x3 joint positions.
+ * Replaces LegInvKinBase.calculate_fk (seqikpy/leg_inverse_kinematics.py:71-77) on the stage-4 chain.
+ *   angles [n_chain][n_frame][7], origin [n_chain][n_frame][3] (or [n_chain][3] with
+ *   origin_frame_stride = 0), params as above, fk [n_chain][n_frame][9][3]; all dense. */
+int seqik_fk_f32(const float* angles, const float* origin, int64_t origin_frame_stride, const float* params,
+                 float* fk, int64_t n_chain, int64_t n_frame, void* stream);
+
+/* Head roll/pitch/yaw and antenna yaw/pitch (L then R).
+ * Replaces HeadInverseKinematics.compute_head_angles (seqikpy/head_inverse_kinematics.py:103-142, 163-307).
+ *   r_head, l_head [n_trial][n_frame][2][3] (base, tip); neck [n_trial][n_frame][3] (neck_stride 3) or
+ *   [n_trial][3] (neck_stride 0: one point per trial, the (1,1,3) template Neck of alignment.py:375-376)
+ *   affine_r, affine_l: NULL, or [n_trial][8] head-alignment rows (see seqik_head_affine_f32) applied on load
+ *   rest [n_trial][2] = (rest_head_pitch, rest_antenna_pitch) (head_inverse_kinematics.py:309-329)
+ *   out [n_trial][7][n_frame]: head_roll, head_pitch, head_yaw, antenna_yaw_L, antenna_pitch_L,
+ *   antenna_yaw_R, antenna_pitch_R */
+int seqik_head_angles_f32(const float* r_head, const float* l_head, const float* neck, int64_t neck_stride,
+                          const float* affine_r, const float* affine_l, const float* rest,
+                          float* out, int64_t n_trial, int64_t n_frame, void* stream);
+
+/* AlignPose statistics: mean of the 0.45 and 0.55 quantiles (numpy "linear" interpolation) of each series.
+ * Replaces _get_mean_quantile over the series built by AlignPose.get_fixed_pos / get_mean_length
+ * (seqikpy/alignment.py:83-87, 392-415).
+ *   series [n_series][n] (dense rows); counts NULL, or [n_series] int32: only the counts[i] SMALLEST values of
+ *   row i take part (rows padded with +inf, see seqik_head_series_f32); out [n_series];
+ *   scratch: caller-provided [n_series][4] floats */
+int seqik_mid_quantile_f32(const float* series, const int32_t* counts, float* scratch, float* out,
+                           int64_t n_series, int64_t n, void* stream);
+
+/* Leg-segment series for the statistics: for each chain the 3 coordinates of key point 0 and the 4
+ * segment lengths |kp[s+1]-kp[s]| per frame -> series [n_chain][7][n_frame].
+ * Replaces the array construction of AlignPose.get_fixed_pos / get_mean_length (alignment.py:392-415). */
+int seqik_leg_series_f32(const float* pose, int64_t pose_chain_stride, int64_t pose_frame_stride,
+                         float* series, int64_t n_chain, int64_t n_frame, void* stream);
+
+/* Leg affine rows from the statistics (AlignPose.find_scale_leg + align_leg, alignment.py:417-423, 465-485).
+ *   stats [n_chain][7] (seqik_mid_quantile_f32 of the leg series); consts [n_chain][4] = (template
+ *   {leg}_Coxa xyz, model leg length already reduced by the tarsus unless include_claw);
+ *   affine [n_chain][8] out = (fixed_coxa xyz, scale, template xyz, 0) */
+int seqik_leg_affine_f32(const float* stats, const float* consts, int include_claw, float* affine,
+                         int64_t n_chain, void* stream);
+
+/* The affine map of AlignPose.align_leg (alignment.py:471-485) as a standalone elementwise pass:
+ * out[:,0] = template, out[:,i] = (pose[:,i] - fixed) * scale + template.   affine [n_chain][8] as above. */
+int seqik_align_apply_f32(const float* pose, int64_t pose_chain_stride, int64_t pose_frame_stride,
+                          const float* affine, float* out, int64_t n_chain, int64_t n_frame, void* stream);
+
+/* Antenna series of AlignPose.align_head (alignment.py:489-555).
+ *   head [n_trial][n_frame][2][3] (base, tip), thorax [n_trial][n_frame][n_thorax_kp][3] (first and last
+ *   key point are averaged, alignment.py:385-390).  Per trial, series [n_trial][5][n_frame]:
+ *   rows 0-2 base xyz and row 3 d = |base - thorax_mid| at the "stationary" frames i with
+ *   d[i+2] - 2 d[i+1] + d[i] < threshold (find_stationary_indices, alignment.py:425-434), +inf elsewhere;
+ *   row 4 = |tip - base| at every frame.  counts [n_trial][5] int32: valid entries per row. */
+int seqik_head_series_f32(const float* head, const float* thorax, int64_t n_thorax_kp, float threshold,
+                          float* series, int32_t* counts, int64_t n_trial, int64_t n_frame, void* stream);
+
+/* Head affine rows (alignment.py:515-553): stats [n_trial][5] (seqik_mid_quantile_f32 of the head
+ *   series), consts [n_trial][5] = (template {side}_Antenna_base xyz, body_size Antenna_mid_thorax,
+ *   body_size Antenna); affine [n_trial][8] out = (origin xyz, scale_base, template xyz, scale_tip) */
+int seqik_head_affine_f32(const float* stats, const float* consts, float* affine, int64_t n_trial, void* stream);
+
+/* out[:,0] = (base - origin) * scale_base + template; out[:,1] = (tip - origin) * scale_tip + template
+ * (alignment.py:547-553).  head, out [n_trial][n_frame][2][3]. */
+int seqik_head_apply_f32(const float* head, const float* affine, float* out, int64_t n_trial, int64_t n_frame,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEQIK_H_ */

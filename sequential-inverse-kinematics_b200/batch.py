@@ -1,0 +1,101 @@
+"""Batched, multi-trial front end of the leg-IK hot path (BASELINE.json configs 3-5).
+
+The reference handles one recording per ``LegInvKinSeq`` object and parallelises, at most, over the six
+legs with ``multiprocessing.Pool`` (examples/example_leg_inv_kinematics_parallel.py:143-193).  Here many
+trials are solved by one kernel launch: every (trial, leg) pair is an independent chain.
+
+Layout (chain-major, float32): ``pose[trial, leg, frame, 5, 3]`` -> ``angles[trial, leg, frame, 7]``,
+``fk[trial, leg, frame, 9, 3]``.  ``synthetic.to_chains`` converts from the frame-major
+``(trial, frame, leg, 5, 3)`` layout.
+
+Multi-GPU: trials are split into contiguous shards, one per rank (``shard_range``); there is no
+collective on the data path -- chains never exchange data -- and results are gathered on the host once.
+"""
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+from . import _native as N
+from . import engine
+
+
+def shard_range(n_trial: int, rank: int, world_size: int):
+    """Contiguous, balanced [lo, hi) trial range of ``rank`` (first ``n_trial % world_size`` ranks get one more)."""
+    if world_size < 1 or not 0 <= rank < world_size:
+        raise ValueError(f"bad rank/world_size {rank}/{world_size}")
+    base, extra = divmod(int(n_trial), world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def chain_param_table(kinematic_chain_class, initial_angles: Dict[str, Dict[str, np.ndarray]], legs: Sequence[str],
+                      n_trial: int) -> np.ndarray:
+    """(n_trial * n_leg, 32) float32 constant rows (include/seqik.h) -- the same six rows repeated per trial."""
+    row = np.stack([kinematic_chain_class.pack_chain_params(leg, initial_angles[leg]) for leg in legs])
+    return np.tile(row, (int(n_trial), 1)).astype(np.float32)
+
+
+class BatchedLegIK:
+    """Solver session for ``n_trial`` trials x ``len(legs)`` legs x ``n_frame`` frames on one device.
+
+    Device buffers and pinned host result buffers are allocated once and reused by every call.
+    """
+
+    def __init__(self, kinematic_chain_class, initial_angles, legs: Sequence[str], n_trial: int, n_frame: int,
+                 device="cuda", want_fk: bool = True, schedule: int = N.SCHED_AUTO, host_buffers: bool = True):
+        torch = N.require_cuda()
+        N.load_library()
+        self.torch = torch
+        self.legs = list(legs)
+        self.n_trial, self.n_leg, self.n_frame = int(n_trial), len(self.legs), int(n_frame)
+        self.n_chain = self.n_trial * self.n_leg
+        self.device = torch.device(device)
+        self.schedule = schedule
+        self.params = torch.from_numpy(chain_param_table(kinematic_chain_class, initial_angles, self.legs, n_trial)).to(self.device)
+        f32 = dict(dtype=torch.float32, device=self.device)
+        self.d_pose = torch.empty((self.n_chain, self.n_frame, 5, 3), **f32)
+        self.d_angles = torch.empty((self.n_chain, self.n_frame, 7), **f32)
+        self.d_fk = torch.empty((self.n_chain, self.n_frame, 9, 3), **f32) if want_fk else None
+        self.h_angles = self.h_fk = None
+        if host_buffers:
+            self.h_angles = torch.empty((self.n_chain, self.n_frame, 7), dtype=torch.float32, pin_memory=True)
+            self.h_fk = torch.empty((self.n_chain, self.n_frame, 9, 3), dtype=torch.float32, pin_memory=True) if want_fk else None
+        self.status = self.nfev = None
+
+    @property
+    def leg_frames(self) -> int:
+        return self.n_chain * self.n_frame
+
+    def solve_device(self, pose=None, affine=None, want_stats: bool = True):
+        """One pass of the hot path over device-resident pose (default: the session's own pose buffer).
+        Asynchronous on the current stream.  Returns (angles, fk) device tensors (session buffers)."""
+        pose = self.d_pose if pose is None else pose.reshape(self.n_chain, self.n_frame, 5, 3)
+        _, _, self.status, self.nfev = engine.leg_solve(pose, self.params, affine=affine, angles=self.d_angles, fk=self.d_fk,
+                                                        want_fk=self.d_fk is not None, schedule=self.schedule,
+                                                        want_stats=want_stats)
+        return self.d_angles, self.d_fk
+
+    def solve_host(self, pose_host, synchronize: bool = True):
+        """Host (ideally pinned) pose (n_trial, n_leg, n_frame, 5, 3) float32 -> pinned host (angles, fk).
+        Host->device copy, solve and device->host copies are enqueued on the current stream."""
+        torch = self.torch
+        if self.h_angles is None:
+            raise RuntimeError("session was created with host_buffers=False")
+        src = pose_host if isinstance(pose_host, torch.Tensor) else torch.from_numpy(pose_host)
+        if src.dtype != torch.float32:
+            raise ValueError("pose_host must be float32")
+        self.d_pose.copy_(src.reshape(self.n_chain, self.n_frame, 5, 3), non_blocking=True)
+        self.solve_device(want_stats=False)
+        self.h_angles.copy_(self.d_angles, non_blocking=True)
+        if self.h_fk is not None:
+            self.h_fk.copy_(self.d_fk, non_blocking=True)
+        if synchronize:
+            torch.cuda.current_stream(self.device).synchronize()
+        return self.h_angles, self.h_fk
+
+    def mean_fk_error(self, pose=None) -> float:
+        """Mean over chains, frames and the 4 distal joints of |fk[5..8] - pose[1..4]| in mm.
+        Reduction of RESULTS for reporting (torch ops on the device tensors), not part of the solve."""
+        pose = self.d_pose if pose is None else pose.reshape(self.n_chain, self.n_frame, 5, 3)
+        d = self.d_fk[:, :, 5:9, :] - pose[:, :, 1:5, :]
+        return float(d.square().sum(-1).sqrt().mean())

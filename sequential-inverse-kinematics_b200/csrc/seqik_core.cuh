@@ -104,9 +104,10 @@ SK_HD void stage_point(int kind, R L, R has_a, R sa, R ca, R sb, R cb,
 template <typename R>
 struct StageSolve {
     // problem
-    int kind; R L, has_a; Vec3<R> q; R span0, span1;   // span = ub - lb (inf if unbounded)
+    int kind; R L, has_a; R span0, span1;   // span = ub - lb (inf if unbounded)
     bool fin_lb0, fin_ub0, fin_lb1, fin_ub1;
     R null_sq; int max_nfev;
+    bool gn_mode;   // true: take the Gauss-Newton step when it fits the trust region (see trip())
     // iterate
     R x0, x1, dl0, dl1, du0, du1;      // angles and distances to the bounds
     R sa, ca, sb, cb;                   // sin/cos of the iterate
@@ -125,9 +126,10 @@ struct StageSolve {
     }
 
     // least_squares prologue: x0 made strictly feasible (rstep 1e-10), f, J, g, Delta0
-    SK_HD void init(int kind_, R L_, R has_a_, const Vec3<R>& q_, R a, R b,
-                    R lb0, R ub0, R lb1, R ub1, R null_sq_, int n_full) {
-        kind = kind_; L = L_; has_a = has_a_; q = q_; null_sq = null_sq_; max_nfev = 100 * n_full;
+    SK_HD void init(int kind_, R L_, R has_a_, const Vec3<R>& q, R a, R b,
+                    R lb0, R ub0, R lb1, R ub1, R null_sq_, int n_full, bool gn_mode_ = false) {
+        gn_mode = gn_mode_;
+        kind = kind_; L = L_; has_a = has_a_; null_sq = null_sq_; max_nfev = 100 * n_full;
         fin_lb0 = lb0 > -N::inf(); fin_ub0 = ub0 < N::inf(); fin_lb1 = lb1 > -N::inf(); fin_ub1 = ub1 < N::inf();
         span0 = ub0 - lb0; span1 = ub1 - lb1;
         x0 = a; x1 = b;
@@ -273,7 +275,16 @@ struct StageSolve {
         }
         // ---- solve_lsq_trust_region, rank-deficient branch
         R t0, t1;
-        {
+        bool gn_taken = false;
+        if (gn_mode && lam1 > R(0)) {
+            // scipy's SVD leaves ~1e-17 singular values on the inert slots of the longer chains; the
+            // Levenberg parameter then decays to ~1e-20 and that null-space noise absorbs the trust-region
+            // norm, i.e. the active pair receives the plain Gauss-Newton step whenever it fits in Delta.
+            t0 = suf0 / lam0; t1 = suf1 / lam1;
+            gn_taken = (t0 * t0 + t1 * t1 <= Delta * Delta);
+            if (gn_taken) alpha = R(0);
+        }
+        if (!gn_taken) {
             R a_up = N::sqrt_(suf0 * suf0 + suf1 * suf1) / Delta, a_lo = R(0);
             if (alpha == R(0)) alpha = R(0.001) * a_up;
             for (int it = 0; it < 10; ++it) {
@@ -296,7 +307,7 @@ struct StageSolve {
             t0 = (e0 != R(0)) ? suf0 / e0 : R(0); t1 = (e1 != R(0)) ? suf1 / e1 : R(0);
         }
         R ph0 = -(ex * t0 - ey * t1), ph1 = -(ey * t0 + ex * t1);
-        {
+        if (!gn_taken) {
             const R sc = Delta / N::sqrt_(ph0 * ph0 + ph1 * ph1);
             ph0 *= sc; ph1 *= sc;
         }
@@ -378,7 +389,7 @@ template <typename R> SK_HD Vec3<R> lin(const Vec3<R>& a, R s, const Vec3<R>& b,
     return {a.x * s + b.x * t, a.y * s + b.y * t, a.z * s + b.z * t};
 }
 // A <- A * Rot_a(a) * Ry(b), Rot_a = Rx (KIND_XY) or Rz (KIND_ZY)
-template <typename R> SK_HD Mat3<R> advance(const Mat3<R>& A, int kind, R sa, R ca, R sb, R cb) {
+template <typename R> SK_HD Mat3<R> rotate_frame(const Mat3<R>& A, int kind, R sa, R ca, R sb, R cb) {
     Mat3<R> B;
     if (kind == KIND_XY) { B.c0 = A.c0; B.c1 = lin(A.c1, ca, A.c2, sa); B.c2 = lin(A.c1, -sa, A.c2, ca); }
     else { B.c0 = lin(A.c0, ca, A.c1, sa); B.c1 = lin(A.c0, -sa, A.c1, ca); B.c2 = A.c2; }
@@ -386,6 +397,107 @@ template <typename R> SK_HD Mat3<R> advance(const Mat3<R>& A, int kind, R sa, R 
     C.c0 = lin(B.c0, cb, B.c2, -sb); C.c1 = B.c1; C.c2 = lin(B.c0, sb, B.c2, cb);
     return C;
 }
+
+
+// ---------------------------------------------------------------------------------
+// ChainRunner: one (trial, leg) chain advanced ONE function evaluation per step().
+//
+// The kernels give every lane one runner and call step() in a convergent loop: lanes of a
+// warp then sit at different (frame, stage) positions of their own chains ("decoupled"
+// schedule), so a slow solve delays only its own chain instead of the whole warp.  The
+// data dependences of the reference are kept exactly: stage s of frame t starts from the
+// stage-s angles of frame t-1 (leg_inverse_kinematics.py:272) and from the frame built by
+// stages 1..s-1 of frame t (kinematic_chain.py stage builders).
+//
+// IO is a policy: kp(t,row) -> key point (already aligned), put_angles(t, ang7),
+// put_fk(t,row,v), and chain constants.
+// ---------------------------------------------------------------------------------
+template <typename R, typename IO>
+struct ChainRunner {
+    IO io;
+    int64_t t, n_frame;
+    int s;                       // current stage 0..3
+    int lo, hi, gn_mask;         // stages lo..hi are solved; stages < lo are frozen at the angles read from io
+    Mat3<R> A; Vec3<R> piv, o, rel;
+    R ang0, ang1, ang2, ang3, ang4, ang5, ang6;   // scalars, not an array: `s` is a run-time index
+    StageSolve<R> S;
+    uint32_t nf0, nf1, nf2, nf3; int worst_status;
+
+    SK_HD void begin_frame() {
+        A = {{R(1), R(0), R(0)}, {R(0), R(1), R(0)}, {R(0), R(0), R(1)}};
+        piv = {R(0), R(0), R(0)};
+        o = io.kp(t, 0);
+        for (int r = 0; r < 4; ++r) io.put_fk(t, r, o);
+        s = 0;
+    }
+    SK_HD void begin_stage() {
+        const Vec3<R> k = io.kp(t, s + 1);
+        rel = {(k.x - o.x) - piv.x, (k.y - o.y) - piv.y, (k.z - o.z) - piv.z};
+        const Vec3<R> q = mulT(A, rel);
+        const R inf = Num<R>::inf();
+        const int n_full = (s == 0) ? 4 : (s == 1) ? 6 : (s == 2) ? 8 : 9;
+        const bool gn = (gn_mask >> s) & 1;
+        const bool frozen = s < lo;
+        if (frozen) {   // kinematic_chain.py: earlier-stage DOFs are `fixed` links at angles[...][t]
+            if (s == 0) { ang0 = io.angle_in(t, 0); ang1 = io.angle_in(t, 1); }
+            else if (s == 1) { ang2 = io.angle_in(t, 2); ang3 = io.angle_in(t, 3); }
+            else { ang4 = io.angle_in(t, 4); ang5 = io.angle_in(t, 5); }
+        }
+        if (s == 3) S.init(KIND_ZY, io.seg(3), R(0), q, R(0), ang6, -inf, inf, io.lb(6), io.ub(6), io.null_sq(3), n_full, gn);
+        else {
+            const int ia = 2 * s, ib = 2 * s + 1;
+            const R a = (s == 0) ? ang0 : (s == 1) ? ang2 : ang4;
+            const R b = (s == 0) ? ang1 : (s == 1) ? ang3 : ang5;
+            if (frozen) S.init(s == 0 ? KIND_XY : KIND_ZY, io.seg(s), R(1), q, a, b, -inf, inf, -inf, inf, R(0), n_full, gn);
+            else S.init(s == 0 ? KIND_XY : KIND_ZY, io.seg(s), R(1), q, a, b, io.lb(ia), io.ub(ia), io.lb(ib), io.ub(ib),
+                        io.null_sq(s), n_full, gn);
+        }
+        if (frozen) S.status = ST_GTOL;
+    }
+    // stage_mask: contiguous bits lo..hi
+    SK_HD void start(const IO& io_, int64_t n_frame_, const R* seed, int stage_mask_, int gn_mask_) {
+        io = io_; n_frame = n_frame_; t = 0; s = 0; gn_mask = gn_mask_;
+        lo = 0; while (lo < 3 && !((stage_mask_ >> lo) & 1)) ++lo;
+        hi = 3; while (hi > 0 && !((stage_mask_ >> hi) & 1)) --hi;
+        ang0 = seed[0]; ang1 = seed[1]; ang2 = seed[2]; ang3 = seed[3]; ang4 = seed[4]; ang5 = seed[5]; ang6 = seed[6];
+        nf0 = nf1 = nf2 = nf3 = 0;
+        worst_status = ST_GTOL;
+        if (n_frame > 0) { begin_frame(); begin_stage(); }
+    }
+    SK_HD bool finished() const { return t >= n_frame; }
+
+    // close the converged stage, open the next one (possibly of the next frame)
+    SK_HD void advance() {
+        if (s >= lo) {
+            if (s == 0) { ang0 = S.x0; ang1 = S.x1; nf0 += (uint32_t)S.nfev; }
+            else if (s == 1) { ang2 = S.x0; ang3 = S.x1; nf1 += (uint32_t)S.nfev; }
+            else if (s == 2) { ang4 = S.x0; ang5 = S.x1; nf2 += (uint32_t)S.nfev; }
+            else { ang6 = S.x1; nf3 += (uint32_t)S.nfev; }
+            if (S.status == ST_MAXFEV) worst_status = ST_MAXFEV;
+        }
+        // next pivot = pivot + A w(x) = target + A f   (q = A^T rel, f = w - q)
+        const Vec3<R> Af = mul(A, S.f);
+        piv = {(piv.x + rel.x) + Af.x, (piv.y + rel.y) + Af.y, (piv.z + rel.z) + Af.z};
+        const Vec3<R> jw = {piv.x + o.x, piv.y + o.y, piv.z + o.z};
+        if (s == 0) { io.put_fk(t, 4, jw); io.put_fk(t, 5, jw); } else io.put_fk(t, 5 + s, jw);
+        if (s < hi) {
+            A = rotate_frame(A, S.kind, S.sa, S.ca, S.sb, S.cb);
+            ++s;
+            begin_stage();
+        } else {
+            const R out7[7] = {ang0, ang1, ang2, ang3, ang4, ang5, ang6};
+            io.put_angles(t, out7, 2 * lo, hi == 3 ? 7 : 2 * hi + 2);
+            ++t;
+            if (t < n_frame) { begin_frame(); begin_stage(); }
+        }
+    }
+    // one evaluation for this lane (no-op when the chain is finished)
+    SK_HD void step() {
+        if (finished()) return;
+        if (S.done()) advance();
+        if (!finished() && !S.done()) S.trip();
+    }
+};
 
 // Per-chain constants (one leg of one trial)
 template <typename R> struct ChainParams {
@@ -401,7 +513,7 @@ struct FrameStats { int nfev[4]; int status[4]; };
 // angles (warm start, leg_inverse_kinematics.py:272) -> this frame's.
 // `kp`: 5 key points (row 0 = ThC origin).  `fk`: 9x3 output rows (may be null).
 template <typename R>
-SK_HD void solve_frame(const ChainParams<R>& P, const R* kp, R* ang, R* fk, FrameStats* fs, int stage_mask = 0xF) {
+SK_HD void solve_frame(const ChainParams<R>& P, const R* kp, R* ang, R* fk, FrameStats* fs, int stage_mask = 0xF, int gn_mask = 0) {
     const int n_full[4] = {4, 6, 8, 9};
     const Vec3<R> o = {kp[0], kp[1], kp[2]};
     Mat3<R> A = {{R(1), R(0), R(0)}, {R(0), R(1), R(0)}, {R(0), R(0), R(1)}};
@@ -415,17 +527,17 @@ SK_HD void solve_frame(const ChainParams<R>& P, const R* kp, R* ang, R* fk, Fram
         const int ia = (s == 3) ? -1 : 2 * s, ib = (s == 3) ? 6 : 2 * s + 1;
         StageSolve<R> S;
         const R inf = Num<R>::inf();
-        if (s == 3) S.init(kind, P.seg[s], R(0), q, R(0), ang[ib], -inf, inf, P.lb[ib], P.ub[ib], P.null_sq[s], n_full[s]);
-        else S.init(kind, P.seg[s], R(1), q, ang[ia], ang[ib], P.lb[ia], P.ub[ia], P.lb[ib], P.ub[ib], P.null_sq[s], n_full[s]);
+        if (s == 3) S.init(kind, P.seg[s], R(0), q, R(0), ang[ib], -inf, inf, P.lb[ib], P.ub[ib], P.null_sq[s], n_full[s], (gn_mask >> s) & 1);
+        else S.init(kind, P.seg[s], R(1), q, ang[ia], ang[ib], P.lb[ia], P.ub[ia], P.lb[ib], P.ub[ib], P.null_sq[s], n_full[s], (gn_mask >> s) & 1);
         if (stage_mask & (1 << s)) { while (!S.done()) S.trip(); }
         if (s != 3) ang[ia] = S.x0;
         ang[ib] = S.x1;
         if (fs) { fs->nfev[s] = S.nfev; fs->status[s] = S.status; }
         // next pivot = pivot + A w = target + A f
         const Vec3<R> Af = mul(A, S.f);
-        piv = {tgt.x + Af.x, tgt.y + Af.y, tgt.z + Af.z};
+        piv = {(piv.x + rel.x) + Af.x, (piv.y + rel.y) + Af.y, (piv.z + rel.z) + Af.z};
         joint[s] = piv;
-        A = advance(A, kind, S.sa, S.ca, S.sb, S.cb);
+        A = rotate_frame(A, kind, S.sa, S.ca, S.sb, S.cb);
     }
     if (fk) {
         for (int r = 0; r < 4; ++r) { fk[3 * r] = o.x; fk[3 * r + 1] = o.y; fk[3 * r + 2] = o.z; }

@@ -1,0 +1,551 @@
+// seqik_kernels.cu -- sm_100a kernels + C ABI (include/seqik.h) of the SeqIKPy leg-IK hot path.
+//
+// Kernels
+//   leg_solve_kernel   4-stage sequential IK + FK.  Latency/FP32-issue bound: every lane owns
+//                      one (trial, leg) chain and runs ChainRunner::step() -- one residual evaluation of its
+//                      current (frame, stage) solve per trip -- in a convergent loop.
+//   fk_kernel          angles -> 9x3 joint positions, HBM-bound streaming kernel (smem-staged, 128-bit I/O)
+//   head_kernel        7 head/antenna angles per frame, HBM-bound elementwise
+//   leg_series_kernel / mid_quantile_kernel / align_apply_kernel   AlignPose statistics + affine map
+//
+// No tensor cores: the work is scalar FP32 2x2 / 3x3 algebra (BASELINE.json north_star).
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/seqik.h"
+#include "seqik_core.cuh"
+
+using namespace seqik;
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, const char* a = "") {
+    snprintf(g_err, sizeof(g_err), fmt, a);
+    return code;
+}
+static int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+        return SEQIK_ECUDA;
+    }
+    return SEQIK_OK;
+}
+
+extern "C" int seqik_abi_version(void) { return SEQIK_ABI_VERSION; }
+extern "C" const char* seqik_last_error(void) { return g_err; }
+
+// ---------------------------------------------------------------------------------------------
+// leg solver
+// ---------------------------------------------------------------------------------------------
+struct LegArgs {
+    const float* pose; int64_t pose_cs, pose_fs;
+    const float* affine; const float* params;
+    float* angles; int64_t ang_cs, ang_fs;
+    float* fk; int64_t fk_cs, fk_fs;
+    int32_t* status; uint32_t* nfev;
+    int64_t n_chain, n_frame;
+    int stage_mask, gn_mask;
+};
+
+// Global-memory IO policy of one chain.  Key points are read with plain (L1-cached) loads: a chain's
+// frames are contiguous (60 B apart), so consecutive frames share 128 B lines.
+struct DevIO {
+    const float* pose; int64_t fs;          // base of this chain, frame stride
+    const float* prm;                       // 32 floats
+    float* ang; int64_t ang_fs;
+    float* fk; int64_t fk_fs;
+    float fx, fy, fz, sc, tx, ty, tz;       // alignment map (identity when no affine)
+    bool has_affine;
+
+    __device__ __forceinline__ Vec3<float> kp(int64_t t, int row) const {
+        const float* p = pose + t * fs + row * 3;
+        Vec3<float> v = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+        if (has_affine) {
+            if (row == 0) v = {tx, ty, tz};
+            else v = {(v.x - fx) * sc + tx, (v.y - fy) * sc + ty, (v.z - fz) * sc + tz};
+        }
+        return v;
+    }
+    __device__ __forceinline__ void put_angles(int64_t t, const float* a, int i0, int i1) const {
+        float* p = ang + t * ang_fs;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) if (i >= i0 && i < i1) p[i] = a[i];
+    }
+    __device__ __forceinline__ float angle_in(int64_t t, int i) const { return ang[t * ang_fs + i]; }
+    __device__ __forceinline__ void put_fk(int64_t t, int row, const Vec3<float>& v) const {
+        if (fk) { float* p = fk + t * fk_fs + row * 3; p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+    }
+    __device__ __forceinline__ float seg(int i) const { return __ldg(prm + i); }
+    __device__ __forceinline__ float lb(int i) const { return __ldg(prm + 4 + i); }
+    __device__ __forceinline__ float ub(int i) const { return __ldg(prm + 11 + i); }
+    __device__ __forceinline__ float null_sq(int i) const { return __ldg(prm + 25 + i); }
+};
+
+// schedule 1: one lane per chain, decoupled trips
+__global__ void __launch_bounds__(64) leg_solve_kernel(LegArgs a) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_chain) return;
+    DevIO io;
+    io.pose = a.pose + c * a.pose_cs; io.fs = a.pose_fs;
+    io.prm = a.params + c * SEQIK_CHAIN_PARAM_FLOATS;
+    io.ang = a.angles + c * a.ang_cs; io.ang_fs = a.ang_fs;
+    io.fk = a.fk ? a.fk + c * a.fk_cs : nullptr; io.fk_fs = a.fk_fs;
+    io.has_affine = a.affine != nullptr;
+    io.fx = io.fy = io.fz = 0.f; io.sc = 1.f; io.tx = io.ty = io.tz = 0.f;
+    if (io.has_affine) {
+        const float* q = a.affine + c * 8;
+        io.fx = q[0]; io.fy = q[1]; io.fz = q[2]; io.sc = q[3]; io.tx = q[4]; io.ty = q[5]; io.tz = q[6];
+    }
+    float seed[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) seed[i] = io.prm[18 + i];
+    ChainRunner<float, DevIO> run;
+    run.start(io, a.n_frame, seed, a.stage_mask, a.gn_mask);
+    while (!run.finished()) run.step();
+    if (a.status) a.status[c] = run.worst_status;
+    if (a.nfev) { uint32_t* nf = a.nfev + c * 4; nf[0] = run.nf0; nf[1] = run.nf1; nf[2] = run.nf2; nf[3] = run.nf3; }
+}
+
+extern "C" int seqik_leg_solve_f32(const float* pose, int64_t pose_chain_stride, int64_t pose_frame_stride,
+                                   const float* affine, const float* params,
+                                   float* angles, int64_t ang_chain_stride, int64_t ang_frame_stride,
+                                   float* fk, int64_t fk_chain_stride, int64_t fk_frame_stride,
+                                   int32_t* status, uint32_t* nfev,
+                                   int64_t n_chain, int64_t n_frame, uint32_t stage_mask, uint32_t flags, void* stream) {
+    if (n_chain < 0 || n_frame < 0) return fail(SEQIK_EINVAL, "seqik_leg_solve_f32: negative size");
+    if (n_chain == 0 || n_frame == 0) return SEQIK_OK;
+    if (!pose || !params || !angles) return fail(SEQIK_EINVAL, "seqik_leg_solve_f32: pose, params and angles must not be NULL");
+    {
+        uint32_t m = stage_mask;
+        while (m && !(m & 1u)) m >>= 1;
+        if (stage_mask == 0 || stage_mask > 0xF || (m & (m + 1)) != 0)
+            return fail(SEQIK_EINVAL, "seqik_leg_solve_f32: stage_mask must be a contiguous run of bits within 0xF");
+    }
+    if (pose_frame_stride < 15 || ang_frame_stride < 7 || (fk && fk_frame_stride < 27))
+        return fail(SEQIK_EINVAL, "seqik_leg_solve_f32: frame stride smaller than the innermost block");
+    LegArgs a;
+    a.pose = pose; a.pose_cs = pose_chain_stride; a.pose_fs = pose_frame_stride;
+    a.affine = affine; a.params = params;
+    a.angles = angles; a.ang_cs = ang_chain_stride; a.ang_fs = ang_frame_stride;
+    a.fk = fk; a.fk_cs = fk_chain_stride; a.fk_fs = fk_frame_stride;
+    a.status = status; a.nfev = nfev; a.n_chain = n_chain; a.n_frame = n_frame;
+    a.stage_mask = (int)stage_mask; a.gn_mask = (int)(flags & 0xF);
+    const int block = 32;
+    const int64_t grid = (n_chain + block - 1) / block;
+    leg_solve_kernel<<<(unsigned)grid, block, 0, (cudaStream_t)stream>>>(a);
+    return check_launch("seqik_leg_solve_f32");
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward kinematics (streaming)
+// ---------------------------------------------------------------------------------------------
+// One thread per leg-frame; a block of 256 leg-frames stages its 256x7 angles through shared memory with
+// coalesced loads and its 256x27 outputs back with coalesced stores.
+constexpr int FK_BLOCK = 256;
+
+__global__ void __launch_bounds__(FK_BLOCK) fk_kernel(const float* __restrict__ angles, const float* __restrict__ origin,
+                                                      int64_t origin_fs, const float* __restrict__ params,
+                                                      float* __restrict__ fk, int64_t n_chain, int64_t n_frame) {
+    __shared__ float s_in[FK_BLOCK * 7];
+    __shared__ float s_out[FK_BLOCK * 27];
+    const int64_t total = n_chain * n_frame;
+    const int64_t base = (int64_t)blockIdx.x * FK_BLOCK;
+    const int n_here = (int)min((int64_t)FK_BLOCK, total - base);
+    for (int i = threadIdx.x; i < n_here * 7; i += FK_BLOCK) s_in[i] = angles[base * 7 + i];
+    __syncthreads();
+    if (threadIdx.x < n_here) {
+        const int64_t lf = base + threadIdx.x;
+        const int64_t c = lf / n_frame, t = lf - c * n_frame;
+        const float* prm = params + c * SEQIK_CHAIN_PARAM_FLOATS;
+        const float* op = origin + (origin_fs ? (c * n_frame + t) * origin_fs : c * 3);
+        const Vec3<float> o = {op[0], op[1], op[2]};
+        const float* q = s_in + threadIdx.x * 7;
+        float* out = s_out + threadIdx.x * 27;
+        Mat3<float> A = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
+        Vec3<float> p = o;
+        float sa, ca, sb, cb;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) { out[3 * r] = o.x; out[3 * r + 1] = o.y; out[3 * r + 2] = o.z; }
+        // stage 1: Rx(yaw) Ry(pitch), coxa
+        sincosf(q[0], &sa, &ca); sincosf(q[1], &sb, &cb);
+        A = rotate_frame(A, KIND_XY, sa, ca, sb, cb);
+        p = {p.x - prm[0] * A.c2.x, p.y - prm[0] * A.c2.y, p.z - prm[0] * A.c2.z};
+        out[12] = out[15] = p.x; out[13] = out[16] = p.y; out[14] = out[17] = p.z;
+        // stage 2: Rz(roll) Ry(CTr_pitch), femur
+        sincosf(q[2], &sa, &ca); sincosf(q[3], &sb, &cb);
+        A = rotate_frame(A, KIND_ZY, sa, ca, sb, cb);
+        p = {p.x - prm[1] * A.c2.x, p.y - prm[1] * A.c2.y, p.z - prm[1] * A.c2.z};
+        out[18] = p.x; out[19] = p.y; out[20] = p.z;
+        // stage 3: Rz(CTr_roll) Ry(FTi_pitch), tibia
+        sincosf(q[4], &sa, &ca); sincosf(q[5], &sb, &cb);
+        A = rotate_frame(A, KIND_ZY, sa, ca, sb, cb);
+        p = {p.x - prm[2] * A.c2.x, p.y - prm[2] * A.c2.y, p.z - prm[2] * A.c2.z};
+        out[21] = p.x; out[22] = p.y; out[23] = p.z;
+        // stage 4: Ry(TiTa_pitch), tarsus
+        sincosf(q[6], &sb, &cb);
+        A = rotate_frame(A, KIND_ZY, 0.f, 1.f, sb, cb);
+        p = {p.x - prm[3] * A.c2.x, p.y - prm[3] * A.c2.y, p.z - prm[3] * A.c2.z};
+        out[24] = p.x; out[25] = p.y; out[26] = p.z;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_here * 27; i += FK_BLOCK) fk[base * 27 + i] = s_out[i];
+}
+
+extern "C" int seqik_fk_f32(const float* angles, const float* origin, int64_t origin_frame_stride, const float* params,
+                            float* fk, int64_t n_chain, int64_t n_frame, void* stream) {
+    if (n_chain < 0 || n_frame < 0) return fail(SEQIK_EINVAL, "seqik_fk_f32: negative size");
+    if (n_chain == 0 || n_frame == 0) return SEQIK_OK;
+    if (!angles || !origin || !params || !fk) return fail(SEQIK_EINVAL, "seqik_fk_f32: NULL pointer");
+    if (origin_frame_stride != 0 && origin_frame_stride != 3) return fail(SEQIK_EINVAL, "seqik_fk_f32: origin_frame_stride must be 0 or 3");
+    const int64_t total = n_chain * n_frame;
+    const int64_t grid = (total + FK_BLOCK - 1) / FK_BLOCK;
+    fk_kernel<<<(unsigned)grid, FK_BLOCK, 0, (cudaStream_t)stream>>>(angles, origin, origin_frame_stride, params, fk, n_chain, n_frame);
+    return check_launch("seqik_fk_f32");
+}
+
+// ---------------------------------------------------------------------------------------------
+// head / antenna angles (elementwise)
+// ---------------------------------------------------------------------------------------------
+// angle_between_segments (head_inverse_kinematics.py:163-183) for vectors that live in a coordinate plane:
+// arccos(v1^.v2^) * (det > 0 ? 1 : -1), evaluated as atan2(|det|, dot) which keeps FP32 accuracy near 0 and pi.
+__device__ __forceinline__ float signed_angle(float dotp, float det) {
+    const float a = atan2f(fabsf(det), dotp);
+    return det > 0.f ? a : -a;
+}
+
+// head-alignment row: (origin xyz, scale_base, template xyz, scale_tip)
+__device__ __forceinline__ void head_point(const float* __restrict__ p, const float* __restrict__ aff, bool tip,
+                                           float& x, float& y, float& z) {
+    x = p[0]; y = p[1]; z = p[2];
+    if (aff) {
+        const float sc = tip ? aff[7] : aff[3];
+        x = (x - aff[0]) * sc + aff[4]; y = (y - aff[1]) * sc + aff[5]; z = (z - aff[2]) * sc + aff[6];
+    }
+}
+
+__global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ r_head, const float* __restrict__ l_head,
+                                                   const float* __restrict__ neck, int64_t neck_stride,
+                                                   const float* __restrict__ affine_r, const float* __restrict__ affine_l,
+                                                   const float* __restrict__ rest,
+                                                   float* __restrict__ out, int64_t n_trial, int64_t n_frame) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_trial * n_frame) return;
+    const int64_t tr = i / n_frame, t = i - tr * n_frame;
+    const float* r = r_head + i * 6; const float* l = l_head + i * 6;
+    const float* nk = neck + (neck_stride ? i * 3 : tr * 3);
+    const float* ar = affine_r ? affine_r + tr * 8 : nullptr;
+    const float* al = affine_l ? affine_l + tr * 8 : nullptr;
+    const float rest_head_pitch = rest[tr * 2], rest_ant_pitch = rest[tr * 2 + 1];
+    float rbx, rby, rbz, rtx, rty, rtz, lbx, lby, lbz, ltx, lty, ltz;
+    head_point(r, ar, false, rbx, rby, rbz); head_point(r + 3, ar, true, rtx, rty, rtz);
+    head_point(l, al, false, lbx, lby, lbz); head_point(l + 3, al, true, ltx, lty, ltz);
+    const float nx = nk[0], ny = nk[1], nz = nk[2];
+    const float hx = lbx - rbx, hy = lby - rby, hz = lbz - rbz;                                   // horizontal
+    const float mx = (rbx + lbx) * 0.5f - nx, mz = (rbz + lbz) * 0.5f - nz;                      // mid - neck
+    // roll: Y -> hor|x=0 about X; pitch: X -> mid|y=0 about Y (+rest); yaw: Y -> hor|z=0 about Z
+    const float roll = signed_angle(hy, hz);
+    const float pitch = signed_angle(mx, -mz) + rest_head_pitch;
+    const float yaw = signed_angle(hy, -hx);
+    float* o = out + tr * 7 * n_frame + t;
+    o[0] = roll; o[n_frame] = pitch; o[2 * n_frame] = yaw;
+    // derotation by -roll about X:  y' = y c + z s,  z' = -y s + z c
+    float s, c; sincosf(roll, &s, &c);
+    const float hdy = hy * c + hz * s, hdz = -hy * s + hz * c;                                    // derotated hor (x dropped)
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {   // 0 = L, 1 = R  (reference loops ["L", "R"])
+        const float bx = side ? rbx : lbx, by = side ? rby : lby, bz = side ? rbz : lbz;
+        const float tx = side ? rtx : ltx, ty = side ? rty : lty, tz = side ? rtz : ltz;
+        const float ax = tx - bx, ay = ty - by, az = tz - bz;                                     // antenna vector
+        const float ady = ay * c + az * s, adz = -ay * s + az * c;
+        // yaw: antenna|x=0 -> hor|x=0 about X ; det = X . (v1 x v2) = v1y v2z - v1z v2y
+        float ayaw = signed_angle(ady * hdy + adz * hdz, ady * hdz - adz * hdy);
+        if (side) ayaw = 3.14159265358979323846f - ayaw;
+        // pitch: (neck - base)|y=0 -> antenna|y=0 about Y ; det = Y . (v1 x v2) = v1z v2x - v1x v2z
+        const float gx = nx - bx, gy = ny - by, gz = nz - bz;
+        const float gdz = -gy * s + gz * c;
+        const float apitch = signed_angle(gx * ax + gdz * adz, gdz * ax - gx * adz) - rest_ant_pitch;
+        o[(3 + 2 * side) * n_frame] = ayaw; o[(4 + 2 * side) * n_frame] = apitch;
+    }
+}
+
+extern "C" int seqik_head_angles_f32(const float* r_head, const float* l_head, const float* neck, int64_t neck_stride,
+                                     const float* affine_r, const float* affine_l, const float* rest,
+                                     float* out, int64_t n_trial, int64_t n_frame, void* stream) {
+    if (n_trial < 0 || n_frame < 0) return fail(SEQIK_EINVAL, "seqik_head_angles_f32: negative size");
+    if (n_trial == 0 || n_frame == 0) return SEQIK_OK;
+    if (!r_head || !l_head || !neck || !rest || !out) return fail(SEQIK_EINVAL, "seqik_head_angles_f32: NULL pointer");
+    if (neck_stride != 0 && neck_stride != 3) return fail(SEQIK_EINVAL, "seqik_head_angles_f32: neck_stride must be 0 or 3");
+    if ((affine_r == nullptr) != (affine_l == nullptr))
+        return fail(SEQIK_EINVAL, "seqik_head_angles_f32: affine_r and affine_l must both be given or both be NULL");
+    const int64_t n = n_trial * n_frame;
+    head_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(r_head, l_head, neck, neck_stride, affine_r, affine_l,
+                                                                              rest, out, n_trial, n_frame);
+    return check_launch("seqik_head_angles_f32");
+}
+
+// ---------------------------------------------------------------------------------------------
+// AlignPose: series, mid-quantiles, affine maps
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) leg_series_kernel(const float* __restrict__ pose, int64_t cs, int64_t fs,
+                                                         float* __restrict__ series, int64_t n_chain, int64_t n_frame) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_chain * n_frame) return;
+    const int64_t c = i / n_frame, t = i - c * n_frame;
+    const float* p = pose + c * cs + t * fs;
+    float k[15];
+#pragma unroll
+    for (int j = 0; j < 15; ++j) k[j] = p[j];
+    float* s = series + c * 7 * n_frame + t;
+    s[0] = k[0]; s[n_frame] = k[1]; s[2 * n_frame] = k[2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float dx = k[3 * j + 3] - k[3 * j], dy = k[3 * j + 4] - k[3 * j + 1], dz = k[3 * j + 5] - k[3 * j + 2];
+        s[(3 + j) * n_frame] = sqrtf(dx * dx + dy * dy + dz * dz);
+    }
+}
+
+extern "C" int seqik_leg_series_f32(const float* pose, int64_t pose_chain_stride, int64_t pose_frame_stride,
+                                    float* series, int64_t n_chain, int64_t n_frame, void* stream) {
+    if (n_chain < 0 || n_frame < 0) return fail(SEQIK_EINVAL, "seqik_leg_series_f32: negative size");
+    if (n_chain == 0 || n_frame == 0) return SEQIK_OK;
+    if (!pose || !series) return fail(SEQIK_EINVAL, "seqik_leg_series_f32: NULL pointer");
+    const int64_t total = n_chain * n_frame;
+    leg_series_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pose, pose_chain_stride, pose_frame_stride,
+                                                                                        series, n_chain, n_frame);
+    return check_launch("seqik_leg_series_f32");
+}
+
+// Order statistic by 4-pass MSB radix select on order-preserving keys; one block per (series, rank).
+__device__ __forceinline__ uint32_t order_key(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_value(uint32_t k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+constexpr int SEL_BLOCK = 256;
+
+// ranks of numpy.quantile(..., method="linear") at q = 0.45 and 0.55: floor(q (n-1)) and the next one
+__device__ __forceinline__ void quantile_pos(double q, int64_t n, int64_t& lo, float& frac) {
+    const double v = q * (double)(n - 1);
+    lo = (int64_t)floor(v);
+    if (lo > n - 1) lo = n - 1;
+    frac = (float)(v - (double)lo);
+}
+
+__global__ void __launch_bounds__(SEL_BLOCK) mid_quantile_select_kernel(const float* __restrict__ series,
+                                                                        const int32_t* __restrict__ counts, int64_t n,
+                                                                        float* __restrict__ picked) {
+    __shared__ unsigned int hist[256];
+    __shared__ uint32_t s_prefix; __shared__ unsigned long long s_rank;
+    const int64_t sidx = blockIdx.x; const int which = blockIdx.y;   // 0: lo(.45) 1: lo+1 2: lo(.55) 3: lo+1
+    const float* v = series + sidx * n;
+    const int64_t m = counts ? (int64_t)counts[sidx] : n;             // values that take part (the m smallest)
+    if (m <= 0) { if (threadIdx.x == 0) picked[sidx * 4 + which] = __int_as_float(0x7fc00000); return; }
+    int64_t lo; float frac;
+    quantile_pos(which < 2 ? 0.45 : 0.55, m, lo, frac);
+    int64_t rank = lo + (which & 1); if (rank > m - 1) rank = m - 1;
+    uint32_t prefix = 0, mask = 0;
+    for (int pass = 3; pass >= 0; --pass) {
+        const int shift = 8 * pass;
+        hist[threadIdx.x] = 0;
+        __syncthreads();
+        for (int64_t i = threadIdx.x; i < n; i += SEL_BLOCK) {
+            const uint32_t k = order_key(v[i]);
+            if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 0xFF], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned long long r = (unsigned long long)rank, acc = 0; int d = 0;
+            for (; d < 256; ++d) { if (acc + hist[d] > r) break; acc += hist[d]; }
+            if (d > 255) d = 255;
+            s_prefix = prefix | ((uint32_t)d << shift); s_rank = r - acc;
+        }
+        __syncthreads();
+        prefix = s_prefix; rank = (int64_t)s_rank; mask |= 0xFFu << shift;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) picked[sidx * 4 + which] = key_value(prefix);
+}
+
+__global__ void mid_quantile_combine_kernel(const float* __restrict__ picked, const int32_t* __restrict__ counts,
+                                            float* __restrict__ out, int64_t n_series, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_series) return;
+    const int64_t m = counts ? (int64_t)counts[i] : n;
+    if (m <= 0) { out[i] = __int_as_float(0x7fc00000); return; }
+    int64_t lo; float f0, f1;
+    quantile_pos(0.45, m, lo, f0); quantile_pos(0.55, m, lo, f1);
+    const float* p = picked + i * 4;
+    const float q0 = p[0] + (p[1] - p[0]) * f0, q1 = p[2] + (p[3] - p[2]) * f1;
+    out[i] = 0.5f * (q0 + q1);
+}
+
+extern "C" int seqik_mid_quantile_f32(const float* series, const int32_t* counts, float* scratch, float* out,
+                                      int64_t n_series, int64_t n, void* stream) {
+    if (n_series < 0 || n < 0) return fail(SEQIK_EINVAL, "seqik_mid_quantile_f32: negative size");
+    if (n_series == 0) return SEQIK_OK;
+    if (n == 0) return fail(SEQIK_EINVAL, "seqik_mid_quantile_f32: empty series");
+    if (!series || !scratch || !out) return fail(SEQIK_EINVAL, "seqik_mid_quantile_f32: NULL pointer (scratch needs 4*n_series floats)");
+    if (n_series > 2147483647LL) return fail(SEQIK_EINVAL, "seqik_mid_quantile_f32: too many series");
+    dim3 grid((unsigned)n_series, 4);
+    mid_quantile_select_kernel<<<grid, SEL_BLOCK, 0, (cudaStream_t)stream>>>(series, counts, n, scratch);
+    int rc = check_launch("seqik_mid_quantile_f32(select)");
+    if (rc) return rc;
+    mid_quantile_combine_kernel<<<(unsigned)((n_series + 127) / 128), 128, 0, (cudaStream_t)stream>>>(scratch, counts, out, n_series, n);
+    return check_launch("seqik_mid_quantile_f32(combine)");
+}
+
+__global__ void leg_affine_kernel(const float* __restrict__ stats, const float* __restrict__ consts, int include_claw,
+                                  float* __restrict__ affine, int64_t n_chain) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_chain) return;
+    const float* s = stats + c * 7; const float* k = consts + c * 4;
+    float len = s[3] + s[4] + s[5];
+    if (include_claw) len += s[6];
+    float* a = affine + c * 8;
+    a[0] = s[0]; a[1] = s[1]; a[2] = s[2]; a[3] = k[3] / len;
+    a[4] = k[0]; a[5] = k[1]; a[6] = k[2]; a[7] = 0.f;
+}
+
+extern "C" int seqik_leg_affine_f32(const float* stats, const float* consts, int include_claw, float* affine,
+                                    int64_t n_chain, void* stream) {
+    if (n_chain < 0) return fail(SEQIK_EINVAL, "seqik_leg_affine_f32: negative size");
+    if (n_chain == 0) return SEQIK_OK;
+    if (!stats || !consts || !affine) return fail(SEQIK_EINVAL, "seqik_leg_affine_f32: NULL pointer");
+    leg_affine_kernel<<<(unsigned)((n_chain + 127) / 128), 128, 0, (cudaStream_t)stream>>>(stats, consts, include_claw, affine, n_chain);
+    return check_launch("seqik_leg_affine_f32");
+}
+
+__global__ void __launch_bounds__(256) align_apply_kernel(const float* __restrict__ pose, int64_t cs, int64_t fs,
+                                                          const float* __restrict__ affine, float* __restrict__ out,
+                                                          int64_t n_chain, int64_t n_frame) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (leg-frame, key point)
+    if (i >= n_chain * n_frame * 5) return;
+    const int64_t lf = i / 5; const int kp = (int)(i - lf * 5);
+    const int64_t c = lf / n_frame, t = lf - c * n_frame;
+    const float* a = affine + c * 8;
+    const float* p = pose + c * cs + t * fs + kp * 3;
+    float* o = out + i * 3;
+    if (kp == 0) { o[0] = a[4]; o[1] = a[5]; o[2] = a[6]; }
+    else { o[0] = (p[0] - a[0]) * a[3] + a[4]; o[1] = (p[1] - a[1]) * a[3] + a[5]; o[2] = (p[2] - a[2]) * a[3] + a[6]; }
+}
+
+extern "C" int seqik_align_apply_f32(const float* pose, int64_t pose_chain_stride, int64_t pose_frame_stride,
+                                     const float* affine, float* out, int64_t n_chain, int64_t n_frame, void* stream) {
+    if (n_chain < 0 || n_frame < 0) return fail(SEQIK_EINVAL, "seqik_align_apply_f32: negative size");
+    if (n_chain == 0 || n_frame == 0) return SEQIK_OK;
+    if (!pose || !affine || !out) return fail(SEQIK_EINVAL, "seqik_align_apply_f32: NULL pointer");
+    const int64_t total = n_chain * n_frame * 5;
+    align_apply_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pose, pose_chain_stride, pose_frame_stride,
+                                                                                         affine, out, n_chain, n_frame);
+    return check_launch("seqik_align_apply_f32");
+}
+
+// ---- antenna (AlignPose.align_head)
+__device__ __forceinline__ float base_to_thorax_mid(const float* __restrict__ head, const float* __restrict__ thorax,
+                                                    int64_t n_kp, int64_t i) {
+    const float* b = head + i * 6;
+    const float* t0 = thorax + i * n_kp * 3; const float* t1 = t0 + (n_kp - 1) * 3;
+    const float dx = b[0] - 0.5f * (t0[0] + t1[0]), dy = b[1] - 0.5f * (t0[1] + t1[1]), dz = b[2] - 0.5f * (t0[2] + t1[2]);
+    return sqrtf(dx * dx + dy * dy + dz * dz);
+}
+
+__global__ void __launch_bounds__(256) head_series_kernel(const float* __restrict__ head, const float* __restrict__ thorax,
+                                                          int64_t n_kp, float threshold, float* __restrict__ series,
+                                                          int32_t* __restrict__ counts, int64_t n_trial, int64_t n_frame) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool in = i < n_trial * n_frame;
+    const int64_t tr = in ? i / n_frame : 0, t = in ? i - tr * n_frame : 0;
+    bool stationary = false;
+    if (in) {
+        const float* b = head + i * 6;
+        const float d0 = base_to_thorax_mid(head, thorax, n_kp, i);
+        if (t + 2 < n_frame) {
+            const float d1 = base_to_thorax_mid(head, thorax, n_kp, i + 1), d2 = base_to_thorax_mid(head, thorax, n_kp, i + 2);
+            stationary = ((d2 - d1) - (d1 - d0)) < threshold;   // np.diff(np.diff(d)) < threshold, signed
+        }
+        const float inf = __int_as_float(0x7f800000);
+        float* s = series + tr * 5 * n_frame + t;
+        s[0] = stationary ? b[0] : inf; s[n_frame] = stationary ? b[1] : inf; s[2 * n_frame] = stationary ? b[2] : inf;
+        s[3 * n_frame] = stationary ? d0 : inf;
+        const float ax = b[3] - b[0], ay = b[4] - b[1], az = b[5] - b[2];
+        s[4 * n_frame] = sqrtf(ax * ax + ay * ay + az * az);
+    }
+    // count stationary frames per trial: warp vote, one atomic per (warp, trial) when the warp sits in one trial
+    const unsigned ballot = __ballot_sync(0xffffffffu, stationary);
+    const int64_t tr0 = __shfl_sync(0xffffffffu, tr, 0);
+    const bool uniform = __all_sync(0xffffffffu, !in || tr == tr0);
+    if (uniform) {
+        if ((threadIdx.x & 31) == 0 && ballot) atomicAdd(&counts[tr0 * 5], __popc(ballot));
+    } else if (stationary) atomicAdd(&counts[tr * 5], 1);
+}
+
+__global__ void head_counts_finish_kernel(int32_t* __restrict__ counts, int64_t n_trial, int64_t n_frame) {
+    const int64_t tr = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tr >= n_trial) return;
+    int32_t* c = counts + tr * 5;
+    c[1] = c[0]; c[2] = c[0]; c[3] = c[0]; c[4] = (int32_t)n_frame;
+}
+
+extern "C" int seqik_head_series_f32(const float* head, const float* thorax, int64_t n_thorax_kp, float threshold,
+                                     float* series, int32_t* counts, int64_t n_trial, int64_t n_frame, void* stream) {
+    if (n_trial < 0 || n_frame < 0) return fail(SEQIK_EINVAL, "seqik_head_series_f32: negative size");
+    if (n_trial == 0 || n_frame == 0) return SEQIK_OK;
+    if (!head || !thorax || !series || !counts) return fail(SEQIK_EINVAL, "seqik_head_series_f32: NULL pointer");
+    if (n_thorax_kp < 1) return fail(SEQIK_EINVAL, "seqik_head_series_f32: thorax needs at least one key point");
+    if (n_frame > 2147483647LL) return fail(SEQIK_EINVAL, "seqik_head_series_f32: too many frames");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (cudaMemsetAsync(counts, 0, sizeof(int32_t) * 5 * n_trial, st) != cudaSuccess) return check_launch("seqik_head_series_f32(memset)");
+    const int64_t n = n_trial * n_frame;
+    head_series_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(head, thorax, n_thorax_kp, threshold, series, counts, n_trial, n_frame);
+    int rc = check_launch("seqik_head_series_f32");
+    if (rc) return rc;
+    head_counts_finish_kernel<<<(unsigned)((n_trial + 127) / 128), 128, 0, st>>>(counts, n_trial, n_frame);
+    return check_launch("seqik_head_series_f32(counts)");
+}
+
+__global__ void head_affine_kernel(const float* __restrict__ stats, const float* __restrict__ consts, float* __restrict__ affine,
+                                   int64_t n_trial) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_trial) return;
+    const float* s = stats + c * 5; const float* k = consts + c * 5;
+    float* a = affine + c * 8;
+    a[0] = s[0]; a[1] = s[1]; a[2] = s[2]; a[3] = k[3] / s[3];
+    a[4] = k[0]; a[5] = k[1]; a[6] = k[2]; a[7] = k[4] / s[4];
+}
+
+extern "C" int seqik_head_affine_f32(const float* stats, const float* consts, float* affine, int64_t n_trial, void* stream) {
+    if (n_trial < 0) return fail(SEQIK_EINVAL, "seqik_head_affine_f32: negative size");
+    if (n_trial == 0) return SEQIK_OK;
+    if (!stats || !consts || !affine) return fail(SEQIK_EINVAL, "seqik_head_affine_f32: NULL pointer");
+    head_affine_kernel<<<(unsigned)((n_trial + 127) / 128), 128, 0, (cudaStream_t)stream>>>(stats, consts, affine, n_trial);
+    return check_launch("seqik_head_affine_f32");
+}
+
+__global__ void __launch_bounds__(256) head_apply_kernel(const float* __restrict__ head, const float* __restrict__ affine,
+                                                         float* __restrict__ out, int64_t n_trial, int64_t n_frame) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (frame, key point)
+    if (i >= n_trial * n_frame * 2) return;
+    const int64_t tr = (i >> 1) / n_frame;
+    float x, y, z;
+    head_point(head + i * 3, affine + tr * 8, (i & 1) != 0, x, y, z);
+    out[i * 3] = x; out[i * 3 + 1] = y; out[i * 3 + 2] = z;
+}
+
+extern "C" int seqik_head_apply_f32(const float* head, const float* affine, float* out, int64_t n_trial, int64_t n_frame,
+                                    void* stream) {
+    if (n_trial < 0 || n_frame < 0) return fail(SEQIK_EINVAL, "seqik_head_apply_f32: negative size");
+    if (n_trial == 0 || n_frame == 0) return SEQIK_OK;
+    if (!head || !affine || !out) return fail(SEQIK_EINVAL, "seqik_head_apply_f32: NULL pointer");
+    const int64_t n = n_trial * n_frame * 2;
+    head_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(head, affine, out, n_trial, n_frame);
+    return check_launch("seqik_head_apply_f32");
+}

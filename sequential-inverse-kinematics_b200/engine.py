@@ -1,0 +1,231 @@
+"""Tensor-level entry points: torch CUDA tensors in, torch CUDA tensors out.
+
+This is the batched face of the hot path -- ``(trial, leg)`` chains by frames -- that the
+reference-compatible classes (``LegInvKinSeq`` & co.) and ``bench.py`` both sit on.  Every
+function enqueues hand-written sm_100a kernels from ``libseqik_sm100.so`` (C ABI:
+include/seqik.h) on the CURRENT torch stream of the tensors' device and returns without
+synchronising.  torch supplies device memory and streams only; there is no CPU fallback.
+
+Shapes (float32, contiguous):
+  pose    (n_chain, n_frame, 5, 3)   key points: ThC origin, then the targets of stages 1-4
+  params  (n_chain, 32)              per-chain constants, see ``KinematicChainSeq.pack_chain_params``
+  angles  (n_chain, n_frame, 7)      DOF order ThC_yaw, ThC_pitch, ThC_roll, CTr_pitch, CTr_roll, FTi_pitch, TiTa_pitch
+  fk      (n_chain, n_frame, 9, 3)   joint positions of the stage-4 chain
+"""
+from typing import Optional, Sequence, Tuple
+
+from . import _native as N
+
+
+def _check(t, name, shape_tail, dtype=None):
+    torch = N.require_cuda()
+    dtype = torch.float32 if dtype is None else dtype
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise N.SeqIKNativeError(f"{name} must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    if tuple(t.shape[-len(shape_tail):]) != tuple(shape_tail):
+        raise ValueError(f"{name} must end in shape {tuple(shape_tail)}, got {tuple(t.shape)}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+def stages_to_mask(stages: Sequence[int]) -> int:
+    """[a..b] -> bit mask; ValueError like leg_inverse_kinematics.py:350-353."""
+    stages = [int(s) for s in stages]
+    if len(stages) == 0 or max(stages) > 4 or min(stages) < 1 or any(b - a != 1 for a, b in zip(stages, stages[1:])):
+        raise ValueError("Maximum stage number is 4 and the list should be strictly incremental.")
+    mask = 0
+    for s in stages:
+        mask |= 1 << (s - 1)
+    return mask
+
+
+def leg_solve(pose, params, affine=None, stages: Sequence[int] = (1, 2, 3, 4), want_fk: bool = True,
+              angles=None, fk=None, flags: int = N.FLAG_DEFAULT, schedule: int = N.SCHED_AUTO,
+              want_stats: bool = True):
+    """4-stage sequential IK (+FK) of every chain.  Returns (angles, fk|None, status|None, nfev|None).
+
+    ``angles`` must be given (and is updated in place) when ``stages`` does not start at 1:
+    the DOFs of the earlier stages are then read from it and frozen.
+    """
+    torch = N.require_cuda()
+    lib = N.load_library()
+    pose = _check(pose, "pose", (5, 3))
+    if pose.dim() != 4:
+        raise ValueError(f"pose must be (n_chain, n_frame, 5, 3), got {tuple(pose.shape)}")
+    n_chain, n_frame = int(pose.shape[0]), int(pose.shape[1])
+    params = _check(params, "params", (N.CHAIN_PARAM_FLOATS,))
+    if params.shape[0] != n_chain:
+        raise ValueError("params must have one row per chain")
+    mask = stages_to_mask(stages)
+    dev = pose.device
+    if angles is None:
+        if not mask & 1:
+            raise ValueError("stages do not start at 1: pass the angles tensor holding the earlier stages' DOFs")
+        angles = torch.empty((n_chain, n_frame, 7), dtype=torch.float32, device=dev)
+    else:
+        _check(angles, "angles", (7,))
+        if tuple(angles.shape) != (n_chain, n_frame, 7):
+            raise ValueError("angles must be (n_chain, n_frame, 7)")
+    if want_fk and fk is None:
+        fk = torch.empty((n_chain, n_frame, 9, 3), dtype=torch.float32, device=dev)
+    if fk is not None:
+        _check(fk, "fk", (9, 3))
+    if affine is not None:
+        _check(affine, "affine", (8,))
+    status = torch.empty((n_chain,), dtype=torch.int32, device=dev) if want_stats else None
+    nfev = torch.empty((n_chain, 4), dtype=torch.int32, device=dev) if want_stats else None
+    with torch.cuda.device(dev):
+        rc = lib.seqik_leg_solve_f32(
+            N.ptr(pose), n_frame * 15, 15, N.ptr(affine), N.ptr(params),
+            N.ptr(angles), n_frame * 7, 7, N.ptr(fk), n_frame * 27, 27,
+            N.ptr(status), N.ptr(nfev), n_chain, n_frame, mask,
+            (flags & 0xFF) | ((schedule & 0xF) << N.FLAG_SCHED_SHIFT), N.stream_ptr(torch, dev))
+    N.check(rc, "seqik_leg_solve_f32")
+    return angles, fk, status, nfev
+
+
+def forward_kinematics(angles, origin, params):
+    """angles (n_chain, n_frame, 7) + origin (n_chain, n_frame, 3) or (n_chain, 3) -> fk (n_chain, n_frame, 9, 3)."""
+    torch = N.require_cuda()
+    lib = N.load_library()
+    angles = _check(angles, "angles", (7,))
+    n_chain, n_frame = int(angles.shape[0]), int(angles.shape[1])
+    origin = _check(origin, "origin", (3,))
+    params = _check(params, "params", (N.CHAIN_PARAM_FLOATS,))
+    if origin.dim() == 3 and tuple(origin.shape[:2]) == (n_chain, n_frame):
+        stride = 3
+    elif origin.dim() == 2 and origin.shape[0] == n_chain:
+        stride = 0
+    else:
+        raise ValueError("origin must be (n_chain, n_frame, 3) or (n_chain, 3)")
+    fk = torch.empty((n_chain, n_frame, 9, 3), dtype=torch.float32, device=angles.device)
+    with torch.cuda.device(angles.device):
+        rc = lib.seqik_fk_f32(N.ptr(angles), N.ptr(origin), stride, N.ptr(params), N.ptr(fk), n_chain, n_frame,
+                              N.stream_ptr(torch, angles.device))
+    N.check(rc, "seqik_fk_f32")
+    return fk
+
+
+def head_angles(r_head, l_head, neck, rest, affine_r=None, affine_l=None):
+    """r_head, l_head (n_trial, n_frame, 2, 3); neck (n_trial, n_frame, 3) or (n_trial, 3); rest (n_trial, 2)
+    -> (n_trial, 7, n_frame): head roll, pitch, yaw, antenna yaw L, pitch L, yaw R, pitch R."""
+    torch = N.require_cuda()
+    lib = N.load_library()
+    r_head = _check(r_head, "r_head", (2, 3))
+    l_head = _check(l_head, "l_head", (2, 3))
+    if r_head.dim() != 4 or r_head.shape != l_head.shape:
+        raise ValueError("r_head and l_head must both be (n_trial, n_frame, 2, 3)")
+    n_trial, n_frame = int(r_head.shape[0]), int(r_head.shape[1])
+    neck = _check(neck, "neck", (3,))
+    if neck.dim() == 3 and tuple(neck.shape[:2]) == (n_trial, n_frame):
+        stride = 3
+    elif neck.dim() == 2 and neck.shape[0] == n_trial:
+        stride = 0
+    else:
+        raise ValueError("neck must be (n_trial, n_frame, 3) or (n_trial, 3)")
+    rest = _check(rest, "rest", (2,))
+    if affine_r is not None:
+        _check(affine_r, "affine_r", (8,))
+        _check(affine_l, "affine_l", (8,))
+    out = torch.empty((n_trial, 7, n_frame), dtype=torch.float32, device=r_head.device)
+    with torch.cuda.device(r_head.device):
+        rc = lib.seqik_head_angles_f32(N.ptr(r_head), N.ptr(l_head), N.ptr(neck), stride, N.ptr(affine_r), N.ptr(affine_l),
+                                       N.ptr(rest), N.ptr(out), n_trial, n_frame, N.stream_ptr(torch, r_head.device))
+    N.check(rc, "seqik_head_angles_f32")
+    return out
+
+
+def mid_quantile(series, counts=None):
+    """Mean of the 0.45 and 0.55 quantiles of each row of ``series`` (n_series, n) -> (n_series,)."""
+    torch = N.require_cuda()
+    lib = N.load_library()
+    if series.dim() != 2:
+        raise ValueError("series must be (n_series, n)")
+    series = _check(series, "series", (series.shape[-1],))
+    n_series, n = int(series.shape[0]), int(series.shape[1])
+    if counts is not None:
+        counts = _check(counts, "counts", (n_series,), torch.int32)
+    scratch = torch.empty((n_series, 4), dtype=torch.float32, device=series.device)
+    out = torch.empty((n_series,), dtype=torch.float32, device=series.device)
+    with torch.cuda.device(series.device):
+        rc = lib.seqik_mid_quantile_f32(N.ptr(series), N.ptr(counts), N.ptr(scratch), N.ptr(out), n_series, n,
+                                        N.stream_ptr(torch, series.device))
+    N.check(rc, "seqik_mid_quantile_f32")
+    return out
+
+
+def leg_affine(pose, consts, include_claw: bool = False):
+    """AlignPose.align_leg statistics: pose (n_chain, n_frame, 5, 3), consts (n_chain, 4) = template coxa xyz + model
+    length -> affine (n_chain, 8) = (fixed_coxa xyz, scale, template xyz, 0)."""
+    torch = N.require_cuda()
+    lib = N.load_library()
+    pose = _check(pose, "pose", (5, 3))
+    n_chain, n_frame = int(pose.shape[0]), int(pose.shape[1])
+    consts = _check(consts, "consts", (4,))
+    dev = pose.device
+    series = torch.empty((n_chain * 7, n_frame), dtype=torch.float32, device=dev)
+    affine = torch.empty((n_chain, 8), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = N.stream_ptr(torch, dev)
+        N.check(lib.seqik_leg_series_f32(N.ptr(pose), n_frame * 15, 15, N.ptr(series), n_chain, n_frame, st),
+                "seqik_leg_series_f32")
+        stats = mid_quantile(series)
+        N.check(lib.seqik_leg_affine_f32(N.ptr(stats), N.ptr(consts), int(bool(include_claw)), N.ptr(affine), n_chain, st),
+                "seqik_leg_affine_f32")
+    return affine
+
+
+def align_apply(pose, affine):
+    """The affine map of align_leg as a standalone pass -> aligned pose (n_chain, n_frame, 5, 3)."""
+    torch = N.require_cuda()
+    lib = N.load_library()
+    pose = _check(pose, "pose", (5, 3))
+    affine = _check(affine, "affine", (8,))
+    n_chain, n_frame = int(pose.shape[0]), int(pose.shape[1])
+    out = torch.empty_like(pose)
+    with torch.cuda.device(pose.device):
+        rc = lib.seqik_align_apply_f32(N.ptr(pose), n_frame * 15, 15, N.ptr(affine), N.ptr(out), n_chain, n_frame,
+                                       N.stream_ptr(torch, pose.device))
+    N.check(rc, "seqik_align_apply_f32")
+    return out
+
+
+def head_affine(head, thorax, consts, threshold: float = 5e-5):
+    """AlignPose.align_head statistics: head (n_trial, n_frame, 2, 3), thorax (n_trial, n_frame, k, 3),
+    consts (n_trial, 5) = template antenna base xyz, Antenna_mid_thorax, Antenna
+    -> affine (n_trial, 8) = (origin xyz, scale_base, template xyz, scale_tip)."""
+    torch = N.require_cuda()
+    lib = N.load_library()
+    head = _check(head, "head", (2, 3))
+    n_trial, n_frame = int(head.shape[0]), int(head.shape[1])
+    if thorax.dim() != 4 or tuple(thorax.shape[:2]) != (n_trial, n_frame):
+        raise ValueError("thorax must be (n_trial, n_frame, n_kp, 3)")
+    thorax = _check(thorax, "thorax", (3,))
+    consts = _check(consts, "consts", (5,))
+    dev = head.device
+    series = torch.empty((n_trial * 5, n_frame), dtype=torch.float32, device=dev)
+    counts = torch.empty((n_trial * 5,), dtype=torch.int32, device=dev)
+    affine = torch.empty((n_trial, 8), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        st = N.stream_ptr(torch, dev)
+        N.check(lib.seqik_head_series_f32(N.ptr(head), N.ptr(thorax), int(thorax.shape[2]), float(threshold), N.ptr(series),
+                                          N.ptr(counts), n_trial, n_frame, st), "seqik_head_series_f32")
+        stats = mid_quantile(series, counts)
+        N.check(lib.seqik_head_affine_f32(N.ptr(stats), N.ptr(consts), N.ptr(affine), n_trial, st), "seqik_head_affine_f32")
+    return affine, counts.view(n_trial, 5)
+
+
+def head_apply(head, affine):
+    torch = N.require_cuda()
+    lib = N.load_library()
+    head = _check(head, "head", (2, 3))
+    affine = _check(affine, "affine", (8,))
+    n_trial, n_frame = int(head.shape[0]), int(head.shape[1])
+    out = torch.empty_like(head)
+    with torch.cuda.device(head.device):
+        rc = lib.seqik_head_apply_f32(N.ptr(head), N.ptr(affine), N.ptr(out), n_trial, n_frame, N.stream_ptr(torch, head.device))
+    N.check(rc, "seqik_head_apply_f32")
+    return out

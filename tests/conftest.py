@@ -1,0 +1,47 @@
+import os
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+for p in (ROOT, ROOT / "tests"):
+    if str(p) not in sys.path:
+        sys.path.insert(0, str(p))
+os.environ.setdefault("OMP_NUM_THREADS", "1")
+
+GOLDEN = ROOT / "tests" / "golden"
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def _npz(name):
+    return dict(np.load(GOLDEN / name, allow_pickle=False))
+
+
+@pytest.fixture(scope="session")
+def grooming_leg():
+    return _npz("grooming_leg.npz")
+
+
+@pytest.fixture(scope="session")
+def grooming_head():
+    return _npz("grooming_head.npz")
+
+
+@pytest.fixture(scope="session")
+def grooming_align():
+    return _npz("grooming_align.npz")
+
+
+@pytest.fixture(scope="session")
+def locomotion():
+    return _npz("locomotion.npz")
+
+
+@pytest.fixture(scope="session")
+def synthetic_gold():
+    return _npz("synthetic.npz")

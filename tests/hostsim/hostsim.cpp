@@ -9,7 +9,7 @@ using namespace seqik;
 template <typename R>
 static void run_chain(const R* pose, int64_t n_frame, const R* seg, const R* lb, const R* ub,
                       const R* null_sq, const R* seed, R* angles, R* fk, int32_t* nfev, int32_t* status,
-                      int stage_mask) {
+                      int stage_mask, int gn_mask) {
     ChainParams<R> P;
     for (int i = 0; i < 4; ++i) { P.seg[i] = seg[i]; P.null_sq[i] = null_sq[i]; }
     for (int i = 0; i < 7; ++i) { P.lb[i] = lb[i]; P.ub[i] = ub[i]; }
@@ -17,21 +17,50 @@ static void run_chain(const R* pose, int64_t n_frame, const R* seg, const R* lb,
     for (int i = 0; i < 7; ++i) ang[i] = seed[i];
     for (int64_t t = 0; t < n_frame; ++t) {
         FrameStats fs;
-        solve_frame<R>(P, pose + t * 15, ang, fk ? fk + t * 27 : nullptr, &fs, stage_mask);
+        solve_frame<R>(P, pose + t * 15, ang, fk ? fk + t * 27 : nullptr, &fs, stage_mask, gn_mask);
         for (int i = 0; i < 7; ++i) angles[t * 7 + i] = ang[i];
         if (nfev) for (int s = 0; s < 4; ++s) { nfev[t * 4 + s] = fs.nfev[s]; status[t * 4 + s] = fs.status[s]; }
     }
 }
 
+// ---- the decoupled per-lane runner, driven serially (one step() at a time) ----
+template <typename R> struct HostIO {
+    const R* pose; const R* seg_; const R* lb_; const R* ub_; const R* nsq_; R* angles; R* fk;
+    Vec3<R> kp(int64_t t, int row) const { const R* p = pose + t * 15 + row * 3; return {p[0], p[1], p[2]}; }
+    void put_angles(int64_t t, const R* a, int i0, int i1) const { for (int i = i0; i < i1; ++i) angles[t * 7 + i] = a[i]; }
+    R angle_in(int64_t t, int i) const { return angles[t * 7 + i]; }
+    void put_fk(int64_t t, int row, const Vec3<R>& v) const { R* p = fk + t * 27 + row * 3; p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+    R seg(int i) const { return seg_[i]; }
+    R lb(int i) const { return lb_[i]; }
+    R ub(int i) const { return ub_[i]; }
+    R null_sq(int i) const { return nsq_[i]; }
+};
+template <typename R>
+static int64_t run_runner(const R* pose, int64_t n_frame, const R* seg, const R* lb, const R* ub, const R* null_sq,
+                          const R* seed, R* angles, R* fk, uint32_t* nfev_sum, int stage_mask, int gn_mask) {
+    HostIO<R> io{pose, seg, lb, ub, null_sq, angles, fk};
+    ChainRunner<R, HostIO<R>> run;
+    run.start(io, n_frame, seed, stage_mask, gn_mask);
+    int64_t steps = 0;
+    while (!run.finished()) { run.step(); ++steps; }
+    nfev_sum[0] = run.nf0; nfev_sum[1] = run.nf1; nfev_sum[2] = run.nf2; nfev_sum[3] = run.nf3;
+    return steps;
+}
+
 extern "C" {
+int64_t hostsim_runner_f32(const float* pose, int64_t n_frame, const float* seg, const float* lb, const float* ub,
+                           const float* null_sq, const float* seed, float* angles, float* fk, uint32_t* nfev_sum,
+                           int stage_mask, int gn_mask) {
+    return run_runner<float>(pose, n_frame, seg, lb, ub, null_sq, seed, angles, fk, nfev_sum, stage_mask, gn_mask);
+}
 void hostsim_chain_f32(const float* pose, int64_t n_frame, const float* seg, const float* lb, const float* ub,
                        const float* null_sq, const float* seed, float* angles, float* fk, int32_t* nfev,
-                       int32_t* status, int stage_mask) {
-    run_chain<float>(pose, n_frame, seg, lb, ub, null_sq, seed, angles, fk, nfev, status, stage_mask);
+                       int32_t* status, int stage_mask, int gn_mask) {
+    run_chain<float>(pose, n_frame, seg, lb, ub, null_sq, seed, angles, fk, nfev, status, stage_mask, gn_mask);
 }
 void hostsim_chain_f64(const double* pose, int64_t n_frame, const double* seg, const double* lb, const double* ub,
                        const double* null_sq, const double* seed, double* angles, double* fk, int32_t* nfev,
-                       int32_t* status, int stage_mask) {
-    run_chain<double>(pose, n_frame, seg, lb, ub, null_sq, seed, angles, fk, nfev, status, stage_mask);
+                       int32_t* status, int stage_mask, int gn_mask) {
+    run_chain<double>(pose, n_frame, seg, lb, ub, null_sq, seed, angles, fk, nfev, status, stage_mask, gn_mask);
 }
 }

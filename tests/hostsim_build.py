@@ -28,7 +28,7 @@ def load():
     return _lib
 
 
-def solve_chain(pose, seg, lb, ub, null_sq, seed, dtype=np.float32, stage_mask=0xF):
+def solve_chain(pose, seg, lb, ub, null_sq, seed, dtype=np.float32, stage_mask=0xF, gn_mask=0):
     """pose (N,5,3) -> angles (N,7), fk (N,9,3), nfev (N,4), status (N,4) computed by the host build."""
     lib = load()
     fn = lib.hostsim_chain_f32 if dtype == np.float32 else lib.hostsim_chain_f64
@@ -40,8 +40,27 @@ def solve_chain(pose, seg, lb, ub, null_sq, seed, dtype=np.float32, stage_mask=0
     nfev = np.zeros((n, 4), dtype=np.int32)
     status = np.zeros((n, 4), dtype=np.int32)
     P = ctypes.c_void_p
-    fn.argtypes = [P, ctypes.c_int64, P, P, P, P, P, P, P, P, P, ctypes.c_int]
+    fn.argtypes = [P, ctypes.c_int64, P, P, P, P, P, P, P, P, P, ctypes.c_int, ctypes.c_int]
     fn.restype = None
     fn(pose.ctypes.data, n, *(a.ctypes.data for a in args), angles.ctypes.data, fk.ctypes.data,
-       nfev.ctypes.data, status.ctypes.data, stage_mask)
+       nfev.ctypes.data, status.ctypes.data, stage_mask, gn_mask)
     return angles, fk, nfev, status
+
+
+def run_runner_f32(pose, seg, lb, ub, null_sq, seed, stage_mask=0xF, gn_mask=0):
+    """Same chain through ChainRunner::step() (the kernels' per-lane state machine)."""
+    lib = load()
+    dtype = np.float32
+    pose = np.ascontiguousarray(pose, dtype=dtype)
+    n = pose.shape[0]
+    args = [np.ascontiguousarray(a, dtype=dtype) for a in (seg, lb, ub, null_sq, seed)]
+    angles = np.zeros((n, 7), dtype=dtype)
+    fk = np.zeros((n, 9, 3), dtype=dtype)
+    nfev_sum = np.zeros(4, dtype=np.uint32)
+    P = ctypes.c_void_p
+    fn = lib.hostsim_runner_f32
+    fn.argtypes = [P, ctypes.c_int64, P, P, P, P, P, P, P, P, ctypes.c_int, ctypes.c_int]
+    fn.restype = ctypes.c_int64
+    steps = fn(pose.ctypes.data, n, *(a.ctypes.data for a in args), angles.ctypes.data, fk.ctypes.data,
+               nfev_sum.ctypes.data, stage_mask, gn_mask)
+    return angles, fk, nfev_sum, steps

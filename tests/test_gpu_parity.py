@@ -1,0 +1,299 @@
+"""GPU parity tests: the CUDA path (through the reference-compatible classes -> ctypes C ABI) against
+the reference's shipped outputs and the CPU oracle's outputs held in tests/golden/.
+
+Tolerances (BASELINE.json north_star): joint angles within 1e-3 rad; FK residual not worse than the
+reference's by more than 1e-4 mm per joint.  SURVEY.md finding 4 documents the one place where the
+reference itself is irreproducible (LF frames ~280-304 of the grooming trial: a noise-driven
+bound-to-bound flip at the CTr_pitch = 0 singularity); those frames are bounded, not skipped.
+"""
+import numpy as np
+import pytest
+
+from helpers import ANGLE_TOL, F32_FK_NOISE, FK_TOL, angles_dict_to_array, bad_frames, fk_residual, residual_of_angles
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    import torch
+    assert torch.cuda.is_available(), "these tests need the B200"
+    from seqikpy_b200 import _native, data, engine, synthetic
+    from seqikpy_b200.alignment import AlignPose
+    from seqikpy_b200.head_inverse_kinematics import HeadInverseKinematics
+    from seqikpy_b200.kinematic_chain import KinematicChainSeq
+    from seqikpy_b200.leg_inverse_kinematics import LegInvKinSeq
+    _native.load_library()
+
+    class A:
+        pass
+    a = A()
+    a.torch, a.native, a.data, a.engine, a.synthetic = torch, _native, data, engine, synthetic
+    a.AlignPose, a.Head, a.Chain, a.Leg = AlignPose, HeadInverseKinematics, KinematicChainSeq, LegInvKinSeq
+    return a
+
+
+def seg_of(size, leg):
+    return [size[f"{leg}_{s}"] for s in ("Coxa", "Femur", "Tibia", "Tarsus")]
+
+
+# ------------------------------------------------------------------------------------------ grooming trial (config 2)
+@pytest.fixture(scope="module")
+def grooming_run(api, grooming_leg):
+    pose = {"RF_leg": grooming_leg["pose"][0], "LF_leg": grooming_leg["pose"][1]}
+    chain = api.Chain(api.data.BOUNDS, ["RF", "LF"])
+    ik = api.Leg(pose, chain, api.data.INITIAL_ANGLES, log_level="ERROR")
+    angles, fk = ik.run_ik_and_fk(hide_progress_bar=True)
+    return pose, chain, ik, angles, fk
+
+
+def test_grooming_layout(grooming_run, grooming_leg):
+    pose, chain, ik, angles, fk = grooming_run
+    assert list(angles.keys()) == list(grooming_leg["angle_keys"])          # insertion order of the reference pickle
+    assert list(fk.keys()) == ["RF_leg", "LF_leg"]
+    for v in angles.values():
+        assert v.shape == (6000,) and v.dtype == np.float64
+    for v in fk.values():
+        assert v.shape == (6000, 9, 3) and v.dtype == np.float64
+    assert ik.solver_stats["RF"]["status"] == 1 and ik.solver_stats["LF"]["status"] == 1
+
+
+def test_grooming_rf_angles_all_frames(grooming_run, grooming_leg):
+    _, _, _, angles, _ = grooming_run
+    ours = angles_dict_to_array(angles, "RF")
+    assert len(bad_frames(ours, grooming_leg["ref_angles"][0])) == 0          # vs the reference's shipped angles
+    assert len(bad_frames(ours, grooming_leg["oracle_angles"][0])) == 0       # vs the CPU oracle
+    assert np.median(np.abs(ours - grooming_leg["ref_angles"][0])) < 5e-6
+
+
+def test_grooming_lf_angles(grooming_run, grooming_leg):
+    _, _, _, angles, _ = grooming_run
+    ours = angles_dict_to_array(angles, "LF")
+    bad = bad_frames(ours, grooming_leg["ref_angles"][1])
+    # the reference's own irreproducible cluster (SURVEY.md finding 4); everything else must match
+    assert len(bad) <= 30 and (len(bad) == 0 or (bad.min() >= 270 and bad.max() <= 310)), bad
+    good = np.setdiff1d(np.arange(6000), np.arange(270, 311))
+    assert np.abs(ours[good] - grooming_leg["ref_angles"][1][good]).max() < ANGLE_TOL
+
+
+def test_grooming_bounds_respected(grooming_run, api):
+    _, _, _, angles, _ = grooming_run
+    for key, v in angles.items():
+        lb, ub = api.data.BOUNDS[key.replace("Angle_", "")]
+        assert v.min() >= lb - 1e-6 and v.max() <= ub + 1e-6, key
+
+
+def test_grooming_fk_consistent_and_residual(grooming_run, grooming_leg):
+    pose, chain, _, angles, fk = grooming_run
+    for li, leg in enumerate(("RF", "LF")):
+        ours = angles_dict_to_array(angles, leg)
+        seg = seg_of(chain.body_size, leg)
+        # the FK the kernel returns is the FK of the angles it returns
+        from oracle import seqik_oracle as O
+        fk64 = O.fk_closed_form(ours, seg, pose[f"{leg}_leg"][:, 0])
+        assert np.abs(fk64 - fk[f"{leg}_leg"]).max() < 5e-6
+        assert np.abs(fk[f"{leg}_leg"][:600] - grooming_leg["ref_fk"][li]).max() < (1e-3 if leg == "RF" else 2.0)
+        # FK residual vs the reference's residual, per (frame, joint)
+        r_ours = fk_residual(fk[f"{leg}_leg"], pose[f"{leg}_leg"])
+        r_ref = residual_of_angles(grooming_leg["ref_angles"][li], seg, pose[f"{leg}_leg"])
+        worse = (r_ours - r_ref) > FK_TOL + F32_FK_NOISE
+        if leg == "RF":
+            assert worse.sum() == 0
+        else:
+            frames = np.where(worse.any(axis=1))[0]
+            assert len(frames) <= 30 and (len(frames) == 0 or (frames.min() >= 270 and frames.max() <= 310)), frames
+        assert abs(r_ours.mean() - r_ref.mean()) < 1e-3
+    
+
+def test_stagewise_calls_equal_one_shot(grooming_run, api):
+    """calculate_ik_stage stage by stage (frozen earlier DOFs read back from joint_angles_dict) == run_ik_and_fk."""
+    pose, chain, _, angles, fk = grooming_run
+    n = 400
+    arr = pose["RF_leg"][:n]
+    ik = api.Leg({"RF_leg": arr}, chain, api.data.INITIAL_ANGLES, log_level="ERROR")
+    for stage in (1, 2, 3, 4):
+        out = ik.calculate_ik_stage(arr[:, stage], arr[:, 0], api.data.INITIAL_ANGLES["RF"][f"stage_{stage}"], "RF",
+                                    stage=stage, hide_progress_bar=True)
+        assert out.shape == (n, (4, 6, 8, 9)[stage - 1], 3)
+    for k in ik.joint_angles_dict:
+        assert np.array_equal(ik.joint_angles_dict[k], angles[k][:n]), k
+    assert np.allclose(out, fk["RF_leg"][:n], atol=2e-6)
+    # stages=[1,2] then [3,4]
+    ik2 = api.Leg({"RF_leg": arr}, chain, api.data.INITIAL_ANGLES, log_level="ERROR")
+    a12, fk12 = ik2.run_ik_and_fk(stages=[1, 2], hide_progress_bar=True)
+    assert list(a12.keys()) == [f"Angle_RF_{d}" for d in ("ThC_yaw", "ThC_pitch", "ThC_roll", "CTr_pitch")]
+    assert fk12["RF_leg"].shape == (n, 6, 3)
+    a, f = ik2.run_ik_and_fk(stages=[3, 4], hide_progress_bar=True)
+    for k in a:
+        assert np.array_equal(a[k], angles[k][:n]), k
+
+
+# ------------------------------------------------------------------------------------------ locomotion (config 1)
+def test_locomotion_pipeline(api, locomotion):
+    legs = list(locomotion["legs"])
+    raw = {f"{leg}_leg": locomotion["raw"][i] for i, leg in enumerate(legs)}
+    al = api.AlignPose(raw, legs_list=legs, include_claw=False, body_template=api.data.TEMPLATE_NMF_LOCOMOTION,
+                       log_level="ERROR").align_pose()
+    assert list(al.keys()) == [f"{leg}_leg" for leg in legs]
+    for i, leg in enumerate(legs):
+        assert al[f"{leg}_leg"].dtype == np.float64
+        assert np.abs(al[f"{leg}_leg"] - locomotion["aligned"][i]).max() < 2e-6
+    chain = api.Chain(api.data.BOUNDS_LOCOMOTION, legs, body_size=None)
+    from seqikpy_b200.utils import calculate_body_size
+    chain = api.Chain(api.data.BOUNDS_LOCOMOTION, legs, calculate_body_size(api.data.TEMPLATE_NMF_LOCOMOTION, legs))
+    aligned = {f"{leg}_leg": locomotion["aligned"][i] for i, leg in enumerate(legs)}
+    angles, fk = api.Leg(aligned, chain, api.data.INITIAL_ANGLES_LOCOMOTION, log_level="ERROR").run_ik_and_fk()
+    for i, leg in enumerate(legs):
+        ours = angles_dict_to_array(angles, leg)
+        assert np.abs(ours - locomotion["oracle_angles"][i]).max() < ANGLE_TOL, leg
+        r_ours = fk_residual(fk[f"{leg}_leg"], aligned[f"{leg}_leg"])
+        r_ref = fk_residual(locomotion["oracle_fk"][i], aligned[f"{leg}_leg"])
+        assert (r_ours - r_ref).max() < FK_TOL + F32_FK_NOISE, leg
+    # the fused path: raw pose + affine applied inside the solver load == align then solve
+    t = api.torch
+    d_raw = t.from_numpy(np.ascontiguousarray(locomotion["raw"], dtype=np.float32)).cuda()
+    consts = np.array([list(api.data.TEMPLATE_NMF_LOCOMOTION[f"{leg}_Coxa"])
+                       + [chain.body_size[leg] - chain.body_size[f"{leg}_Tarsus"]] for leg in legs], dtype=np.float32)
+    aff = api.engine.leg_affine(d_raw, t.from_numpy(consts).cuda())
+    params = t.from_numpy(np.stack([chain.pack_chain_params(leg, api.data.INITIAL_ANGLES_LOCOMOTION[leg])
+                                    for leg in legs]).astype(np.float32)).cuda()
+    a_fused, fk_fused, _, _ = api.engine.leg_solve(d_raw, params, affine=aff)
+    a_two, fk_two, _, _ = api.engine.leg_solve(api.engine.align_apply(d_raw, aff), params)
+    assert t.equal(a_fused, a_two) and t.equal(fk_fused, fk_two)
+    assert np.abs(a_fused.cpu().numpy() - locomotion["oracle_angles"]).max() < ANGLE_TOL
+
+
+# ------------------------------------------------------------------------------------------ synthetic (configs 3-5)
+def test_synthetic_vs_oracle_and_shard_invariance(api, synthetic_gold):
+    S, t = api.synthetic, api.torch
+    n_frame = synthetic_gold["pose"].shape[1]
+    pose = S.make_trials([0, 1, 2, 3], 1000)[:, :n_frame]
+    assert np.abs(pose[:2] - synthetic_gold["pose"]).max() < 1e-6            # the generator is pinned by the fixture
+    size, bounds, init = S.chain_constants()
+    chain = api.Chain(bounds, list(S.LEGS), size)
+    row = np.stack([chain.pack_chain_params(leg, init[leg]) for leg in S.LEGS]).astype(np.float32)
+    params = t.from_numpy(np.tile(row, (4, 1))).cuda()
+    chains = S.to_chains(t.from_numpy(np.ascontiguousarray(pose)).cuda())
+    ang, fk, status, nfev = api.engine.leg_solve(chains, params)
+    a = ang.cpu().numpy().reshape(4, 6, n_frame, 7)
+    assert np.abs(a[:2] - synthetic_gold["oracle_angles"]).max() < ANGLE_TOL
+    f = fk.cpu().numpy().reshape(4, 6, n_frame, 9, 3)
+    pose_c = pose.transpose(0, 2, 1, 3, 4)
+    for tr in range(2):
+        for li in range(6):
+            r_ours = fk_residual(f[tr, li], pose_c[tr, li])
+            r_ref = fk_residual(synthetic_gold["oracle_fk"][tr, li], pose_c[tr, li])
+            assert (r_ours - r_ref).max() < FK_TOL + F32_FK_NOISE
+    assert int(status.min()) == 1
+    # chains are independent: any shard gives bit-identical results (what the multi-GPU split relies on)
+    for lo, hi in ((0, 6), (6, 24), (5, 7)):
+        a_s, f_s, _, _ = api.engine.leg_solve(chains[lo:hi].contiguous(), params[lo:hi].contiguous())
+        assert t.equal(a_s, ang[lo:hi]) and t.equal(f_s, fk[lo:hi])
+    # both kernel schedules give bit-identical results
+    a1, f1, _, n1 = api.engine.leg_solve(chains, params, schedule=api.native.SCHED_LANE_PER_CHAIN)
+    a2, f2, _, n2 = api.engine.leg_solve(chains, params, schedule=api.native.SCHED_STAGE_PIPELINE)
+    assert t.equal(a1, a2) and t.equal(f1, f2) and t.equal(n1, n2)
+
+
+def test_fk_kernel_matches_solver_and_oracle(api, synthetic_gold):
+    S, t = api.synthetic, api.torch
+    size, bounds, init = S.chain_constants()
+    chain = api.Chain(bounds, list(S.LEGS), size)
+    ang = t.from_numpy(synthetic_gold["oracle_angles"][0].astype(np.float32)).cuda()          # (6, F, 7)
+    origin = t.from_numpy(np.ascontiguousarray(synthetic_gold["pose"][0][:, :, 0].transpose(1, 0, 2), dtype=np.float32)).cuda()
+    params = t.from_numpy(np.stack([chain.pack_chain_params(leg, init[leg]) for leg in S.LEGS]).astype(np.float32)).cuda()
+    fk = api.engine.forward_kinematics(ang, origin, params).cpu().numpy()
+    assert np.abs(fk - synthetic_gold["oracle_fk"][0]).max() < 3e-6
+    fk0 = api.engine.forward_kinematics(ang, origin[:, 0].contiguous(), params).cpu().numpy()   # constant origin per chain
+    assert np.abs(fk0 - fk).max() < 1e-6
+
+
+# ------------------------------------------------------------------------------------------ head
+def test_head_angles_vs_reference(api, grooming_head):
+    pos = {"R_head": grooming_head["r_head"], "L_head": grooming_head["l_head"], "Neck": grooming_head["neck"]}
+    hk = api.Head(pos, api.data.NMF_TEMPLATE, log_level="ERROR")
+    assert abs(hk.rest_head_pitch[0] - grooming_head["rest"][0]) < 1e-12
+    assert abs(hk.rest_antenna_pitch[0] - grooming_head["rest"][1]) < 1e-12
+    out = hk.compute_head_angles()
+    assert list(out.keys()) == list(grooming_head["keys"])
+    for i, k in enumerate(out):
+        assert out[k].shape == (6000,) and out[k].dtype == np.float64
+        assert np.abs(out[k] - grooming_head["ref_angles"][i]).max() < 2e-5, k     # FP32 atan2 of ~0.1 mm vectors
+    assert list(hk.compute_head_angles(compute_ant_angles=False).keys()) == list(grooming_head["keys"][:3])
+    # per-frame neck (N,1,3) gives the same result as the broadcast template neck
+    pos2 = dict(pos, Neck=np.tile(grooming_head["neck"], (6000, 1, 1)))
+    out2 = api.Head(pos2, api.data.NMF_TEMPLATE, log_level="ERROR").compute_head_angles()
+    for k in out:
+        assert np.array_equal(out[k], out2[k])
+    with pytest.raises(ValueError):
+        api.Head({"R_head": pos["R_head"]}, api.data.NMF_TEMPLATE)
+
+
+# ------------------------------------------------------------------------------------------ alignment
+def test_alignment_vs_reference(api, grooming_align):
+    raw = {k: grooming_align[f"raw_{k}"] for k in grooming_align["raw_keys"]}
+    al = api.AlignPose(raw, legs_list=["RF", "LF"], include_claw=False, log_level="ERROR")
+    out = al.align_pose()
+    assert list(out.keys()) == list(grooming_align["ref_keys"])
+    for k in out:
+        ref = grooming_align[f"ref_{k}"]
+        assert out[k].shape == ref.shape and out[k].dtype == np.float64
+        assert np.allclose(out[k], ref, rtol=1e-5, atol=2e-6), (k, np.abs(out[k] - ref).max())   # cf. reference tests/test_alignment.py:93
+    # known answers of reference tests/test_alignment.py:54-78 on the full trial
+    for leg in ("RF", "LF"):
+        ml = al.get_mean_length(grooming_align[f"raw_full_{leg}"], segment_is_leg=True)
+        got = np.array([ml[s] for s in ("coxa", "femur", "tibia", "tarsus")])
+        assert np.allclose(got, grooming_align[f"{leg}_lengths"], rtol=2e-7, atol=0)
+        assert np.isclose(al.find_scale_leg(leg, ml), float(grooming_align[f"{leg}_scale"]), rtol=1e-6)
+    assert np.allclose(api.AlignPose.get_fixed_pos(grooming_align["raw_full_RF"][:, 0]), grooming_align["full_RF_coxa_fixed"], rtol=2e-7)
+    no_thorax = {k: v for k, v in raw.items() if k != "Thorax"}
+    with pytest.raises(AssertionError):
+        api.AlignPose(no_thorax, legs_list=["RF", "LF"], log_level="ERROR").align_pose()
+
+
+def test_mid_quantile_matches_numpy(api):
+    t = api.torch
+    rng = np.random.default_rng(7)
+    for n in (1, 2, 3, 10, 11, 100, 1000, 4097):
+        x = rng.normal(size=(5, n)).astype(np.float32)
+        x[1] = np.round(x[1], 1)                       # many ties
+        x[2] = -np.abs(x[2])                           # all negative
+        x[3, : n // 2] = 0.0                           # zeros and signs
+        got = api.engine.mid_quantile(t.from_numpy(x).cuda()).cpu().numpy()
+        ref = 0.5 * (np.quantile(x.astype(np.float64), 0.45, axis=1) + np.quantile(x.astype(np.float64), 0.55, axis=1))
+        assert np.allclose(got, ref, rtol=3e-7, atol=1e-7), n
+    with pytest.raises(ValueError):
+        api.engine.mid_quantile(t.zeros((3, 0), device="cuda"))
+
+
+# ------------------------------------------------------------------------------------------ edge cases and errors
+def test_edge_cases(api):
+    chain = api.Chain(api.data.BOUNDS, ["RF", "LF"])
+    empty = api.Leg({"RF_leg": np.zeros((0, 5, 3))}, chain, log_level="ERROR").run_ik_and_fk()
+    assert empty[0]["Angle_RF_ThC_yaw"].shape == (0,) and empty[1]["RF_leg"].shape == (0, 9, 3)
+    rng = np.random.default_rng(3)
+    one = rng.normal(scale=0.5, size=(1, 5, 3))
+    a, f = api.Leg({"RF_leg": one, "Neck": np.zeros((1, 1, 3)), "XX_leg": one}, chain, log_level="ERROR").run_ik_and_fk()
+    assert len(a) == 7 and list(f.keys()) == ["RF_leg"] and np.isfinite(f["RF_leg"]).all()     # XX skipped (not in body_size)
+    with pytest.raises(ValueError):
+        api.Leg({"RF_leg": one}, chain, log_level="ERROR").run_ik_and_fk(stages=[1, 3])
+    with pytest.raises(ValueError):
+        api.Leg({"RF_leg": one}, chain, log_level="ERROR").run_ik_and_fk(stages=[3, 4, 5])
+    bad_seed = {"RF": {k: v.copy() for k, v in api.data.INITIAL_ANGLES["RF"].items()}}
+    bad_seed["RF"]["stage_3"][7] = 0.5                                                           # inert slot, TiTa ub = 0
+    with pytest.raises(ValueError, match="Initial guess is outside of provided bounds"):
+        api.Leg({"RF_leg": one}, chain, bad_seed, log_level="ERROR").run_ik_and_fk()
+    ik = api.Leg({"RF_leg": one}, chain, log_level="ERROR")
+    with pytest.raises(ValueError):
+        ik.calculate_ik_stage(one[:, 1], one[:, 0], api.data.INITIAL_ANGLES["RF"]["stage_1"], "XX", stage=1)
+    with pytest.raises(ValueError):
+        ik.calculate_ik_stage(one[:, 1], one[:, 0], api.data.INITIAL_ANGLES["RF"]["stage_1"], "RF", stage=5)
+    # unreachable / degenerate targets still terminate with finite angles inside the bounds
+    wild = np.zeros((4, 5, 3))
+    wild[1, 1:] = 100.0
+    wild[2, 1:] = 1e-30
+    wild[3, 1:] = -50.0
+    a, f = api.Leg({"LF_leg": wild}, chain, log_level="ERROR").run_ik_and_fk()
+    for k, v in a.items():
+        lb, ub = api.data.BOUNDS[k.replace("Angle_", "")]
+        assert np.isfinite(v).all() and v.min() >= lb - 1e-6 and v.max() <= ub + 1e-6
