@@ -39,8 +39,9 @@ extern "C" {
                                                 trust region (what scipy's TRF does on the longer chains) */
 #define SEQIK_FLAG_DEFAULT (SEQIK_FLAG_GN_STAGE(1) | SEQIK_FLAG_GN_STAGE(2))
 #define SEQIK_FLAG_SCHED_SHIFT 8             /* bits 8..11: kernel schedule, 0 = automatic,
-                                                1 = one lane per chain, 2 = one lane per (chain, stage) pipeline */
+                                                1 = one lane per chain, 2 = stage pipeline (one warp per stage) */
 #define SEQIK_FLAG_SCHED_MASK (0xFu << SEQIK_FLAG_SCHED_SHIFT)
+#define SEQIK_FLAG_CPW_SHIFT 12              /* bits 12..17: chains per warp of schedule 2 (1..32), 0 = automatic */
 
 int seqik_abi_version(void);
 const char* seqik_last_error(void);
@@ -139,6 +140,10 @@ int seqik_align_apply_f32(const float* pose, int64_t pose_chain_stride, int64_t 
  *   d[i+2] - 2 d[i+1] + d[i] < threshold (find_stationary_indices, alignment.py:425-434), +inf elsewhere;
  *   row 4 = |tip - base| at every frame.  counts [n_trial][5] int32: valid entries per row. */
 int seqik_head_series_f32(const float* head, const float* thorax, int64_t n_thorax_kp, float threshold,
+                          float* series, int32_t* counts, int64_t n_trial, int64_t n_frame, void* stream);
+/* Same with FP64 key points (the dict API hands float64 arrays over).  Both variants evaluate the distances and the
+ * stationarity test in FP64: one frame flipping in or out of the stationary set moves the quantiles by ~1e-4. */
+int seqik_head_series_f64(const double* head, const double* thorax, int64_t n_thorax_kp, double threshold,
                           float* series, int32_t* counts, int64_t n_trial, int64_t n_frame, void* stream);
 
 /* Head affine rows (alignment.py:515-553): stats [n_trial][5] (seqik_mid_quantile_f32 of the head

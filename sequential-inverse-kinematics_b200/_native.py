@@ -35,6 +35,7 @@ _SIGNATURES = {
     "seqik_leg_affine_f32": (_int, [_vp, _vp, _int, _vp, _i64, _vp]),
     "seqik_align_apply_f32": (_int, [_vp, _i64, _i64, _vp, _vp, _i64, _i64, _vp]),
     "seqik_head_series_f32": (_int, [_vp, _vp, _i64, _f32, _vp, _vp, _i64, _i64, _vp]),
+    "seqik_head_series_f64": (_int, [_vp, _vp, _i64, ctypes.c_double, _vp, _vp, _i64, _i64, _vp]),
     "seqik_head_affine_f32": (_int, [_vp, _vp, _vp, _i64, _vp]),
     "seqik_head_apply_f32": (_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
 }

@@ -168,12 +168,15 @@ class AlignPose:
                 a key name <Antenna_mid_thorax> or <Antenna>
                 Please check the dictionary you provided.""")
         head_array = np.asarray(head_array)
-        d_head = self._to_device(head_array[None, :, :2])
-        d_thorax = self._to_device(np.asarray(self.pose_data_dict["Thorax"])[None])
+        dev = torch.device(self.device)
+        # statistics from the float64 key points (the stationarity threshold is ill-conditioned in float32)
+        d_head64 = torch.from_numpy(np.ascontiguousarray(head_array[None, :, :2], dtype=np.float64)).to(dev)
+        d_thorax = torch.from_numpy(np.ascontiguousarray(np.asarray(self.pose_data_dict["Thorax"])[None], dtype=np.float64)).to(dev)
+        d_head = d_head64.to(torch.float32)
         tmpl = np.asarray(self.body_template[f"{side}_Antenna_base"], dtype=float)
         consts = np.concatenate([tmpl, [antbase2thoraxmid_tmp, ant_tmp]]).astype(np.float32)
         d_consts = torch.from_numpy(consts[None]).to(d_head.device)
-        d_aff, d_counts = engine.head_affine(d_head, d_thorax, d_consts)
+        d_aff, d_counts = engine.head_affine(d_head64, d_thorax, d_consts)
         aff = d_aff[0].cpu().numpy()
         assert int(d_counts[0, 0]) > 0, "Threshold (5e-05) is too low to find stationary points, please increase it."
         self.logger.info("Scale factor antenna base %s: %s, ant itself: %s", side, aff[3], aff[7])

@@ -10,20 +10,31 @@
 // (scipy/optimize/_lsq/trf.py:206-413, common.py) on that active pair, in the pivot
 // frame of the stage, so that the whole solve is closed-form scalar arithmetic that
 // lives in registers:
-//   * the SVD of the augmented Jacobian becomes the eigen-decomposition of a 2x2 matrix;
+//   * in the pivot frame the two Jacobian columns are ORTHOGONAL (ja.jb = 0, |jb| = L,
+//     |ja| = L |cos b| or L |sin b|), so J^T J + diag is diagonal and the SVD of the
+//     augmented Jacobian (trf.py:296-303) is the identity: no 2x2 eigen-solve;
 //   * the inert slots enter only through `null_sq` (their squared norm: initial trust
 //     radius trf.py:236 and the xtol test common.py:705-718) and `max_nfev = 100 n`;
 //   * m = 3 < n always, so solve_lsq_trust_region (common.py:57-168) always takes its
 //     rank-deficient branch -- restated literally, including the final rescale of the
-//     step to the trust radius and the Levenberg parameter that may end negative.
+//     step to the trust radius and the Levenberg parameter carried between iterations.
 //
 // FP32 specifics (none change the FP64 instantiation's results beyond rounding):
 //   * distances to the bounds (dl, du) are carried as separate scalars and updated
 //     incrementally, so Coleman-Li scaling near an active bound keeps full relative
 //     accuracy (scipy iterates sit 1e-14 inside the bounds);
-//   * a trial point is evaluated through the angle-addition form (sin/cos of the STEP),
-//     which yields the change of the end point, hence the actual cost reduction, with
-//     relative accuracy ~1e-6 even when it is 1e-9 of the cost (ftol = 1e-8).
+//   * a trial point is evaluated through the angle-addition form (sin/cos/versine of the
+//     STEP), which yields the change of the end point, hence the actual cost reduction,
+//     with relative accuracy ~1e-6 even when it is 1e-9 of the cost (ftol = 1e-8);
+//   * device arithmetic: reciprocal / square root through the SFU approximations
+//     (rcp/sqrt/rsqrt.approx, <= 2 ulp), sin/cos by an in-line Cody-Waite reduction valid for
+//     |x| <= 2 pi (all angles are bounded by the joint limits), multiply-adds written as
+//     explicit fma so that every kernel that includes this header rounds identically
+//     (the library is compiled with -fmad=false).
+//
+// One trip() = one function evaluation.  Nothing is kept between trips except the iterate:
+// the scaling / model quantities are recomputed from it (they are cheap and it makes a trip
+// one straight-line block, which is what a warp of lanes at different positions needs).
 //
 // The same header is compiled by nvcc for the kernels and by g++ for the host-side
 // test harness in tests/hostsim (test infrastructure; never loaded by the product).
@@ -44,29 +55,71 @@ namespace seqik {
 // ---------------------------------------------------------------------------------
 template <typename R> struct Num;
 template <> struct Num<float> {
-    static SK_HD float sqrt_(float x) { return sqrtf(x); }
+    static SK_HD float fma_(float a, float b, float c) { return fmaf(a, b, c); }
     static SK_HD float abs_(float x) { return fabsf(x); }
     static SK_HD float max_(float a, float b) { return fmaxf(a, b); }
     static SK_HD float min_(float a, float b) { return fminf(a, b); }
     static SK_HD float copysign_(float a, float b) { return copysignf(a, b); }
-    static SK_HD void sincos_(float x, float* s, float* c) {
+    static SK_HD float rcp_(float x) {
 #if defined(__CUDA_ARCH__)
-        sincosf(x, s, c);
+        float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
 #else
-        *s = sinf(x); *c = cosf(x);
+        return 1.0f / x;
 #endif
+    }
+    static SK_HD float sqrt_(float x) {
+#if defined(__CUDA_ARCH__)
+        float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+        return sqrtf(x);
+#endif
+    }
+    static SK_HD float rsqrt_(float x) {
+#if defined(__CUDA_ARCH__)
+        float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+        return 1.0f / sqrtf(x);
+#endif
+    }
+    // sin, cos and versine (1 - cos) of x, |x| <= 2 pi: quadrant reduction + minimax polynomials on
+    // [-pi/4, pi/4]; the versine keeps full relative accuracy for tiny x (no 1 - cos cancellation).
+    static SK_HD void sincosv_(float x, float* s, float* c, float* v) {
+        const float kf = rintf(x * 0.636619772367581343f);                 // x * 2/pi
+        float r = fmaf(kf, -1.57079601287841796875f, x);                   // Cody-Waite, pi/2 = hi + mid + lo
+        r = fmaf(kf, -3.1391647326017846e-07f, r);
+        r = fmaf(kf, -5.390302529957764e-15f, r);
+        const float z = r * r;
+        float sp = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
+        sp = fmaf(sp, z, -1.6666654611e-1f);
+        const float sn = fmaf(sp * z, r, r);                               // sin r
+        float cp = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+        cp = fmaf(cp, z, 4.166664568298827e-2f);
+        const float vr = fmaf(-cp * z, z, 0.5f * z);                       // 1 - cos r = z/2 - z^2 (...)
+        const float cs = 1.0f - vr;                                        // cos r
+        const int q = ((int)kf) & 3;
+        const float ss = (q & 1) ? cs : sn, cc = (q & 1) ? sn : cs;
+        *s = (q & 2) ? -ss : ss;
+        *c = ((q + 1) & 2) ? -cc : cc;
+        *v = (q == 0) ? vr : 1.0f - *c;
     }
     static SK_HD float inf() { return INFINITY; }
     static SK_HD float tiny() { return 1.17549435e-38f; }     // stands in for nextafter(0, .)
     static SK_HD float eps_in() { return 2.220446e-16f; }     // fp64 ulp: strict-feasibility gap
 };
 template <> struct Num<double> {
-    static SK_HD double sqrt_(double x) { return sqrt(x); }
+    static SK_HD double fma_(double a, double b, double c) { return fma(a, b, c); }
     static SK_HD double abs_(double x) { return fabs(x); }
     static SK_HD double max_(double a, double b) { return fmax(a, b); }
     static SK_HD double min_(double a, double b) { return fmin(a, b); }
     static SK_HD double copysign_(double a, double b) { return copysign(a, b); }
-    static SK_HD void sincos_(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
+    static SK_HD double rcp_(double x) { return 1.0 / x; }
+    static SK_HD double sqrt_(double x) { return sqrt(x); }
+    static SK_HD double rsqrt_(double x) { return 1.0 / sqrt(x); }
+    static SK_HD void sincosv_(double x, double* s, double* c, double* v) {
+        *s = sin(x); *c = cos(x);
+        const double h = sin(0.5 * x);
+        *v = 2.0 * h * h;
+    }
     static SK_HD double inf() { return (double)INFINITY; }
     static SK_HD double tiny() { return 4.9406564584124654e-324; }
     static SK_HD double eps_in() { return 2.220446049250313e-16; }
@@ -79,58 +132,66 @@ enum : int {
 };
 
 template <typename R> struct Vec3 { R x, y, z; };
-template <typename R> SK_HD R dot(const Vec3<R>& a, const Vec3<R>& b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-
-// End point of the solved segment in the pivot frame, w = Rot_a Ry(b) (0,0,-L), and its
-// two Jacobian columns.  `has_a` = 0 turns variable a into an inert slot (stage 4).
-template <typename R>
-SK_HD void stage_point(int kind, R L, R has_a, R sa, R ca, R sb, R cb,
-                       Vec3<R>& w, Vec3<R>& ja, Vec3<R>& jb) {
-    const R Lsb = L * sb, Lcb = L * cb;
-    if (kind == KIND_XY) {
-        w = {-Lsb, Lcb * sa, -Lcb * ca};
-        ja = {R(0), Lcb * ca, Lcb * sa};
-        jb = {-Lcb, -Lsb * sa, Lsb * ca};
-    } else {
-        w = {-Lsb * ca, -Lsb * sa, -Lcb};
-        ja = {has_a * Lsb * sa, -has_a * Lsb * ca, R(0)};
-        jb = {-Lcb * ca, -Lcb * sa, Lsb};
-    }
+template <typename R> SK_HD R dot(const Vec3<R>& a, const Vec3<R>& b) {
+    return Num<R>::fma_(a.z, b.z, Num<R>::fma_(a.y, b.y, a.x * b.x));
 }
 
 // ---------------------------------------------------------------------------------
-// One stage solve: state + one evaluation per trip()
+// One stage solve: the iterate + one evaluation per trip()
 // ---------------------------------------------------------------------------------
-template <typename R>
+// KIND / HASA >= 0 fix the rotation kind / the presence of variable `a` at compile time (the stage-pipeline
+// kernel instantiates one solver per stage); -1 = run-time members (one lane walks all four stages).
+template <typename R, int KIND = -1, int HASA = -1>
 struct StageSolve {
     // problem
-    int kind; R L, has_a; R span0, span1;   // span = ub - lb (inf if unbounded)
-    bool fin_lb0, fin_ub0, fin_lb1, fin_ub1;
+    int kind_rt; R L, has_a_rt; R span0, span1;   // span = ub - lb (inf if unbounded)
     R null_sq; int max_nfev;
     bool gn_mode;   // true: take the Gauss-Newton step when it fits the trust region (see trip())
     // iterate
-    R x0, x1, dl0, dl1, du0, du1;      // angles and distances to the bounds
+    R x0, x1, dl0, dl1, du0, du1;      // angles and distances to the bounds (inf = no bound)
     R sa, ca, sb, cb;                   // sin/cos of the iterate
-    Vec3<R> f, ja, jb; R cost, g0, g1;
-    R Delta, alpha; int nfev, status; bool fresh;
-    // outer-iteration quantities (valid while !fresh)
-    R d0, d1, dh0, dh1, gh0, gh1, lam0, lam1, ex, ey, suf0, suf1, theta;
-    Vec3<R> jh0, jh1;
+    Vec3<R> f; R cost, g0, g1;         // residual w(x) - q, 0.5 |f|^2, gradient J^T f
+    R Delta, alpha; int nfev, status;
 
     typedef Num<R> N;
+    SK_HD int kind_() const { return KIND >= 0 ? KIND : kind_rt; }
+    SK_HD R has_a_() const { return HASA >= 0 ? R(HASA) : has_a_rt; }
 
+    // end point w = Rot_a Ry(b) (0,0,-L) of the solved segment in the pivot frame
+    SK_HD Vec3<R> point() const {
+        const R Lsb = L * sb, Lcb = L * cb;
+        if (kind_() == KIND_XY) return {-Lsb, Lcb * sa, -Lcb * ca};
+        return {-Lsb * ca, -Lsb * sa, -Lcb};
+    }
+    // gradient g = J^T f with the two Jacobian columns of w
+    SK_HD void gradient() {
+        const R Lsb = L * sb, Lcb = L * cb;
+        if (kind_() == KIND_XY) {
+            // ja = (0, Lcb ca, Lcb sa)   jb = (-Lcb, -Lsb sa, Lsb ca)
+            g0 = Lcb * N::fma_(ca, f.y, sa * f.z);
+            g1 = N::fma_(-Lcb, f.x, Lsb * N::fma_(ca, f.z, -(sa * f.y)));
+        } else {
+            // ja = has_a (Lsb sa, -Lsb ca, 0)   jb = (-Lcb ca, -Lcb sa, Lsb)
+            g0 = has_a_() * Lsb * N::fma_(sa, f.x, -(ca * f.y));
+            g1 = N::fma_(Lsb, f.z, -(Lcb * N::fma_(ca, f.x, sa * f.y)));
+        }
+    }
+    // |ja|^2 (|jb|^2 = L^2, ja.jb = 0)
+    SK_HD R ja_sq() const { const R m = (kind_() == KIND_XY) ? cb : sb; return has_a_() * (L * m) * (L * m); }
+
+    // Coleman-Li scaling (common.py CL_scaling_vector): v = distance to the bound the anti-gradient points at
     SK_HD void cl_scaling(R& v0, R& v1, R& dv0, R& dv1) const {
+        const R inf = N::inf();
         v0 = R(1); dv0 = R(0); v1 = R(1); dv1 = R(0);
-        if (g0 < R(0) && fin_ub0) { v0 = du0; dv0 = R(-1); } else if (g0 > R(0) && fin_lb0) { v0 = dl0; dv0 = R(1); }
-        if (g1 < R(0) && fin_ub1) { v1 = du1; dv1 = R(-1); } else if (g1 > R(0) && fin_lb1) { v1 = dl1; dv1 = R(1); }
+        if (g0 < R(0) && du0 < inf) { v0 = du0; dv0 = R(-1); } else if (g0 > R(0) && dl0 < inf) { v0 = dl0; dv0 = R(1); }
+        if (g1 < R(0) && du1 < inf) { v1 = du1; dv1 = R(-1); } else if (g1 > R(0) && dl1 < inf) { v1 = dl1; dv1 = R(1); }
     }
 
-    // least_squares prologue: x0 made strictly feasible (rstep 1e-10), f, J, g, Delta0
-    SK_HD void init(int kind_, R L_, R has_a_, const Vec3<R>& q, R a, R b,
+    // least_squares prologue: x0 made strictly feasible (rstep 1e-10), f, g, Delta0
+    SK_HD void init(int kind_in, R L_, R has_a_in, const Vec3<R>& q, R a, R b,
                     R lb0, R ub0, R lb1, R ub1, R null_sq_, int n_full, bool gn_mode_ = false) {
         gn_mode = gn_mode_;
-        kind = kind_; L = L_; has_a = has_a_; null_sq = null_sq_; max_nfev = 100 * n_full;
-        fin_lb0 = lb0 > -N::inf(); fin_ub0 = ub0 < N::inf(); fin_lb1 = lb1 > -N::inf(); fin_ub1 = ub1 < N::inf();
+        kind_rt = kind_in; L = L_; has_a_rt = has_a_in; null_sq = null_sq_; max_nfev = 100 * n_full;
         span0 = ub0 - lb0; span1 = ub1 - lb1;
         x0 = a; x1 = b;
         dl0 = a - lb0; du0 = ub0 - a; dl1 = b - lb1; du1 = ub1 - b;
@@ -139,30 +200,27 @@ struct StageSolve {
         if (du0 <= R(0)) { du0 = rs * N::max_(R(1), N::abs_(ub0)); x0 = ub0 - du0; dl0 = span0 - du0; }
         if (dl1 <= R(0)) { dl1 = rs * N::max_(R(1), N::abs_(lb1)); x1 = lb1 + dl1; du1 = span1 - dl1; }
         if (du1 <= R(0)) { du1 = rs * N::max_(R(1), N::abs_(ub1)); x1 = ub1 - du1; dl1 = span1 - du1; }
-        N::sincos_(x0, &sa, &ca); N::sincos_(x1, &sb, &cb);
-        Vec3<R> w; stage_point(kind, L, has_a, sa, ca, sb, cb, w, ja, jb);
+        R va, vb;
+        N::sincosv_(x0, &sa, &ca, &va); N::sincosv_(x1, &sb, &cb, &vb);
+        const Vec3<R> w = point();
         f = {w.x - q.x, w.y - q.y, w.z - q.z};
         cost = R(0.5) * dot(f, f);
-        g0 = dot(ja, f); g1 = dot(jb, f);
+        gradient();
         R v0, v1, dv0, dv1; cl_scaling(v0, v1, dv0, dv1);
-        Delta = N::sqrt_(null_sq + x0 * x0 / v0 + x1 * x1 / v1);
+        // true divisions: v can be ~1e-38 (an iterate parked on a bound at 0) where x*x underflows to 0 and
+        // 0 * rcp(v) would be 0 * inf
+        Delta = N::sqrt_(null_sq + (x0 * x0) / v0 + (x1 * x1) / v1);
         if (Delta == R(0)) Delta = R(1);
-        alpha = R(0); nfev = 1; status = ST_RUNNING; fresh = true;
+        alpha = R(0); nfev = 1; status = ST_RUNNING;
     }
 
     SK_HD bool done() const { return status != ST_RUNNING; }
 
-    // value of the hat-space quadratic model at s (evaluate_quadratic, common.py)
-    SK_HD R model(R s0, R s1) const {
-        const R jx = jh0.x * s0 + jh1.x * s1, jy = jh0.y * s0 + jh1.y * s1, jz = jh0.z * s0 + jh1.z * s1;
-        return R(0.5) * (jx * jx + jy * jy + jz * jz + s0 * dh0 * s0 + s1 * dh1 * s1) + s0 * gh0 + s1 * gh1;
-    }
-
     // step_size_to_bound from distances (dl, du) along p; hit flags
     static SK_HD R to_bound(R dl0_, R du0_, R dl1_, R du1_, R p0, R p1, bool& h0, bool& h1) {
         R s0 = N::inf(), s1 = N::inf();
-        if (p0 != R(0)) s0 = N::max_(-dl0_ / p0, du0_ / p0);
-        if (p1 != R(0)) s1 = N::max_(-dl1_ / p1, du1_ / p1);
+        if (p0 != R(0)) { const R r = N::rcp_(p0); s0 = N::max_(-dl0_ * r, du0_ * r); }
+        if (p1 != R(0)) { const R r = N::rcp_(p1); s1 = N::max_(-dl1_ * r, du1_ * r); }
         const R m = N::min_(s0, s1);
         h0 = (p0 != R(0)) && (s0 == m); h1 = (p1 != R(0)) && (s1 == m);
         return m;
@@ -170,36 +228,44 @@ struct StageSolve {
 
     // minimize_quadratic_1d(a, b, lo, hi, c)
     static SK_HD void minq(R a, R b, R lo, R hi, R c, R& t_best, R& y_best) {
-        t_best = lo; y_best = lo * (a * lo + b) + c;
-        const R yh = hi * (a * hi + b) + c;
+        t_best = lo; y_best = N::fma_(lo, N::fma_(a, lo, b), c);
+        const R yh = N::fma_(hi, N::fma_(a, hi, b), c);
         if (yh < y_best) { y_best = yh; t_best = hi; }
         if (a != R(0)) {
-            const R e = R(-0.5) * b / a;
+            const R e = R(-0.5) * b * N::rcp_(a);
             if (lo < e && e < hi) {
-                const R ye = e * (a * e + b) + c;
+                const R ye = N::fma_(e, N::fma_(a, e, b), c);
                 if (ye < y_best) { y_best = ye; t_best = e; }
             }
         }
     }
 
+    // Quantities of one outer iteration in the scaled ("hat") variables: B = Jh^T Jh + diag (diagonal), gh
+    struct Hat { R d0, d1, B0, B1, gh0, gh1, theta; };
+
+    // value of the hat-space quadratic model at s (evaluate_quadratic, common.py)
+    static SK_HD R model(const Hat& h, R s0, R s1) {
+        return N::fma_(s1, h.gh1, N::fma_(s0, h.gh0, R(0.5) * N::fma_(h.B1 * s1, s1, h.B0 * s0 * s0)));
+    }
+
     // select_step (trf.py:129-203) restricted to the active pair
-    SK_HD void select_step(R p0, R p1, R ph0, R ph1, R& st0, R& st1, R& sh0, R& sh1, R& pred) const {
+    SK_HD void select_step(const Hat& h, R p0, R p1, R ph0, R ph1, R& st0, R& st1, R& sh0, R& sh1, R& pred) const {
         const bool inb = (dl0 + p0 >= R(0)) && (du0 - p0 >= R(0)) && (dl1 + p1 >= R(0)) && (du1 - p1 >= R(0));
-        if (inb) { st0 = p0; st1 = p1; sh0 = ph0; sh1 = ph1; pred = -model(ph0, ph1); return; }
+        if (inb) { st0 = p0; st1 = p1; sh0 = ph0; sh1 = ph1; pred = -model(h, ph0, ph1); return; }
         bool h0, h1;
         const R p_stride = to_bound(dl0, du0, dl1, du1, p0, p1, h0, h1);
         R rh0 = h0 ? -ph0 : ph0, rh1 = h1 ? -ph1 : ph1;
-        R r0 = d0 * rh0, r1 = d1 * rh1;
+        R r0 = h.d0 * rh0, r1 = h.d1 * rh1;
         p0 *= p_stride; p1 *= p_stride; ph0 *= p_stride; ph1 *= p_stride;
         // intersect_trust_region(ph, rh, Delta): positive root
         R to_tr;
         {
-            const R a = rh0 * rh0 + rh1 * rh1, b = ph0 * rh0 + ph1 * rh1;
-            const R c = N::min_(ph0 * ph0 + ph1 * ph1 - Delta * Delta, R(0));
-            const R disc = N::sqrt_(N::max_(b * b - a * c, R(0)));
+            const R a = N::fma_(rh1, rh1, rh0 * rh0), b = N::fma_(ph1, rh1, ph0 * rh0);
+            const R c = N::min_(N::fma_(ph1, ph1, ph0 * ph0) - Delta * Delta, R(0));
+            const R disc = N::sqrt_(N::max_(N::fma_(b, b, -(a * c)), R(0)));
             const R qq = -(b + N::copysign_(disc, b));
             R t1 = R(0), t2 = R(0);
-            if (qq != R(0)) { t1 = qq / a; t2 = c / qq; }
+            if (qq != R(0)) { t1 = qq * N::rcp_(a); t2 = c * N::rcp_(qq); }
             to_tr = N::max_(t1, t2);
         }
         bool u0, u1;
@@ -207,36 +273,32 @@ struct StageSolve {
         const R r_stride = N::min_(to_bd, to_tr);
         R r_l, r_u;
         if (r_stride > R(0)) {
-            r_l = (R(1) - theta) * p_stride / r_stride;
-            r_u = (r_stride == to_bd) ? theta * to_bd : to_tr;
+            r_l = (R(1) - h.theta) * p_stride * N::rcp_(r_stride);
+            r_u = (r_stride == to_bd) ? h.theta * to_bd : to_tr;
         } else { r_l = R(0); r_u = R(-1); }
         R r_value = N::inf();
         if (r_l <= r_u) {
-            // build_quadratic_1d(Jh, gh, rh, s0=ph, diag=dh)
-            const R vx = jh0.x * rh0 + jh1.x * rh1, vy = jh0.y * rh0 + jh1.y * rh1, vz = jh0.z * rh0 + jh1.z * rh1;
-            const R ux = jh0.x * ph0 + jh1.x * ph1, uy = jh0.y * ph0 + jh1.y * ph1, uz = jh0.z * ph0 + jh1.z * ph1;
-            const R a = R(0.5) * (vx * vx + vy * vy + vz * vz + rh0 * dh0 * rh0 + rh1 * dh1 * rh1);
-            const R b = gh0 * rh0 + gh1 * rh1 + (ux * vx + uy * vy + uz * vz) + ph0 * dh0 * rh0 + ph1 * dh1 * rh1;
-            const R c = R(0.5) * (ux * ux + uy * uy + uz * uz) + gh0 * ph0 + gh1 * ph1
-                        + R(0.5) * (ph0 * dh0 * ph0 + ph1 * dh1 * ph1);
+            // build_quadratic_1d(Jh, gh, rh, s0=ph, diag=dh) with the diagonal B
+            const R a = R(0.5) * N::fma_(h.B1 * rh1, rh1, h.B0 * rh0 * rh0);
+            const R b = N::fma_(h.gh1, rh1, h.gh0 * rh0) + N::fma_(h.B1 * ph1, rh1, h.B0 * ph0 * rh0);
+            const R c = model(h, ph0, ph1);
             R rs; minq(a, b, r_l, r_u, c, rs, r_value);
-            rh0 = rh0 * rs + ph0; rh1 = rh1 * rs + ph1;
-            r0 = rh0 * d0; r1 = rh1 * d1;
+            rh0 = N::fma_(rh0, rs, ph0); rh1 = N::fma_(rh1, rs, ph1);
+            r0 = rh0 * h.d0; r1 = rh1 * h.d1;
         }
         // strictly interior truncated step
-        p0 *= theta; p1 *= theta; ph0 *= theta; ph1 *= theta;
-        const R p_value = model(ph0, ph1);
+        p0 *= h.theta; p1 *= h.theta; ph0 *= h.theta; ph1 *= h.theta;
+        const R p_value = model(h, ph0, ph1);
         // scaled anti-gradient
-        R ah0 = -gh0, ah1 = -gh1;
-        R a0 = d0 * ah0, a1 = d1 * ah1;
-        const R to_tr2 = Delta / N::sqrt_(ah0 * ah0 + ah1 * ah1);
+        R ah0 = -h.gh0, ah1 = -h.gh1;
+        R a0 = h.d0 * ah0, a1 = h.d1 * ah1;
+        const R to_tr2 = Delta * N::rsqrt_(N::fma_(ah1, ah1, ah0 * ah0));
         const R to_bd2 = to_bound(dl0, du0, dl1, du1, a0, a1, u0, u1);
-        const R ag_hi = (to_bd2 < to_tr2) ? theta * to_bd2 : to_tr2;
+        const R ag_hi = (to_bd2 < to_tr2) ? h.theta * to_bd2 : to_tr2;
         R ag_value, ags;
         {
-            const R vx = jh0.x * ah0 + jh1.x * ah1, vy = jh0.y * ah0 + jh1.y * ah1, vz = jh0.z * ah0 + jh1.z * ah1;
-            const R a = R(0.5) * (vx * vx + vy * vy + vz * vz + ah0 * dh0 * ah0 + ah1 * dh1 * ah1);
-            const R b = gh0 * ah0 + gh1 * ah1;
+            const R a = R(0.5) * N::fma_(h.B1 * ah1, ah1, h.B0 * ah0 * ah0);
+            const R b = N::fma_(h.gh1, ah1, h.gh0 * ah0);
             minq(a, b, R(0), ag_hi, R(0), ags, ag_value);
         }
         if (p_value < r_value && p_value < ag_value) { st0 = p0; st1 = p1; sh0 = ph0; sh1 = ph1; pred = -p_value; }
@@ -244,77 +306,61 @@ struct StageSolve {
         else { st0 = a0 * ags; st1 = a1 * ags; sh0 = ah0 * ags; sh1 = ah1 * ags; pred = -ag_value; }
     }
 
-    // One function evaluation (one pass of the inner `while actual_reduction <= 0` loop,
-    // preceded by the outer-iteration head when the previous step was accepted).
+    // One function evaluation: one pass of scipy's inner `while actual_reduction <= 0` loop, preceded by
+    // the head of the outer iteration (recomputed from the iterate: it is unchanged after a rejected step).
     SK_HD void trip() {
         const R gtol = R(1e-8), ftol = R(1e-8), xtol = R(1e-8);
-        if (fresh) {
-            R v0, v1, dv0, dv1; cl_scaling(v0, v1, dv0, dv1);
-            const R g_norm = N::max_(N::abs_(g0 * v0), N::abs_(g1 * v1));
-            if (g_norm < gtol) { status = ST_GTOL; return; }
-            if (nfev >= max_nfev) { status = ST_MAXFEV; return; }
-            d0 = N::sqrt_(v0); d1 = N::sqrt_(v1);
-            dh0 = g0 * dv0; dh1 = g1 * dv1;
-            gh0 = d0 * g0; gh1 = d1 * g1;
-            jh0 = {ja.x * d0, ja.y * d0, ja.z * d0};
-            jh1 = {jb.x * d1, jb.y * d1, jb.z * d1};
-            // B = Jh^T Jh + diag(dh); eigen-decomposition (== SVD of [Jh; sqrt(dh)])
-            const R b00 = dot(jh0, jh0) + dh0, b01 = dot(jh0, jh1), b11 = dot(jh1, jh1) + dh1;
-            const R tr = R(0.5) * (b00 + b11), df = R(0.5) * (b00 - b11);
-            const R rad = N::sqrt_(df * df + b01 * b01);
-            lam0 = tr + rad;
-            lam1 = (lam0 != R(0)) ? N::max_((b00 * b11 - b01 * b01) / lam0, R(0)) : R(0);
-            R vx, vy;
-            if (df >= R(0)) { vx = df + rad; vy = b01; } else { vx = b01; vy = rad - df; }
-            const R nrm = N::sqrt_(vx * vx + vy * vy);
-            if (nrm == R(0)) { ex = R(1); ey = R(0); } else { ex = vx / nrm; ey = vy / nrm; }
-            // suf = V^T gh with V = [[ex, -ey], [ey, ex]]
-            suf0 = ex * gh0 + ey * gh1; suf1 = -ey * gh0 + ex * gh1;
-            theta = N::max_(R(0.995), R(1) - g_norm);
-            fresh = false;
-        }
-        // ---- solve_lsq_trust_region, rank-deficient branch
+        Hat h;
+        R v0, v1, dv0, dv1; cl_scaling(v0, v1, dv0, dv1);
+        const R g_norm = N::max_(N::abs_(g0 * v0), N::abs_(g1 * v1));
+        if (g_norm < gtol) { status = ST_GTOL; return; }
+        if (nfev >= max_nfev) { status = ST_MAXFEV; return; }
+        h.d0 = N::sqrt_(v0); h.d1 = N::sqrt_(v1);
+        h.gh0 = h.d0 * g0; h.gh1 = h.d1 * g1;
+        h.B0 = N::fma_(v0, ja_sq(), g0 * dv0); h.B1 = N::fma_(v1, L * L, g1 * dv1);   // Jh^T Jh + diag(g dv), diagonal
+        h.theta = N::max_(R(0.995), R(1) - g_norm);
+        // ---- solve_lsq_trust_region, rank-deficient branch; singular values^2 = (B0, B1), V = I
         R t0, t1;
         bool gn_taken = false;
-        if (gn_mode && lam1 > R(0)) {
+        if (gn_mode && h.B0 > R(0) && h.B1 > R(0)) {
             // scipy's SVD leaves ~1e-17 singular values on the inert slots of the longer chains; the
             // Levenberg parameter then decays to ~1e-20 and that null-space noise absorbs the trust-region
             // norm, i.e. the active pair receives the plain Gauss-Newton step whenever it fits in Delta.
-            t0 = suf0 / lam0; t1 = suf1 / lam1;
-            gn_taken = (t0 * t0 + t1 * t1 <= Delta * Delta);
+            t0 = h.gh0 * N::rcp_(h.B0); t1 = h.gh1 * N::rcp_(h.B1);
+            gn_taken = (N::fma_(t1, t1, t0 * t0) <= Delta * Delta);
             if (gn_taken) alpha = R(0);
         }
         if (!gn_taken) {
-            R a_up = N::sqrt_(suf0 * suf0 + suf1 * suf1) / Delta, a_lo = R(0);
+            const R rDelta = N::rcp_(Delta);
+            R a_up = N::sqrt_(N::fma_(h.gh1, h.gh1, h.gh0 * h.gh0)) * rDelta, a_lo = R(0);
             if (alpha == R(0)) alpha = R(0.001) * a_up;
             for (int it = 0; it < 10; ++it) {
                 if (alpha < a_lo || alpha > a_up) alpha = N::max_(R(0.001) * a_up, N::sqrt_(a_lo * a_up));
-                const R e0 = lam0 + alpha, e1 = lam1 + alpha;
-                t0 = (e0 != R(0)) ? suf0 / e0 : R(0); t1 = (e1 != R(0)) ? suf1 / e1 : R(0);
-                const R pn = N::sqrt_(t0 * t0 + t1 * t1);
+                const R e0 = h.B0 + alpha, e1 = h.B1 + alpha;
+                const R r0 = (e0 != R(0)) ? N::rcp_(e0) : R(0), r1 = (e1 != R(0)) ? N::rcp_(e1) : R(0);
+                t0 = (h.gh0 != R(0)) ? h.gh0 * r0 : R(0); t1 = (h.gh1 != R(0)) ? h.gh1 * r1 : R(0);
+                const R pn = N::sqrt_(N::fma_(t1, t1, t0 * t0));
                 const R phi = pn - Delta;
-                R dd = R(0);
-                if (e0 != R(0)) dd += t0 * t0 / e0;
-                if (e1 != R(0)) dd += t1 * t1 / e1;
-                const R dphi = -dd / pn;
+                const R dd = N::fma_(t1 * t1, r1, t0 * t0 * r0);        // -phi' * pn
                 if (phi < R(0)) a_up = alpha;
-                const R ratio = phi / dphi;
+                const R ratio = (dd > R(0)) ? -(phi * pn) * N::rcp_(dd) : R(0);   // phi / phi'
                 a_lo = N::max_(a_lo, alpha - ratio);
-                alpha -= (phi + Delta) * ratio / Delta;
+                alpha -= pn * ratio * rDelta;                            // (phi + Delta) * ratio / Delta
                 if (N::abs_(phi) < R(0.01) * Delta) break;
             }
-            const R e0 = lam0 + alpha, e1 = lam1 + alpha;
-            t0 = (e0 != R(0)) ? suf0 / e0 : R(0); t1 = (e1 != R(0)) ? suf1 / e1 : R(0);
+            const R e0 = h.B0 + alpha, e1 = h.B1 + alpha;
+            t0 = (e0 != R(0) && h.gh0 != R(0)) ? h.gh0 * N::rcp_(e0) : R(0);
+            t1 = (e1 != R(0) && h.gh1 != R(0)) ? h.gh1 * N::rcp_(e1) : R(0);
         }
-        R ph0 = -(ex * t0 - ey * t1), ph1 = -(ey * t0 + ex * t1);
+        R ph0 = -t0, ph1 = -t1;
         if (!gn_taken) {
-            const R sc = Delta / N::sqrt_(ph0 * ph0 + ph1 * ph1);
+            const R sc = Delta * N::rsqrt_(N::fma_(ph1, ph1, ph0 * ph0));
             ph0 *= sc; ph1 *= sc;
         }
         R st0, st1, sh0, sh1, pred;
-        select_step(d0 * ph0, d1 * ph1, ph0, ph1, st0, st1, sh0, sh1, pred);
+        select_step(h, h.d0 * ph0, h.d1 * ph1, ph0, ph1, st0, st1, sh0, sh1, pred);
 
-        // ---- trial point: strictly feasible, evaluated through the step's sin/cos
+        // ---- trial point: strictly feasible, evaluated through the step's sin/cos/versine
         R nx0 = x0 + st0, nx1 = x1 + st1;
         R ndl0 = dl0 + st0, ndu0 = du0 - st0, ndl1 = dl1 + st1, ndu1 = du1 - st1;
         R e0 = st0, e1 = st1;   // applied step
@@ -322,47 +368,43 @@ struct StageSolve {
         if (ndu0 <= R(0)) { const R gap = inner_gap(nx0 + ndu0); e0 = du0 - gap; ndu0 = gap; ndl0 = span0 - gap; nx0 = x0 + e0; }
         if (ndl1 <= R(0)) { const R gap = inner_gap(nx1 - ndl1); e1 = gap - dl1; ndl1 = gap; ndu1 = span1 - gap; nx1 = x1 + e1; }
         if (ndu1 <= R(0)) { const R gap = inner_gap(nx1 + ndu1); e1 = du1 - gap; ndu1 = gap; ndl1 = span1 - gap; nx1 = x1 + e1; }
-        R sda, cda, sdb, cdb;
-        N::sincos_(e0, &sda, &cda); N::sincos_(e1, &sdb, &cdb);
-        const R va = (cda > R(0)) ? sda * sda / (R(1) + cda) : R(1) - cda;   // 1 - cos(step)
-        const R vb = (cdb > R(0)) ? sdb * sdb / (R(1) + cdb) : R(1) - cdb;
-        const R dsa = ca * sda - sa * va, dca = -sa * sda - ca * va;
-        const R dsb = cb * sdb - sb * vb, dcb = -sb * sdb - cb * vb;
+        R sda, cda, va, sdb, cdb, vb;
+        N::sincosv_(e0, &sda, &cda, &va); N::sincosv_(e1, &sdb, &cdb, &vb);
+        const R dsa = N::fma_(ca, sda, -(sa * va)), dca = -N::fma_(sa, sda, ca * va);   // sin/cos(a + e0) - sin/cos(a)
+        const R dsb = N::fma_(cb, sdb, -(sb * vb)), dcb = -N::fma_(sb, sdb, cb * vb);
         const R nsa = sa + dsa, nca = ca + dca, nsb = sb + dsb, ncb = cb + dcb;
-        Vec3<R> dw;
-        if (kind == KIND_XY) {
-            dw = {-L * dsb, L * (dcb * nsa + cb * dsa), -L * (dcb * nca + cb * dca)};
+        Vec3<R> dw;   // w(x + e) - w(x)
+        if (kind_() == KIND_XY) {
+            dw = {-L * dsb, L * N::fma_(dcb, nsa, cb * dsa), -L * N::fma_(dcb, nca, cb * dca)};
         } else {
-            dw = {-L * (dsb * nca + sb * dca), -L * (dsb * nsa + sb * dsa), -L * dcb};
+            dw = {-L * N::fma_(dsb, nca, sb * dca), -L * N::fma_(dsb, nsa, sb * dsa), -L * dcb};
         }
         nfev += 1;
-        const R actual = -(dot(f, dw) + R(0.5) * dot(dw, dw));
-        const R step_h_norm = N::sqrt_(sh0 * sh0 + sh1 * sh1);
+        const R actual = -N::fma_(R(0.5), dot(dw, dw), dot(f, dw));
+        const R step_h_sq = N::fma_(sh1, sh1, sh0 * sh0);
         // update_tr_radius
         R ratio;
-        if (pred > R(0)) ratio = actual / pred; else if (pred == R(0) && actual == R(0)) ratio = R(1); else ratio = R(0);
+        if (pred > R(0)) ratio = (actual != R(0)) ? actual * N::rcp_(pred) : R(0); else if (pred == R(0) && actual == R(0)) ratio = R(1); else ratio = R(0);
         R Delta_new = Delta;
-        if (ratio < R(0.25)) Delta_new = R(0.25) * step_h_norm;
-        else if (ratio > R(0.75) && step_h_norm > R(0.95) * Delta) Delta_new = R(2) * Delta;
+        if (ratio < R(0.25)) Delta_new = R(0.25) * N::sqrt_(step_h_sq);
+        else if (ratio > R(0.75) && step_h_sq > R(0.9025) * Delta * Delta) Delta_new = R(2) * Delta;
         // check_termination
-        const R step_norm = N::sqrt_(st0 * st0 + st1 * st1);
-        const R x_norm = N::sqrt_(null_sq + x0 * x0 + x1 * x1);
+        const R step_sq = N::fma_(st1, st1, st0 * st0);
+        const R x_norm = N::sqrt_(N::fma_(x1, x1, N::fma_(x0, x0, null_sq)));
+        const R xt_rhs = xtol * (xtol + x_norm);
         const bool ft = (actual < ftol * cost) && (ratio > R(0.25));
-        const bool xt = step_norm < xtol * (xtol + x_norm);
+        const bool xt = step_sq < xt_rhs * xt_rhs;
         int term = ST_RUNNING;
         if (ft && xt) term = ST_BOTH; else if (ft) term = ST_FTOL; else if (xt) term = ST_XTOL;
-        if (term == ST_RUNNING) { alpha *= Delta / Delta_new; Delta = Delta_new; }
+        if (term == ST_RUNNING) { alpha *= Delta * N::rcp_(Delta_new); Delta = Delta_new; }
         if (actual > R(0)) {
             x0 = nx0; x1 = nx1; dl0 = ndl0; du0 = ndu0; dl1 = ndl1; du1 = ndu1;
             sa = nsa; ca = nca; sb = nsb; cb = ncb;
             f = {f.x + dw.x, f.y + dw.y, f.z + dw.z};
             cost = cost - actual;
-            Vec3<R> w; stage_point(kind, L, has_a, sa, ca, sb, cb, w, ja, jb);
-            g0 = dot(ja, f); g1 = dot(jb, f);
-            fresh = true;
+            gradient();
         }
         if (term != ST_RUNNING) status = term;
-        else if (!(actual > R(0)) && nfev >= max_nfev) status = ST_MAXFEV;
     }
 
     // make_strictly_feasible(x, lb, ub, rstep=0): one fp64 ulp inside the bound `b`
@@ -381,12 +423,14 @@ template <typename R> SK_HD Vec3<R> mulT(const Mat3<R>& A, const Vec3<R>& v) {  
     return {dot(A.c0, v), dot(A.c1, v), dot(A.c2, v)};
 }
 template <typename R> SK_HD Vec3<R> mul(const Mat3<R>& A, const Vec3<R>& v) {    // A v
-    return {A.c0.x * v.x + A.c1.x * v.y + A.c2.x * v.z,
-            A.c0.y * v.x + A.c1.y * v.y + A.c2.y * v.z,
-            A.c0.z * v.x + A.c1.z * v.y + A.c2.z * v.z};
+    typedef Num<R> N;
+    return {N::fma_(A.c2.x, v.z, N::fma_(A.c1.x, v.y, A.c0.x * v.x)),
+            N::fma_(A.c2.y, v.z, N::fma_(A.c1.y, v.y, A.c0.y * v.x)),
+            N::fma_(A.c2.z, v.z, N::fma_(A.c1.z, v.y, A.c0.z * v.x))};
 }
 template <typename R> SK_HD Vec3<R> lin(const Vec3<R>& a, R s, const Vec3<R>& b, R t) {
-    return {a.x * s + b.x * t, a.y * s + b.y * t, a.z * s + b.z * t};
+    typedef Num<R> N;
+    return {N::fma_(b.x, t, a.x * s), N::fma_(b.y, t, a.y * s), N::fma_(b.z, t, a.z * s)};
 }
 // A <- A * Rot_a(a) * Ry(b), Rot_a = Rx (KIND_XY) or Rz (KIND_ZY)
 template <typename R> SK_HD Mat3<R> rotate_frame(const Mat3<R>& A, int kind, R sa, R ca, R sb, R cb) {
@@ -481,7 +525,7 @@ struct ChainRunner {
         const Vec3<R> jw = {piv.x + o.x, piv.y + o.y, piv.z + o.z};
         if (s == 0) { io.put_fk(t, 4, jw); io.put_fk(t, 5, jw); } else io.put_fk(t, 5 + s, jw);
         if (s < hi) {
-            A = rotate_frame(A, S.kind, S.sa, S.ca, S.sb, S.cb);
+            A = rotate_frame(A, S.kind_(), S.sa, S.ca, S.sb, S.cb);
             ++s;
             begin_stage();
         } else {

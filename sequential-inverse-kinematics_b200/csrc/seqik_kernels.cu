@@ -1,9 +1,7 @@
 // seqik_kernels.cu -- sm_100a kernels + C ABI (include/seqik.h) of the SeqIKPy leg-IK hot path.
 //
 // Kernels
-//   leg_solve_kernel   4-stage sequential IK + FK.  Latency/FP32-issue bound: every lane owns
-//                      one (trial, leg) chain and runs ChainRunner::step() -- one residual evaluation of its
-//                      current (frame, stage) solve per trip -- in a convergent loop.
+//   (the leg solver kernels live in seqik_solver.cu)
 //   fk_kernel          angles -> 9x3 joint positions, HBM-bound streaming kernel (smem-staged, 128-bit I/O)
 //   head_kernel        7 head/antenna angles per frame, HBM-bound elementwise
 //   leg_series_kernel / mid_quantile_kernel / align_apply_kernel   AlignPose statistics + affine map
@@ -15,6 +13,7 @@
 #include <string.h>
 
 #include "../../include/seqik.h"
+#include "seqik_common.h"
 #include "seqik_core.cuh"
 
 using namespace seqik;
@@ -24,11 +23,11 @@ using namespace seqik;
 // ---------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
 
-static int fail(int code, const char* fmt, const char* a = "") {
+int seqik_fail(int code, const char* fmt, const char* a) {
     snprintf(g_err, sizeof(g_err), fmt, a);
     return code;
 }
-static int check_launch(const char* what) {
+int seqik_check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
@@ -36,111 +35,11 @@ static int check_launch(const char* what) {
     }
     return SEQIK_OK;
 }
+static inline int fail(int code, const char* fmt, const char* a = "") { return seqik_fail(code, fmt, a); }
+static inline int check_launch(const char* what) { return seqik_check_launch(what); }
 
 extern "C" int seqik_abi_version(void) { return SEQIK_ABI_VERSION; }
 extern "C" const char* seqik_last_error(void) { return g_err; }
-
-// ---------------------------------------------------------------------------------------------
-// leg solver
-// ---------------------------------------------------------------------------------------------
-struct LegArgs {
-    const float* pose; int64_t pose_cs, pose_fs;
-    const float* affine; const float* params;
-    float* angles; int64_t ang_cs, ang_fs;
-    float* fk; int64_t fk_cs, fk_fs;
-    int32_t* status; uint32_t* nfev;
-    int64_t n_chain, n_frame;
-    int stage_mask, gn_mask;
-};
-
-// Global-memory IO policy of one chain.  Key points are read with plain (L1-cached) loads: a chain's
-// frames are contiguous (60 B apart), so consecutive frames share 128 B lines.
-struct DevIO {
-    const float* pose; int64_t fs;          // base of this chain, frame stride
-    const float* prm;                       // 32 floats
-    float* ang; int64_t ang_fs;
-    float* fk; int64_t fk_fs;
-    float fx, fy, fz, sc, tx, ty, tz;       // alignment map (identity when no affine)
-    bool has_affine;
-
-    __device__ __forceinline__ Vec3<float> kp(int64_t t, int row) const {
-        const float* p = pose + t * fs + row * 3;
-        Vec3<float> v = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
-        if (has_affine) {
-            if (row == 0) v = {tx, ty, tz};
-            else v = {(v.x - fx) * sc + tx, (v.y - fy) * sc + ty, (v.z - fz) * sc + tz};
-        }
-        return v;
-    }
-    __device__ __forceinline__ void put_angles(int64_t t, const float* a, int i0, int i1) const {
-        float* p = ang + t * ang_fs;
-#pragma unroll
-        for (int i = 0; i < 7; ++i) if (i >= i0 && i < i1) p[i] = a[i];
-    }
-    __device__ __forceinline__ float angle_in(int64_t t, int i) const { return ang[t * ang_fs + i]; }
-    __device__ __forceinline__ void put_fk(int64_t t, int row, const Vec3<float>& v) const {
-        if (fk) { float* p = fk + t * fk_fs + row * 3; p[0] = v.x; p[1] = v.y; p[2] = v.z; }
-    }
-    __device__ __forceinline__ float seg(int i) const { return __ldg(prm + i); }
-    __device__ __forceinline__ float lb(int i) const { return __ldg(prm + 4 + i); }
-    __device__ __forceinline__ float ub(int i) const { return __ldg(prm + 11 + i); }
-    __device__ __forceinline__ float null_sq(int i) const { return __ldg(prm + 25 + i); }
-};
-
-// schedule 1: one lane per chain, decoupled trips
-__global__ void __launch_bounds__(64) leg_solve_kernel(LegArgs a) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= a.n_chain) return;
-    DevIO io;
-    io.pose = a.pose + c * a.pose_cs; io.fs = a.pose_fs;
-    io.prm = a.params + c * SEQIK_CHAIN_PARAM_FLOATS;
-    io.ang = a.angles + c * a.ang_cs; io.ang_fs = a.ang_fs;
-    io.fk = a.fk ? a.fk + c * a.fk_cs : nullptr; io.fk_fs = a.fk_fs;
-    io.has_affine = a.affine != nullptr;
-    io.fx = io.fy = io.fz = 0.f; io.sc = 1.f; io.tx = io.ty = io.tz = 0.f;
-    if (io.has_affine) {
-        const float* q = a.affine + c * 8;
-        io.fx = q[0]; io.fy = q[1]; io.fz = q[2]; io.sc = q[3]; io.tx = q[4]; io.ty = q[5]; io.tz = q[6];
-    }
-    float seed[7];
-#pragma unroll
-    for (int i = 0; i < 7; ++i) seed[i] = io.prm[18 + i];
-    ChainRunner<float, DevIO> run;
-    run.start(io, a.n_frame, seed, a.stage_mask, a.gn_mask);
-    while (!run.finished()) run.step();
-    if (a.status) a.status[c] = run.worst_status;
-    if (a.nfev) { uint32_t* nf = a.nfev + c * 4; nf[0] = run.nf0; nf[1] = run.nf1; nf[2] = run.nf2; nf[3] = run.nf3; }
-}
-
-extern "C" int seqik_leg_solve_f32(const float* pose, int64_t pose_chain_stride, int64_t pose_frame_stride,
-                                   const float* affine, const float* params,
-                                   float* angles, int64_t ang_chain_stride, int64_t ang_frame_stride,
-                                   float* fk, int64_t fk_chain_stride, int64_t fk_frame_stride,
-                                   int32_t* status, uint32_t* nfev,
-                                   int64_t n_chain, int64_t n_frame, uint32_t stage_mask, uint32_t flags, void* stream) {
-    if (n_chain < 0 || n_frame < 0) return fail(SEQIK_EINVAL, "seqik_leg_solve_f32: negative size");
-    if (n_chain == 0 || n_frame == 0) return SEQIK_OK;
-    if (!pose || !params || !angles) return fail(SEQIK_EINVAL, "seqik_leg_solve_f32: pose, params and angles must not be NULL");
-    {
-        uint32_t m = stage_mask;
-        while (m && !(m & 1u)) m >>= 1;
-        if (stage_mask == 0 || stage_mask > 0xF || (m & (m + 1)) != 0)
-            return fail(SEQIK_EINVAL, "seqik_leg_solve_f32: stage_mask must be a contiguous run of bits within 0xF");
-    }
-    if (pose_frame_stride < 15 || ang_frame_stride < 7 || (fk && fk_frame_stride < 27))
-        return fail(SEQIK_EINVAL, "seqik_leg_solve_f32: frame stride smaller than the innermost block");
-    LegArgs a;
-    a.pose = pose; a.pose_cs = pose_chain_stride; a.pose_fs = pose_frame_stride;
-    a.affine = affine; a.params = params;
-    a.angles = angles; a.ang_cs = ang_chain_stride; a.ang_fs = ang_frame_stride;
-    a.fk = fk; a.fk_cs = fk_chain_stride; a.fk_fs = fk_frame_stride;
-    a.status = status; a.nfev = nfev; a.n_chain = n_chain; a.n_frame = n_frame;
-    a.stage_mask = (int)stage_mask; a.gn_mask = (int)(flags & 0xF);
-    const int block = 32;
-    const int64_t grid = (n_chain + block - 1) / block;
-    leg_solve_kernel<<<(unsigned)grid, block, 0, (cudaStream_t)stream>>>(a);
-    return check_launch("seqik_leg_solve_f32");
-}
 
 // ---------------------------------------------------------------------------------------------
 // forward kinematics (streaming)
@@ -450,34 +349,40 @@ extern "C" int seqik_align_apply_f32(const float* pose, int64_t pose_chain_strid
 }
 
 // ---- antenna (AlignPose.align_head)
-__device__ __forceinline__ float base_to_thorax_mid(const float* __restrict__ head, const float* __restrict__ thorax,
-                                                    int64_t n_kp, int64_t i) {
-    const float* b = head + i * 6;
-    const float* t0 = thorax + i * n_kp * 3; const float* t1 = t0 + (n_kp - 1) * 3;
-    const float dx = b[0] - 0.5f * (t0[0] + t1[0]), dy = b[1] - 0.5f * (t0[1] + t1[1]), dz = b[2] - 0.5f * (t0[2] + t1[2]);
-    return sqrtf(dx * dx + dy * dy + dz * dz);
+// The stationarity test thresholds a SECOND DIFFERENCE of distances (5e-5 against values ~1): it is evaluated in
+// FP64 whatever the input type, because a single flipped frame moves the order statistics that follow by ~1e-4.
+template <typename T>
+__device__ __forceinline__ double base_to_thorax_mid(const T* __restrict__ head, const T* __restrict__ thorax,
+                                                     int64_t n_kp, int64_t i) {
+    const T* b = head + i * 6;
+    const T* t0 = thorax + i * n_kp * 3; const T* t1 = t0 + (n_kp - 1) * 3;
+    const double dx = (double)b[0] - 0.5 * ((double)t0[0] + (double)t1[0]);
+    const double dy = (double)b[1] - 0.5 * ((double)t0[1] + (double)t1[1]);
+    const double dz = (double)b[2] - 0.5 * ((double)t0[2] + (double)t1[2]);
+    return sqrt(dx * dx + dy * dy + dz * dz);
 }
 
-__global__ void __launch_bounds__(256) head_series_kernel(const float* __restrict__ head, const float* __restrict__ thorax,
-                                                          int64_t n_kp, float threshold, float* __restrict__ series,
+template <typename T>
+__global__ void __launch_bounds__(256) head_series_kernel(const T* __restrict__ head, const T* __restrict__ thorax,
+                                                          int64_t n_kp, double threshold, float* __restrict__ series,
                                                           int32_t* __restrict__ counts, int64_t n_trial, int64_t n_frame) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool in = i < n_trial * n_frame;
     const int64_t tr = in ? i / n_frame : 0, t = in ? i - tr * n_frame : 0;
     bool stationary = false;
     if (in) {
-        const float* b = head + i * 6;
-        const float d0 = base_to_thorax_mid(head, thorax, n_kp, i);
+        const T* b = head + i * 6;
+        const double d0 = base_to_thorax_mid(head, thorax, n_kp, i);
         if (t + 2 < n_frame) {
-            const float d1 = base_to_thorax_mid(head, thorax, n_kp, i + 1), d2 = base_to_thorax_mid(head, thorax, n_kp, i + 2);
+            const double d1 = base_to_thorax_mid(head, thorax, n_kp, i + 1), d2 = base_to_thorax_mid(head, thorax, n_kp, i + 2);
             stationary = ((d2 - d1) - (d1 - d0)) < threshold;   // np.diff(np.diff(d)) < threshold, signed
         }
         const float inf = __int_as_float(0x7f800000);
         float* s = series + tr * 5 * n_frame + t;
-        s[0] = stationary ? b[0] : inf; s[n_frame] = stationary ? b[1] : inf; s[2 * n_frame] = stationary ? b[2] : inf;
-        s[3 * n_frame] = stationary ? d0 : inf;
-        const float ax = b[3] - b[0], ay = b[4] - b[1], az = b[5] - b[2];
-        s[4 * n_frame] = sqrtf(ax * ax + ay * ay + az * az);
+        s[0] = stationary ? (float)b[0] : inf; s[n_frame] = stationary ? (float)b[1] : inf; s[2 * n_frame] = stationary ? (float)b[2] : inf;
+        s[3 * n_frame] = stationary ? (float)d0 : inf;
+        const double ax = (double)b[3] - (double)b[0], ay = (double)b[4] - (double)b[1], az = (double)b[5] - (double)b[2];
+        s[4 * n_frame] = (float)sqrt(ax * ax + ay * ay + az * az);
     }
     // count stationary frames per trial: warp vote, one atomic per (warp, trial) when the warp sits in one trial
     const unsigned ballot = __ballot_sync(0xffffffffu, stationary);
@@ -495,21 +400,33 @@ __global__ void head_counts_finish_kernel(int32_t* __restrict__ counts, int64_t 
     c[1] = c[0]; c[2] = c[0]; c[3] = c[0]; c[4] = (int32_t)n_frame;
 }
 
-extern "C" int seqik_head_series_f32(const float* head, const float* thorax, int64_t n_thorax_kp, float threshold,
-                                     float* series, int32_t* counts, int64_t n_trial, int64_t n_frame, void* stream) {
-    if (n_trial < 0 || n_frame < 0) return fail(SEQIK_EINVAL, "seqik_head_series_f32: negative size");
+template <typename T>
+static int head_series_launch(const char* name, const T* head, const T* thorax, int64_t n_thorax_kp, double threshold,
+                              float* series, int32_t* counts, int64_t n_trial, int64_t n_frame, void* stream) {
+    if (n_trial < 0 || n_frame < 0) return fail(SEQIK_EINVAL, "%s: negative size", name);
     if (n_trial == 0 || n_frame == 0) return SEQIK_OK;
-    if (!head || !thorax || !series || !counts) return fail(SEQIK_EINVAL, "seqik_head_series_f32: NULL pointer");
-    if (n_thorax_kp < 1) return fail(SEQIK_EINVAL, "seqik_head_series_f32: thorax needs at least one key point");
-    if (n_frame > 2147483647LL) return fail(SEQIK_EINVAL, "seqik_head_series_f32: too many frames");
+    if (!head || !thorax || !series || !counts) return fail(SEQIK_EINVAL, "%s: NULL pointer", name);
+    if (n_thorax_kp < 1) return fail(SEQIK_EINVAL, "%s: thorax needs at least one key point", name);
+    if (n_frame > 2147483647LL) return fail(SEQIK_EINVAL, "%s: too many frames", name);
     cudaStream_t st = (cudaStream_t)stream;
-    if (cudaMemsetAsync(counts, 0, sizeof(int32_t) * 5 * n_trial, st) != cudaSuccess) return check_launch("seqik_head_series_f32(memset)");
+    if (cudaMemsetAsync(counts, 0, sizeof(int32_t) * 5 * n_trial, st) != cudaSuccess) return check_launch(name);
     const int64_t n = n_trial * n_frame;
-    head_series_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(head, thorax, n_thorax_kp, threshold, series, counts, n_trial, n_frame);
-    int rc = check_launch("seqik_head_series_f32");
+    head_series_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(head, thorax, n_thorax_kp, threshold, series, counts, n_trial, n_frame);
+    int rc = check_launch(name);
     if (rc) return rc;
     head_counts_finish_kernel<<<(unsigned)((n_trial + 127) / 128), 128, 0, st>>>(counts, n_trial, n_frame);
-    return check_launch("seqik_head_series_f32(counts)");
+    return check_launch(name);
+}
+
+extern "C" int seqik_head_series_f32(const float* head, const float* thorax, int64_t n_thorax_kp, float threshold,
+                                     float* series, int32_t* counts, int64_t n_trial, int64_t n_frame, void* stream) {
+    return head_series_launch<float>("seqik_head_series_f32", head, thorax, n_thorax_kp, (double)threshold, series, counts,
+                                     n_trial, n_frame, stream);
+}
+extern "C" int seqik_head_series_f64(const double* head, const double* thorax, int64_t n_thorax_kp, double threshold,
+                                     float* series, int32_t* counts, int64_t n_trial, int64_t n_frame, void* stream) {
+    return head_series_launch<double>("seqik_head_series_f64", head, thorax, n_thorax_kp, threshold, series, counts,
+                                      n_trial, n_frame, stream);
 }
 
 __global__ void head_affine_kernel(const float* __restrict__ stats, const float* __restrict__ consts, float* __restrict__ affine,

@@ -1,0 +1,328 @@
+// seqik_solver.cu -- the sequential leg-IK solver kernels (sm_100a) behind seqik_leg_solve_f32.
+//
+// Work decomposition.  A chain = one leg of one trial.  Inside a chain the reference's data dependences are
+// kept exactly (leg_inverse_kinematics.py:259-282): the stage-s solve of frame t starts from the stage-s
+// result of frame t-1 (warm start, :272) and from the frame built by stages 1..s-1 of frame t (frozen links).
+// That dependence graph is a 4 x n_frame wavefront: solve(s+1, t) and solve(s, t+1) are independent.
+//
+//   schedule 1, "lane per chain"        one lane runs stages 1..4 of frame t, then frame t+1, ...
+//                                       Fewest lanes per chain: the throughput schedule for very many chains.
+//   schedule 2, "stage pipeline"        four adjacent lanes own one chain, lane s runs stage s+1 of every frame and
+//                                       hands the frame (3x3 orientation + pivot) to lane s+1 through a small
+//                                       shared-memory ring.  Chain latency drops from the sum of the four stages'
+//                                       evaluations per frame to the slowest stage's.  The schedule for the
+//                                       benchmark configurations (6 000 - 7 500 chains per GPU leave a B200 mostly
+//                                       idle under schedule 1).
+//
+// Both run the same per-lane arithmetic (seqik_core.cuh: StageSolve::init / trip), one function evaluation per
+// loop trip, in a warp-convergent loop; lanes sit at different (frame, stage) positions ("decoupled" trips).
+// No tensor cores: the work is scalar FP32 2x2 / 3x3 algebra (BASELINE.json north_star).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/seqik.h"
+#include "seqik_common.h"
+#include "seqik_core.cuh"
+
+using namespace seqik;
+
+struct LegArgs {
+    const float* pose; int64_t pose_cs, pose_fs;
+    const float* affine; const float* params;
+    float* angles; int64_t ang_cs, ang_fs;
+    float* fk; int64_t fk_cs, fk_fs;
+    int32_t* status; uint32_t* nfev;
+    int64_t n_chain, n_frame;
+    int stage_mask, gn_mask;
+};
+
+// alignment map applied on load (AlignPose.align_leg, alignment.py:471-485)
+struct LoadMap {
+    float fx, fy, fz, sc, tx, ty, tz; bool on;
+    __device__ __forceinline__ void init(const float* affine, int64_t c) {
+        on = affine != nullptr; fx = fy = fz = 0.f; sc = 1.f; tx = ty = tz = 0.f;
+        if (on) { const float* q = affine + c * 8; fx = q[0]; fy = q[1]; fz = q[2]; sc = q[3]; tx = q[4]; ty = q[5]; tz = q[6]; }
+    }
+    __device__ __forceinline__ Vec3<float> apply(Vec3<float> v, int row) const {
+        if (on) {
+            if (row == 0) v = {tx, ty, tz};
+            else v = {(v.x - fx) * sc + tx, (v.y - fy) * sc + ty, (v.z - fz) * sc + tz};
+        }
+        return v;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// schedule 1: one lane per chain
+// ---------------------------------------------------------------------------------------------
+// Global-memory IO policy of one chain.  Key points are read with plain (L1-cached) loads: a chain's
+// frames are contiguous (60 B apart), so consecutive frames share 128 B lines.
+struct DevIO {
+    const float* pose; int64_t fs;          // base of this chain, frame stride
+    const float* prm;                       // 32 floats
+    float* ang; int64_t ang_fs;
+    float* fk; int64_t fk_fs;
+    LoadMap map;
+
+    __device__ __forceinline__ Vec3<float> kp(int64_t t, int row) const {
+        const float* p = pose + t * fs + row * 3;
+        return map.apply({__ldg(p), __ldg(p + 1), __ldg(p + 2)}, row);
+    }
+    __device__ __forceinline__ void put_angles(int64_t t, const float* a, int i0, int i1) const {
+        float* p = ang + t * ang_fs;
+#pragma unroll
+        for (int i = 0; i < 7; ++i) if (i >= i0 && i < i1) p[i] = a[i];
+    }
+    __device__ __forceinline__ float angle_in(int64_t t, int i) const { return ang[t * ang_fs + i]; }
+    __device__ __forceinline__ void put_fk(int64_t t, int row, const Vec3<float>& v) const {
+        if (fk) { float* p = fk + t * fk_fs + row * 3; p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+    }
+    __device__ __forceinline__ float seg(int i) const { return __ldg(prm + i); }
+    __device__ __forceinline__ float lb(int i) const { return __ldg(prm + 4 + i); }
+    __device__ __forceinline__ float ub(int i) const { return __ldg(prm + 11 + i); }
+    __device__ __forceinline__ float null_sq(int i) const { return __ldg(prm + 25 + i); }
+};
+
+__global__ void __launch_bounds__(32) leg_solve_lane_kernel(LegArgs a) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_chain) return;
+    DevIO io;
+    io.pose = a.pose + c * a.pose_cs; io.fs = a.pose_fs;
+    io.prm = a.params + c * SEQIK_CHAIN_PARAM_FLOATS;
+    io.ang = a.angles + c * a.ang_cs; io.ang_fs = a.ang_fs;
+    io.fk = a.fk ? a.fk + c * a.fk_cs : nullptr; io.fk_fs = a.fk_fs;
+    io.map.init(a.affine, c);
+    float seed[7];
+#pragma unroll
+    for (int i = 0; i < 7; ++i) seed[i] = io.prm[18 + i];
+    ChainRunner<float, DevIO> run;
+    run.start(io, a.n_frame, seed, a.stage_mask, a.gn_mask);
+    while (!run.finished()) run.step();
+    if (a.status) a.status[c] = run.worst_status;
+    if (a.nfev) { uint32_t* nf = a.nfev + c * 4; nf[0] = run.nf0; nf[1] = run.nf1; nf[2] = run.nf2; nf[3] = run.nf3; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// schedule 2: stage pipeline -- one WARP per stage, lane = chain
+// ---------------------------------------------------------------------------------------------
+// A block of 4 warps owns `cpw` (chains per warp, <= 32) chains.  Warp w runs stage (w + blockIdx) & 3 of all of
+// them (the rotation spreads the slow stage over the four SM sub-partitions), lane l = chain l.  Every lane of a
+// warp therefore executes the same stage code (instantiated with the stage as a compile-time constant); lanes
+// differ only in where they are inside their own solve.  Stage s hands frame t (orientation A after its own
+// rotation + the next pivot, 12 floats) to stage s+1 through a shared-memory ring of PIPE_DEPTH frames per
+// chain, published with a counter (`done`) and recycled with another (`started`).
+constexpr int PIPE_DEPTH = 8;               // frames a stage may run ahead of the next one
+constexpr int PIPE_SLOT = 12;               // 3x3 frame (columns) + pivot
+
+struct PipeShared {
+    volatile int* done;      // [4][cpw] frames finished (hand-off published) by stage s of chain l
+    volatile int* started;   // [4][cpw] frames whose hand-off stage s has consumed
+    float* ring;             // [3][PIPE_DEPTH][PIPE_SLOT][cpw]  (chain innermost: conflict-free)
+    int cpw;
+    __device__ __forceinline__ float* slot(int s, int t, int l) const {
+        return ring + ((size_t)(s * PIPE_DEPTH + (t & (PIPE_DEPTH - 1))) * PIPE_SLOT) * cpw + l;
+    }
+};
+
+template <int STAGE>
+__device__ __forceinline__ void pipe_stage(const LegArgs& a, const PipeShared& sh, int lo, int hi) {
+    constexpr int s = STAGE;
+    constexpr int KIND = (s == 0) ? KIND_XY : KIND_ZY;
+    constexpr int HASA = (s == 3) ? 0 : 1;
+    const unsigned full = 0xffffffffu;
+    const int l = threadIdx.x & 31;
+    const int cpw = sh.cpw;
+    const int64_t c = (int64_t)blockIdx.x * cpw + l;
+    const bool live = l < cpw && c < a.n_chain && s <= hi;   // warps of stages after the last requested one idle
+    const bool frozen = s < lo;                               // DOFs read from the angles buffer, not solved
+    const int n_frame = (int)a.n_frame;
+
+    // per-lane constants of (chain, stage)
+    const int64_t cc = live ? c : 0;
+    const float* prm = a.params + cc * SEQIK_CHAIN_PARAM_FLOATS;
+    const float* pose = a.pose + cc * a.pose_cs;
+    float* ang = a.angles + cc * a.ang_cs;
+    float* fk = a.fk ? a.fk + cc * a.fk_cs : nullptr;
+    LoadMap map; map.init(a.affine, cc);
+    const float seg = __ldg(prm + s);
+    constexpr int ia = 2 * s, ib = (s == 3) ? 6 : 2 * s + 1;
+    const float inf = Num<float>::inf();
+    const float lb0 = (s == 3 || frozen) ? -inf : __ldg(prm + 4 + ia), ub0 = (s == 3 || frozen) ? inf : __ldg(prm + 11 + ia);
+    const float lb1 = frozen ? -inf : __ldg(prm + 4 + ib), ub1 = frozen ? inf : __ldg(prm + 11 + ib);
+    const float null_sq = frozen ? 0.f : __ldg(prm + 25 + s);
+    constexpr int n_full = (s == 0) ? 4 : (s == 1) ? 6 : (s == 2) ? 8 : 9;
+    const bool gn = (a.gn_mask >> s) & 1;
+    float xa = (s == 3) ? 0.f : __ldg(prm + 18 + ia), xb = __ldg(prm + 18 + ib);   // warm start, frame to frame
+
+    StageSolve<float, KIND, HASA> S;
+    Mat3<float> A = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
+    Vec3<float> piv = {0.f, 0.f, 0.f}, o = {0.f, 0.f, 0.f}, rel = {0.f, 0.f, 0.f};
+    int t = 0;                       // frame this lane works on
+    bool solving = false;
+    uint32_t nf = 0; int worst = ST_GTOL;
+    S.status = ST_GTOL;
+    // key points of frame t, fetched one frame ahead so the load latency hides behind the previous solve
+    Vec3<float> ko = {0.f, 0.f, 0.f}, kt = {0.f, 0.f, 0.f};
+    if (live && n_frame > 0) {
+        const float* p = pose;
+        ko = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+        kt = {__ldg(p + 3 * (s + 1)), __ldg(p + 3 * (s + 1) + 1), __ldg(p + 3 * (s + 1) + 2)};
+    }
+
+    while (__any_sync(full, live && t < n_frame)) {
+        const bool running = live && t < n_frame;
+        // ---- close the converged solve: outputs + hand-off to the next stage (needs a free ring slot)
+        if (running && solving && S.done() && (s == hi || t < sh.started[(s + 1) * cpw + l] + PIPE_DEPTH)) {
+            if (!frozen) {
+                xa = S.x0; xb = S.x1; nf += (uint32_t)S.nfev;
+                if (S.status == ST_MAXFEV) worst = ST_MAXFEV;
+                float* pa = ang + (int64_t)t * a.ang_fs;
+                if (s != 3) pa[ia] = xa;
+                pa[ib] = xb;
+            }
+            // joint position = pivot + A w(x) = target + A f   (q = A^T rel, f = w - q)
+            const Vec3<float> Af = mul(A, S.f);
+            const Vec3<float> np_ = {(piv.x + rel.x) + Af.x, (piv.y + rel.y) + Af.y, (piv.z + rel.z) + Af.z};
+            if (fk) {
+                float* pf = fk + (int64_t)t * a.fk_fs;
+                const Vec3<float> jw = {np_.x + o.x, np_.y + o.y, np_.z + o.z};
+                if (s == 0) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) { pf[3 * r] = o.x; pf[3 * r + 1] = o.y; pf[3 * r + 2] = o.z; }
+                    pf[12] = jw.x; pf[13] = jw.y; pf[14] = jw.z; pf[15] = jw.x; pf[16] = jw.y; pf[17] = jw.z;
+                } else { pf[15 + 3 * s] = jw.x; pf[16 + 3 * s] = jw.y; pf[17 + 3 * s] = jw.z; }
+            }
+            if (s < hi) {
+                const Mat3<float> B = rotate_frame(A, KIND, S.sa, S.ca, S.sb, S.cb);
+                float* q = sh.slot(s, t, l);
+                q[0] = B.c0.x; q[cpw] = B.c0.y; q[2 * cpw] = B.c0.z; q[3 * cpw] = B.c1.x; q[4 * cpw] = B.c1.y; q[5 * cpw] = B.c1.z;
+                q[6 * cpw] = B.c2.x; q[7 * cpw] = B.c2.y; q[8 * cpw] = B.c2.z;
+                q[9 * cpw] = np_.x; q[10 * cpw] = np_.y; q[11 * cpw] = np_.z;
+                __threadfence_block();                        // slot before counter
+            }
+            solving = false; ++t;
+            sh.done[s * cpw + l] = t;
+        }
+        // ---- open the next solve when the previous stage has published this frame
+        if (live && t < n_frame && !solving && (s == 0 || t < sh.done[(s - 1) * cpw + l])) {
+            if (s > 0) {
+                __threadfence_block();                        // counter before slot
+                const float* q = sh.slot(s - 1, t, l);
+                A.c0 = {q[0], q[cpw], q[2 * cpw]}; A.c1 = {q[3 * cpw], q[4 * cpw], q[5 * cpw]};
+                A.c2 = {q[6 * cpw], q[7 * cpw], q[8 * cpw]};
+                piv = {q[9 * cpw], q[10 * cpw], q[11 * cpw]};
+                __threadfence_block();                        // slot reads before the recycle counter
+                sh.started[s * cpw + l] = t + 1;
+            }
+            o = map.apply(ko, 0);
+            const Vec3<float> k = map.apply(kt, s + 1);
+            rel = {(k.x - o.x) - piv.x, (k.y - o.y) - piv.y, (k.z - o.z) - piv.z};
+            const Vec3<float> q3 = mulT(A, rel);
+            if (frozen) {
+                const float* pa = ang + (int64_t)t * a.ang_fs;
+                xa = (s == 3) ? 0.f : pa[ia]; xb = pa[ib];
+            }
+            S.init(KIND, seg, (float)HASA, q3, xa, xb, lb0, ub0, lb1, ub1, null_sq, n_full, gn);
+            if (frozen) S.status = ST_GTOL;
+            solving = true;
+            if (t + 1 < n_frame) {   // prefetch the next frame's key points
+                const float* p = pose + (int64_t)(t + 1) * a.pose_fs;
+                ko = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+                kt = {__ldg(p + 3 * (s + 1)), __ldg(p + 3 * (s + 1) + 1), __ldg(p + 3 * (s + 1) + 2)};
+            }
+        }
+        // ---- one function evaluation
+        const bool work = live && solving && !S.done();
+        const bool any_work = __any_sync(full, work);
+        if (work) S.trip();
+        if (!any_work) __nanosleep(64);   // the whole warp waits for another stage: leave the issue slots to it
+    }
+    if (live) {
+        if (a.nfev) a.nfev[c * 4 + s] = nf;
+        if (a.status && worst == ST_MAXFEV) atomicMin(&a.status[c], ST_MAXFEV);
+    }
+}
+
+__global__ void __launch_bounds__(128) leg_solve_pipe_kernel(LegArgs a, int cpw) {
+    extern __shared__ float smem[];
+    PipeShared sh;
+    sh.cpw = cpw;
+    sh.done = (volatile int*)smem;
+    sh.started = sh.done + 4 * cpw;
+    sh.ring = smem + 8 * cpw;
+    for (int i = threadIdx.x; i < 8 * cpw; i += blockDim.x) ((int*)smem)[i] = 0;
+    int lo = 0; while (lo < 3 && !((a.stage_mask >> lo) & 1)) ++lo;
+    int hi = 3; while (hi > 0 && !((a.stage_mask >> hi) & 1)) --hi;
+    const int warp = threadIdx.x >> 5;
+    const int64_t c = (int64_t)blockIdx.x * cpw + (threadIdx.x & 31);
+    if (warp == 0 && (threadIdx.x & 31) < cpw && c < a.n_chain) {
+        if (a.status) a.status[c] = ST_GTOL;
+        if (a.nfev) { a.nfev[c * 4] = 0; a.nfev[c * 4 + 1] = 0; a.nfev[c * 4 + 2] = 0; a.nfev[c * 4 + 3] = 0; }
+    }
+    __syncthreads();
+    switch ((warp + blockIdx.x) & 3) {
+        case 0: pipe_stage<0>(a, sh, lo, hi); break;
+        case 1: pipe_stage<1>(a, sh, lo, hi); break;
+        case 2: pipe_stage<2>(a, sh, lo, hi); break;
+        default: pipe_stage<3>(a, sh, lo, hi); break;
+    }
+}
+
+static size_t pipe_smem_bytes(int cpw) { return sizeof(float) * (size_t)cpw * (8 + 3 * PIPE_DEPTH * PIPE_SLOT); }
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+extern "C" int seqik_leg_solve_f32(const float* pose, int64_t pose_chain_stride, int64_t pose_frame_stride,
+                                   const float* affine, const float* params,
+                                   float* angles, int64_t ang_chain_stride, int64_t ang_frame_stride,
+                                   float* fk, int64_t fk_chain_stride, int64_t fk_frame_stride,
+                                   int32_t* status, uint32_t* nfev,
+                                   int64_t n_chain, int64_t n_frame, uint32_t stage_mask, uint32_t flags, void* stream) {
+    if (n_chain < 0 || n_frame < 0) return seqik_fail(SEQIK_EINVAL, "seqik_leg_solve_f32: negative size");
+    if (n_chain == 0 || n_frame == 0) return SEQIK_OK;
+    if (!pose || !params || !angles) return seqik_fail(SEQIK_EINVAL, "seqik_leg_solve_f32: pose, params and angles must not be NULL");
+    {
+        uint32_t m = stage_mask;
+        while (m && !(m & 1u)) m >>= 1;
+        if (stage_mask == 0 || stage_mask > 0xF || (m & (m + 1)) != 0)
+            return seqik_fail(SEQIK_EINVAL, "seqik_leg_solve_f32: stage_mask must be a contiguous run of bits within 0xF");
+    }
+    if (pose_frame_stride < 15 || ang_frame_stride < 7 || (fk && fk_frame_stride < 27))
+        return seqik_fail(SEQIK_EINVAL, "seqik_leg_solve_f32: frame stride smaller than the innermost block");
+    if (n_frame > 2147483647LL) return seqik_fail(SEQIK_EINVAL, "seqik_leg_solve_f32: too many frames");
+    uint32_t sched = (flags & SEQIK_FLAG_SCHED_MASK) >> SEQIK_FLAG_SCHED_SHIFT;
+    if (sched > 2) return seqik_fail(SEQIK_EINVAL, "seqik_leg_solve_f32: unknown schedule");
+    // automatic: the pipeline while its 4x lanes still fit a B200 comfortably (measured crossover)
+    if (sched == 0) sched = (n_chain <= 40000) ? 2 : 1;
+    LegArgs a;
+    a.pose = pose; a.pose_cs = pose_chain_stride; a.pose_fs = pose_frame_stride;
+    a.affine = affine; a.params = params;
+    a.angles = angles; a.ang_cs = ang_chain_stride; a.ang_fs = ang_frame_stride;
+    a.fk = fk; a.fk_cs = fk_chain_stride; a.fk_fs = fk_frame_stride;
+    a.status = status; a.nfev = nfev; a.n_chain = n_chain; a.n_frame = n_frame;
+    a.stage_mask = (int)stage_mask; a.gn_mask = (int)(flags & 0xF);
+    if (sched == 1) {
+        const int64_t grid = (n_chain + 31) / 32;
+        leg_solve_lane_kernel<<<(unsigned)grid, 32, 0, (cudaStream_t)stream>>>(a);
+    } else {
+        // chains per warp: as few as still fit all blocks on the device at once (a second wave would double
+        // the run time of this latency-bound kernel); fewer lanes per warp = fewer divergent paths per trip
+        int dev = 0, n_sm = 148, per_sm = 1;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        int cpw = 32;
+        const uint32_t forced = (flags >> 12) & 0x3F;           // bits 12..17: force chains per warp (tuning/tests)
+        if (forced) cpw = (int)forced;
+        else {
+            for (int cand = 4; cand <= 32; cand *= 2) {
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, leg_solve_pipe_kernel, 128, pipe_smem_bytes(cand));
+                if ((n_chain + cand - 1) / cand <= (int64_t)per_sm * n_sm) { cpw = cand; break; }
+            }
+        }
+        if (cpw < 1 || cpw > 32) return seqik_fail(SEQIK_EINVAL, "seqik_leg_solve_f32: chains per warp must be 1..32");
+        const int64_t grid = (n_chain + cpw - 1) / cpw;
+        leg_solve_pipe_kernel<<<(unsigned)grid, 128, pipe_smem_bytes(cpw), (cudaStream_t)stream>>>(a, cpw);
+    }
+    return seqik_check_launch("seqik_leg_solve_f32");
+}

@@ -44,11 +44,12 @@ def stages_to_mask(stages: Sequence[int]) -> int:
 
 def leg_solve(pose, params, affine=None, stages: Sequence[int] = (1, 2, 3, 4), want_fk: bool = True,
               angles=None, fk=None, flags: int = N.FLAG_DEFAULT, schedule: int = N.SCHED_AUTO,
-              want_stats: bool = True):
+              want_stats: bool = True, chains_per_warp: int = 0):
     """4-stage sequential IK (+FK) of every chain.  Returns (angles, fk|None, status|None, nfev|None).
 
     ``angles`` must be given (and is updated in place) when ``stages`` does not start at 1:
-    the DOFs of the earlier stages are then read from it and frozen.
+    the DOFs of the earlier stages are then read from it and frozen.  ``schedule`` / ``chains_per_warp``
+    override the automatic kernel schedule (tuning and tests); results do not depend on them.
     """
     torch = N.require_cuda()
     lib = N.load_library()
@@ -82,7 +83,8 @@ def leg_solve(pose, params, affine=None, stages: Sequence[int] = (1, 2, 3, 4), w
             N.ptr(pose), n_frame * 15, 15, N.ptr(affine), N.ptr(params),
             N.ptr(angles), n_frame * 7, 7, N.ptr(fk), n_frame * 27, 27,
             N.ptr(status), N.ptr(nfev), n_chain, n_frame, mask,
-            (flags & 0xFF) | ((schedule & 0xF) << N.FLAG_SCHED_SHIFT), N.stream_ptr(torch, dev))
+            (flags & 0xFF) | ((schedule & 0xF) << N.FLAG_SCHED_SHIFT) | ((chains_per_warp & 0x3F) << 12),
+            N.stream_ptr(torch, dev))
     N.check(rc, "seqik_leg_solve_f32")
     return angles, fk, status, nfev
 
@@ -194,25 +196,29 @@ def align_apply(pose, affine):
 
 
 def head_affine(head, thorax, consts, threshold: float = 5e-5):
-    """AlignPose.align_head statistics: head (n_trial, n_frame, 2, 3), thorax (n_trial, n_frame, k, 3),
-    consts (n_trial, 5) = template antenna base xyz, Antenna_mid_thorax, Antenna
-    -> affine (n_trial, 8) = (origin xyz, scale_base, template xyz, scale_tip)."""
+    """AlignPose.align_head statistics: head (n_trial, n_frame, 2, 3), thorax (n_trial, n_frame, k, 3) -- both float32
+    or both float64 --, consts (n_trial, 5) float32 = template antenna base xyz, Antenna_mid_thorax, Antenna
+    -> affine (n_trial, 8) = (origin xyz, scale_base, template xyz, scale_tip), counts (n_trial, 5)."""
     torch = N.require_cuda()
     lib = N.load_library()
-    head = _check(head, "head", (2, 3))
+    dtype = head.dtype
+    if dtype not in (torch.float32, torch.float64) or thorax.dtype != dtype:
+        raise ValueError("head and thorax must both be float32 or both float64")
+    head = _check(head, "head", (2, 3), dtype)
     n_trial, n_frame = int(head.shape[0]), int(head.shape[1])
     if thorax.dim() != 4 or tuple(thorax.shape[:2]) != (n_trial, n_frame):
         raise ValueError("thorax must be (n_trial, n_frame, n_kp, 3)")
-    thorax = _check(thorax, "thorax", (3,))
+    thorax = _check(thorax, "thorax", (3,), dtype)
     consts = _check(consts, "consts", (5,))
     dev = head.device
     series = torch.empty((n_trial * 5, n_frame), dtype=torch.float32, device=dev)
     counts = torch.empty((n_trial * 5,), dtype=torch.int32, device=dev)
     affine = torch.empty((n_trial, 8), dtype=torch.float32, device=dev)
+    fn = lib.seqik_head_series_f32 if dtype == torch.float32 else lib.seqik_head_series_f64
     with torch.cuda.device(dev):
         st = N.stream_ptr(torch, dev)
-        N.check(lib.seqik_head_series_f32(N.ptr(head), N.ptr(thorax), int(thorax.shape[2]), float(threshold), N.ptr(series),
-                                          N.ptr(counts), n_trial, n_frame, st), "seqik_head_series_f32")
+        N.check(fn(N.ptr(head), N.ptr(thorax), int(thorax.shape[2]), float(threshold), N.ptr(series),
+                   N.ptr(counts), n_trial, n_frame, st), "seqik_head_series")
         stats = mid_quantile(series, counts)
         N.check(lib.seqik_head_affine_f32(N.ptr(stats), N.ptr(consts), N.ptr(affine), n_trial, st), "seqik_head_affine_f32")
     return affine, counts.view(n_trial, 5)
