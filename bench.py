@@ -190,7 +190,7 @@ def run_ours(args):
     T, F = args.trials, args.frames
     size, bounds, init = S.chain_constants()
     chain = KinematicChainSeq(bounds, list(S.LEGS), size)
-    sess = BatchedLegIK(chain, init, S.LEGS, T, F, device=dev, schedule=args.schedule)
+    sess = BatchedLegIK(chain, init, S.LEGS, T, F, device=dev, schedule=args.schedule, chains_per_warp=args.cpw)
 
     # synthetic pose of this rank's trials, chain-major, in pinned host memory
     t_gen = time.perf_counter()
@@ -306,6 +306,7 @@ def main():
     ap.add_argument("--trials", type=int, default=1000, help="trials per GPU")
     ap.add_argument("--frames", type=int, default=1000)
     ap.add_argument("--schedule", type=int, default=0, help="kernel schedule (0 auto, 1 lane per chain, 2 stage pipeline)")
+    ap.add_argument("--cpw", type=int, default=0, help="chains per warp of schedule 2 (0 auto)")
     ap.add_argument("--cpu-frames", type=int, default=200, help="frames per leg of the cpu_baseline sample")
     ap.add_argument("--ref-frames", type=int, default=100, help="frames per chain and step of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -37,11 +37,11 @@ extern "C" {
 /* flags of seqik_leg_solve_f32 */
 #define SEQIK_FLAG_GN_STAGE(s) (1u << (s))   /* s = 0..3: stage s+1 takes the Gauss-Newton step when it fits the
                                                 trust region (what scipy's TRF does on the longer chains) */
-#define SEQIK_FLAG_DEFAULT (SEQIK_FLAG_GN_STAGE(1) | SEQIK_FLAG_GN_STAGE(2))
+#define SEQIK_FLAG_DEFAULT 0xFu              /* all four stages (validated against the reference's shipped angles) */
 #define SEQIK_FLAG_SCHED_SHIFT 8             /* bits 8..11: kernel schedule, 0 = automatic,
-                                                1 = one lane per chain, 2 = stage pipeline (one warp per stage) */
+                                                1 = one lane per chain, 2 = stage pipeline (four lanes per chain) */
 #define SEQIK_FLAG_SCHED_MASK (0xFu << SEQIK_FLAG_SCHED_SHIFT)
-#define SEQIK_FLAG_CPW_SHIFT 12              /* bits 12..17: chains per warp of schedule 2 (1..32), 0 = automatic */
+#define SEQIK_FLAG_CPW_SHIFT 12              /* bits 12..17: chains per warp of schedule 2 (1..8), 0 = automatic */
 
 int seqik_abi_version(void);
 const char* seqik_last_error(void);

@@ -14,7 +14,7 @@ LIB_PATH = _HERE / "csrc" / "libseqik_sm100.so"
 
 ABI_VERSION = 2
 CHAIN_PARAM_FLOATS = 32
-FLAG_DEFAULT = (1 << 1) | (1 << 2)      # SEQIK_FLAG_DEFAULT: stages 2 and 3 in Gauss-Newton mode
+FLAG_DEFAULT = 0xF                      # SEQIK_FLAG_DEFAULT: Gauss-Newton mode in all four stages
 FLAG_SCHED_SHIFT = 8
 SCHED_AUTO, SCHED_LANE_PER_CHAIN, SCHED_STAGE_PIPELINE = 0, 1, 2
 

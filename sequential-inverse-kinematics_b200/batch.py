@@ -42,7 +42,8 @@ class BatchedLegIK:
     """
 
     def __init__(self, kinematic_chain_class, initial_angles, legs: Sequence[str], n_trial: int, n_frame: int,
-                 device="cuda", want_fk: bool = True, schedule: int = N.SCHED_AUTO, host_buffers: bool = True):
+                 device="cuda", want_fk: bool = True, schedule: int = N.SCHED_AUTO, host_buffers: bool = True,
+                 chains_per_warp: int = 0):
         torch = N.require_cuda()
         N.load_library()
         self.torch = torch
@@ -51,6 +52,7 @@ class BatchedLegIK:
         self.n_chain = self.n_trial * self.n_leg
         self.device = torch.device(device)
         self.schedule = schedule
+        self.chains_per_warp = chains_per_warp
         self.params = torch.from_numpy(chain_param_table(kinematic_chain_class, initial_angles, self.legs, n_trial)).to(self.device)
         f32 = dict(dtype=torch.float32, device=self.device)
         self.d_pose = torch.empty((self.n_chain, self.n_frame, 5, 3), **f32)
@@ -72,6 +74,7 @@ class BatchedLegIK:
         pose = self.d_pose if pose is None else pose.reshape(self.n_chain, self.n_frame, 5, 3)
         _, _, self.status, self.nfev = engine.leg_solve(pose, self.params, affine=affine, angles=self.d_angles, fk=self.d_fk,
                                                         want_fk=self.d_fk is not None, schedule=self.schedule,
+                                                        chains_per_warp=self.chains_per_warp,
                                                         want_stats=want_stats)
         return self.d_angles, self.d_fk
 

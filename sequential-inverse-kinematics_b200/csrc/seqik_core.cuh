@@ -216,28 +216,24 @@ struct StageSolve {
 
     SK_HD bool done() const { return status != ST_RUNNING; }
 
-    // step_size_to_bound from distances (dl, du) along p; hit flags
+    // step_size_to_bound from distances (dl, du) along p; hit flags.  rcp(0) = inf gives +inf for a zero component.
     static SK_HD R to_bound(R dl0_, R du0_, R dl1_, R du1_, R p0, R p1, bool& h0, bool& h1) {
-        R s0 = N::inf(), s1 = N::inf();
-        if (p0 != R(0)) { const R r = N::rcp_(p0); s0 = N::max_(-dl0_ * r, du0_ * r); }
-        if (p1 != R(0)) { const R r = N::rcp_(p1); s1 = N::max_(-dl1_ * r, du1_ * r); }
+        const R r0 = N::rcp_(p0), r1 = N::rcp_(p1);
+        const R s0 = (p0 != R(0)) ? N::max_(-dl0_ * r0, du0_ * r0) : N::inf();
+        const R s1 = (p1 != R(0)) ? N::max_(-dl1_ * r1, du1_ * r1) : N::inf();
         const R m = N::min_(s0, s1);
         h0 = (p0 != R(0)) && (s0 == m); h1 = (p1 != R(0)) && (s1 == m);
         return m;
     }
 
-    // minimize_quadratic_1d(a, b, lo, hi, c)
+    // minimize_quadratic_1d(a, b, lo, hi, c): straight-line (selects only)
     static SK_HD void minq(R a, R b, R lo, R hi, R c, R& t_best, R& y_best) {
-        t_best = lo; y_best = N::fma_(lo, N::fma_(a, lo, b), c);
-        const R yh = N::fma_(hi, N::fma_(a, hi, b), c);
+        const R yl = N::fma_(lo, N::fma_(a, lo, b), c), yh = N::fma_(hi, N::fma_(a, hi, b), c);
+        const R e = R(-0.5) * b * N::rcp_(a);
+        const R ye = N::fma_(e, N::fma_(a, e, b), c);
+        t_best = lo; y_best = yl;
         if (yh < y_best) { y_best = yh; t_best = hi; }
-        if (a != R(0)) {
-            const R e = R(-0.5) * b * N::rcp_(a);
-            if (lo < e && e < hi) {
-                const R ye = N::fma_(e, N::fma_(a, e, b), c);
-                if (ye < y_best) { y_best = ye; t_best = e; }
-            }
-        }
+        if (a != R(0) && lo < e && e < hi && ye < y_best) { y_best = ye; t_best = e; }
     }
 
     // Quantities of one outer iteration in the scaled ("hat") variables: B = Jh^T Jh + diag (diagonal), gh
@@ -248,10 +244,13 @@ struct StageSolve {
         return N::fma_(s1, h.gh1, N::fma_(s0, h.gh0, R(0.5) * N::fma_(h.B1 * s1, s1, h.B0 * s0 * s0)));
     }
 
-    // select_step (trf.py:129-203) restricted to the active pair
+    // select_step (trf.py:129-203) restricted to the active pair.  Written as one straight-line block: the three
+    // candidates (truncated step, reflected step, scaled anti-gradient) are always evaluated and the in-bounds
+    // case -- where scipy returns the plain step -- is a final select.  (Lanes of a warp sit in different cases.)
     SK_HD void select_step(const Hat& h, R p0, R p1, R ph0, R ph1, R& st0, R& st1, R& sh0, R& sh1, R& pred) const {
         const bool inb = (dl0 + p0 >= R(0)) && (du0 - p0 >= R(0)) && (dl1 + p1 >= R(0)) && (du1 - p1 >= R(0));
-        if (inb) { st0 = p0; st1 = p1; sh0 = ph0; sh1 = ph1; pred = -model(h, ph0, ph1); return; }
+        const R full_value = model(h, ph0, ph1);
+        const R fp0 = p0, fp1 = p1, fph0 = ph0, fph1 = ph1;
         bool h0, h1;
         const R p_stride = to_bound(dl0, du0, dl1, du1, p0, p1, h0, h1);
         R rh0 = h0 ? -ph0 : ph0, rh1 = h1 ? -ph1 : ph1;
@@ -264,34 +263,34 @@ struct StageSolve {
             const R c = N::min_(N::fma_(ph1, ph1, ph0 * ph0) - Delta * Delta, R(0));
             const R disc = N::sqrt_(N::max_(N::fma_(b, b, -(a * c)), R(0)));
             const R qq = -(b + N::copysign_(disc, b));
-            R t1 = R(0), t2 = R(0);
-            if (qq != R(0)) { t1 = qq * N::rcp_(a); t2 = c * N::rcp_(qq); }
+            const R t1 = (qq != R(0)) ? qq * N::rcp_(a) : R(0), t2 = (qq != R(0)) ? c * N::rcp_(qq) : R(0);
             to_tr = N::max_(t1, t2);
         }
         bool u0, u1;
         const R to_bd = to_bound(dl0 + p0, du0 - p0, dl1 + p1, du1 - p1, r0, r1, u0, u1);
         const R r_stride = N::min_(to_bd, to_tr);
-        R r_l, r_u;
-        if (r_stride > R(0)) {
-            r_l = (R(1) - h.theta) * p_stride * N::rcp_(r_stride);
-            r_u = (r_stride == to_bd) ? h.theta * to_bd : to_tr;
-        } else { r_l = R(0); r_u = R(-1); }
+        const bool rpos = r_stride > R(0);
+        const R r_l = rpos ? (R(1) - h.theta) * p_stride * N::rcp_(r_stride) : R(0);
+        const R r_u = rpos ? ((r_stride == to_bd) ? h.theta * to_bd : to_tr) : R(-1);
         R r_value = N::inf();
-        if (r_l <= r_u) {
+        {
             // build_quadratic_1d(Jh, gh, rh, s0=ph, diag=dh) with the diagonal B
             const R a = R(0.5) * N::fma_(h.B1 * rh1, rh1, h.B0 * rh0 * rh0);
             const R b = N::fma_(h.gh1, rh1, h.gh0 * rh0) + N::fma_(h.B1 * ph1, rh1, h.B0 * ph0 * rh0);
             const R c = model(h, ph0, ph1);
-            R rs; minq(a, b, r_l, r_u, c, rs, r_value);
-            rh0 = N::fma_(rh0, rs, ph0); rh1 = N::fma_(rh1, rs, ph1);
-            r0 = rh0 * h.d0; r1 = rh1 * h.d1;
+            R rs, rv; minq(a, b, r_l, r_u, c, rs, rv);
+            if (r_l <= r_u) {
+                r_value = rv;
+                rh0 = N::fma_(rh0, rs, ph0); rh1 = N::fma_(rh1, rs, ph1);
+                r0 = rh0 * h.d0; r1 = rh1 * h.d1;
+            }
         }
         // strictly interior truncated step
         p0 *= h.theta; p1 *= h.theta; ph0 *= h.theta; ph1 *= h.theta;
         const R p_value = model(h, ph0, ph1);
         // scaled anti-gradient
-        R ah0 = -h.gh0, ah1 = -h.gh1;
-        R a0 = h.d0 * ah0, a1 = h.d1 * ah1;
+        const R ah0 = -h.gh0, ah1 = -h.gh1;
+        const R a0 = h.d0 * ah0, a1 = h.d1 * ah1;
         const R to_tr2 = Delta * N::rsqrt_(N::fma_(ah1, ah1, ah0 * ah0));
         const R to_bd2 = to_bound(dl0, du0, dl1, du1, a0, a1, u0, u1);
         const R ag_hi = (to_bd2 < to_tr2) ? h.theta * to_bd2 : to_tr2;
@@ -301,9 +300,12 @@ struct StageSolve {
             const R b = N::fma_(h.gh1, ah1, h.gh0 * ah0);
             minq(a, b, R(0), ag_hi, R(0), ags, ag_value);
         }
-        if (p_value < r_value && p_value < ag_value) { st0 = p0; st1 = p1; sh0 = ph0; sh1 = ph1; pred = -p_value; }
-        else if (r_value < p_value && r_value < ag_value) { st0 = r0; st1 = r1; sh0 = rh0; sh1 = rh1; pred = -r_value; }
-        else { st0 = a0 * ags; st1 = a1 * ags; sh0 = ah0 * ags; sh1 = ah1 * ags; pred = -ag_value; }
+        const bool take_p = p_value < r_value && p_value < ag_value;
+        const bool take_r = !take_p && r_value < p_value && r_value < ag_value;
+        st0 = take_p ? p0 : take_r ? r0 : a0 * ags; st1 = take_p ? p1 : take_r ? r1 : a1 * ags;
+        sh0 = take_p ? ph0 : take_r ? rh0 : ah0 * ags; sh1 = take_p ? ph1 : take_r ? rh1 : ah1 * ags;
+        pred = -(take_p ? p_value : take_r ? r_value : ag_value);
+        if (inb) { st0 = fp0; st1 = fp1; sh0 = fph0; sh1 = fph1; pred = -full_value; }
     }
 
     // One function evaluation: one pass of scipy's inner `while actual_reduction <= 0` loop, preceded by
@@ -320,43 +322,49 @@ struct StageSolve {
         h.B0 = N::fma_(v0, ja_sq(), g0 * dv0); h.B1 = N::fma_(v1, L * L, g1 * dv1);   // Jh^T Jh + diag(g dv), diagonal
         h.theta = N::max_(R(0.995), R(1) - g_norm);
         // ---- solve_lsq_trust_region, rank-deficient branch; singular values^2 = (B0, B1), V = I
-        R t0, t1;
-        bool gn_taken = false;
-        if (gn_mode && h.B0 > R(0) && h.B1 > R(0)) {
-            // scipy's SVD leaves ~1e-17 singular values on the inert slots of the longer chains; the
-            // Levenberg parameter then decays to ~1e-20 and that null-space noise absorbs the trust-region
-            // norm, i.e. the active pair receives the plain Gauss-Newton step whenever it fits in Delta.
-            t0 = h.gh0 * N::rcp_(h.B0); t1 = h.gh1 * N::rcp_(h.B1);
-            gn_taken = (N::fma_(t1, t1, t0 * t0) <= Delta * Delta);
-            if (gn_taken) alpha = R(0);
-        }
+        // gn_mode: scipy's SVD of the full chain leaves ~1e-17 singular values on the inert slots; the Levenberg
+        // parameter then decays to ~1e-20 and that null-space noise absorbs the trust-region norm, i.e. the active
+        // pair receives the plain Gauss-Newton step whenever it fits in Delta.  Measured against the reference's
+        // shipped angles (6000 frames x 2 legs) this reproduces the reference's evaluation counts and termination
+        // statuses; the literal rank-deficient branch below is kept for the steps that do not fit.
+        const bool one_var = has_a_() == R(0);
+        const R tg0 = one_var ? R(0) : h.gh0 * N::rcp_(h.B0), tg1 = h.gh1 * N::rcp_(h.B1);
+        const bool gn_taken = gn_mode && (one_var || h.B0 > R(0)) && h.B1 > R(0) && (N::fma_(tg1, tg1, tg0 * tg0) <= Delta * Delta);
+        R t0 = tg0, t1 = tg1;
+        if (gn_taken) alpha = R(0);
         if (!gn_taken) {
-            const R rDelta = N::rcp_(Delta);
-            R a_up = N::sqrt_(N::fma_(h.gh1, h.gh1, h.gh0 * h.gh0)) * rDelta, a_lo = R(0);
-            if (alpha == R(0)) alpha = R(0.001) * a_up;
-            for (int it = 0; it < 10; ++it) {
-                if (alpha < a_lo || alpha > a_up) alpha = N::max_(R(0.001) * a_up, N::sqrt_(a_lo * a_up));
+            if (has_a_() == R(0)) {
+                // one variable: whatever the Levenberg parameter, the step is rescaled to the trust radius below,
+                // i.e. p_h = -sign(gh1) Delta (the parameter is never used again for this stage)
+                t0 = R(0); t1 = h.gh1;
+            } else {
+                const R rDelta = N::rcp_(Delta);
+                R a_up = N::sqrt_(N::fma_(h.gh1, h.gh1, h.gh0 * h.gh0)) * rDelta, a_lo = R(0);
+                if (alpha == R(0)) alpha = R(0.001) * a_up;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+                for (int it = 0; it < 10; ++it) {
+                    if (alpha < a_lo || alpha > a_up) alpha = N::max_(R(0.001) * a_up, N::sqrt_(a_lo * a_up));
+                    const R e0 = h.B0 + alpha, e1 = h.B1 + alpha;
+                    const R r0 = (e0 != R(0)) ? N::rcp_(e0) : R(0), r1 = (e1 != R(0)) ? N::rcp_(e1) : R(0);
+                    t0 = (h.gh0 != R(0)) ? h.gh0 * r0 : R(0); t1 = (h.gh1 != R(0)) ? h.gh1 * r1 : R(0);
+                    const R pn = N::sqrt_(N::fma_(t1, t1, t0 * t0));
+                    const R phi = pn - Delta;
+                    const R dd = N::fma_(t1 * t1, r1, t0 * t0 * r0);        // -phi' * pn
+                    if (phi < R(0)) a_up = alpha;
+                    const R ratio = (dd > R(0)) ? -(phi * pn) * N::rcp_(dd) : R(0);   // phi / phi'
+                    a_lo = N::max_(a_lo, alpha - ratio);
+                    alpha -= pn * ratio * rDelta;                            // (phi + Delta) * ratio / Delta
+                    if (N::abs_(phi) < R(0.01) * Delta) break;
+                }
                 const R e0 = h.B0 + alpha, e1 = h.B1 + alpha;
-                const R r0 = (e0 != R(0)) ? N::rcp_(e0) : R(0), r1 = (e1 != R(0)) ? N::rcp_(e1) : R(0);
-                t0 = (h.gh0 != R(0)) ? h.gh0 * r0 : R(0); t1 = (h.gh1 != R(0)) ? h.gh1 * r1 : R(0);
-                const R pn = N::sqrt_(N::fma_(t1, t1, t0 * t0));
-                const R phi = pn - Delta;
-                const R dd = N::fma_(t1 * t1, r1, t0 * t0 * r0);        // -phi' * pn
-                if (phi < R(0)) a_up = alpha;
-                const R ratio = (dd > R(0)) ? -(phi * pn) * N::rcp_(dd) : R(0);   // phi / phi'
-                a_lo = N::max_(a_lo, alpha - ratio);
-                alpha -= pn * ratio * rDelta;                            // (phi + Delta) * ratio / Delta
-                if (N::abs_(phi) < R(0.01) * Delta) break;
+                t0 = (e0 != R(0) && h.gh0 != R(0)) ? h.gh0 * N::rcp_(e0) : R(0);
+                t1 = (e1 != R(0) && h.gh1 != R(0)) ? h.gh1 * N::rcp_(e1) : R(0);
             }
-            const R e0 = h.B0 + alpha, e1 = h.B1 + alpha;
-            t0 = (e0 != R(0) && h.gh0 != R(0)) ? h.gh0 * N::rcp_(e0) : R(0);
-            t1 = (e1 != R(0) && h.gh1 != R(0)) ? h.gh1 * N::rcp_(e1) : R(0);
         }
-        R ph0 = -t0, ph1 = -t1;
-        if (!gn_taken) {
-            const R sc = Delta * N::rsqrt_(N::fma_(ph1, ph1, ph0 * ph0));
-            ph0 *= sc; ph1 *= sc;
-        }
+        const R sc = gn_taken ? R(1) : Delta * N::rsqrt_(N::fma_(t1, t1, t0 * t0));
+        const R ph0 = -t0 * sc, ph1 = -t1 * sc;
         R st0, st1, sh0, sh1, pred;
         select_step(h, h.d0 * ph0, h.d1 * ph1, ph0, ph1, st0, st1, sh0, sh1, pred);
 
@@ -394,8 +402,7 @@ struct StageSolve {
         const R xt_rhs = xtol * (xtol + x_norm);
         const bool ft = (actual < ftol * cost) && (ratio > R(0.25));
         const bool xt = step_sq < xt_rhs * xt_rhs;
-        int term = ST_RUNNING;
-        if (ft && xt) term = ST_BOTH; else if (ft) term = ST_FTOL; else if (xt) term = ST_XTOL;
+        const int term = (ft && xt) ? ST_BOTH : ft ? ST_FTOL : xt ? ST_XTOL : ST_RUNNING;
         if (term == ST_RUNNING) { alpha *= Delta * N::rcp_(Delta_new); Delta = Delta_new; }
         if (actual > R(0)) {
             x0 = nx0; x1 = nx1; dl0 = ndl0; du0 = ndu0; dl1 = ndl1; du1 = ndu1;
@@ -404,7 +411,7 @@ struct StageSolve {
             cost = cost - actual;
             gradient();
         }
-        if (term != ST_RUNNING) status = term;
+        status = term;
     }
 
     // make_strictly_feasible(x, lb, ub, rstep=0): one fp64 ulp inside the bound `b`

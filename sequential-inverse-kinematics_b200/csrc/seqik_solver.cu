@@ -12,7 +12,7 @@
 //                                       shared-memory ring.  Chain latency drops from the sum of the four stages'
 //                                       evaluations per frame to the slowest stage's.  The schedule for the
 //                                       benchmark configurations (6 000 - 7 500 chains per GPU leave a B200 mostly
-//                                       idle under schedule 1).
+//                                       idle under schedule 1, whose run time is one chain's latency).
 //
 // Both run the same per-lane arithmetic (seqik_core.cuh: StageSolve::init / trip), one function evaluation per
 // loop trip, in a warp-convergent loop; lanes sit at different (frame, stage) positions ("decoupled" trips).
@@ -103,61 +103,55 @@ __global__ void __launch_bounds__(32) leg_solve_lane_kernel(LegArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// schedule 2: stage pipeline -- one WARP per stage, lane = chain
+// schedule 2: stage pipeline -- four adjacent lanes own one chain, lane s runs stage s+1 of every frame
 // ---------------------------------------------------------------------------------------------
-// A block of 4 warps owns `cpw` (chains per warp, <= 32) chains.  Warp w runs stage (w + blockIdx) & 3 of all of
-// them (the rotation spreads the slow stage over the four SM sub-partitions), lane l = chain l.  Every lane of a
-// warp therefore executes the same stage code (instantiated with the stage as a compile-time constant); lanes
-// differ only in where they are inside their own solve.  Stage s hands frame t (orientation A after its own
-// rotation + the next pivot, 12 floats) to stage s+1 through a shared-memory ring of PIPE_DEPTH frames per
-// chain, published with a counter (`done`) and recycled with another (`started`).
-constexpr int PIPE_DEPTH = 8;               // frames a stage may run ahead of the next one
+// One warp = `cpw` chains (1, 2, 4 or 8) x 4 stage lanes; lanes >= 4 cpw idle.  All lanes run the SAME straight-line
+// code (StageSolve::trip is branch-free, the rotation kind is a per-lane select), so a warp iteration costs one trip
+// whatever mix of positions its lanes are in.  Stage s hands frame t (orientation after its own rotation + the
+// next pivot, 12 floats) to stage s+1 through a shared-memory ring of PIPE_DEPTH frames; progress counters travel
+// by warp shuffle.  No block-level synchronisation: a block is one warp.
+constexpr int PIPE_DEPTH = 4;               // frames a stage may run ahead of the next one
 constexpr int PIPE_SLOT = 12;               // 3x3 frame (columns) + pivot
+constexpr int PIPE_CHAINS = 8;              // chains per warp (maximum)
 
-struct PipeShared {
-    volatile int* done;      // [4][cpw] frames finished (hand-off published) by stage s of chain l
-    volatile int* started;   // [4][cpw] frames whose hand-off stage s has consumed
-    float* ring;             // [3][PIPE_DEPTH][PIPE_SLOT][cpw]  (chain innermost: conflict-free)
-    int cpw;
-    __device__ __forceinline__ float* slot(int s, int t, int l) const {
-        return ring + ((size_t)(s * PIPE_DEPTH + (t & (PIPE_DEPTH - 1))) * PIPE_SLOT) * cpw + l;
-    }
-};
-
-template <int STAGE>
-__device__ __forceinline__ void pipe_stage(const LegArgs& a, const PipeShared& sh, int lo, int hi) {
-    constexpr int s = STAGE;
-    constexpr int KIND = (s == 0) ? KIND_XY : KIND_ZY;
-    constexpr int HASA = (s == 3) ? 0 : 1;
+__global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw) {
+    __shared__ float ring[3][PIPE_DEPTH][PIPE_SLOT][PIPE_CHAINS];      // chain innermost: conflict-free per stage
     const unsigned full = 0xffffffffu;
-    const int l = threadIdx.x & 31;
-    const int cpw = sh.cpw;
-    const int64_t c = (int64_t)blockIdx.x * cpw + l;
-    const bool live = l < cpw && c < a.n_chain && s <= hi;   // warps of stages after the last requested one idle
+    const int lane = threadIdx.x;
+    const int s = lane & 3;                                   // this lane's stage (0..3)
+    const int cw = lane >> 2;                                 // chain within the warp
+    const int64_t c = (int64_t)blockIdx.x * cpw + cw;
+    int lo = 0; while (lo < 3 && !((a.stage_mask >> lo) & 1)) ++lo;
+    int hi = 3; while (hi > 0 && !((a.stage_mask >> hi) & 1)) --hi;
+    const bool owner = cw < cpw && c < a.n_chain;
+    const bool live = owner && s <= hi;                       // lanes of stages after the last requested one idle
     const bool frozen = s < lo;                               // DOFs read from the angles buffer, not solved
     const int n_frame = (int)a.n_frame;
 
     // per-lane constants of (chain, stage)
-    const int64_t cc = live ? c : 0;
+    const int64_t cc = owner ? c : 0;
     const float* prm = a.params + cc * SEQIK_CHAIN_PARAM_FLOATS;
     const float* pose = a.pose + cc * a.pose_cs;
     float* ang = a.angles + cc * a.ang_cs;
     float* fk = a.fk ? a.fk + cc * a.fk_cs : nullptr;
     LoadMap map; map.init(a.affine, cc);
+    const int kind = (s == 0) ? KIND_XY : KIND_ZY;
     const float seg = __ldg(prm + s);
-    constexpr int ia = 2 * s, ib = (s == 3) ? 6 : 2 * s + 1;
+    const int ia = 2 * s, ib = (s == 3) ? 6 : 2 * s + 1;
     const float inf = Num<float>::inf();
     const float lb0 = (s == 3 || frozen) ? -inf : __ldg(prm + 4 + ia), ub0 = (s == 3 || frozen) ? inf : __ldg(prm + 11 + ia);
     const float lb1 = frozen ? -inf : __ldg(prm + 4 + ib), ub1 = frozen ? inf : __ldg(prm + 11 + ib);
     const float null_sq = frozen ? 0.f : __ldg(prm + 25 + s);
-    constexpr int n_full = (s == 0) ? 4 : (s == 1) ? 6 : (s == 2) ? 8 : 9;
+    const int n_full = (s == 0) ? 4 : (s == 1) ? 6 : (s == 2) ? 8 : 9;
     const bool gn = (a.gn_mask >> s) & 1;
+    const float has_a = (s == 3) ? 0.f : 1.f;
     float xa = (s == 3) ? 0.f : __ldg(prm + 18 + ia), xb = __ldg(prm + 18 + ib);   // warm start, frame to frame
 
-    StageSolve<float, KIND, HASA> S;
+    StageSolve<float> S;
     Mat3<float> A = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
     Vec3<float> piv = {0.f, 0.f, 0.f}, o = {0.f, 0.f, 0.f}, rel = {0.f, 0.f, 0.f};
     int t = 0;                       // frame this lane works on
+    int started = 0, done = 0;       // frames whose hand-off was consumed / produced by this lane
     bool solving = false;
     uint32_t nf = 0; int worst = ST_GTOL;
     S.status = ST_GTOL;
@@ -170,9 +164,9 @@ __device__ __forceinline__ void pipe_stage(const LegArgs& a, const PipeShared& s
     }
 
     while (__any_sync(full, live && t < n_frame)) {
-        const bool running = live && t < n_frame;
+        const int started_next = __shfl_sync(full, started, (lane + 1) & 31);   // consumer's progress (lane + 1)
         // ---- close the converged solve: outputs + hand-off to the next stage (needs a free ring slot)
-        if (running && solving && S.done() && (s == hi || t < sh.started[(s + 1) * cpw + l] + PIPE_DEPTH)) {
+        if (live && t < n_frame && solving && S.done() && (s == hi || t < started_next + PIPE_DEPTH)) {
             if (!frozen) {
                 xa = S.x0; xb = S.x1; nf += (uint32_t)S.nfev;
                 if (S.status == ST_MAXFEV) worst = ST_MAXFEV;
@@ -193,26 +187,21 @@ __device__ __forceinline__ void pipe_stage(const LegArgs& a, const PipeShared& s
                 } else { pf[15 + 3 * s] = jw.x; pf[16 + 3 * s] = jw.y; pf[17 + 3 * s] = jw.z; }
             }
             if (s < hi) {
-                const Mat3<float> B = rotate_frame(A, KIND, S.sa, S.ca, S.sb, S.cb);
-                float* q = sh.slot(s, t, l);
-                q[0] = B.c0.x; q[cpw] = B.c0.y; q[2 * cpw] = B.c0.z; q[3 * cpw] = B.c1.x; q[4 * cpw] = B.c1.y; q[5 * cpw] = B.c1.z;
-                q[6 * cpw] = B.c2.x; q[7 * cpw] = B.c2.y; q[8 * cpw] = B.c2.z;
-                q[9 * cpw] = np_.x; q[10 * cpw] = np_.y; q[11 * cpw] = np_.z;
-                __threadfence_block();                        // slot before counter
+                const Mat3<float> B = rotate_frame(A, kind, S.sa, S.ca, S.sb, S.cb);
+                float (*q)[PIPE_CHAINS] = ring[s][t & (PIPE_DEPTH - 1)];
+                q[0][cw] = B.c0.x; q[1][cw] = B.c0.y; q[2][cw] = B.c0.z; q[3][cw] = B.c1.x; q[4][cw] = B.c1.y; q[5][cw] = B.c1.z;
+                q[6][cw] = B.c2.x; q[7][cw] = B.c2.y; q[8][cw] = B.c2.z; q[9][cw] = np_.x; q[10][cw] = np_.y; q[11][cw] = np_.z;
             }
-            solving = false; ++t;
-            sh.done[s * cpw + l] = t;
+            solving = false; ++t; done = t;
         }
+        __syncwarp(full);            // ring writes above are visible to the reads below
+        const int done_prev = __shfl_sync(full, done, (lane + 31) & 31);        // producer's progress (lane - 1)
         // ---- open the next solve when the previous stage has published this frame
-        if (live && t < n_frame && !solving && (s == 0 || t < sh.done[(s - 1) * cpw + l])) {
+        if (live && t < n_frame && !solving && (s == 0 || t < done_prev)) {
             if (s > 0) {
-                __threadfence_block();                        // counter before slot
-                const float* q = sh.slot(s - 1, t, l);
-                A.c0 = {q[0], q[cpw], q[2 * cpw]}; A.c1 = {q[3 * cpw], q[4 * cpw], q[5 * cpw]};
-                A.c2 = {q[6 * cpw], q[7 * cpw], q[8 * cpw]};
-                piv = {q[9 * cpw], q[10 * cpw], q[11 * cpw]};
-                __threadfence_block();                        // slot reads before the recycle counter
-                sh.started[s * cpw + l] = t + 1;
+                const float (*q)[PIPE_CHAINS] = ring[s - 1][t & (PIPE_DEPTH - 1)];
+                A.c0 = {q[0][cw], q[1][cw], q[2][cw]}; A.c1 = {q[3][cw], q[4][cw], q[5][cw]}; A.c2 = {q[6][cw], q[7][cw], q[8][cw]};
+                piv = {q[9][cw], q[10][cw], q[11][cw]};
             }
             o = map.apply(ko, 0);
             const Vec3<float> k = map.apply(kt, s + 1);
@@ -222,9 +211,9 @@ __device__ __forceinline__ void pipe_stage(const LegArgs& a, const PipeShared& s
                 const float* pa = ang + (int64_t)t * a.ang_fs;
                 xa = (s == 3) ? 0.f : pa[ia]; xb = pa[ib];
             }
-            S.init(KIND, seg, (float)HASA, q3, xa, xb, lb0, ub0, lb1, ub1, null_sq, n_full, gn);
+            S.init(kind, seg, has_a, q3, xa, xb, lb0, ub0, lb1, ub1, null_sq, n_full, gn);
             if (frozen) S.status = ST_GTOL;
-            solving = true;
+            solving = true; started = t + 1;
             if (t + 1 < n_frame) {   // prefetch the next frame's key points
                 const float* p = pose + (int64_t)(t + 1) * a.pose_fs;
                 ko = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
@@ -232,43 +221,16 @@ __device__ __forceinline__ void pipe_stage(const LegArgs& a, const PipeShared& s
             }
         }
         // ---- one function evaluation
-        const bool work = live && solving && !S.done();
-        const bool any_work = __any_sync(full, work);
-        if (work) S.trip();
-        if (!any_work) __nanosleep(64);   // the whole warp waits for another stage: leave the issue slots to it
+        if (live && solving && !S.done()) S.trip();
     }
-    if (live) {
+    // per-chain statistics
+    const int w1 = min(worst, __shfl_xor_sync(full, worst, 1));
+    const int w2 = min(w1, __shfl_xor_sync(full, w1, 2));
+    if (owner) {
         if (a.nfev) a.nfev[c * 4 + s] = nf;
-        if (a.status && worst == ST_MAXFEV) atomicMin(&a.status[c], ST_MAXFEV);
+        if (a.status && s == 0) a.status[c] = w2;
     }
 }
-
-__global__ void __launch_bounds__(128) leg_solve_pipe_kernel(LegArgs a, int cpw) {
-    extern __shared__ float smem[];
-    PipeShared sh;
-    sh.cpw = cpw;
-    sh.done = (volatile int*)smem;
-    sh.started = sh.done + 4 * cpw;
-    sh.ring = smem + 8 * cpw;
-    for (int i = threadIdx.x; i < 8 * cpw; i += blockDim.x) ((int*)smem)[i] = 0;
-    int lo = 0; while (lo < 3 && !((a.stage_mask >> lo) & 1)) ++lo;
-    int hi = 3; while (hi > 0 && !((a.stage_mask >> hi) & 1)) --hi;
-    const int warp = threadIdx.x >> 5;
-    const int64_t c = (int64_t)blockIdx.x * cpw + (threadIdx.x & 31);
-    if (warp == 0 && (threadIdx.x & 31) < cpw && c < a.n_chain) {
-        if (a.status) a.status[c] = ST_GTOL;
-        if (a.nfev) { a.nfev[c * 4] = 0; a.nfev[c * 4 + 1] = 0; a.nfev[c * 4 + 2] = 0; a.nfev[c * 4 + 3] = 0; }
-    }
-    __syncthreads();
-    switch ((warp + blockIdx.x) & 3) {
-        case 0: pipe_stage<0>(a, sh, lo, hi); break;
-        case 1: pipe_stage<1>(a, sh, lo, hi); break;
-        case 2: pipe_stage<2>(a, sh, lo, hi); break;
-        default: pipe_stage<3>(a, sh, lo, hi); break;
-    }
-}
-
-static size_t pipe_smem_bytes(int cpw) { return sizeof(float) * (size_t)cpw * (8 + 3 * PIPE_DEPTH * PIPE_SLOT); }
 
 // ---------------------------------------------------------------------------------------------
 // C ABI
@@ -306,23 +268,22 @@ extern "C" int seqik_leg_solve_f32(const float* pose, int64_t pose_chain_stride,
         const int64_t grid = (n_chain + 31) / 32;
         leg_solve_lane_kernel<<<(unsigned)grid, 32, 0, (cudaStream_t)stream>>>(a);
     } else {
-        // chains per warp: as few as still fit all blocks on the device at once (a second wave would double
-        // the run time of this latency-bound kernel); fewer lanes per warp = fewer divergent paths per trip
+        // chains per warp: as few as still fit every warp on the device at once (a second wave would double the
+        // run time of this latency-bound kernel); fewer chains per warp = fewer lanes whose slow paths a trip pays for
         int dev = 0, n_sm = 148, per_sm = 1;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        int cpw = 32;
-        const uint32_t forced = (flags >> 12) & 0x3F;           // bits 12..17: force chains per warp (tuning/tests)
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, leg_solve_pipe_kernel, 32, 0);
+        int cpw = PIPE_CHAINS;
+        const uint32_t forced = (flags >> SEQIK_FLAG_CPW_SHIFT) & 0x3F;     // tuning / tests
         if (forced) cpw = (int)forced;
         else {
-            for (int cand = 4; cand <= 32; cand *= 2) {
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, leg_solve_pipe_kernel, 128, pipe_smem_bytes(cand));
+            for (int cand = 1; cand <= PIPE_CHAINS; cand *= 2)
                 if ((n_chain + cand - 1) / cand <= (int64_t)per_sm * n_sm) { cpw = cand; break; }
-            }
         }
-        if (cpw < 1 || cpw > 32) return seqik_fail(SEQIK_EINVAL, "seqik_leg_solve_f32: chains per warp must be 1..32");
+        if (cpw < 1 || cpw > PIPE_CHAINS) return seqik_fail(SEQIK_EINVAL, "seqik_leg_solve_f32: chains per warp must be 1..8");
         const int64_t grid = (n_chain + cpw - 1) / cpw;
-        leg_solve_pipe_kernel<<<(unsigned)grid, 128, pipe_smem_bytes(cpw), (cudaStream_t)stream>>>(a, cpw);
+        leg_solve_pipe_kernel<<<(unsigned)grid, 32, 0, (cudaStream_t)stream>>>(a, cpw);
     }
     return seqik_check_launch("seqik_leg_solve_f32");
 }

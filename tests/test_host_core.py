@@ -9,7 +9,7 @@ import model_trf2 as M
 from helpers import ANGLE_TOL, FK_TOL, bad_frames, fk_residual, residual_of_angles
 from oracle import seqik_oracle as O
 
-GN = 0b0110   # SEQIK_FLAG_DEFAULT: stages 2 and 3 in Gauss-Newton mode
+GN = 0b1111   # SEQIK_FLAG_DEFAULT: Gauss-Newton mode in all four stages
 
 
 def leg_consts(size, bounds, init, leg):
