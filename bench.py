@@ -232,8 +232,8 @@ def run_ours(args):
     ms_step = ms_total / args.steps
     # ---- end to end through the public batched call with host buffers
     for _ in range(2):
-        sess.solve_host(host_pose)
-    ms_e2e = timed(lambda: sess.solve_host(host_pose, synchronize=False), args.steps) / args.steps
+        sess.solve_host(host_pose, n_chunks=args.chunks)
+    ms_e2e = timed(lambda: sess.solve_host(host_pose, synchronize=False, n_chunks=args.chunks), args.steps) / args.steps
     clocks = sampler.stop() if sampler else None
 
     sess.solve_device()
@@ -280,7 +280,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
             "e2e": {"value": leg_frames / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": leg_frames_rank * 60, "d2h_bytes_per_step": leg_frames_rank * (28 + 108),
-                    "bytes_are": "per GPU"},
+                    "bytes_are": "per GPU", "frame_chunks": args.chunks, "gpu_launches": args.steps * sess.launches_per_call},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                          "traffic": traffic, "kernel": "leg_solve", "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback",
@@ -306,6 +306,7 @@ def main():
     ap.add_argument("--trials", type=int, default=1000, help="trials per GPU")
     ap.add_argument("--frames", type=int, default=1000)
     ap.add_argument("--schedule", type=int, default=0, help="kernel schedule (0 auto, 1 lane per chain, 2 stage pipeline)")
+    ap.add_argument("--chunks", type=int, default=8, help="frame chunks of the host pipeline (e2e)")
     ap.add_argument("--cpw", type=int, default=0, help="chains per warp of schedule 2 (0 auto)")
     ap.add_argument("--cpu-frames", type=int, default=200, help="frames per leg of the cpu_baseline sample")
     ap.add_argument("--ref-frames", type=int, default=100, help="frames per chain and step of --impl reference")

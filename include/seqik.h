@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SEQIK_ABI_VERSION 2
+#define SEQIK_ABI_VERSION 3
 #define SEQIK_OK 0
 #define SEQIK_EINVAL (-1)
 #define SEQIK_ECUDA (-3)
@@ -75,6 +75,10 @@ const char* seqik_last_error(void);
  *   fk      NULL, or [n_chain][n_frame][9][3] out (rows 0-3 origin, 4-5 Coxa-Femur joint,
  *           6 Femur-Tibia, 7 Tibia-Tarsus, 8 Claw: leg_inverse_kinematics.py:71-77,279-282);
  *           rows of stages after the last solved one are left untouched
+ *   warm    NULL, or 7 angles per chain (addressed warm + c*warm_chain_stride) that replace the seeds of `params`:
+ *           pass the last solved frame of the same chains (angles + (t0-1)*ang_frame_stride) to continue a
+ *           recording in frame chunks -- bit-identical to one call over all frames, which is what lets the host
+ *           pipeline copy chunk k+1 in and chunk k-1 out while chunk k is solved
  *   status  NULL, or [n_chain] out: 0 if some solve hit max_nfev, else 1
  *   nfev    NULL, or [n_chain][4] out: function evaluations summed over frames, per stage
  *   stage_mask  bit s set = solve stage s+1; the set bits must be contiguous
@@ -84,6 +88,7 @@ int seqik_leg_solve_f32(const float* pose, int64_t pose_chain_stride, int64_t po
                         const float* affine, const float* params,
                         float* angles, int64_t ang_chain_stride, int64_t ang_frame_stride,
                         float* fk, int64_t fk_chain_stride, int64_t fk_frame_stride,
+                        const float* warm, int64_t warm_chain_stride,
                         int32_t* status, uint32_t* nfev,
                         int64_t n_chain, int64_t n_frame, uint32_t stage_mask, uint32_t flags, void* stream);
 
@@ -155,6 +160,12 @@ int seqik_head_affine_f32(const float* stats, const float* consts, float* affine
  * (alignment.py:547-553).  head, out [n_trial][n_frame][2][3]. */
 int seqik_head_apply_f32(const float* head, const float* affine, float* out, int64_t n_trial, int64_t n_frame,
                          void* stream);
+
+/* Strided copy between host (pinned) and device buffers: `height` rows of `width_bytes`, row pitches in bytes.
+ * direction 1 = host to device, 2 = device to host.  Plumbing for the chunked host pipeline (a frame range of a
+ * chain-major array is a 2-D block); a thin wrapper over cudaMemcpy2DAsync so that callers need no CUDA binding. */
+int seqik_memcpy2d_async(void* dst, int64_t dst_pitch_bytes, const void* src, int64_t src_pitch_bytes,
+                         int64_t width_bytes, int64_t height, int direction, void* stream);
 
 #ifdef __cplusplus
 }

@@ -12,7 +12,7 @@ import numpy as np
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "csrc" / "libseqik_sm100.so"
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 CHAIN_PARAM_FLOATS = 32
 FLAG_DEFAULT = 0xF                      # SEQIK_FLAG_DEFAULT: Gauss-Newton mode in all four stages
 FLAG_SCHED_SHIFT = 8
@@ -26,8 +26,9 @@ _vp, _i64, _u32, _f32, _int = ctypes.c_void_p, ctypes.c_int64, ctypes.c_uint32, 
 _SIGNATURES = {
     "seqik_abi_version": (_int, []),
     "seqik_last_error": (ctypes.c_char_p, []),
-    "seqik_leg_solve_f32": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _vp,
+    "seqik_leg_solve_f32": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp,
                                    _i64, _i64, _u32, _u32, _vp]),
+    "seqik_memcpy2d_async": (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _int, _vp]),
     "seqik_fk_f32": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp]),
     "seqik_head_angles_f32": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),
     "seqik_mid_quantile_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp]),

@@ -63,6 +63,9 @@ class BatchedLegIK:
             self.h_angles = torch.empty((self.n_chain, self.n_frame, 7), dtype=torch.float32, pin_memory=True)
             self.h_fk = torch.empty((self.n_chain, self.n_frame, 9, 3), dtype=torch.float32, pin_memory=True) if want_fk else None
         self.status = self.nfev = None
+        self._copy_streams = None
+        self.default_chunks = 8
+        self.launches_per_call = 1
 
     @property
     def leg_frames(self) -> int:
@@ -78,22 +81,57 @@ class BatchedLegIK:
                                                         want_stats=want_stats)
         return self.d_angles, self.d_fk
 
-    def solve_host(self, pose_host, synchronize: bool = True):
-        """Host (ideally pinned) pose (n_trial, n_leg, n_frame, 5, 3) float32 -> pinned host (angles, fk).
-        Host->device copy, solve and device->host copies are enqueued on the current stream."""
-        torch = self.torch
+    def solve_host(self, pose_host, synchronize: bool = True, n_chunks: Optional[int] = None):
+        """Host (pinned) pose (n_trial, n_leg, n_frame, 5, 3) float32 -> pinned host (angles, fk).
+
+        The frames are cut into ``n_chunks`` ranges.  While range k is solved (warm-started from the last frame of
+        range k-1: bit-identical to one launch over all frames), range k+1 is copied host->device and the results of
+        range k-1 device->host on two copy streams, so PCIe traffic in both directions overlaps the kernel.
+        """
+        torch, lib = self.torch, N.load_library()
         if self.h_angles is None:
             raise RuntimeError("session was created with host_buffers=False")
         src = pose_host if isinstance(pose_host, torch.Tensor) else torch.from_numpy(pose_host)
-        if src.dtype != torch.float32:
-            raise ValueError("pose_host must be float32")
-        self.d_pose.copy_(src.reshape(self.n_chain, self.n_frame, 5, 3), non_blocking=True)
-        self.solve_device(want_stats=False)
-        self.h_angles.copy_(self.d_angles, non_blocking=True)
-        if self.h_fk is not None:
-            self.h_fk.copy_(self.d_fk, non_blocking=True)
+        if src.dtype != torch.float32 or not src.is_contiguous() or src.numel() != self.n_chain * self.n_frame * 15:
+            raise ValueError("pose_host must be a contiguous float32 array of (n_trial, n_leg, n_frame, 5, 3)")
+        if n_chunks is None:
+            n_chunks = self.default_chunks
+        n_chunks = max(1, min(int(n_chunks), self.n_frame))
+        main = torch.cuda.current_stream(self.device)
+        if self._copy_streams is None:
+            self._copy_streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        s_in, s_out = self._copy_streams
+        s_in.wait_stream(main)
+        s_out.wait_stream(main)
+        F = self.n_frame
+        bounds = [(F * k) // n_chunks for k in range(n_chunks + 1)]
+
+        def copy2d(dst, src_, row_floats, t0, t1, direction, stream):
+            off = 4 * row_floats * t0
+            N.check(lib.seqik_memcpy2d_async(dst.data_ptr() + off, 4 * row_floats * F, src_.data_ptr() + off, 4 * row_floats * F,
+                                             4 * row_floats * (t1 - t0), self.n_chain, direction, stream.cuda_stream),
+                    "seqik_memcpy2d_async")
+        with torch.cuda.device(self.device):
+            for k in range(n_chunks):
+                t0, t1 = bounds[k], bounds[k + 1]
+                if t1 == t0:
+                    continue
+                copy2d(self.d_pose, src, 15, t0, t1, 1, s_in)
+                ev_in = torch.cuda.Event()
+                ev_in.record(s_in)
+                main.wait_event(ev_in)
+                engine.leg_solve(self.d_pose, self.params, angles=self.d_angles, fk=self.d_fk, want_fk=self.d_fk is not None,
+                                 schedule=self.schedule, chains_per_warp=self.chains_per_warp, want_stats=False, frames=(t0, t1))
+                ev_k = torch.cuda.Event()
+                ev_k.record(main)
+                s_out.wait_event(ev_k)
+                copy2d(self.h_angles, self.d_angles, 7, t0, t1, 2, s_out)
+                if self.h_fk is not None:
+                    copy2d(self.h_fk, self.d_fk, 27, t0, t1, 2, s_out)
+            main.wait_stream(s_out)
+        self.launches_per_call = n_chunks
         if synchronize:
-            torch.cuda.current_stream(self.device).synchronize()
+            main.synchronize()
         return self.h_angles, self.h_fk
 
     def mean_fk_error(self, pose=None) -> float:

@@ -39,6 +39,19 @@ static inline int fail(int code, const char* fmt, const char* a = "") { return s
 static inline int check_launch(const char* what) { return seqik_check_launch(what); }
 
 extern "C" int seqik_abi_version(void) { return SEQIK_ABI_VERSION; }
+
+extern "C" int seqik_memcpy2d_async(void* dst, int64_t dst_pitch_bytes, const void* src, int64_t src_pitch_bytes,
+                                    int64_t width_bytes, int64_t height, int direction, void* stream) {
+    if (width_bytes < 0 || height < 0) return fail(SEQIK_EINVAL, "seqik_memcpy2d_async: negative size");
+    if (width_bytes == 0 || height == 0) return SEQIK_OK;
+    if (!dst || !src) return fail(SEQIK_EINVAL, "seqik_memcpy2d_async: NULL pointer");
+    if (direction != 1 && direction != 2) return fail(SEQIK_EINVAL, "seqik_memcpy2d_async: direction must be 1 (H2D) or 2 (D2H)");
+    if (dst_pitch_bytes < width_bytes || src_pitch_bytes < width_bytes) return fail(SEQIK_EINVAL, "seqik_memcpy2d_async: pitch smaller than width");
+    cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)dst_pitch_bytes, src, (size_t)src_pitch_bytes, (size_t)width_bytes, (size_t)height,
+                                      direction == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e != cudaSuccess) { snprintf(g_err, sizeof(g_err), "seqik_memcpy2d_async: %s", cudaGetErrorString(e)); return SEQIK_ECUDA; }
+    return SEQIK_OK;
+}
 extern "C" const char* seqik_last_error(void) { return g_err; }
 
 // ---------------------------------------------------------------------------------------------

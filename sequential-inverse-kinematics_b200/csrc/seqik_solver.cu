@@ -31,6 +31,7 @@ struct LegArgs {
     const float* affine; const float* params;
     float* angles; int64_t ang_cs, ang_fs;
     float* fk; int64_t fk_cs, fk_fs;
+    const float* warm; int64_t warm_cs;
     int32_t* status; uint32_t* nfev;
     int64_t n_chain, n_frame;
     int stage_mask, gn_mask;
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(32) leg_solve_lane_kernel(LegArgs a) {
     io.map.init(a.affine, c);
     float seed[7];
 #pragma unroll
-    for (int i = 0; i < 7; ++i) seed[i] = io.prm[18 + i];
+    for (int i = 0; i < 7; ++i) seed[i] = a.warm ? a.warm[c * a.warm_cs + i] : io.prm[18 + i];
     ChainRunner<float, DevIO> run;
     run.start(io, a.n_frame, seed, a.stage_mask, a.gn_mask);
     while (!run.finished()) run.step();
@@ -145,7 +146,8 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw) 
     const int n_full = (s == 0) ? 4 : (s == 1) ? 6 : (s == 2) ? 8 : 9;
     const bool gn = (a.gn_mask >> s) & 1;
     const float has_a = (s == 3) ? 0.f : 1.f;
-    float xa = (s == 3) ? 0.f : __ldg(prm + 18 + ia), xb = __ldg(prm + 18 + ib);   // warm start, frame to frame
+    const float* seed = a.warm ? a.warm + cc * a.warm_cs : prm + 18;
+    float xa = (s == 3) ? 0.f : seed[ia], xb = seed[ib];                           // warm start, frame to frame
 
     StageSolve<float> S;
     Mat3<float> A = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
@@ -239,6 +241,7 @@ extern "C" int seqik_leg_solve_f32(const float* pose, int64_t pose_chain_stride,
                                    const float* affine, const float* params,
                                    float* angles, int64_t ang_chain_stride, int64_t ang_frame_stride,
                                    float* fk, int64_t fk_chain_stride, int64_t fk_frame_stride,
+                                   const float* warm, int64_t warm_chain_stride,
                                    int32_t* status, uint32_t* nfev,
                                    int64_t n_chain, int64_t n_frame, uint32_t stage_mask, uint32_t flags, void* stream) {
     if (n_chain < 0 || n_frame < 0) return seqik_fail(SEQIK_EINVAL, "seqik_leg_solve_f32: negative size");
@@ -262,6 +265,7 @@ extern "C" int seqik_leg_solve_f32(const float* pose, int64_t pose_chain_stride,
     a.affine = affine; a.params = params;
     a.angles = angles; a.ang_cs = ang_chain_stride; a.ang_fs = ang_frame_stride;
     a.fk = fk; a.fk_cs = fk_chain_stride; a.fk_fs = fk_frame_stride;
+    a.warm = warm; a.warm_cs = warm_chain_stride;
     a.status = status; a.nfev = nfev; a.n_chain = n_chain; a.n_frame = n_frame;
     a.stage_mask = (int)stage_mask; a.gn_mask = (int)(flags & 0xF);
     if (sched == 1) {

@@ -44,12 +44,14 @@ def stages_to_mask(stages: Sequence[int]) -> int:
 
 def leg_solve(pose, params, affine=None, stages: Sequence[int] = (1, 2, 3, 4), want_fk: bool = True,
               angles=None, fk=None, flags: int = N.FLAG_DEFAULT, schedule: int = N.SCHED_AUTO,
-              want_stats: bool = True, chains_per_warp: int = 0):
+              want_stats: bool = True, chains_per_warp: int = 0, frames=None):
     """4-stage sequential IK (+FK) of every chain.  Returns (angles, fk|None, status|None, nfev|None).
 
     ``angles`` must be given (and is updated in place) when ``stages`` does not start at 1:
     the DOFs of the earlier stages are then read from it and frozen.  ``schedule`` / ``chains_per_warp``
     override the automatic kernel schedule (tuning and tests); results do not depend on them.
+    ``frames=(t0, t1)`` solves only that frame range IN PLACE of the full-size pose/angles/fk tensors, warm-started
+    from frame t0-1 of ``angles`` (t0 > 0): chunked calls over consecutive ranges equal one call over all frames.
     """
     torch = N.require_cuda()
     lib = N.load_library()
@@ -78,11 +80,19 @@ def leg_solve(pose, params, affine=None, stages: Sequence[int] = (1, 2, 3, 4), w
         _check(affine, "affine", (8,))
     status = torch.empty((n_chain,), dtype=torch.int32, device=dev) if want_stats else None
     nfev = torch.empty((n_chain, 4), dtype=torch.int32, device=dev) if want_stats else None
+    t0, t1 = (0, n_frame) if frames is None else (int(frames[0]), int(frames[1]))
+    if not 0 <= t0 <= t1 <= n_frame:
+        raise ValueError(f"frames {frames} outside [0, {n_frame}]")
+    if t0 > 0 and not mask & 1:
+        raise ValueError("a frame range that does not start at 0 needs stages starting at 1")
+    p_fk = 0 if fk is None else fk.data_ptr() + 4 * 27 * t0
+    warm = 0 if t0 == 0 else angles.data_ptr() + 4 * 7 * (t0 - 1)
     with torch.cuda.device(dev):
         rc = lib.seqik_leg_solve_f32(
-            N.ptr(pose), n_frame * 15, 15, N.ptr(affine), N.ptr(params),
-            N.ptr(angles), n_frame * 7, 7, N.ptr(fk), n_frame * 27, 27,
-            N.ptr(status), N.ptr(nfev), n_chain, n_frame, mask,
+            pose.data_ptr() + 4 * 15 * t0, n_frame * 15, 15, N.ptr(affine), N.ptr(params),
+            angles.data_ptr() + 4 * 7 * t0, n_frame * 7, 7, p_fk, n_frame * 27, 27,
+            warm, n_frame * 7,
+            N.ptr(status), N.ptr(nfev), n_chain, t1 - t0, mask,
             (flags & 0xFF) | ((schedule & 0xF) << N.FLAG_SCHED_SHIFT) | ((chains_per_warp & 0x3F) << 12),
             N.stream_ptr(torch, dev))
     N.check(rc, "seqik_leg_solve_f32")

@@ -36,13 +36,15 @@ def test_argument_validation_without_gpu():
     """Size/NULL checks happen before any CUDA call, so they can be exercised on a CPU-only host."""
     from seqikpy_b200 import _native as N
     lib = N.load_library()
-    assert lib.seqik_leg_solve_f32(0, 0, 15, 0, 0, 0, 0, 7, 0, 0, 27, 0, 0, -1, 10, 0xF, 0, 0) == -1
+    assert lib.seqik_leg_solve_f32(0, 0, 15, 0, 0, 0, 0, 7, 0, 0, 27, 0, 0, 0, 0, -1, 10, 0xF, 0, 0) == -1
     assert b"negative" in lib.seqik_last_error()
-    assert lib.seqik_leg_solve_f32(0, 0, 15, 0, 0, 0, 0, 7, 0, 0, 27, 0, 0, 0, 10, 0xF, 0, 0) == 0      # empty: ok
-    assert lib.seqik_leg_solve_f32(0, 0, 15, 0, 0, 0, 0, 7, 0, 0, 27, 0, 0, 4, 10, 0xF, 0, 0) == -1     # NULL pose
-    assert lib.seqik_leg_solve_f32(8, 150, 15, 0, 8, 8, 70, 7, 0, 0, 27, 0, 0, 4, 10, 0x5, 0, 0) == -1  # mask with a hole
+    assert lib.seqik_leg_solve_f32(0, 0, 15, 0, 0, 0, 0, 7, 0, 0, 27, 0, 0, 0, 0, 0, 10, 0xF, 0, 0) == 0      # empty: ok
+    assert lib.seqik_leg_solve_f32(0, 0, 15, 0, 0, 0, 0, 7, 0, 0, 27, 0, 0, 0, 0, 4, 10, 0xF, 0, 0) == -1     # NULL pose
+    assert lib.seqik_leg_solve_f32(8, 150, 15, 0, 8, 8, 70, 7, 0, 0, 27, 0, 0, 0, 0, 4, 10, 0x5, 0, 0) == -1  # mask with a hole
     assert lib.seqik_mid_quantile_f32(8, 0, 8, 8, 3, 0, 0) == -1                                         # empty series
     assert lib.seqik_head_angles_f32(8, 8, 8, 5, 0, 0, 8, 8, 1, 1, 0) == -1                              # bad neck stride
+    assert lib.seqik_memcpy2d_async(8, 4, 8, 16, 8, 2, 1, 0) == -1                                       # pitch < width
+    assert lib.seqik_memcpy2d_async(8, 16, 8, 16, 8, 2, 3, 0) == -1                                      # bad direction
     with pytest.raises(ValueError):
         N.check(-1, "x")
 

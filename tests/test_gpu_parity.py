@@ -205,6 +205,32 @@ def test_synthetic_vs_oracle_and_shard_invariance(api, synthetic_gold):
         assert t.equal(a1, a2) and t.equal(f1, f2) and t.equal(n1, n2) and t.equal(s1, s2), cpw
 
 
+def test_frame_chunks_and_host_pipeline_equal_one_launch(api):
+    """Frames solved in chunks (warm start from the previous chunk's last frame) and the pipelined host call
+    (2-D async copies on side streams) are bit-identical to one launch over all frames."""
+    S, t = api.synthetic, api.torch
+    from seqikpy_b200.batch import BatchedLegIK
+    n_trial, n_frame = 3, 97
+    size, bounds, init = S.chain_constants()
+    chain = api.Chain(bounds, list(S.LEGS), size)
+    pose = S.make_trials(range(n_trial), 1000)[:, :n_frame]
+    host = t.from_numpy(np.ascontiguousarray(pose.transpose(0, 2, 1, 3, 4))).pin_memory()
+    sess = BatchedLegIK(chain, init, S.LEGS, n_trial, n_frame)
+    sess.d_pose.copy_(host.reshape(sess.n_chain, n_frame, 5, 3))
+    a_ref, f_ref = (x.clone() for x in sess.solve_device())
+    ang = t.zeros_like(a_ref)
+    fk = t.zeros_like(f_ref)
+    for lo, hi in ((0, 1), (1, 40), (40, 41), (41, 97)):
+        api.engine.leg_solve(sess.d_pose, sess.params, angles=ang, fk=fk, frames=(lo, hi))
+    assert t.equal(ang, a_ref) and t.equal(fk, f_ref)
+    for chunks in (1, 4, 97, 200):
+        sess.d_angles.zero_(); sess.d_fk.zero_()
+        h_a, h_f = sess.solve_host(host, n_chunks=chunks)
+        assert t.equal(h_a, a_ref.cpu()) and t.equal(h_f, f_ref.cpu()), chunks
+    with pytest.raises(ValueError):
+        api.engine.leg_solve(sess.d_pose, sess.params, angles=ang, fk=fk, frames=(5, 200))
+
+
 def test_fk_kernel_matches_solver_and_oracle(api, synthetic_gold):
     S, t = api.synthetic, api.torch
     size, bounds, init = S.chain_constants()
