@@ -195,11 +195,13 @@ struct StageSolve {
         span0 = ub0 - lb0; span1 = ub1 - lb1;
         x0 = a; x1 = b;
         dl0 = a - lb0; du0 = ub0 - a; dl1 = b - lb1; du1 = ub1 - b;
-        const R rs = R(1e-10);
-        if (dl0 <= R(0)) { dl0 = rs * N::max_(R(1), N::abs_(lb0)); x0 = lb0 + dl0; du0 = span0 - dl0; }
-        if (du0 <= R(0)) { du0 = rs * N::max_(R(1), N::abs_(ub0)); x0 = ub0 - du0; dl0 = span0 - du0; }
-        if (dl1 <= R(0)) { dl1 = rs * N::max_(R(1), N::abs_(lb1)); x1 = lb1 + dl1; du1 = span1 - dl1; }
-        if (du1 <= R(0)) { du1 = rs * N::max_(R(1), N::abs_(ub1)); x1 = ub1 - du1; dl1 = span1 - du1; }
+        if (N::min_(N::min_(dl0, du0), N::min_(dl1, du1)) <= R(0)) {   // a seed ON a bound (legal): nudge it inside
+            const R rs = R(1e-10);
+            if (dl0 <= R(0)) { dl0 = rs * N::max_(R(1), N::abs_(lb0)); x0 = lb0 + dl0; du0 = span0 - dl0; }
+            if (du0 <= R(0)) { du0 = rs * N::max_(R(1), N::abs_(ub0)); x0 = ub0 - du0; dl0 = span0 - du0; }
+            if (dl1 <= R(0)) { dl1 = rs * N::max_(R(1), N::abs_(lb1)); x1 = lb1 + dl1; du1 = span1 - dl1; }
+            if (du1 <= R(0)) { du1 = rs * N::max_(R(1), N::abs_(ub1)); x1 = ub1 - du1; dl1 = span1 - du1; }
+        }
         R va, vb;
         N::sincosv_(x0, &sa, &ca, &va); N::sincosv_(x1, &sb, &cb, &vb);
         const Vec3<R> w = point();
@@ -207,9 +209,10 @@ struct StageSolve {
         cost = R(0.5) * dot(f, f);
         gradient();
         R v0, v1, dv0, dv1; cl_scaling(v0, v1, dv0, dv1);
-        // true divisions: v can be ~1e-38 (an iterate parked on a bound at 0) where x*x underflows to 0 and
-        // 0 * rcp(v) would be 0 * inf
-        Delta = N::sqrt_(null_sq + (x0 * x0) / v0 + (x1 * x1) / v1);
+        // v can be ~1e-38 (an iterate parked on a bound at 0): there x = +-v, the term x^2 / v = v is negligible
+        // against null_sq >= 1 and x * x underflows, so it is dropped instead of evaluating 0 * rcp(tiny) = 0 * inf
+        const R q0 = (v0 > R(1e-30)) ? x0 * x0 * N::rcp_(v0) : R(0), q1 = (v1 > R(1e-30)) ? x1 * x1 * N::rcp_(v1) : R(0);
+        Delta = N::sqrt_(null_sq + q0 + q1);
         if (Delta == R(0)) Delta = R(1);
         alpha = R(0); nfev = 1; status = ST_RUNNING;
     }
@@ -244,13 +247,12 @@ struct StageSolve {
         return N::fma_(s1, h.gh1, N::fma_(s0, h.gh0, R(0.5) * N::fma_(h.B1 * s1, s1, h.B0 * s0 * s0)));
     }
 
-    // select_step (trf.py:129-203) restricted to the active pair.  Written as one straight-line block: the three
-    // candidates (truncated step, reflected step, scaled anti-gradient) are always evaluated and the in-bounds
-    // case -- where scipy returns the plain step -- is a final select.  (Lanes of a warp sit in different cases.)
+    // select_step (trf.py:129-203) restricted to the active pair.
     SK_HD void select_step(const Hat& h, R p0, R p1, R ph0, R ph1, R& st0, R& st1, R& sh0, R& sh1, R& pred) const {
         const bool inb = (dl0 + p0 >= R(0)) && (du0 - p0 >= R(0)) && (dl1 + p1 >= R(0)) && (du1 - p1 >= R(0));
-        const R full_value = model(h, ph0, ph1);
-        const R fp0 = p0, fp1 = p1, fph0 = ph0, fph1 = ph1;
+        // in_bounds: scipy returns the plain step.  By far the common case once the trust region has adapted; the
+        // three-candidate search below is straight-line code that only runs for lanes whose step leaves the box.
+        if (inb) { st0 = p0; st1 = p1; sh0 = ph0; sh1 = ph1; pred = -model(h, ph0, ph1); return; }
         bool h0, h1;
         const R p_stride = to_bound(dl0, du0, dl1, du1, p0, p1, h0, h1);
         R rh0 = h0 ? -ph0 : ph0, rh1 = h1 ? -ph1 : ph1;
@@ -305,7 +307,6 @@ struct StageSolve {
         st0 = take_p ? p0 : take_r ? r0 : a0 * ags; st1 = take_p ? p1 : take_r ? r1 : a1 * ags;
         sh0 = take_p ? ph0 : take_r ? rh0 : ah0 * ags; sh1 = take_p ? ph1 : take_r ? rh1 : ah1 * ags;
         pred = -(take_p ? p_value : take_r ? r_value : ag_value);
-        if (inb) { st0 = fp0; st1 = fp1; sh0 = fph0; sh1 = fph1; pred = -full_value; }
     }
 
     // One function evaluation: one pass of scipy's inner `while actual_reduction <= 0` loop, preceded by

@@ -180,13 +180,14 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw) 
             const Vec3<float> Af = mul(A, S.f);
             const Vec3<float> np_ = {(piv.x + rel.x) + Af.x, (piv.y + rel.y) + Af.y, (piv.z + rel.z) + Af.z};
             if (fk) {
+                // rows 0-3 repeat the origin, 4 and 5 are both the Coxa-Femur joint: lane s writes origin row s and its
+                // own joint row(s), which spreads the 27 floats of a frame over the four lanes
                 float* pf = fk + (int64_t)t * a.fk_fs;
                 const Vec3<float> jw = {np_.x + o.x, np_.y + o.y, np_.z + o.z};
-                if (s == 0) {
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) { pf[3 * r] = o.x; pf[3 * r + 1] = o.y; pf[3 * r + 2] = o.z; }
-                    pf[12] = jw.x; pf[13] = jw.y; pf[14] = jw.z; pf[15] = jw.x; pf[16] = jw.y; pf[17] = jw.z;
-                } else { pf[15 + 3 * s] = jw.x; pf[16 + 3 * s] = jw.y; pf[17 + 3 * s] = jw.z; }
+                pf[3 * s] = o.x; pf[3 * s + 1] = o.y; pf[3 * s + 2] = o.z;
+                pf[15 + 3 * s] = jw.x; pf[16 + 3 * s] = jw.y; pf[17 + 3 * s] = jw.z;
+                if (s == 0) { pf[12] = jw.x; pf[13] = jw.y; pf[14] = jw.z; }
+                if (s == hi) for (int r = hi + 1; r < 4; ++r) { pf[3 * r] = o.x; pf[3 * r + 1] = o.y; pf[3 * r + 2] = o.z; }
             }
             if (s < hi) {
                 const Mat3<float> B = rotate_frame(A, kind, S.sa, S.ca, S.sb, S.cb);
@@ -258,8 +259,8 @@ extern "C" int seqik_leg_solve_f32(const float* pose, int64_t pose_chain_stride,
     if (n_frame > 2147483647LL) return seqik_fail(SEQIK_EINVAL, "seqik_leg_solve_f32: too many frames");
     uint32_t sched = (flags & SEQIK_FLAG_SCHED_MASK) >> SEQIK_FLAG_SCHED_SHIFT;
     if (sched > 2) return seqik_fail(SEQIK_EINVAL, "seqik_leg_solve_f32: unknown schedule");
-    // automatic: the pipeline while its 4x lanes still fit a B200 comfortably (measured crossover)
-    if (sched == 0) sched = (n_chain <= 40000) ? 2 : 1;
+    // automatic: the stage pipeline (measured faster than one lane per chain from 600 to 60 000 chains)
+    if (sched == 0) sched = 2;
     LegArgs a;
     a.pose = pose; a.pose_cs = pose_chain_stride; a.pose_fs = pose_frame_stride;
     a.affine = affine; a.params = params;
@@ -272,19 +273,16 @@ extern "C" int seqik_leg_solve_f32(const float* pose, int64_t pose_chain_stride,
         const int64_t grid = (n_chain + 31) / 32;
         leg_solve_lane_kernel<<<(unsigned)grid, 32, 0, (cudaStream_t)stream>>>(a);
     } else {
-        // chains per warp: as few as still fit every warp on the device at once (a second wave would double the
-        // run time of this latency-bound kernel); fewer chains per warp = fewer lanes whose slow paths a trip pays for
-        int dev = 0, n_sm = 148, per_sm = 1;
+        // chains per warp (measured): 8 -- every lane of the warp used -- as soon as that still leaves
+        // about one warp per SM sub-partition (4 x 148); fewer chains per warp only for small batches, where the
+        // kernel is pure chain latency and a warp that hosts fewer chains pays for fewer lanes' open/close phases
+        int dev = 0, n_sm = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, leg_solve_pipe_kernel, 32, 0);
-        int cpw = PIPE_CHAINS;
+        int cpw = 1;
+        while (cpw < PIPE_CHAINS && n_chain / (2 * cpw) >= 4LL * n_sm) cpw *= 2;
         const uint32_t forced = (flags >> SEQIK_FLAG_CPW_SHIFT) & 0x3F;     // tuning / tests
         if (forced) cpw = (int)forced;
-        else {
-            for (int cand = 1; cand <= PIPE_CHAINS; cand *= 2)
-                if ((n_chain + cand - 1) / cand <= (int64_t)per_sm * n_sm) { cpw = cand; break; }
-        }
         if (cpw < 1 || cpw > PIPE_CHAINS) return seqik_fail(SEQIK_EINVAL, "seqik_leg_solve_f32: chains per warp must be 1..8");
         const int64_t grid = (n_chain + cpw - 1) / cpw;
         leg_solve_pipe_kernel<<<(unsigned)grid, 32, 0, (cudaStream_t)stream>>>(a, cpw);
