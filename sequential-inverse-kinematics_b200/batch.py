@@ -18,6 +18,8 @@ import numpy as np
 from . import _native as N
 from . import engine
 
+RESYNC_FRAMES = 64      # SEQIK_RESYNC of csrc/seqik_core.cuh
+
 
 def shard_range(n_trial: int, rank: int, world_size: int):
     """Contiguous, balanced [lo, hi) trial range of ``rank`` (first ``n_trial % world_size`` ranks get one more)."""
@@ -104,7 +106,9 @@ class BatchedLegIK:
         s_in.wait_stream(main)
         s_out.wait_stream(main)
         F = self.n_frame
-        bounds = [(F * k) // n_chunks for k in range(n_chunks + 1)]
+        # chunk starts on multiples of 64 frames (the kernel's resync period): then chunking is bit-identical
+        # to one launch over all frames
+        bounds = sorted({0, F} | {min(F, RESYNC_FRAMES * round(F * k / n_chunks / RESYNC_FRAMES)) for k in range(1, n_chunks)})
 
         def copy2d(dst, src_, row_floats, t0, t1, direction, stream):
             off = 4 * row_floats * t0
@@ -112,7 +116,7 @@ class BatchedLegIK:
                                              4 * row_floats * (t1 - t0), self.n_chain, direction, stream.cuda_stream),
                     "seqik_memcpy2d_async")
         with torch.cuda.device(self.device):
-            for k in range(n_chunks):
+            for k in range(len(bounds) - 1):
                 t0, t1 = bounds[k], bounds[k + 1]
                 if t1 == t0:
                     continue
@@ -129,7 +133,7 @@ class BatchedLegIK:
                 if self.h_fk is not None:
                     copy2d(self.h_fk, self.d_fk, 27, t0, t1, 2, s_out)
             main.wait_stream(s_out)
-        self.launches_per_call = n_chunks
+        self.launches_per_call = len(bounds) - 1
         if synchronize:
             main.synchronize()
         return self.h_angles, self.h_fk

@@ -125,6 +125,8 @@ template <> struct Num<double> {
     static SK_HD double eps_in() { return 2.220446049250313e-16; }
 };
 
+constexpr int SEQIK_RESYNC = 64;          // frames between full re-initialisations of a carried solve
+
 enum : int { KIND_XY = 0, KIND_ZY = 1 };   // Rx(a)Ry(b) (stage 1)  |  Rz(a)Ry(b) (stages 2-4)
 
 enum : int {
@@ -211,6 +213,22 @@ struct StageSolve {
         R v0, v1, dv0, dv1; cl_scaling(v0, v1, dv0, dv1);
         // v can be ~1e-38 (an iterate parked on a bound at 0): there x = +-v, the term x^2 / v = v is negligible
         // against null_sq >= 1 and x * x underflows, so it is dropped instead of evaluating 0 * rcp(tiny) = 0 * inf
+        const R q0 = (v0 > R(1e-30)) ? x0 * x0 * N::rcp_(v0) : R(0), q1 = (v1 > R(1e-30)) ? x1 * x1 * N::rcp_(v1) : R(0);
+        Delta = N::sqrt_(null_sq + q0 + q1);
+        if (Delta == R(0)) Delta = R(1);
+        alpha = R(0); nfev = 1; status = ST_RUNNING;
+    }
+
+    // Next frame of the same (chain, stage): the warm start IS the previous solve's final iterate, so its sin/cos and
+    // bound distances are carried over and only the residual against the new target is rebuilt (least_squares
+    // prologue without the trigonometry).  Callers re-run init() every SEQIK_RESYNC frames so that the carried
+    // sin/cos cannot drift from the angle (float32 random walk, < 1e-6 rad over 64 frames).
+    SK_HD void restart(const Vec3<R>& q) {
+        const Vec3<R> w = point();
+        f = {w.x - q.x, w.y - q.y, w.z - q.z};
+        cost = R(0.5) * dot(f, f);
+        gradient();
+        R v0, v1, dv0, dv1; cl_scaling(v0, v1, dv0, dv1);
         const R q0 = (v0 > R(1e-30)) ? x0 * x0 * N::rcp_(v0) : R(0), q1 = (v1 > R(1e-30)) ? x1 * x1 * N::rcp_(v1) : R(0);
         Delta = N::sqrt_(null_sq + q0 + q1);
         if (Delta == R(0)) Delta = R(1);

@@ -117,6 +117,7 @@ constexpr int PIPE_CHAINS = 8;              // chains per warp (maximum)
 
 __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw) {
     __shared__ float ring[3][PIPE_DEPTH][PIPE_SLOT][PIPE_CHAINS];      // chain innermost: conflict-free per stage
+    __shared__ float kpbuf[6][32];                                     // prefetched key points, one column per lane
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x;
     const int s = lane & 3;                                   // this lane's stage (0..3)
@@ -157,13 +158,22 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw) 
     bool solving = false;
     uint32_t nf = 0; int worst = ST_GTOL;
     S.status = ST_GTOL;
-    // key points of frame t, fetched one frame ahead so the load latency hides behind the previous solve
-    Vec3<float> ko = {0.f, 0.f, 0.f}, kt = {0.f, 0.f, 0.f};
-    if (live && n_frame > 0) {
-        const float* p = pose;
-        ko = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
-        kt = {__ldg(p + 3 * (s + 1)), __ldg(p + 3 * (s + 1) + 1), __ldg(p + 3 * (s + 1) + 2)};
-    }
+    // key points of frame t (origin + this stage's target, 6 floats), fetched one frame ahead with cp.async into
+    // shared memory: the copy is in flight during the previous solve and does not hold a register scoreboard
+    // (plain loads made the first dependent instruction of every open wait a full DRAM latency)
+    const uint32_t kp_dst = (uint32_t)__cvta_generic_to_shared(&kpbuf[0][lane]);
+    auto prefetch = [&](int tf) {
+        const float* p = pose + (int64_t)tf * a.pose_fs;
+        const float* q = p + 3 * (s + 1);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(kp_dst), "l"(p) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(kp_dst + 128), "l"(p + 1) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(kp_dst + 256), "l"(p + 2) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(kp_dst + 384), "l"(q) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(kp_dst + 512), "l"(q + 1) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(kp_dst + 640), "l"(q + 2) : "memory");
+    };
+    if (live && n_frame > 0) prefetch(0);
+    bool carried = false;            // S holds the previous frame's solve of this (chain, stage)
 
     while (__any_sync(full, live && t < n_frame)) {
         const int started_next = __shfl_sync(full, started, (lane + 1) & 31);   // consumer's progress (lane + 1)
@@ -206,22 +216,26 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw) 
                 A.c0 = {q[0][cw], q[1][cw], q[2][cw]}; A.c1 = {q[3][cw], q[4][cw], q[5][cw]}; A.c2 = {q[6][cw], q[7][cw], q[8][cw]};
                 piv = {q[9][cw], q[10][cw], q[11][cw]};
             }
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            const Vec3<float> ko = {kpbuf[0][lane], kpbuf[1][lane], kpbuf[2][lane]};
+            const Vec3<float> kt = {kpbuf[3][lane], kpbuf[4][lane], kpbuf[5][lane]};
+            if (t + 1 < n_frame) prefetch(t + 1);
             o = map.apply(ko, 0);
             const Vec3<float> k = map.apply(kt, s + 1);
             rel = {(k.x - o.x) - piv.x, (k.y - o.y) - piv.y, (k.z - o.z) - piv.z};
             const Vec3<float> q3 = mulT(A, rel);
-            if (frozen) {
-                const float* pa = ang + (int64_t)t * a.ang_fs;
-                xa = (s == 3) ? 0.f : pa[ia]; xb = pa[ib];
+            if (carried && !frozen && (t & (SEQIK_RESYNC - 1)) != 0) {
+                S.restart(q3);
+            } else {
+                if (frozen) {
+                    const float* pa = ang + (int64_t)t * a.ang_fs;
+                    xa = (s == 3) ? 0.f : pa[ia]; xb = pa[ib];
+                }
+                S.init(kind, seg, has_a, q3, xa, xb, lb0, ub0, lb1, ub1, null_sq, n_full, gn);
+                if (frozen) S.status = ST_GTOL;
+                carried = true;
             }
-            S.init(kind, seg, has_a, q3, xa, xb, lb0, ub0, lb1, ub1, null_sq, n_full, gn);
-            if (frozen) S.status = ST_GTOL;
             solving = true; started = t + 1;
-            if (t + 1 < n_frame) {   // prefetch the next frame's key points
-                const float* p = pose + (int64_t)(t + 1) * a.pose_fs;
-                ko = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
-                kt = {__ldg(p + 3 * (s + 1)), __ldg(p + 3 * (s + 1) + 1), __ldg(p + 3 * (s + 1) + 2)};
-            }
         }
         // ---- one function evaluation
         if (live && solving && !S.done()) S.trip();

@@ -197,12 +197,13 @@ def test_synthetic_vs_oracle_and_shard_invariance(api, synthetic_gold):
     for lo, hi in ((0, 6), (6, 24), (5, 7)):
         a_s, f_s, _, _ = api.engine.leg_solve(chains[lo:hi].contiguous(), params[lo:hi].contiguous())
         assert t.equal(a_s, ang[lo:hi]) and t.equal(f_s, fk[lo:hi])
-    # every kernel schedule gives bit-identical results (explicit fma, -fmad=false: same rounding everywhere)
-    a1, f1, s1, n1 = api.engine.leg_solve(chains, params, schedule=api.native.SCHED_LANE_PER_CHAIN)
-    assert t.equal(a1, ang) and t.equal(f1, fk)
+    # results do not depend on how chains are packed into warps (bit-identical); the one-lane-per-chain schedule
+    # re-derives sin/cos from the angle at every frame instead of every 64 and agrees to float32 rounding
     for cpw in (1, 2, 3, 8):
         a2, f2, s2, n2 = api.engine.leg_solve(chains, params, schedule=api.native.SCHED_STAGE_PIPELINE, chains_per_warp=cpw)
-        assert t.equal(a1, a2) and t.equal(f1, f2) and t.equal(n1, n2) and t.equal(s1, s2), cpw
+        assert t.equal(ang, a2) and t.equal(fk, f2) and t.equal(nfev, n2) and t.equal(status, s2), cpw
+    a1, f1, s1, n1 = api.engine.leg_solve(chains, params, schedule=api.native.SCHED_LANE_PER_CHAIN)
+    assert (a1 - ang).abs().max() < 2e-5 and (f1 - fk).abs().max() < 2e-5 and int(s1.min()) == 1
 
 
 def test_frame_chunks_and_host_pipeline_equal_one_launch(api):
@@ -210,7 +211,7 @@ def test_frame_chunks_and_host_pipeline_equal_one_launch(api):
     (2-D async copies on side streams) are bit-identical to one launch over all frames."""
     S, t = api.synthetic, api.torch
     from seqikpy_b200.batch import BatchedLegIK
-    n_trial, n_frame = 3, 97
+    n_trial, n_frame = 3, 197
     size, bounds, init = S.chain_constants()
     chain = api.Chain(bounds, list(S.LEGS), size)
     pose = S.make_trials(range(n_trial), 1000)[:, :n_frame]
@@ -220,10 +221,13 @@ def test_frame_chunks_and_host_pipeline_equal_one_launch(api):
     a_ref, f_ref = (x.clone() for x in sess.solve_device())
     ang = t.zeros_like(a_ref)
     fk = t.zeros_like(f_ref)
-    for lo, hi in ((0, 1), (1, 40), (40, 41), (41, 97)):
+    for lo, hi in ((0, 64), (64, 128), (128, 192), (192, 197)):          # chunk starts on the 64-frame resync grid
         api.engine.leg_solve(sess.d_pose, sess.params, angles=ang, fk=fk, frames=(lo, hi))
     assert t.equal(ang, a_ref) and t.equal(fk, f_ref)
-    for chunks in (1, 4, 97, 200):
+    for lo, hi in ((0, 1), (1, 40), (40, 41), (41, 197)):                # any other split: equal to float32 rounding
+        api.engine.leg_solve(sess.d_pose, sess.params, angles=ang, fk=fk, frames=(lo, hi))
+    assert (ang - a_ref).abs().max() < 2e-5 and (fk - f_ref).abs().max() < 2e-5
+    for chunks in (1, 2, 3, 200):
         sess.d_angles.zero_(); sess.d_fk.zero_()
         h_a, h_f = sess.solve_host(host, n_chunks=chunks)
         assert t.equal(h_a, a_ref.cpu()) and t.equal(h_f, f_ref.cpu()), chunks
