@@ -189,21 +189,26 @@ struct StageSolve {
         if (g1 < R(0) && du1 < inf) { v1 = du1; dv1 = R(-1); } else if (g1 > R(0) && dl1 < inf) { v1 = dl1; dv1 = R(1); }
     }
 
-    // least_squares prologue: x0 made strictly feasible (rstep 1e-10), f, g, Delta0
-    SK_HD void init(int kind_in, R L_, R has_a_in, const Vec3<R>& q, R a, R b,
-                    R lb0, R ub0, R lb1, R ub1, R null_sq_, int n_full, bool gn_mode_ = false) {
-        gn_mode = gn_mode_;
-        kind_rt = kind_in; L = L_; has_a_rt = has_a_in; null_sq = null_sq_; max_nfev = 100 * n_full;
+    // x0 and its distances to the bounds; a seed ON a bound (legal) is nudged inside (make_strictly_feasible, rstep 1e-10)
+    SK_HD void place(R a, R b, R lb0, R ub0, R lb1, R ub1) {
         span0 = ub0 - lb0; span1 = ub1 - lb1;
         x0 = a; x1 = b;
         dl0 = a - lb0; du0 = ub0 - a; dl1 = b - lb1; du1 = ub1 - b;
-        if (N::min_(N::min_(dl0, du0), N::min_(dl1, du1)) <= R(0)) {   // a seed ON a bound (legal): nudge it inside
+        if (N::min_(N::min_(dl0, du0), N::min_(dl1, du1)) <= R(0)) {
             const R rs = R(1e-10);
             if (dl0 <= R(0)) { dl0 = rs * N::max_(R(1), N::abs_(lb0)); x0 = lb0 + dl0; du0 = span0 - dl0; }
             if (du0 <= R(0)) { du0 = rs * N::max_(R(1), N::abs_(ub0)); x0 = ub0 - du0; dl0 = span0 - du0; }
             if (dl1 <= R(0)) { dl1 = rs * N::max_(R(1), N::abs_(lb1)); x1 = lb1 + dl1; du1 = span1 - dl1; }
             if (du1 <= R(0)) { du1 = rs * N::max_(R(1), N::abs_(ub1)); x1 = ub1 - du1; dl1 = span1 - du1; }
         }
+    }
+
+    // least_squares prologue: x0 made strictly feasible (rstep 1e-10), f, g, Delta0
+    SK_HD void init(int kind_in, R L_, R has_a_in, const Vec3<R>& q, R a, R b,
+                    R lb0, R ub0, R lb1, R ub1, R null_sq_, int n_full, bool gn_mode_ = false) {
+        gn_mode = gn_mode_;
+        kind_rt = kind_in; L = L_; has_a_rt = has_a_in; null_sq = null_sq_; max_nfev = 100 * n_full;
+        place(a, b, lb0, ub0, lb1, ub1);
         R va, vb;
         N::sincosv_(x0, &sa, &ca, &va); N::sincosv_(x1, &sb, &cb, &vb);
         const Vec3<R> w = point();
@@ -219,11 +224,12 @@ struct StageSolve {
         alpha = R(0); nfev = 1; status = ST_RUNNING;
     }
 
-    // Next frame of the same (chain, stage): the warm start IS the previous solve's final iterate, so its sin/cos and
-    // bound distances are carried over and only the residual against the new target is rebuilt (least_squares
+    // Next frame of the same (chain, stage): the warm start IS the previous solve's final iterate, so its sin/cos are
+    // carried over and only the bound distances and the residual against the new target is rebuilt (least_squares
     // prologue without the trigonometry).  Callers re-run init() every SEQIK_RESYNC frames so that the carried
     // sin/cos cannot drift from the angle (float32 random walk, < 1e-6 rad over 64 frames).
-    SK_HD void restart(const Vec3<R>& q) {
+    SK_HD void restart(const Vec3<R>& q, R lb0, R ub0, R lb1, R ub1) {
+        place(x0, x1, lb0, ub0, lb1, ub1);      // bound distances re-derived from the angle, exactly as init() would
         const Vec3<R> w = point();
         f = {w.x - q.x, w.y - q.y, w.z - q.z};
         cost = R(0.5) * dot(f, f);

@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw) 
             rel = {(k.x - o.x) - piv.x, (k.y - o.y) - piv.y, (k.z - o.z) - piv.z};
             const Vec3<float> q3 = mulT(A, rel);
             if (carried && !frozen && (t & (SEQIK_RESYNC - 1)) != 0) {
-                S.restart(q3);
+                S.restart(q3, lb0, ub0, lb1, ub1);
             } else {
                 if (frozen) {
                     const float* pa = ang + (int64_t)t * a.ang_fs;

@@ -25,3 +25,15 @@ def residual_of_angles(ang7, seg, pose5):
 
 def bad_frames(a, b, tol=ANGLE_TOL):
     return np.where(np.abs(np.asarray(a) - np.asarray(b)).max(axis=1) > tol)[0]
+
+
+def singular_windows(ref_angles7, margin=20, tol=1e-6):
+    """Frames within `margin` of a frame where the REFERENCE's own solution sits on the CTr_pitch = 0 kinematic
+    singularity (there d(end point)/d(ThC_roll) vanishes; the reference leaves such a corner only through the
+    rounding noise of its finite-difference Jacobian, bound-to-bound, so its path is not reproducible -- SURVEY.md
+    finding 4).  On the bundled grooming trial: none for RF, two episodes for LF (frames 280-287 and 3347-3350)."""
+    sing = np.where(np.abs(np.asarray(ref_angles7)[:, 3]) < tol)[0]
+    frames = set()
+    for t in sing:
+        frames.update(range(max(0, t - margin), t + margin + 1))
+    return frames
