@@ -144,3 +144,58 @@ class BatchedLegIK:
         pose = self.d_pose if pose is None else pose.reshape(self.n_chain, self.n_frame, 5, 3)
         d = self.d_fk[:, :, 5:9, :] - pose[:, :, 1:5, :]
         return float(d.square().sum(-1).sqrt().mean())
+
+
+class FusedPipeline:
+    """AlignPose + LegInvKinSeq + HeadInverseKinematics of many trials in one device-resident pass (BASELINE config 5).
+
+    raw leg key points -> per-chain alignment statistics (series, radix-select mid-quantiles, affine rows) -> the
+    solver with the affine map applied on load (no aligned copy of the pose is written) -> angles + FK;
+    raw antenna key points + thorax -> head alignment rows -> head/antenna angles with the map applied on load.
+    Equivalent to running the three drop-in classes one after the other for every trial (tests/test_gpu_parity.py).
+    """
+
+    def __init__(self, kinematic_chain_class, initial_angles, legs: Sequence[str], body_template, body_size,
+                 n_trial: int, n_frame: int, device="cuda", include_claw: bool = False, with_head: bool = True):
+        torch = N.require_cuda()
+        self.torch = torch
+        self.legs = list(legs)
+        self.n_trial, self.n_frame = int(n_trial), int(n_frame)
+        self.include_claw = bool(include_claw)
+        self.with_head = with_head
+        self.session = BatchedLegIK(kinematic_chain_class, initial_angles, legs, n_trial, n_frame, device=device,
+                                    host_buffers=False)
+        dev = self.session.device
+        size = body_size
+        rows = []
+        for leg in self.legs:
+            length = size[leg] - (0.0 if include_claw else size[f"{leg}_Tarsus"])
+            rows.append(list(np.asarray(body_template[f"{leg}_Coxa"], dtype=float)) + [length])
+        self.leg_consts = torch.from_numpy(np.tile(np.asarray(rows, dtype=np.float32), (self.n_trial, 1))).to(dev)
+        if with_head:
+            from .head_inverse_kinematics import HeadInverseKinematics
+            dummy = {"R_head": np.zeros((1, 2, 3)), "L_head": np.ones((1, 2, 3)), "Neck": np.zeros((1, 1, 3))}
+            hk = HeadInverseKinematics(dummy, body_template, log_level="ERROR", device=str(dev))
+            self.rest = torch.tensor([[float(hk.rest_head_pitch[0]), float(hk.rest_antenna_pitch[0])]] * self.n_trial,
+                                     dtype=torch.float32, device=dev)
+            self.neck = torch.from_numpy(np.tile(np.asarray(body_template["Neck"], dtype=np.float32), (self.n_trial, 1))).to(dev)
+            self.head_consts = {
+                side: torch.from_numpy(np.tile(np.asarray(list(body_template[f"{side}_Antenna_base"])
+                                                          + [size["Antenna_mid_thorax"], size["Antenna"]], dtype=np.float32),
+                                               (self.n_trial, 1))).to(dev) for side in ("R", "L")}
+
+    def run(self, raw_legs, r_head=None, l_head=None, thorax=None):
+        """raw_legs (n_trial, n_leg, n_frame, 5, 3); r_head, l_head (n_trial, n_frame, 2, 3); thorax (n_trial, n_frame, k, 3):
+        float32 CUDA tensors.  Returns a dict of device tensors (asynchronous on the current stream)."""
+        sess = self.session
+        pose = raw_legs.reshape(sess.n_chain, sess.n_frame, 5, 3)
+        leg_aff = engine.leg_affine(pose, self.leg_consts, include_claw=self.include_claw)
+        angles, fk = sess.solve_device(pose, affine=leg_aff, want_stats=True)
+        out = {"angles": angles.view(self.n_trial, sess.n_leg, sess.n_frame, 7),
+               "fk": fk.view(self.n_trial, sess.n_leg, sess.n_frame, 9, 3), "leg_affine": leg_aff.view(self.n_trial, sess.n_leg, 8)}
+        if self.with_head and r_head is not None:
+            aff_r, _ = engine.head_affine(r_head, thorax, self.head_consts["R"])
+            aff_l, _ = engine.head_affine(l_head, thorax, self.head_consts["L"])
+            out["head_angles"] = engine.head_angles(r_head, l_head, self.neck, self.rest, affine_r=aff_r, affine_l=aff_l)
+            out["head_affine_r"], out["head_affine_l"] = aff_r, aff_l
+        return out

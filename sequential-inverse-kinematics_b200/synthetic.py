@@ -102,3 +102,47 @@ def to_chains(pose):
     if hasattr(pose, "permute"):
         return pose.permute(0, 2, 1, 3, 4).reshape(n_trial * n_leg, n_frame, 5, 3).contiguous()
     return np.ascontiguousarray(pose.transpose(0, 2, 1, 3, 4).reshape(n_trial * n_leg, n_frame, 5, 3))
+
+
+# ---------------------------------------------------------------------------------------------
+# Head / antenna key points and raw (un-aligned) poses for the fused-pipeline configuration (BASELINE config 5)
+# ---------------------------------------------------------------------------------------------
+HEAD_SEED_BASE = 30240611
+HEAD_NOISE_MM = 0.005
+RAW_SCALE = 1.0 / 1.05
+RAW_OFFSET = np.array([0.1, -0.2, 0.3])
+
+
+def _rot_xyz(roll, pitch, yaw, v):
+    """Rz(yaw) Ry(pitch) Rx(roll) v for per-frame angles (F,) and vectors (F, 3)."""
+    return _rot_apply(2, yaw, _rot_apply(1, pitch, _rot_apply(0, roll, v)))
+
+
+def make_head_trial(trial: int, n_frame: int = 1000, template=None, dtype=np.float64):
+    """Antenna bases/tips and thorax key points of one trial, already in template scale:
+    r_head, l_head (n_frame, 2, 3), thorax (n_frame, 3, 3), neck (3,).  The template antenna points are rotated about
+    the neck by head roll/pitch/yaw sinusoids (0.2 rad), the tips additionally pitched about their base (0.3 rad)."""
+    from .data import NMF_TEMPLATE
+    tmpl = NMF_TEMPLATE if template is None else template
+    rng = np.random.default_rng(HEAD_SEED_BASE + int(trial))
+    t = np.arange(n_frame, dtype=float)
+    freq = rng.uniform(0.5, 3.0, 5)
+    phase = rng.uniform(0.0, 2 * np.pi, 5)
+    ang = [amp * np.sin(2 * np.pi * f * t / 1000.0 + p) for amp, f, p in zip((0.2, 0.2, 0.2, 0.3, 0.3), freq, phase)]
+    neck = np.asarray(tmpl["Neck"], dtype=float)
+    out = {}
+    for side, tip_pitch in (("R", ang[3]), ("L", ang[4])):
+        base0 = np.asarray(tmpl[f"{side}_Antenna_base"], dtype=float) - neck
+        stalk0 = np.asarray(tmpl[f"{side}_Antenna_edge"], dtype=float) - np.asarray(tmpl[f"{side}_Antenna_base"], dtype=float)
+        base = _rot_xyz(ang[0], ang[1], ang[2], np.tile(base0, (n_frame, 1)))
+        stalk = _rot_xyz(ang[0], ang[1], ang[2], _rot_apply(1, tip_pitch, np.tile(stalk0, (n_frame, 1))))
+        pts = np.stack([base + neck, base + stalk + neck], 1)
+        out[side] = pts + rng.normal(0.0, HEAD_NOISE_MM, pts.shape)
+    thorax0 = np.stack([np.asarray(tmpl[k], dtype=float) for k in ("R_wing", "Thorax_mid", "L_wing")])
+    thorax = np.tile(thorax0, (n_frame, 1, 1)) + rng.normal(0.0, HEAD_NOISE_MM, (n_frame, 3, 3))
+    return out["R"].astype(dtype), out["L"].astype(dtype), thorax.astype(dtype), neck.astype(dtype)
+
+
+def to_raw(points):
+    """Template-scale key points -> "raw" recording coordinates (what the alignment has to undo): p / 1.05 + offset."""
+    return points * RAW_SCALE + RAW_OFFSET.astype(points.dtype)

@@ -245,6 +245,54 @@ def test_fk_kernel_matches_solver_and_oracle(api, synthetic_gold):
     assert np.abs(fk0 - fk).max() < 1e-6
 
 
+def test_fused_pipeline_equals_the_three_classes(api):
+    """Config-5 style pass (alignment statistics + align-on-load solver + head alignment + head angles, all on the
+    device) against AlignPose -> LegInvKinSeq / HeadInverseKinematics run one after the other through the dict API."""
+    S, t = api.synthetic, api.torch
+    from seqikpy_b200.batch import FusedPipeline
+    from seqikpy_b200.utils import calculate_body_size
+    n_trial, n_frame = 2, 300
+    legs = ["RF", "LF"]
+    tmpl, size = api.data.NMF_TEMPLATE, calculate_body_size(api.data.NMF_TEMPLATE, legs)
+    chain = api.Chain(api.data.BOUNDS, legs, size)
+    # leg key points from the grooming-like ranges of the default seeds, head key points from the synthetic generator
+    rng = np.random.default_rng(5)
+    raw_legs = np.zeros((n_trial, 2, n_frame, 5, 3))
+    heads = []
+    for tr in range(n_trial):
+        for li, leg in enumerate(legs):
+            th0 = np.array(api.data.INITIAL_ANGLES[leg]["stage_4"][1:8], dtype=float)
+            th0[6] = -0.6
+            theta = th0 + 0.2 * np.sin(2 * np.pi * rng.uniform(1, 3, 7) * np.arange(n_frame)[:, None] / 300.0 + rng.uniform(0, 6, 7))
+            lb = np.array([api.data.BOUNDS[f"{leg}_{d}"][0] for d in S.DOF_ORDER]) + 0.05
+            ub = np.array([api.data.BOUNDS[f"{leg}_{d}"][1] for d in S.DOF_ORDER]) - 0.05
+            pts = S.leg_key_points(np.clip(theta, lb, ub), np.array([size[f"{leg}_{s}"] for s in S.SEGMENTS]))
+            coxa = np.asarray(tmpl[f"{leg}_Coxa"]) + rng.normal(0, 0.003, (n_frame, 3))
+            raw_legs[tr, li, :, 0] = coxa
+            raw_legs[tr, li, :, 1:] = pts + coxa[:, None] + rng.normal(0, 0.01, (n_frame, 4, 3))
+        heads.append(S.make_head_trial(tr, n_frame))
+    raw_legs = S.to_raw(raw_legs)
+    r_head = S.to_raw(np.stack([h[0] for h in heads])); l_head = S.to_raw(np.stack([h[1] for h in heads]))
+    thorax = S.to_raw(np.stack([h[2] for h in heads]))
+    f32 = lambda a: t.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+    pipe = FusedPipeline(chain, api.data.INITIAL_ANGLES, legs, tmpl, size, n_trial, n_frame)
+    out = pipe.run(f32(raw_legs), f32(r_head), f32(l_head), f32(thorax))
+    t.cuda.synchronize()
+    for tr in range(n_trial):
+        raw = {"RF_leg": raw_legs[tr, 0].astype(np.float32).astype(np.float64), "LF_leg": raw_legs[tr, 1].astype(np.float32).astype(np.float64),
+               "R_head": r_head[tr].astype(np.float32).astype(np.float64), "L_head": l_head[tr].astype(np.float32).astype(np.float64),
+               "Thorax": thorax[tr].astype(np.float32).astype(np.float64)}
+        al = api.AlignPose(raw, legs_list=legs, include_claw=False, body_template=tmpl, log_level="ERROR").align_pose()
+        ang, fk = api.Leg(al, chain, api.data.INITIAL_ANGLES, log_level="ERROR").run_ik_and_fk()
+        head = api.Head(al, tmpl, log_level="ERROR").compute_head_angles()
+        for li, leg in enumerate(legs):
+            ours = out["angles"][tr, li].cpu().numpy()
+            assert np.abs(ours - angles_dict_to_array(ang, leg)).max() < 2e-4, (tr, leg)          # float32 pose rounding
+            assert np.abs(out["fk"][tr, li].cpu().numpy() - fk[f"{leg}_leg"]).max() < 1e-4
+        for i, k in enumerate(head):
+            assert np.abs(out["head_angles"][tr, i].cpu().numpy() - head[k]).max() < 2e-4, (tr, k)
+
+
 # ------------------------------------------------------------------------------------------ head
 def test_head_angles_vs_reference(api, grooming_head):
     pos = {"R_head": grooming_head["r_head"], "L_head": grooming_head["l_head"], "Neck": grooming_head["neck"]}
