@@ -61,52 +61,73 @@ extern "C" const char* seqik_last_error(void) { return g_err; }
 // coalesced loads and its 256x27 outputs back with coalesced stores.
 constexpr int FK_BLOCK = 256;
 
+// 128-bit copy between global and shared memory when both ends are 16-byte aligned and the count is a multiple of 4
+__device__ __forceinline__ void stage_in(float* __restrict__ dst, const float* __restrict__ src, int n) {
+    if ((n & 3) == 0 && (((uintptr_t)src) & 15) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(src); float4* d4 = reinterpret_cast<float4*>(dst);
+        for (int i = threadIdx.x; i < (n >> 2); i += blockDim.x) d4[i] = __ldg(s4 + i);
+    } else {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+}
+__device__ __forceinline__ void stage_out(float* __restrict__ dst, const float* __restrict__ src, int n) {
+    if ((n & 3) == 0 && (((uintptr_t)dst) & 15) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(src); float4* d4 = reinterpret_cast<float4*>(dst);
+        for (int i = threadIdx.x; i < (n >> 2); i += blockDim.x) __stcs(d4 + i, s4[i]);
+    } else {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+    }
+}
+
 __global__ void __launch_bounds__(FK_BLOCK) fk_kernel(const float* __restrict__ angles, const float* __restrict__ origin,
                                                       int64_t origin_fs, const float* __restrict__ params,
                                                       float* __restrict__ fk, int64_t n_chain, int64_t n_frame) {
-    __shared__ float s_in[FK_BLOCK * 7];
-    __shared__ float s_out[FK_BLOCK * 27];
+    __shared__ __align__(16) float s_in[FK_BLOCK * 7];
+    __shared__ __align__(16) float s_org[FK_BLOCK * 3];
+    __shared__ __align__(16) float s_out[FK_BLOCK * 27];
     const int64_t total = n_chain * n_frame;
     const int64_t base = (int64_t)blockIdx.x * FK_BLOCK;
     const int n_here = (int)min((int64_t)FK_BLOCK, total - base);
-    for (int i = threadIdx.x; i < n_here * 7; i += FK_BLOCK) s_in[i] = angles[base * 7 + i];
+    stage_in(s_in, angles + base * 7, n_here * 7);
+    if (origin_fs) stage_in(s_org, origin + base * 3, n_here * 3);
     __syncthreads();
     if (threadIdx.x < n_here) {
         const int64_t lf = base + threadIdx.x;
-        const int64_t c = lf / n_frame, t = lf - c * n_frame;
+        const int64_t c = lf / n_frame;
         const float* prm = params + c * SEQIK_CHAIN_PARAM_FLOATS;
-        const float* op = origin + (origin_fs ? (c * n_frame + t) * origin_fs : c * 3);
+        const float* op = origin_fs ? s_org + threadIdx.x * 3 : origin + c * 3;
         const Vec3<float> o = {op[0], op[1], op[2]};
         const float* q = s_in + threadIdx.x * 7;
         float* out = s_out + threadIdx.x * 27;
+        const float l0 = __ldg(prm), l1 = __ldg(prm + 1), l2 = __ldg(prm + 2), l3 = __ldg(prm + 3);
         Mat3<float> A = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
         Vec3<float> p = o;
-        float sa, ca, sb, cb;
+        float sa, ca, sb, cb, v;
 #pragma unroll
         for (int r = 0; r < 4; ++r) { out[3 * r] = o.x; out[3 * r + 1] = o.y; out[3 * r + 2] = o.z; }
         // stage 1: Rx(yaw) Ry(pitch), coxa
-        sincosf(q[0], &sa, &ca); sincosf(q[1], &sb, &cb);
+        Num<float>::sincosv_(q[0], &sa, &ca, &v); Num<float>::sincosv_(q[1], &sb, &cb, &v);
         A = rotate_frame(A, KIND_XY, sa, ca, sb, cb);
-        p = {p.x - prm[0] * A.c2.x, p.y - prm[0] * A.c2.y, p.z - prm[0] * A.c2.z};
+        p = {fmaf(-l0, A.c2.x, p.x), fmaf(-l0, A.c2.y, p.y), fmaf(-l0, A.c2.z, p.z)};
         out[12] = out[15] = p.x; out[13] = out[16] = p.y; out[14] = out[17] = p.z;
         // stage 2: Rz(roll) Ry(CTr_pitch), femur
-        sincosf(q[2], &sa, &ca); sincosf(q[3], &sb, &cb);
+        Num<float>::sincosv_(q[2], &sa, &ca, &v); Num<float>::sincosv_(q[3], &sb, &cb, &v);
         A = rotate_frame(A, KIND_ZY, sa, ca, sb, cb);
-        p = {p.x - prm[1] * A.c2.x, p.y - prm[1] * A.c2.y, p.z - prm[1] * A.c2.z};
+        p = {fmaf(-l1, A.c2.x, p.x), fmaf(-l1, A.c2.y, p.y), fmaf(-l1, A.c2.z, p.z)};
         out[18] = p.x; out[19] = p.y; out[20] = p.z;
         // stage 3: Rz(CTr_roll) Ry(FTi_pitch), tibia
-        sincosf(q[4], &sa, &ca); sincosf(q[5], &sb, &cb);
+        Num<float>::sincosv_(q[4], &sa, &ca, &v); Num<float>::sincosv_(q[5], &sb, &cb, &v);
         A = rotate_frame(A, KIND_ZY, sa, ca, sb, cb);
-        p = {p.x - prm[2] * A.c2.x, p.y - prm[2] * A.c2.y, p.z - prm[2] * A.c2.z};
+        p = {fmaf(-l2, A.c2.x, p.x), fmaf(-l2, A.c2.y, p.y), fmaf(-l2, A.c2.z, p.z)};
         out[21] = p.x; out[22] = p.y; out[23] = p.z;
         // stage 4: Ry(TiTa_pitch), tarsus
-        sincosf(q[6], &sb, &cb);
+        Num<float>::sincosv_(q[6], &sb, &cb, &v);
         A = rotate_frame(A, KIND_ZY, 0.f, 1.f, sb, cb);
-        p = {p.x - prm[3] * A.c2.x, p.y - prm[3] * A.c2.y, p.z - prm[3] * A.c2.z};
+        p = {fmaf(-l3, A.c2.x, p.x), fmaf(-l3, A.c2.y, p.y), fmaf(-l3, A.c2.z, p.z)};
         out[24] = p.x; out[25] = p.y; out[26] = p.z;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n_here * 27; i += FK_BLOCK) fk[base * 27 + i] = s_out[i];
+    stage_out(fk + base * 27, s_out, n_here * 27);
 }
 
 extern "C" int seqik_fk_f32(const float* angles, const float* origin, int64_t origin_frame_stride, const float* params,
@@ -132,7 +153,7 @@ __device__ __forceinline__ float signed_angle(float dotp, float det) {
 }
 
 // head-alignment row: (origin xyz, scale_base, template xyz, scale_tip)
-__device__ __forceinline__ void head_point(const float* __restrict__ p, const float* __restrict__ aff, bool tip,
+__device__ __forceinline__ void head_point(const float* p, const float* __restrict__ aff, bool tip,
                                            float& x, float& y, float& z) {
     x = p[0]; y = p[1]; z = p[2];
     if (aff) {
@@ -149,14 +170,19 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ r_h
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_trial * n_frame) return;
     const int64_t tr = i / n_frame, t = i - tr * n_frame;
-    const float* r = r_head + i * 6; const float* l = l_head + i * 6;
+    const float* r = r_head + i * 6; const float* l = l_head + i * 6;        // 24-byte records: three 64-bit loads each
+    const float2 r01 = __ldg(reinterpret_cast<const float2*>(r)), r23 = __ldg(reinterpret_cast<const float2*>(r) + 1),
+                 r45 = __ldg(reinterpret_cast<const float2*>(r) + 2);
+    const float2 l01 = __ldg(reinterpret_cast<const float2*>(l)), l23 = __ldg(reinterpret_cast<const float2*>(l) + 1),
+                 l45 = __ldg(reinterpret_cast<const float2*>(l) + 2);
+    const float rr[6] = {r01.x, r01.y, r23.x, r23.y, r45.x, r45.y}, ll[6] = {l01.x, l01.y, l23.x, l23.y, l45.x, l45.y};
     const float* nk = neck + (neck_stride ? i * 3 : tr * 3);
     const float* ar = affine_r ? affine_r + tr * 8 : nullptr;
     const float* al = affine_l ? affine_l + tr * 8 : nullptr;
     const float rest_head_pitch = rest[tr * 2], rest_ant_pitch = rest[tr * 2 + 1];
     float rbx, rby, rbz, rtx, rty, rtz, lbx, lby, lbz, ltx, lty, ltz;
-    head_point(r, ar, false, rbx, rby, rbz); head_point(r + 3, ar, true, rtx, rty, rtz);
-    head_point(l, al, false, lbx, lby, lbz); head_point(l + 3, al, true, ltx, lty, ltz);
+    head_point(rr, ar, false, rbx, rby, rbz); head_point(rr + 3, ar, true, rtx, rty, rtz);
+    head_point(ll, al, false, lbx, lby, lbz); head_point(ll + 3, al, true, ltx, lty, ltz);
     const float nx = nk[0], ny = nk[1], nz = nk[2];
     const float hx = lbx - rbx, hy = lby - rby, hz = lbz - rbz;                                   // horizontal
     const float mx = (rbx + lbx) * 0.5f - nx, mz = (rbz + lbz) * 0.5f - nz;                      // mid - neck
@@ -167,7 +193,7 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ r_h
     float* o = out + tr * 7 * n_frame + t;
     o[0] = roll; o[n_frame] = pitch; o[2 * n_frame] = yaw;
     // derotation by -roll about X:  y' = y c + z s,  z' = -y s + z c
-    float s, c; sincosf(roll, &s, &c);
+    float s, c, vers; Num<float>::sincosv_(roll, &s, &c, &vers);   // |roll| <= pi
     const float hdy = hy * c + hz * s, hdz = -hy * s + hz * c;                                    // derotated hor (x dropped)
 #pragma unroll
     for (int side = 0; side < 2; ++side) {   // 0 = L, 1 = R  (reference loops ["L", "R"])
@@ -243,6 +269,7 @@ __device__ __forceinline__ float key_value(uint32_t k) {
 }
 
 constexpr int SEL_BLOCK = 256;
+constexpr int SEL_CACHE = 8192;             // order keys of a series cached in shared memory up to this length
 
 // ranks of numpy.quantile(..., method="linear") at q = 0.45 and 0.55: floor(q (n-1)) and the next one
 __device__ __forceinline__ void quantile_pos(double q, int64_t n, int64_t& lo, float& frac) {
@@ -252,67 +279,68 @@ __device__ __forceinline__ void quantile_pos(double q, int64_t n, int64_t& lo, f
     frac = (float)(v - (double)lo);
 }
 
-__global__ void __launch_bounds__(SEL_BLOCK) mid_quantile_select_kernel(const float* __restrict__ series,
-                                                                        const int32_t* __restrict__ counts, int64_t n,
-                                                                        float* __restrict__ picked) {
-    __shared__ unsigned int hist[256];
-    __shared__ uint32_t s_prefix; __shared__ unsigned long long s_rank;
-    const int64_t sidx = blockIdx.x; const int which = blockIdx.y;   // 0: lo(.45) 1: lo+1 2: lo(.55) 3: lo+1
+// One block per series: the four order statistics (two neighbours of each of the 0.45 / 0.55 quantile positions)
+// are found together by a 4-pass MSB radix select -- per pass one sweep over the series (from shared memory when it
+// fits, else re-read from global/L2) feeding four 256-bin histograms -- and combined into the mid-quantile.
+__global__ void __launch_bounds__(SEL_BLOCK) mid_quantile_kernel(const float* __restrict__ series, const int32_t* __restrict__ counts,
+                                                                 int64_t n, float* __restrict__ out) {
+    __shared__ unsigned int hist[4][256];
+    __shared__ uint32_t s_prefix[4]; __shared__ unsigned long long s_rank[4];
+    __shared__ uint32_t cache[SEL_CACHE];
+    const int64_t sidx = blockIdx.x;
     const float* v = series + sidx * n;
     const int64_t m = counts ? (int64_t)counts[sidx] : n;             // values that take part (the m smallest)
-    if (m <= 0) { if (threadIdx.x == 0) picked[sidx * 4 + which] = __int_as_float(0x7fc00000); return; }
-    int64_t lo; float frac;
-    quantile_pos(which < 2 ? 0.45 : 0.55, m, lo, frac);
-    int64_t rank = lo + (which & 1); if (rank > m - 1) rank = m - 1;
-    uint32_t prefix = 0, mask = 0;
+    if (m <= 0) { if (threadIdx.x == 0) out[sidx] = __int_as_float(0x7fc00000); return; }
+    const bool cached = n <= SEL_CACHE;
+    if (cached) for (int64_t i = threadIdx.x; i < n; i += SEL_BLOCK) cache[i] = order_key(__ldg(v + i));
+    int64_t lo45, lo55; float f45, f55;
+    quantile_pos(0.45, m, lo45, f45); quantile_pos(0.55, m, lo55, f55);
+    if (threadIdx.x < 4) {
+        int64_t r = (threadIdx.x < 2 ? lo45 : lo55) + (threadIdx.x & 1);
+        s_rank[threadIdx.x] = (unsigned long long)(r > m - 1 ? m - 1 : r); s_prefix[threadIdx.x] = 0;
+    }
+    uint32_t mask = 0;
     for (int pass = 3; pass >= 0; --pass) {
         const int shift = 8 * pass;
-        hist[threadIdx.x] = 0;
+        for (int k = threadIdx.x; k < 4 * 256; k += SEL_BLOCK) (&hist[0][0])[k] = 0;
         __syncthreads();
+        const uint32_t p0 = s_prefix[0], p1 = s_prefix[1], p2 = s_prefix[2], p3 = s_prefix[3];
         for (int64_t i = threadIdx.x; i < n; i += SEL_BLOCK) {
-            const uint32_t k = order_key(v[i]);
-            if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 0xFF], 1u);
+            const uint32_t k = cached ? cache[i] : order_key(__ldg(v + i));
+            const uint32_t km = k & mask, d = (k >> shift) & 0xFF;
+            if (km == p0) atomicAdd(&hist[0][d], 1u);
+            if (km == p1) atomicAdd(&hist[1][d], 1u);
+            if (km == p2) atomicAdd(&hist[2][d], 1u);
+            if (km == p3) atomicAdd(&hist[3][d], 1u);
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            unsigned long long r = (unsigned long long)rank, acc = 0; int d = 0;
-            for (; d < 256; ++d) { if (acc + hist[d] > r) break; acc += hist[d]; }
+        if (threadIdx.x < 4) {
+            const int w = threadIdx.x;
+            unsigned long long r = s_rank[w], acc = 0; int d = 0;
+            for (; d < 256; ++d) { if (acc + hist[w][d] > r) break; acc += hist[w][d]; }
             if (d > 255) d = 255;
-            s_prefix = prefix | ((uint32_t)d << shift); s_rank = r - acc;
+            s_prefix[w] |= ((uint32_t)d << shift); s_rank[w] = r - acc;
         }
-        __syncthreads();
-        prefix = s_prefix; rank = (int64_t)s_rank; mask |= 0xFFu << shift;
+        mask |= 0xFFu << shift;
         __syncthreads();
     }
-    if (threadIdx.x == 0) picked[sidx * 4 + which] = key_value(prefix);
-}
-
-__global__ void mid_quantile_combine_kernel(const float* __restrict__ picked, const int32_t* __restrict__ counts,
-                                            float* __restrict__ out, int64_t n_series, int64_t n) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_series) return;
-    const int64_t m = counts ? (int64_t)counts[i] : n;
-    if (m <= 0) { out[i] = __int_as_float(0x7fc00000); return; }
-    int64_t lo; float f0, f1;
-    quantile_pos(0.45, m, lo, f0); quantile_pos(0.55, m, lo, f1);
-    const float* p = picked + i * 4;
-    const float q0 = p[0] + (p[1] - p[0]) * f0, q1 = p[2] + (p[3] - p[2]) * f1;
-    out[i] = 0.5f * (q0 + q1);
+    if (threadIdx.x == 0) {
+        const float a0 = key_value(s_prefix[0]), a1 = key_value(s_prefix[1]), b0 = key_value(s_prefix[2]), b1 = key_value(s_prefix[3]);
+        const float q0 = a0 + (a1 - a0) * f45, q1 = b0 + (b1 - b0) * f55;
+        out[sidx] = 0.5f * (q0 + q1);
+    }
 }
 
 extern "C" int seqik_mid_quantile_f32(const float* series, const int32_t* counts, float* scratch, float* out,
                                       int64_t n_series, int64_t n, void* stream) {
+    (void)scratch;   // kept in the signature (ABI): the single-kernel select needs no scratch
     if (n_series < 0 || n < 0) return fail(SEQIK_EINVAL, "seqik_mid_quantile_f32: negative size");
     if (n_series == 0) return SEQIK_OK;
     if (n == 0) return fail(SEQIK_EINVAL, "seqik_mid_quantile_f32: empty series");
-    if (!series || !scratch || !out) return fail(SEQIK_EINVAL, "seqik_mid_quantile_f32: NULL pointer (scratch needs 4*n_series floats)");
+    if (!series || !out) return fail(SEQIK_EINVAL, "seqik_mid_quantile_f32: NULL pointer");
     if (n_series > 2147483647LL) return fail(SEQIK_EINVAL, "seqik_mid_quantile_f32: too many series");
-    dim3 grid((unsigned)n_series, 4);
-    mid_quantile_select_kernel<<<grid, SEL_BLOCK, 0, (cudaStream_t)stream>>>(series, counts, n, scratch);
-    int rc = check_launch("seqik_mid_quantile_f32(select)");
-    if (rc) return rc;
-    mid_quantile_combine_kernel<<<(unsigned)((n_series + 127) / 128), 128, 0, (cudaStream_t)stream>>>(scratch, counts, out, n_series, n);
-    return check_launch("seqik_mid_quantile_f32(combine)");
+    mid_quantile_kernel<<<(unsigned)n_series, SEL_BLOCK, 0, (cudaStream_t)stream>>>(series, counts, n, out);
+    return check_launch("seqik_mid_quantile_f32");
 }
 
 __global__ void leg_affine_kernel(const float* __restrict__ stats, const float* __restrict__ consts, int include_claw,
