@@ -5,8 +5,8 @@ order, ``Neck`` entry and pickle name (reference seqikpy/alignment.py:229-555). 
 mid-quantiles of per-frame series (:83-87, 392-415, 425-434) -- run as a segmented radix select
 on the device, the scale/translate map (:471-485, 547-553) as an elementwise kernel; for the
 batched solver the same map is fused into the solver's pose load (``engine.leg_solve(affine=...)``).
-Raw-format converters (:103-226) are outside the hot path; ``from_file_path`` takes a
-``convert_func`` exactly like the reference.  No CPU path for the per-frame work.
+The raw-format converters (:103-226) are host-side reshapes kept under the reference's names;
+``from_file_path`` takes a ``convert_func`` exactly like the reference.  No CPU path for the per-frame work.
 """
 from pathlib import Path
 from typing import Callable, Dict, List, Literal, Optional, Union
@@ -18,7 +18,7 @@ import numpy as np
 from . import _native as N
 from . import engine
 from .data import NMF_TEMPLATE, PTS2ALIGN
-from .utils import calculate_body_size, save_file
+from .utils import calculate_body_size, dict_to_nparray_pose, save_file
 
 logging.basicConfig(format=" %(asctime)s - %(levelname)s- %(message)s", handlers=[logging.StreamHandler()])
 
@@ -28,6 +28,31 @@ def _leg_length_model(body_size: Dict[str, float], leg_name: str, claw_is_ee: bo
     if claw_is_ee:
         return body_size[leg_name]
     return body_size[leg_name] - body_size[f"{leg_name}_Tarsus"]
+
+
+# ---------------------------------------------------------------------------------------------
+# Raw-format converters (host-side gather/reshape; reference alignment.py:103-226).  They feed AlignPose through
+# ``from_file_path(convert_func=...)`` exactly like the reference's.
+# ---------------------------------------------------------------------------------------------
+def convert_from_anipose_to_dict(pose_3d: Dict[str, np.ndarray], pts2align: Dict[str, List[str]]) -> Dict[str, np.ndarray]:
+    """anipose table ({"<keypoint>_x|_y|_z": (N,)}) -> {"<segment>": (N, n_key_points, 3)} for the segments of ``pts2align``."""
+    out = {}
+    for segment, key_points in pts2align.items():
+        out[segment] = np.stack(
+            [np.stack([np.asarray(pose_3d[f"{kp}_{ax}"], dtype=float) for ax in "xyz"], axis=-1) for kp in key_points], axis=1)
+    return out
+
+
+def convert_from_df3d_to_dict(pose_3d: np.ndarray, pts2align: Dict[str, np.ndarray]) -> Dict[str, np.ndarray]:
+    """DeepFly3D array (N, n_key_points, 3) -> {"<segment>": (N, k, 3)} with ``pts2align`` mapping segments to indices."""
+    return {segment: np.array(pose_3d[:, idx, :], dtype=float) for segment, idx in pts2align.items()}
+
+
+def convert_from_df3dpp_to_dict(pose_3d: Dict[str, Dict[str, np.ndarray]],
+                                pts2align: Optional[List[str]] = None) -> Dict[str, np.ndarray]:
+    """DeepFly3DPostProcessing dictionary -> {"<leg>_leg": (N, 5, 3)} for the legs in ``pts2align`` (default: all)."""
+    segments = list(pose_3d.keys()) if pts2align is None else pts2align
+    return {segment: dict_to_nparray_pose(pose_3d[segment], claw_is_end_effector=True) for segment in segments}
 
 
 class AlignPose:

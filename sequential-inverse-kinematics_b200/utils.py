@@ -1,8 +1,8 @@
 """Helpers on the leg-IK path: template sizes and pickle I/O.
 
-Mirrors the three functions of the reference's ``seqikpy/utils.py`` that the hot path uses:
-``calculate_body_size`` (:89-123), ``save_file`` (:235-238), ``load_file`` (:241-245).  The
-format converters and video helpers of that module are outside the path.
+Mirrors the functions of the reference's ``seqikpy/utils.py`` that the hot path and its input converters use:
+``calculate_body_size`` (:89-123), ``save_file`` (:235-238), ``load_file`` (:241-245), ``dict_to_nparray_pose`` /
+``dict_to_nparray_angle`` (:293-329).  The video / stimulus helpers of that module are outside the path.
 """
 import pickle
 from typing import Dict, List
@@ -35,6 +35,21 @@ def calculate_body_size(
         size["Antenna"] = np.linalg.norm(body_template["R_Antenna_base"] - body_template["R_Antenna_edge"])
         size["Antenna_mid_thorax"] = np.linalg.norm(body_template["R_Antenna_base"] - body_template["Thorax_mid"])
     return size
+
+
+def dict_to_nparray_pose(pose_dict, claw_is_end_effector):
+    """df3dPP leg dictionary ({"Coxa": {"raw_pos_aligned": (N, 3)}, ...}) -> (N, 5 or 4, 3) array
+    (reference utils.py:293-310)."""
+    key_points = _JOINTS if claw_is_end_effector else _JOINTS[:-1]
+    return np.stack([np.asarray(pose_dict[kp]["raw_pos_aligned"], dtype=float) for kp in key_points], axis=1)
+
+
+def dict_to_nparray_angle(angle_dict, leg, claw_is_end_effector):
+    """df3dPP angle dictionary -> (N, 7 or 6) array in the order roll, yaw, pitch, ... (reference utils.py:313-329)."""
+    dofs = ["ThC_roll", "ThC_yaw", "ThC_pitch", "CTr_pitch", "CTr_roll", "FTi_pitch", "TiTa_pitch"]
+    if not claw_is_end_effector:
+        dofs = dofs[:-1]
+    return np.stack([np.asarray(angle_dict[f"{leg}_leg"][d], dtype=float) for d in dofs], axis=1)
 
 
 def save_file(out_fname, data):

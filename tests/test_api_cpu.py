@@ -141,3 +141,46 @@ def test_constants_equal_reference_when_available():
                 assert all(np.array_equal(ours[k][kk], ref[k][kk]) for kk in ref[k]), (name, k)
             else:
                 assert np.array_equal(np.asarray(ours[k]), np.asarray(ref[k])), (name, k)
+
+
+def test_raw_format_converters(locomotion, tmp_path):
+    """Converters feeding AlignPose (reference alignment.py:103-226): shapes, values, and agreement with the reference's
+    own functions where its checkout is present."""
+    import os
+    import pickle
+    import sys
+    from seqikpy_b200.alignment import (AlignPose, convert_from_anipose_to_dict, convert_from_df3d_to_dict,
+                                        convert_from_df3dpp_to_dict)
+    rng = np.random.default_rng(0)
+    n = 17
+    table = {f"{kp}_{ax}": rng.normal(size=n) for kps in D.PTS2ALIGN.values() for kp in kps for ax in "xyz"}
+    conv = convert_from_anipose_to_dict(table, D.PTS2ALIGN)
+    assert list(conv.keys()) == list(D.PTS2ALIGN.keys())
+    assert conv["RF_leg"].shape == (n, 5, 3) and conv["Thorax"].shape == (n, 3, 3) and conv["R_head"].shape == (n, 2, 3)
+    assert np.array_equal(conv["LF_leg"][:, 2, 1], table["femur_tibia_L_y"])
+    arr = rng.normal(size=(n, 38, 3))
+    idx = {"RF_leg": np.arange(0, 5), "LH_leg": np.arange(29, 34)}
+    d3 = convert_from_df3d_to_dict(arr, idx)
+    assert np.array_equal(d3["LH_leg"], arr[:, 29:34]) and d3["RF_leg"].base is None
+    pp = {f"{leg}_leg": {kp: {"raw_pos_aligned": locomotion["raw"][i][:, j]} for j, kp in enumerate(("Coxa", "Femur", "Tibia", "Tarsus", "Claw"))}
+          for i, leg in enumerate(locomotion["legs"])}
+    dpp = convert_from_df3dpp_to_dict(pp, ["RF_leg", "LM_leg"])
+    assert list(dpp.keys()) == ["RF_leg", "LM_leg"] and np.array_equal(dpp["LM_leg"], locomotion["raw"][4])
+    # from_file_path: newest match, optional conversion, FileNotFoundError (reference tests/test_alignment.py:22-27)
+    with open(tmp_path / "pose3d.h5", "wb") as f:
+        pickle.dump(table, f)
+    al = AlignPose.from_file_path(main_dir=tmp_path, file_name="pose3d.*", legs_list=["RF", "LF"],
+                                  convert_func=convert_from_anipose_to_dict, pts2align=D.PTS2ALIGN, log_level="ERROR")
+    assert al.pose_data_dict["RF_leg"].shape == (n, 5, 3) and al.include_claw is False
+    with pytest.raises(FileNotFoundError):
+        AlignPose.from_file_path(main_dir=tmp_path, file_name="nothing.*", legs_list=["RF"])
+    if os.path.isdir("/root/reference/seqikpy"):
+        sys.path.insert(0, "/root/reference")
+        try:
+            from seqikpy import alignment as RA
+        finally:
+            sys.path.remove("/root/reference")
+        ref = RA.convert_from_anipose_to_dict(table, D.PTS2ALIGN)
+        assert all(np.array_equal(ref[k], conv[k]) for k in ref)
+        assert all(np.array_equal(v, dpp[k]) for k, v in RA.convert_from_df3dpp_to_dict(pp, ["RF_leg", "LM_leg"]).items())
+        assert all(np.array_equal(v, d3[k]) for k, v in RA.convert_from_df3d_to_dict(arr, idx).items())

@@ -134,6 +134,33 @@ def test_stagewise_calls_equal_one_shot(grooming_run, api):
         assert np.abs(a[k] - angles[k][:n]).max() < 2e-5, k
 
 
+def test_entire_pipeline_from_raw_like_the_reference_example(api, grooming_align, grooming_leg, grooming_head, tmp_path):
+    """examples/example_entire_pipeline.py:60-101 on the bundled trial: raw key points -> AlignPose -> LegInvKinSeq (+ head)
+    -> pickles, against the reference's shipped aligned pose and joint angles."""
+    raw = {"RF_leg": grooming_align["raw_full_RF"], "LF_leg": grooming_align["raw_full_LF"]}
+    aligned = api.AlignPose(raw, legs_list=["RF", "LF"], include_claw=False, body_template=api.data.NMF_TEMPLATE,
+                            log_level="ERROR").align_pose(export_path=tmp_path)
+    assert list(aligned.keys()) == ["RF_leg", "LF_leg", "Neck"] and aligned["Neck"].shape == (1, 1, 3)
+    for li, leg in enumerate(("RF", "LF")):
+        assert np.allclose(aligned[f"{leg}_leg"], grooming_leg["pose"][li], rtol=1e-5, atol=2e-6)
+    aligned["R_head"], aligned["L_head"] = grooming_head["r_head"], grooming_head["l_head"]
+    head = api.Head(aligned, api.data.NMF_TEMPLATE, log_level="ERROR").compute_head_angles(export_path=tmp_path)
+    ik = api.Leg(aligned, api.Chain(api.data.BOUNDS, ["RF", "LF"], body_size=None), api.data.INITIAL_ANGLES, log_level="ERROR")
+    angles, fk = ik.run_ik_and_fk(export_path=tmp_path, hide_progress_bar=True)
+    body = {**head, **angles}
+    assert len(body) == 21 and list(body.keys())[:3] == ["Angle_head_roll", "Angle_head_pitch", "Angle_head_yaw"]
+    from seqikpy_b200.utils import load_file, save_file
+    save_file(tmp_path / "body_joint_angles.pkl", body)
+    for name in ("pose3d_aligned.pkl", "head_joint_angles.pkl", "leg_joint_angles.pkl", "forward_kinematics.pkl", "body_joint_angles.pkl"):
+        assert (tmp_path / name).exists(), name
+    assert list(load_file(tmp_path / "leg_joint_angles.pkl").keys()) == list(grooming_leg["angle_keys"])
+    assert load_file(tmp_path / "forward_kinematics.pkl")["LF_leg"].shape == (6000, 9, 3)
+    rf = angles_dict_to_array(angles, "RF")
+    assert len(bad_frames(rf, grooming_leg["ref_angles"][0])) == 0
+    lf = angles_dict_to_array(angles, "LF")
+    assert set(bad_frames(lf, grooming_leg["ref_angles"][1])) <= singular_windows(grooming_leg["ref_angles"][1])
+
+
 # ------------------------------------------------------------------------------------------ locomotion (config 1)
 def test_locomotion_pipeline(api, locomotion):
     legs = list(locomotion["legs"])
