@@ -41,6 +41,7 @@ extern "C" {
 #define SEQIK_FLAG_SCHED_SHIFT 8             /* bits 8..11: kernel schedule, 0 = automatic,
                                                 1 = one lane per chain, 2 = stage pipeline (four lanes per chain) */
 #define SEQIK_FLAG_SCHED_MASK (0xFu << SEQIK_FLAG_SCHED_SHIFT)
+#define SEQIK_FLAG_GATE_SHIFT 18             /* bits 18..19: open/close phases of schedule 2 every 1st/2nd/4th iteration (1/2/3), 0 = automatic */
 #define SEQIK_FLAG_CPW_SHIFT 12              /* bits 12..17: chains per warp of schedule 2 (1..8), 0 = automatic */
 
 int seqik_abi_version(void);
