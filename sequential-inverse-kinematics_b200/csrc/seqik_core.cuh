@@ -84,6 +84,17 @@ template <> struct Num<float> {
     // sin, cos and versine (1 - cos) of x, |x| <= 2 pi: quadrant reduction + minimax polynomials on
     // [-pi/4, pi/4]; the versine keeps full relative accuracy for tiny x (no 1 - cos cancellation).
     static SK_HD void sincosv_(float x, float* s, float* c, float* v) {
+        if (fabsf(x) < 0.78f) {          // quadrant 0 (the usual case for a STEP): same polynomials, no reduction
+            const float z = x * x;
+            float sp = fmaf(z, -1.9515295891e-4f, 8.3321608736e-3f);
+            sp = fmaf(sp, z, -1.6666654611e-1f);
+            float cp = fmaf(z, 2.443315711809948e-5f, -1.388731625493765e-3f);
+            cp = fmaf(cp, z, 4.166664568298827e-2f);
+            *s = fmaf(sp * z, x, x);
+            *v = fmaf(-cp * z, z, 0.5f * z);
+            *c = 1.0f - *v;
+            return;
+        }
         const float kf = rintf(x * 0.636619772367581343f);                 // x * 2/pi
         float r = fmaf(kf, -1.57079601287841796875f, x);                   // Cody-Waite, pi/2 = hi + mid + lo
         r = fmaf(kf, -3.1391647326017846e-07f, r);
@@ -397,10 +408,12 @@ struct StageSolve {
         R nx0 = x0 + st0, nx1 = x1 + st1;
         R ndl0 = dl0 + st0, ndu0 = du0 - st0, ndl1 = dl1 + st1, ndu1 = du1 - st1;
         R e0 = st0, e1 = st1;   // applied step
-        if (ndl0 <= R(0)) { const R gap = inner_gap(nx0 - ndl0); e0 = gap - dl0; ndl0 = gap; ndu0 = span0 - gap; nx0 = x0 + e0; }
-        if (ndu0 <= R(0)) { const R gap = inner_gap(nx0 + ndu0); e0 = du0 - gap; ndu0 = gap; ndl0 = span0 - gap; nx0 = x0 + e0; }
-        if (ndl1 <= R(0)) { const R gap = inner_gap(nx1 - ndl1); e1 = gap - dl1; ndl1 = gap; ndu1 = span1 - gap; nx1 = x1 + e1; }
-        if (ndu1 <= R(0)) { const R gap = inner_gap(nx1 + ndu1); e1 = du1 - gap; ndu1 = gap; ndl1 = span1 - gap; nx1 = x1 + e1; }
+        if (N::min_(N::min_(ndl0, ndu0), N::min_(ndl1, ndu1)) <= R(0)) {   // landed on a bound: pull one fp64 ulp inside
+            if (ndl0 <= R(0)) { const R gap = inner_gap(nx0 - ndl0); e0 = gap - dl0; ndl0 = gap; ndu0 = span0 - gap; nx0 = x0 + e0; }
+            if (ndu0 <= R(0)) { const R gap = inner_gap(nx0 + ndu0); e0 = du0 - gap; ndu0 = gap; ndl0 = span0 - gap; nx0 = x0 + e0; }
+            if (ndl1 <= R(0)) { const R gap = inner_gap(nx1 - ndl1); e1 = gap - dl1; ndl1 = gap; ndu1 = span1 - gap; nx1 = x1 + e1; }
+            if (ndu1 <= R(0)) { const R gap = inner_gap(nx1 + ndu1); e1 = du1 - gap; ndu1 = gap; ndl1 = span1 - gap; nx1 = x1 + e1; }
+        }
         R sda, cda, va, sdb, cdb, vb;
         N::sincosv_(e0, &sda, &cda, &va); N::sincosv_(e1, &sdb, &cdb, &vb);
         const R dsa = N::fma_(ca, sda, -(sa * va)), dca = -N::fma_(sa, sda, ca * va);   // sin/cos(a + e0) - sin/cos(a)
