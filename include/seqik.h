@@ -37,7 +37,10 @@ extern "C" {
 /* flags of seqik_leg_solve_f32 */
 #define SEQIK_FLAG_GN_STAGE(s) (1u << (s))   /* s = 0..3: stage s+1 takes the Gauss-Newton step when it fits the
                                                 trust region (what scipy's TRF does on the longer chains) */
-#define SEQIK_FLAG_DEFAULT 0xFu              /* all four stages (validated against the reference's shipped angles) */
+#define SEQIK_FLAG_ESCAPE (1u << 4)          /* singularity escape: a solve that ends on the sin(pitch) = 0 singularity of its
+                                                roll/pitch pair may continue from the closed-form solution */
+#define SEQIK_FLAG_DEFAULT 0x1Fu             /* Gauss-Newton mode in all four stages + escape (validated against the reference's
+                                                shipped angles and forward kinematics) */
 #define SEQIK_FLAG_SCHED_SHIFT 8             /* bits 8..11: kernel schedule, 0 = automatic,
                                                 1 = one lane per chain, 2 = stage pipeline (four lanes per chain) */
 #define SEQIK_FLAG_SCHED_MASK (0xFu << SEQIK_FLAG_SCHED_SHIFT)

@@ -39,6 +39,11 @@ if __name__ == "__main__":
             for gate in (1, 2, 3):
                 run(n_trial, 500, 2, 0, gate=gate)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "cpw":
+        for n_trial in (100, 200, 400, 1000, 1250, 2500):
+            for cpw in (1, 2, 3, 4, 5, 6, 7, 8):
+                run(n_trial, 500, 2, cpw)
+        sys.exit(0)
     for n_trial in (100, 400, 1000, 1250, 2500, 5000, 10000):
         for sched, cpws in ((2, (1, 2, 4, 8)), (1, (0,))):
             for cpw in cpws:

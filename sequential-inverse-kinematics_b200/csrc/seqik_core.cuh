@@ -165,6 +165,7 @@ struct StageSolve {
     R sa, ca, sb, cb;                   // sin/cos of the iterate
     Vec3<R> f; R cost, g0, g1;         // residual w(x) - q, 0.5 |f|^2, gradient J^T f
     R Delta, alpha; int nfev, status;
+    bool escaped;                       // escape() already used in this solve
 
     typedef Num<R> N;
     SK_HD int kind_() const { return KIND >= 0 ? KIND : kind_rt; }
@@ -232,7 +233,7 @@ struct StageSolve {
         const R q0 = (v0 > R(1e-30)) ? x0 * x0 * N::rcp_(v0) : R(0), q1 = (v1 > R(1e-30)) ? x1 * x1 * N::rcp_(v1) : R(0);
         Delta = N::sqrt_(null_sq + q0 + q1);
         if (Delta == R(0)) Delta = R(1);
-        alpha = R(0); nfev = 1; status = ST_RUNNING;
+        alpha = R(0); nfev = 1; status = ST_RUNNING; escaped = false;
     }
 
     // Next frame of the same (chain, stage): the warm start IS the previous solve's final iterate, so its sin/cos are
@@ -249,7 +250,42 @@ struct StageSolve {
         const R q0 = (v0 > R(1e-30)) ? x0 * x0 * N::rcp_(v0) : R(0), q1 = (v1 > R(1e-30)) ? x1 * x1 * N::rcp_(v1) : R(0);
         Delta = N::sqrt_(null_sq + q0 + q1);
         if (Delta == R(0)) Delta = R(1);
-        alpha = R(0); nfev = 1; status = ST_RUNNING;
+        alpha = R(0); nfev = 1; status = ST_RUNNING; escaped = false;
+    }
+
+    // Singularity escape (optional, SEQIK_FLAG_ESCAPE).  For the Rz(a) Ry(b) stages the end point does not depend on
+    // `a` when sin b = 0: a solve that ends there (typically with `a` parked on a bound) has a vanishing gradient
+    // although a far better point may exist.  The reference leaves such a corner only through the rounding noise of
+    // its finite-difference Jacobian (SURVEY.md finding 4), i.e. frames later and irreproducibly.  Here the two
+    // closed-form mirror solutions of "point a segment at the target" (SURVEY.md 3.4), clamped to the box, are
+    // evaluated; if one is clearly better the solve continues from it.  At most once per solve.
+    SK_HD bool escape() {
+        if (escaped || kind_() != KIND_ZY || has_a_() == R(0) || sb * sb > R(1e-8)) return false;
+        escaped = true;
+        const Vec3<R> w = point();
+        const Vec3<R> q = {w.x - f.x, w.y - f.y, w.z - f.z};
+        const R rho2 = N::fma_(q.y, q.y, q.x * q.x), qn = N::sqrt_(rho2 + q.z * q.z);
+        if (rho2 < R(1e-10) * L * L) return false;            // target on the axis: `a` really is irrelevant
+        const R pi = R(3.14159265358979323846);
+        const R phi = atan2(q.y, q.x), bs = acos(N::max_(R(-1), N::min_(R(1), -q.z * N::rcp_(qn))));
+        const R lb0 = x0 - dl0, ub0 = x0 + du0, lb1 = x1 - dl1, ub1 = x1 + du1;
+        R best = cost, ba = x0, bb = x1;
+        for (int k = 0; k < 2; ++k) {
+            R aa = k ? phi : phi + pi, b2 = k ? -bs : bs;
+            if (aa > pi) aa -= R(2) * pi;
+            aa = N::max_(lb0, N::min_(ub0, aa)); b2 = N::max_(lb1, N::min_(ub1, b2));
+            R s_a, c_a, s_b, c_b, v_;
+            N::sincosv_(aa, &s_a, &c_a, &v_); N::sincosv_(b2, &s_b, &c_b, &v_);
+            const R dx = -L * s_b * c_a - q.x, dy = -L * s_b * s_a - q.y, dz = -L * c_b - q.z;
+            const R cst = R(0.5) * N::fma_(dz, dz, N::fma_(dy, dy, dx * dx));
+            if (cst < best) { best = cst; ba = aa; bb = b2; }
+        }
+        nfev += 2;
+        if (!(best < R(0.98) * cost - R(5e-7))) return false;  // clearly better: > 2 % and > (1e-3 mm)^2 / 2
+        const R nsq = null_sq; const int mx = max_nfev; const bool gm = gn_mode; const int nf = nfev;
+        init(kind_rt, L, has_a_rt, q, ba, bb, lb0, ub0, lb1, ub1, nsq, 1, gm);
+        max_nfev = mx; nfev = nf; escaped = true;
+        return true;
     }
 
     SK_HD bool done() const { return status != ST_RUNNING; }
@@ -583,6 +619,7 @@ struct ChainRunner {
     // one evaluation for this lane (no-op when the chain is finished)
     SK_HD void step() {
         if (finished()) return;
+        if (S.done() && (gn_mask & 16) && s >= lo && S.escape()) { /* solve continues from the escape point */ }
         if (S.done()) advance();
         if (!finished() && !S.done()) S.trip();
     }
@@ -618,7 +655,10 @@ SK_HD void solve_frame(const ChainParams<R>& P, const R* kp, R* ang, R* fk, Fram
         const R inf = Num<R>::inf();
         if (s == 3) S.init(kind, P.seg[s], R(0), q, R(0), ang[ib], -inf, inf, P.lb[ib], P.ub[ib], P.null_sq[s], n_full[s], (gn_mask >> s) & 1);
         else S.init(kind, P.seg[s], R(1), q, ang[ia], ang[ib], P.lb[ia], P.ub[ia], P.lb[ib], P.ub[ib], P.null_sq[s], n_full[s], (gn_mask >> s) & 1);
-        if (stage_mask & (1 << s)) { while (!S.done()) S.trip(); }
+        if (stage_mask & (1 << s)) {
+            while (!S.done()) S.trip();
+            if ((gn_mask & 16) && S.escape()) while (!S.done()) S.trip();
+        }
         if (s != 3) ang[ia] = S.x0;
         ang[ib] = S.x1;
         if (fs) { fs->nfev[s] = S.nfev; fs->status[s] = S.status; }

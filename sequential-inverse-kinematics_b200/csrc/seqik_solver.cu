@@ -146,6 +146,7 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, 
     const float null_sq = frozen ? 0.f : __ldg(prm + 25 + s);
     const int n_full = (s == 0) ? 4 : (s == 1) ? 6 : (s == 2) ? 8 : 9;
     const bool gn = (a.gn_mask >> s) & 1;
+    const bool esc = (a.gn_mask >> 4) & 1;
     const float has_a = (s == 3) ? 0.f : 1.f;
     const float* seed = a.warm ? a.warm + cc * a.warm_cs : prm + 18;
     float xa = (s == 3) ? 0.f : seed[ia], xb = seed[ib];                           // warm start, frame to frame
@@ -184,6 +185,8 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, 
     for (int it = 0; __any_sync(full, live && t < n_frame); ++it) {
         const bool gate = (it & gate_mask) == 0;      // open/close phases only every (gate_mask + 1)-th iteration
         const int started_next = __shfl_sync(full, started, (lane + 1) & 31);   // consumer's progress (lane + 1)
+        // ---- optional singularity escape: a solve that ended on sin b = 0 may continue from a closed-form candidate
+        if (gate && esc && live && solving && !frozen && S.done()) S.escape();
         // ---- close the converged solve: outputs + hand-off to the next stage (needs a free ring slot)
         if (gate && live && t < n_frame && solving && S.done() && (s == hi || t < started_next + PIPE_DEPTH)) {
             if (!frozen) {
@@ -286,19 +289,19 @@ extern "C" int seqik_leg_solve_f32(const float* pose, int64_t pose_chain_stride,
     a.fk = fk; a.fk_cs = fk_chain_stride; a.fk_fs = fk_frame_stride;
     a.warm = warm; a.warm_cs = warm_chain_stride;
     a.status = status; a.nfev = nfev; a.n_chain = n_chain; a.n_frame = n_frame;
-    a.stage_mask = (int)stage_mask; a.gn_mask = (int)(flags & 0xF);
+    a.stage_mask = (int)stage_mask; a.gn_mask = (int)(flags & 0x1F);   // bits 0-3 Gauss-Newton mode per stage, bit 4 escape
     if (sched == 1) {
         const int64_t grid = (n_chain + 31) / 32;
         leg_solve_lane_kernel<<<(unsigned)grid, 32, 0, (cudaStream_t)stream>>>(a);
     } else {
-        // chains per warp (measured): 8 -- every lane of the warp used -- as soon as that still leaves
-        // about one warp per SM sub-partition (4 x 148); fewer chains per warp only for small batches, where the
-        // kernel is pure chain latency and a warp that hosts fewer chains pays for fewer lanes' open/close phases
+        // chains per warp (measured): spread the chains over one warp per SM sub-partition (4 x 148) while
+        // that is possible, then fill the warps up to 8 chains (all 32 lanes).  Small batches run at pure chain latency
+        // whatever the packing; large ones are fastest fully packed.
         int dev = 0, n_sm = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-        int cpw = 1;
-        while (cpw < PIPE_CHAINS && n_chain / (2 * cpw) >= 4LL * n_sm) cpw *= 2;
+        int cpw = (int)((n_chain + 4LL * n_sm - 1) / (4LL * n_sm));
+        cpw = cpw < 1 ? 1 : (cpw > PIPE_CHAINS ? PIPE_CHAINS : cpw);
         const uint32_t forced = (flags >> SEQIK_FLAG_CPW_SHIFT) & 0x3F;     // tuning / tests
         if (forced) cpw = (int)forced;
         if (cpw < 1 || cpw > PIPE_CHAINS) return seqik_fail(SEQIK_EINVAL, "seqik_leg_solve_f32: chains per warp must be 1..8");

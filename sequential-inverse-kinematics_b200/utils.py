@@ -62,3 +62,22 @@ def load_file(output_fname):
     """Load a pickle written by :func:`save_file` (or by the reference)."""
     with open(output_fname, "rb") as f:
         return pickle.load(f)
+
+
+def interpolate_signal(signal, original_ts, new_ts):
+    """Resamples a signal sampled every ``original_ts`` onto a ``new_ts`` grid with a shape-preserving cubic (pchip)
+    -- the hand-off of joint angles to a simulation time step (reference utils.py:332-349).  Host-side, after the path."""
+    from scipy.interpolate import pchip_interpolate
+    signal = np.array(signal, dtype=float)
+    total_time = signal.shape[0] * original_ts
+    original_x = np.arange(0, total_time, original_ts)
+    new_x = np.arange(0, total_time, new_ts)
+    if not np.all(np.isfinite(signal)):          # the reference zeroes non-finite samples (and the last one) and retries
+        signal[~np.isfinite(signal)] = 0
+        signal[-1] = 0
+    return np.array(pchip_interpolate(original_x, signal, new_x))
+
+
+def interpolate_joint_angles(joint_angles_dict, **kwargs):
+    """``interpolate_signal`` over every entry of a joint-angle dictionary (reference utils.py:352-359)."""
+    return {dof: interpolate_signal(signal=values, **kwargs) for dof, values in joint_angles_dict.items()}

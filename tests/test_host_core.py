@@ -9,7 +9,7 @@ import model_trf2 as M
 from helpers import ANGLE_TOL, FK_TOL, bad_frames, fk_residual, residual_of_angles, singular_windows
 from oracle import seqik_oracle as O
 
-GN = 0b1111   # SEQIK_FLAG_DEFAULT: Gauss-Newton mode in all four stages
+GN = 0b11111  # SEQIK_FLAG_DEFAULT: Gauss-Newton mode in all four stages + singularity escape
 
 
 def leg_consts(size, bounds, init, leg):
