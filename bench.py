@@ -199,6 +199,8 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: a CUDA device is required (there is no CPU fallback for the product path)")
     _native.load_library()
+    from seqikpy_b200.batch import bind_to_gpu_numa
+    numa_cpus = bind_to_gpu_numa(physical_gpu_index(local_rank)) if not args.no_numa_bind else None
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -307,7 +309,7 @@ def run_ours(args):
                                   "nfev_per_leg_frame_by_stage": nfev_per_lf}},
             "cpu_baseline": cpu,
             "mean_fk_error_mm": float(fk_err.item()) / world, "chains_at_max_nfev": int(maxfev.item()),
-            "clocks": clocks, "data_gen_s": t_gen, "schedule": args.schedule,
+            "clocks": clocks, "data_gen_s": t_gen, "schedule": args.schedule, "numa_cpus_rank0": None if numa_cpus is None else len(numa_cpus),
         }
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
@@ -330,6 +332,7 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=200, help="frames per leg of the cpu_baseline sample")
     ap.add_argument("--ref-frames", type=int, default=100, help="frames per chain and step of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin each rank to its GPU's local CPUs")
     ap.add_argument("--cpu-baseline-only", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--cpu-procs", type=int, default=6, help=argparse.SUPPRESS)
     args = ap.parse_args()

@@ -21,6 +21,27 @@ from . import engine
 RESYNC_FRAMES = 64      # SEQIK_RESYNC of csrc/seqik_core.cuh
 
 
+def bind_to_gpu_numa(device_index: int) -> Optional[Sequence[int]]:
+    """Pin the calling process to the CPUs NVML reports as local to GPU ``device_index`` (before pinned host buffers are
+    allocated, so that they land on the GPU's NUMA node).  With one process per GPU this keeps the host side of the
+    PCIe copies off the inter-socket link.  Returns the CPU list used, or None when NVML / affinity is unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (m >> b) & 1}
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return sorted(allowed)
+    except Exception:
+        return None
+
+
 def shard_range(n_trial: int, rank: int, world_size: int):
     """Contiguous, balanced [lo, hi) trial range of ``rank`` (first ``n_trial % world_size`` ranks get one more)."""
     if world_size < 1 or not 0 <= rank < world_size:
