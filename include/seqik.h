@@ -83,7 +83,9 @@ const char* seqik_last_error(void);
  *           pass the last solved frame of the same chains (angles + (t0-1)*ang_frame_stride) to continue a
  *           recording in frame chunks -- bit-identical to one call over all frames, which is what lets the host
  *           pipeline copy chunk k+1 in and chunk k-1 out while chunk k is solved
- *   status  NULL, or [n_chain] out: 0 if some solve hit max_nfev, else 1
+ *   status  NULL, or [n_chain] out: 1 normal; 0 if some solve stopped at max_nfev; -1 if some solve met a non-finite
+ *           residual (NaN/inf key point; scipy raises "Residuals are not finite in the initial point" there): that
+ *           solve is skipped, its DOFs keep the previous frame's values
  *   nfev    NULL, or [n_chain][4] out: function evaluations summed over frames, per stage
  *   stage_mask  bit s set = solve stage s+1; the set bits must be contiguous
  *           (stages=[a..b] of run_ik_and_fk, leg_inverse_kinematics.py:350-353)

@@ -141,7 +141,8 @@ constexpr int SEQIK_RESYNC = 64;          // frames between full re-initialisati
 enum : int { KIND_XY = 0, KIND_ZY = 1 };   // Rx(a)Ry(b) (stage 1)  |  Rz(a)Ry(b) (stages 2-4)
 
 enum : int {
-    ST_MAXFEV = 0, ST_GTOL = 1, ST_FTOL = 2, ST_XTOL = 3, ST_BOTH = 4, ST_RUNNING = -1
+    ST_MAXFEV = 0, ST_GTOL = 1, ST_FTOL = 2, ST_XTOL = 3, ST_BOTH = 4, ST_RUNNING = -1,
+    ST_NONFINITE = -2      // residual not finite at the start of a solve (scipy raises there): the solve is skipped
 };
 
 template <typename R> struct Vec3 { R x, y, z; };
@@ -233,7 +234,8 @@ struct StageSolve {
         const R q0 = (v0 > R(1e-30)) ? x0 * x0 * N::rcp_(v0) : R(0), q1 = (v1 > R(1e-30)) ? x1 * x1 * N::rcp_(v1) : R(0);
         Delta = N::sqrt_(null_sq + q0 + q1);
         if (Delta == R(0)) Delta = R(1);
-        alpha = R(0); nfev = 1; status = ST_RUNNING; escaped = false;
+        alpha = R(0); nfev = 1; escaped = false;
+        status = (cost < N::inf()) ? ST_RUNNING : ST_NONFINITE;      // false for NaN and inf
     }
 
     // Next frame of the same (chain, stage): the warm start IS the previous solve's final iterate, so its sin/cos are
@@ -250,7 +252,8 @@ struct StageSolve {
         const R q0 = (v0 > R(1e-30)) ? x0 * x0 * N::rcp_(v0) : R(0), q1 = (v1 > R(1e-30)) ? x1 * x1 * N::rcp_(v1) : R(0);
         Delta = N::sqrt_(null_sq + q0 + q1);
         if (Delta == R(0)) Delta = R(1);
-        alpha = R(0); nfev = 1; status = ST_RUNNING; escaped = false;
+        alpha = R(0); nfev = 1; escaped = false;
+        status = (cost < N::inf()) ? ST_RUNNING : ST_NONFINITE;      // false for NaN and inf
     }
 
     // Singularity escape (optional, SEQIK_FLAG_ESCAPE).  For the Rz(a) Ry(b) stages the end point does not depend on
@@ -598,7 +601,8 @@ struct ChainRunner {
             else if (s == 1) { ang2 = S.x0; ang3 = S.x1; nf1 += (uint32_t)S.nfev; }
             else if (s == 2) { ang4 = S.x0; ang5 = S.x1; nf2 += (uint32_t)S.nfev; }
             else { ang6 = S.x1; nf3 += (uint32_t)S.nfev; }
-            if (S.status == ST_MAXFEV) worst_status = ST_MAXFEV;
+            if (S.status == ST_MAXFEV && worst_status > ST_MAXFEV) worst_status = ST_MAXFEV;
+            if (S.status == ST_NONFINITE) worst_status = ST_NONFINITE;
         }
         // next pivot = pivot + A w(x) = target + A f   (q = A^T rel, f = w - q)
         const Vec3<R> Af = mul(A, S.f);

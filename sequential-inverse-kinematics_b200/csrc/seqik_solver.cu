@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(32) leg_solve_lane_kernel(LegArgs a) {
     ChainRunner<float, DevIO> run;
     run.start(io, a.n_frame, seed, a.stage_mask, a.gn_mask);
     while (!run.finished()) run.step();
-    if (a.status) a.status[c] = run.worst_status;
+    if (a.status) a.status[c] = run.worst_status == ST_NONFINITE ? -1 : run.worst_status;
     if (a.nfev) { uint32_t* nf = a.nfev + c * 4; nf[0] = run.nf0; nf[1] = run.nf1; nf[2] = run.nf2; nf[3] = run.nf3; }
 }
 
@@ -191,7 +191,8 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, 
         if (gate && live && t < n_frame && solving && S.done() && (s == hi || t < started_next + PIPE_DEPTH)) {
             if (!frozen) {
                 xa = S.x0; xb = S.x1; nf += (uint32_t)S.nfev;
-                if (S.status == ST_MAXFEV) worst = ST_MAXFEV;
+                if (S.status == ST_MAXFEV && worst > ST_MAXFEV) worst = ST_MAXFEV;
+                if (S.status == ST_NONFINITE) worst = ST_NONFINITE;
                 if (s != 3) *pa_a = xa;
                 *pa_b = xb;
             }
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, 
     const int w2 = min(w1, __shfl_xor_sync(full, w1, 2));
     if (owner) {
         if (a.nfev) a.nfev[c * 4 + s] = nf;
-        if (a.status && s == 0) a.status[c] = w2;
+        if (a.status && s == 0) a.status[c] = w2 == ST_NONFINITE ? -1 : w2;
     }
 }
 

@@ -97,6 +97,8 @@ class LegInvKinSeq(LegInvKinBase):
         status, nfev = d_status.cpu().numpy(), d_nfev.cpu().numpy()
         for i, leg in enumerate(legs):
             self.solver_stats[leg] = {"nfev": nfev[i].astype(np.int64), "status": int(status[i])}
+            if status[i] < 0:       # what scipy.optimize.least_squares raises inside the reference's frame loop
+                raise ValueError(f"Residuals are not finite in the initial point (leg {leg}: NaN/inf key points).")
             if status[i] == 0:
                 self.logger.warning("Leg %s: at least one solve stopped at the evaluation limit", leg)
         return angles, fk

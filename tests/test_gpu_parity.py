@@ -400,6 +400,16 @@ def test_edge_cases(api):
         ik.calculate_ik_stage(one[:, 1], one[:, 0], api.data.INITIAL_ANGLES["RF"]["stage_1"], "XX", stage=1)
     with pytest.raises(ValueError):
         ik.calculate_ik_stage(one[:, 1], one[:, 0], api.data.INITIAL_ANGLES["RF"]["stage_1"], "RF", stage=5)
+    # NaN key points: the reference (scipy) raises; the batched API flags the chain (-1) and keeps going
+    nan_pose = rng.normal(scale=0.5, size=(6, 5, 3))
+    nan_pose[3, 2] = np.nan
+    with pytest.raises(ValueError, match="not finite"):
+        api.Leg({"RF_leg": nan_pose}, chain, log_level="ERROR").run_ik_and_fk()
+    t = api.torch
+    params = t.from_numpy(np.stack([chain.pack_chain_params(l, api.data.INITIAL_ANGLES[l]) for l in ("RF", "LF")]).astype(np.float32)).cuda()
+    both = t.from_numpy(np.stack([nan_pose, rng.normal(scale=0.5, size=(6, 5, 3))]).astype(np.float32)).cuda()
+    ang, _, status, _ = api.engine.leg_solve(both, params)
+    assert status.tolist() == [-1, 1] and bool(t.isfinite(ang).all())
     # unreachable / degenerate targets still terminate with finite angles inside the bounds
     wild = np.zeros((4, 5, 3))
     wild[1, 1:] = 100.0
