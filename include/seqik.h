@@ -122,7 +122,7 @@ int seqik_head_angles_f32(const float* r_head, const float* l_head, const float*
  * (seqikpy/alignment.py:83-87, 392-415).
  *   series [n_series][n] (dense rows); counts NULL, or [n_series] int32: only the counts[i] SMALLEST values of
  *   row i take part (rows padded with +inf, see seqik_head_series_f32); out [n_series];
- *   scratch: caller-provided [n_series][4] floats */
+ *   scratch: unused (may be NULL); kept so that the signature is stable */
 int seqik_mid_quantile_f32(const float* series, const int32_t* counts, float* scratch, float* out,
                            int64_t n_series, int64_t n, void* stream);
 

@@ -162,10 +162,9 @@ def mid_quantile(series, counts=None):
     n_series, n = int(series.shape[0]), int(series.shape[1])
     if counts is not None:
         counts = _check(counts, "counts", (n_series,), torch.int32)
-    scratch = torch.empty((n_series, 4), dtype=torch.float32, device=series.device)
     out = torch.empty((n_series,), dtype=torch.float32, device=series.device)
     with torch.cuda.device(series.device):
-        rc = lib.seqik_mid_quantile_f32(N.ptr(series), N.ptr(counts), N.ptr(scratch), N.ptr(out), n_series, n,
+        rc = lib.seqik_mid_quantile_f32(N.ptr(series), N.ptr(counts), 0, N.ptr(out), n_series, n,
                                         N.stream_ptr(torch, series.device))
     N.check(rc, "seqik_mid_quantile_f32")
     return out

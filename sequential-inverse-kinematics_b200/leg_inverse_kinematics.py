@@ -154,9 +154,7 @@ class LegInvKinSeq(LegInvKinBase):
         pose[0, :, stage] = end_effector_pos
         seeds = [{f"stage_{stage}": np.asarray(initial_angles, dtype=float)}]
         angles_in = None if stage == 1 else self._frozen_angles(segment_name, stage, n_frames)[None]
-        if stage > 1:
-            # key points of the frozen stages are not needed: their joints follow from the frozen angles
-            pass
+        # (key points of the frozen stages are not needed: their joints follow from the frozen angles)
         angles, fk = self._solve([segment_name], pose, seeds, [stage], angles_in)
         self._store(segment_name, [stage], angles[0])
         return fk[0][:, _FK_ROWS[stage], :]
