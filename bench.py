@@ -192,6 +192,7 @@ def run_ours(args):
         try:
             res = json.loads(out.stdout.strip().splitlines()[-1])
             cpu = {"value": res["leg_frames"] / res["seconds"], "unit": UNIT, "cores": procs, "kind": "port",
+                   "one_core_value": res["one_core_leg_frames"] / res["one_core_seconds"],
                    "sample": f"trial 0 x 6 legs x first {n_fr} frames of this workload, CPU oracle (restated ikpy glue + scipy TRF), "
                              f"{procs} processes over legs like the reference's Pool(6) example"}
         except Exception as exc:                      # keep the GPU measurement even if the CPU leg fails
@@ -338,7 +339,10 @@ def main():
     args = ap.parse_args()
     if args.cpu_baseline_only:
         done, times = oracle_throughput(1, args.cpu_frames, args.cpu_procs)
-        print(json.dumps({"leg_frames": done, "seconds": times[0]}))
+        t0 = time.perf_counter()
+        one = _oracle_job((0, 0, min(args.cpu_frames, 100)))          # one chain, one process: the per-core rate
+        t_one = time.perf_counter() - t0
+        print(json.dumps({"leg_frames": done, "seconds": times[0], "one_core_leg_frames": one, "one_core_seconds": t_one}))
         return
     if args.impl == "reference":
         run_reference(args)
