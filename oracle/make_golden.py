@@ -19,6 +19,8 @@ Fixtures
   locomotion.npz     bundled data/df3d_pose_result__210902_PR_Fly1 (BASELINE config 1): raw frames 300:400 of the
                      6 legs, reference AlignPose output (== shipped pose3d_aligned.pkl), oracle angles + FK
   synthetic.npz      trials 0-1 x 6 legs x first 250 frames of the synthetic workload: pose, oracle angles + FK
+  synthetic_long.npz trial 5, legs RM and LH, 2000 frames: oracle angles (float32) -- a long warm-start chain that spans
+                     many of the kernel's 64-frame resync periods
 """
 import argparse
 import os
@@ -73,7 +75,7 @@ def oracle_legs(pose_dict, size, bounds, init, procs=8):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reuse-cache", default=None, help="directory with oracle_full_{RF,LF}.pkl from a previous run")
-    ap.add_argument("--only", default="", help="comma-separated subset: leg,head,align,loco,synth")
+    ap.add_argument("--only", default="", help="comma-separated subset: leg,head,align,loco,synth,long")
     args = ap.parse_args()
     only = set(filter(None, args.only.split(",")))
     GOLD.mkdir(parents=True, exist_ok=True)
@@ -190,6 +192,17 @@ def main():
         print(f"synthetic oracle: {time.time() - t0:.1f} s")
         np.savez_compressed(GOLD / "synthetic.npz", trials=np.array(trials), legs=np.array(S.LEGS),
                             pose=np.stack(poses), oracle_angles=np.stack(angs), oracle_fk=np.stack(fks))
+    # ---------------------------------------------------------------- long warm-start chain (drift check)
+    if not only or "long" in only:
+        n_frame, trial, legs = 2000, 5, ("RM", "LH")
+        size, bounds, init = S.chain_constants()
+        pose = S.make_trial(trial, n_frame)
+        t0 = time.time()
+        d = {f"{leg}_leg": np.ascontiguousarray(pose[:, S.LEGS.index(leg)]) for leg in legs}
+        orc = oracle_legs(d, size, bounds, init)
+        print(f"long-chain oracle: {time.time() - t0:.1f} s")
+        np.savez_compressed(GOLD / "synthetic_long.npz", trial=np.array(trial), legs=np.array(legs), n_frame=np.array(n_frame),
+                            oracle_angles=np.stack([orc[f"{leg}_leg"][0] for leg in legs]).astype(np.float32))
     for f in sorted(GOLD.glob("*.npz")):
         print(f.name, f.stat().st_size // 1024, "KiB")
 

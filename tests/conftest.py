@@ -45,3 +45,8 @@ def locomotion():
 @pytest.fixture(scope="session")
 def synthetic_gold():
     return _npz("synthetic.npz")
+
+
+@pytest.fixture(scope="session")
+def synthetic_long():
+    return _npz("synthetic_long.npz")

@@ -230,6 +230,26 @@ def test_synthetic_vs_oracle_and_shard_invariance(api, synthetic_gold):
     assert (a1 - ang).abs().max() < 2e-4 and (f1 - fk).abs().max() < 1e-4 and int(s1.min()) == 1
 
 
+def test_long_warm_start_chain_vs_oracle(api, synthetic_long):
+    """2000 serially warm-started frames (31 of the kernel's 64-frame resync periods) against the oracle: the carried
+    solver state does not drift."""
+    S, t = api.synthetic, api.torch
+    size, bounds, init = S.chain_constants()
+    chain = api.Chain(bounds, list(S.LEGS), size)
+    n_frame = int(synthetic_long["n_frame"])
+    pose = S.make_trial(int(synthetic_long["trial"]), n_frame)
+    legs = [str(l) for l in synthetic_long["legs"]]
+    d_pose = t.from_numpy(np.ascontiguousarray(np.stack([pose[:, S.LEGS.index(l)] for l in legs]), dtype=np.float32)).cuda()
+    params = t.from_numpy(np.stack([chain.pack_chain_params(l, init[l]) for l in legs]).astype(np.float32)).cuda()
+    ang, fk, status, _ = api.engine.leg_solve(d_pose, params)
+    assert np.abs(ang.cpu().numpy() - synthetic_long["oracle_angles"]).max() < ANGLE_TOL and status.tolist() == [1, 1]
+    from oracle import seqik_oracle as O
+    for i, l in enumerate(legs):          # FK the kernel carries vs float64 FK of the angles it returns
+        seg = [size[f"{l}_{s}"] for s in O.SEGMENTS]
+        fk64 = O.fk_closed_form(ang[i].cpu().numpy().astype(np.float64), seg, pose[:, S.LEGS.index(l), 0])
+        assert np.abs(fk64 - fk[i].cpu().numpy()).max() < 5e-6
+
+
 def test_frame_chunks_and_host_pipeline_equal_one_launch(api):
     """Frames solved in chunks (warm start from the previous chunk's last frame) and the pipelined host call
     (2-D async copies on side streams) are bit-identical to one launch over all frames."""

@@ -67,6 +67,18 @@ def test_locomotion_and_synthetic_vs_oracle(locomotion, synthetic_gold):
             assert np.abs(ang - synthetic_gold["oracle_angles"][tr, li]).max() < ANGLE_TOL, (tr, leg)
 
 
+def test_long_warm_start_chain_vs_oracle(synthetic_long):
+    """2000 serially warm-started frames of two legs against the oracle."""
+    from seqikpy_b200 import synthetic as S
+    size, bounds, init = S.chain_constants()
+    pose = S.make_trial(int(synthetic_long["trial"]), int(synthetic_long["n_frame"]))
+    for i, leg in enumerate(synthetic_long["legs"]):
+        seg, lb, ub, nsq, seed = leg_consts(size, bounds, init, str(leg))
+        ang, _, _, status = H.solve_chain(pose[:, S.LEGS.index(str(leg))], seg, lb, ub, nsq, seed, gn_mask=GN)
+        assert np.abs(ang - synthetic_long["oracle_angles"][i]).max() < ANGLE_TOL
+        assert (status > 0).all()
+
+
 def test_runner_state_machine_equals_serial_composition(grooming_leg):
     """ChainRunner::step() (what a lane executes) gives bit-identical results to the serial frame solve."""
     from seqikpy_b200 import data as D
