@@ -39,8 +39,12 @@ extern "C" {
                                                 trust region (what scipy's TRF does on the longer chains) */
 #define SEQIK_FLAG_ESCAPE (1u << 4)          /* singularity escape: a solve that ends on the sin(pitch) = 0 singularity of its
                                                 roll/pitch pair may continue from the closed-form solution */
-#define SEQIK_FLAG_DEFAULT 0x1Fu             /* Gauss-Newton mode in all four stages + escape (validated against the reference's
-                                                shipped angles and forward kinematics) */
+#define SEQIK_FLAG_SKIP_CONFIRM (1u << 5)    /* stop a solve WITHOUT the evaluation that would only confirm convergence: when the
+                                                model was accurate on the previous step (actual/predicted within 25 % of 1) and now
+                                                predicts a reduction below ftol * cost for a plain Gauss-Newton step.  The skipped
+                                                step is < ~3e-6 rad; saves one of the ~5 evaluations of a warm-started solve */
+#define SEQIK_FLAG_DEFAULT 0x3Fu             /* Gauss-Newton mode in all four stages + escape + skip-confirm (validated against
+                                                the reference's shipped angles and forward kinematics) */
 #define SEQIK_FLAG_SCHED_SHIFT 8             /* bits 8..11: kernel schedule, 0 = automatic,
                                                 1 = one lane per chain, 2 = stage pipeline (four lanes per chain) */
 #define SEQIK_FLAG_SCHED_MASK (0xFu << SEQIK_FLAG_SCHED_SHIFT)

@@ -15,7 +15,8 @@ LIB_PATH = _HERE / "csrc" / "libseqik_sm100.so"
 ABI_VERSION = 3
 CHAIN_PARAM_FLOATS = 32
 FLAG_ESCAPE = 1 << 4
-FLAG_DEFAULT = 0x1F                     # SEQIK_FLAG_DEFAULT: Gauss-Newton mode in all four stages + singularity escape
+FLAG_SKIP_CONFIRM = 1 << 5
+FLAG_DEFAULT = 0x3F                     # SEQIK_FLAG_DEFAULT: Gauss-Newton mode in all four stages + escape + skip-confirm
 FLAG_SCHED_SHIFT = 8
 SCHED_AUTO, SCHED_LANE_PER_CHAIN, SCHED_STAGE_PIPELINE = 0, 1, 2
 

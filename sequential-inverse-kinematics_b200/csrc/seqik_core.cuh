@@ -167,6 +167,8 @@ struct StageSolve {
     Vec3<R> f; R cost, g0, g1;         // residual w(x) - q, 0.5 |f|^2, gradient J^T f
     R Delta, alpha; int nfev, status;
     bool escaped;                       // escape() already used in this solve
+    R last_ratio;                       // actual/predicted reduction of the previous evaluation of this solve (0: none yet)
+    bool skip_confirm;                  // SEQIK_FLAG_SKIP_CONFIRM, see trip()
 
     typedef Num<R> N;
     SK_HD int kind_() const { return KIND >= 0 ? KIND : kind_rt; }
@@ -218,8 +220,8 @@ struct StageSolve {
 
     // least_squares prologue: x0 made strictly feasible (rstep 1e-10), f, g, Delta0
     SK_HD void init(int kind_in, R L_, R has_a_in, const Vec3<R>& q, R a, R b,
-                    R lb0, R ub0, R lb1, R ub1, R null_sq_, int n_full, bool gn_mode_ = false) {
-        gn_mode = gn_mode_;
+                    R lb0, R ub0, R lb1, R ub1, R null_sq_, int n_full, int mode = 0) {
+        gn_mode = (mode & 1) != 0; skip_confirm = (mode & 2) != 0;     // bit 0 Gauss-Newton mode, bit 1 skip-confirm
         kind_rt = kind_in; L = L_; has_a_rt = has_a_in; null_sq = null_sq_; max_nfev = 100 * n_full;
         place(a, b, lb0, ub0, lb1, ub1);
         R va, vb;
@@ -234,7 +236,7 @@ struct StageSolve {
         const R q0 = (v0 > R(1e-30)) ? x0 * x0 * N::rcp_(v0) : R(0), q1 = (v1 > R(1e-30)) ? x1 * x1 * N::rcp_(v1) : R(0);
         Delta = N::sqrt_(null_sq + q0 + q1);
         if (Delta == R(0)) Delta = R(1);
-        alpha = R(0); nfev = 1; escaped = false;
+        alpha = R(0); nfev = 1; escaped = false; last_ratio = R(0);
         status = (cost < N::inf()) ? ST_RUNNING : ST_NONFINITE;      // false for NaN and inf
     }
 
@@ -252,7 +254,7 @@ struct StageSolve {
         const R q0 = (v0 > R(1e-30)) ? x0 * x0 * N::rcp_(v0) : R(0), q1 = (v1 > R(1e-30)) ? x1 * x1 * N::rcp_(v1) : R(0);
         Delta = N::sqrt_(null_sq + q0 + q1);
         if (Delta == R(0)) Delta = R(1);
-        alpha = R(0); nfev = 1; escaped = false;
+        alpha = R(0); nfev = 1; escaped = false; last_ratio = R(0);
         status = (cost < N::inf()) ? ST_RUNNING : ST_NONFINITE;      // false for NaN and inf
     }
 
@@ -285,8 +287,9 @@ struct StageSolve {
         }
         nfev += 2;
         if (!(best < R(0.98) * cost - R(5e-7))) return false;  // clearly better: > 2 % and > (1e-3 mm)^2 / 2
-        const R nsq = null_sq; const int mx = max_nfev; const bool gm = gn_mode; const int nf = nfev;
-        init(kind_rt, L, has_a_rt, q, ba, bb, lb0, ub0, lb1, ub1, nsq, 1, gm);
+        const R nsq = null_sq; const int mx = max_nfev; const int nf = nfev;
+        const int md = (gn_mode ? 1 : 0) | (skip_confirm ? 2 : 0);
+        init(kind_rt, L, has_a_rt, q, ba, bb, lb0, ub0, lb1, ub1, nsq, 1, md);
         max_nfev = mx; nfev = nf; escaped = true;
         return true;
     }
@@ -442,6 +445,13 @@ struct StageSolve {
         const R ph0 = -t0 * sc, ph1 = -t1 * sc;
         R st0, st1, sh0, sh1, pred;
         select_step(h, h.d0 * ph0, h.d1 * ph1, ph0, ph1, st0, st1, sh0, sh1, pred);
+        // Optional: skip the evaluation that would only CONFIRM convergence.  When the model has just been accurate
+        // (previous actual/predicted within 25 % of 1) and now predicts a reduction below ftol * cost for a plain
+        // Gauss-Newton step, the reference evaluates that step, accepts it and stops on ftol; the step is below
+        // sqrt(2 ftol cost) / L ~ 3e-6 rad.  Stopping here saves one of the ~5 evaluations of a warm-started solve.
+        if (skip_confirm && gn_taken && pred < ftol * cost && pred >= R(0) && N::abs_(last_ratio - R(1)) < R(0.25)) {
+            status = ST_FTOL; return;
+        }
 
         // ---- trial point: strictly feasible, evaluated through the step's sin/cos/versine
         R nx0 = x0 + st0, nx1 = x1 + st1;
@@ -470,6 +480,7 @@ struct StageSolve {
         // update_tr_radius
         R ratio;
         if (pred > R(0)) ratio = (actual != R(0)) ? actual * N::rcp_(pred) : R(0); else if (pred == R(0) && actual == R(0)) ratio = R(1); else ratio = R(0);
+        last_ratio = ratio;
         R Delta_new = Delta;
         if (ratio < R(0.25)) Delta_new = R(0.25) * N::sqrt_(step_h_sq);
         else if (ratio > R(0.75) && step_h_sq > R(0.9025) * Delta * Delta) Delta_new = R(2) * Delta;
@@ -564,7 +575,7 @@ struct ChainRunner {
         const Vec3<R> q = mulT(A, rel);
         const R inf = Num<R>::inf();
         const int n_full = (s == 0) ? 4 : (s == 1) ? 6 : (s == 2) ? 8 : 9;
-        const bool gn = (gn_mask >> s) & 1;
+        const int gn = ((gn_mask >> s) & 1) | (((gn_mask >> 5) & 1) << 1);
         const bool frozen = s < lo;
         if (frozen) {   // kinematic_chain.py: earlier-stage DOFs are `fixed` links at angles[...][t]
             if (s == 0) { ang0 = io.angle_in(t, 0); ang1 = io.angle_in(t, 1); }
@@ -657,8 +668,8 @@ SK_HD void solve_frame(const ChainParams<R>& P, const R* kp, R* ang, R* fk, Fram
         const int ia = (s == 3) ? -1 : 2 * s, ib = (s == 3) ? 6 : 2 * s + 1;
         StageSolve<R> S;
         const R inf = Num<R>::inf();
-        if (s == 3) S.init(kind, P.seg[s], R(0), q, R(0), ang[ib], -inf, inf, P.lb[ib], P.ub[ib], P.null_sq[s], n_full[s], (gn_mask >> s) & 1);
-        else S.init(kind, P.seg[s], R(1), q, ang[ia], ang[ib], P.lb[ia], P.ub[ia], P.lb[ib], P.ub[ib], P.null_sq[s], n_full[s], (gn_mask >> s) & 1);
+        if (s == 3) S.init(kind, P.seg[s], R(0), q, R(0), ang[ib], -inf, inf, P.lb[ib], P.ub[ib], P.null_sq[s], n_full[s], ((gn_mask >> s) & 1) | (((gn_mask >> 5) & 1) << 1));
+        else S.init(kind, P.seg[s], R(1), q, ang[ia], ang[ib], P.lb[ia], P.ub[ia], P.lb[ib], P.ub[ib], P.null_sq[s], n_full[s], ((gn_mask >> s) & 1) | (((gn_mask >> 5) & 1) << 1));
         if (stage_mask & (1 << s)) {
             while (!S.done()) S.trip();
             if ((gn_mask & 16) && S.escape()) while (!S.done()) S.trip();

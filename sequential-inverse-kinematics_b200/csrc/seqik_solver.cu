@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, 
     const float lb1 = frozen ? -inf : __ldg(prm + 4 + ib), ub1 = frozen ? inf : __ldg(prm + 11 + ib);
     const float null_sq = frozen ? 0.f : __ldg(prm + 25 + s);
     const int n_full = (s == 0) ? 4 : (s == 1) ? 6 : (s == 2) ? 8 : 9;
-    const bool gn = (a.gn_mask >> s) & 1;
+    const int gn = ((a.gn_mask >> s) & 1) | (((a.gn_mask >> 5) & 1) << 1);   // StageSolve mode: Gauss-Newton, skip-confirm
     const bool esc = (a.gn_mask >> 4) & 1;
     const float has_a = (s == 3) ? 0.f : 1.f;
     const float* seed = a.warm ? a.warm + cc * a.warm_cs : prm + 18;
@@ -290,7 +290,7 @@ extern "C" int seqik_leg_solve_f32(const float* pose, int64_t pose_chain_stride,
     a.fk = fk; a.fk_cs = fk_chain_stride; a.fk_fs = fk_frame_stride;
     a.warm = warm; a.warm_cs = warm_chain_stride;
     a.status = status; a.nfev = nfev; a.n_chain = n_chain; a.n_frame = n_frame;
-    a.stage_mask = (int)stage_mask; a.gn_mask = (int)(flags & 0x1F);   // bits 0-3 Gauss-Newton mode per stage, bit 4 escape
+    a.stage_mask = (int)stage_mask; a.gn_mask = (int)(flags & 0x3F);   // bits 0-3 Gauss-Newton mode per stage, bit 4 escape, bit 5 skip-confirm
     if (sched == 1) {
         const int64_t grid = (n_chain + 31) / 32;
         leg_solve_lane_kernel<<<(unsigned)grid, 32, 0, (cudaStream_t)stream>>>(a);

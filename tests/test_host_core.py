@@ -9,7 +9,7 @@ import model_trf2 as M
 from helpers import ANGLE_TOL, FK_TOL, bad_frames, fk_residual, residual_of_angles, singular_windows
 from oracle import seqik_oracle as O
 
-GN = 0b11111  # SEQIK_FLAG_DEFAULT: Gauss-Newton mode in all four stages + singularity escape
+GN = 0b111111  # SEQIK_FLAG_DEFAULT: Gauss-Newton mode in all four stages + singularity escape + skip-confirm
 
 
 def leg_consts(size, bounds, init, leg):
@@ -30,7 +30,7 @@ def test_grooming_rf_all_frames(grooming_leg, dtype):
     r_ours = fk_residual(fk, grooming_leg["pose"][0])
     r_ref = residual_of_angles(grooming_leg["ref_angles"][0], seg, grooming_leg["pose"][0])
     assert ((r_ours - r_ref) > FK_TOL + 2e-6).sum() == 0
-    assert (status > 0).all() and nfev.mean() < 8
+    assert (status > 0).all() and nfev.mean() < 6
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])

@@ -40,7 +40,7 @@ def _worker(rank, world, port, n_trial, n_frame, out_dir):
             from oracle.seqik_oracle import DOF_ORDER
             lb = [bounds[f"{leg}_{d}"][0] for d in DOF_ORDER]
             ub = [bounds[f"{leg}_{d}"][1] for d in DOF_ORDER]
-            res[i, li] = H.solve_chain(pose[:, li], seg, lb, ub, M.null_sq_from_seeds(init[leg]), M.seeds7(init[leg]), gn_mask=31)[0]
+            res[i, li] = H.solve_chain(pose[:, li], seg, lb, ub, M.null_sq_from_seeds(init[leg]), M.seeds7(init[leg]), gn_mask=63)[0]
     # the only communication: scalar statistics (timing max, leg-frame count), then a gather of results on rank 0
     ms = torch.tensor([10.0 + rank], dtype=torch.float64)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -75,5 +75,5 @@ def test_two_rank_sharding_equals_single_process(tmp_path):
             seg = [size[f"{leg}_{s}"] for s in ("Coxa", "Femur", "Tibia", "Tarsus")]
             lb = [bounds[f"{leg}_{d}"][0] for d in DOF_ORDER]
             ub = [bounds[f"{leg}_{d}"][1] for d in DOF_ORDER]
-            ref = H.solve_chain(pose[:, li], seg, lb, ub, M.null_sq_from_seeds(init[leg]), M.seeds7(init[leg]), gn_mask=31)[0]
+            ref = H.solve_chain(pose[:, li], seg, lb, ub, M.null_sq_from_seeds(init[leg]), M.seeds7(init[leg]), gn_mask=63)[0]
             assert np.array_equal(out["angles"][tr, li], ref)
