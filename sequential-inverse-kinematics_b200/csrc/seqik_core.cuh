@@ -168,6 +168,7 @@ struct StageSolve {
     R Delta, alpha; int nfev, status;
     bool escaped;                       // escape() already used in this solve
     R last_ratio;                       // actual/predicted reduction of the previous evaluation of this solve (0: none yet)
+    R st0, st1, step_h_sq, pred;        // the step plan() chose for the next evaluation, its hat-space length^2, its predicted reduction
     bool skip_confirm;                  // SEQIK_FLAG_SKIP_CONFIRM, see trip()
 
     typedef Num<R> N;
@@ -238,6 +239,7 @@ struct StageSolve {
         if (Delta == R(0)) Delta = R(1);
         alpha = R(0); nfev = 1; escaped = false; last_ratio = R(0);
         status = (cost < N::inf()) ? ST_RUNNING : ST_NONFINITE;      // false for NaN and inf
+        if (status == ST_RUNNING) plan();
     }
 
     // Next frame of the same (chain, stage): the warm start IS the previous solve's final iterate, so its sin/cos are
@@ -256,6 +258,7 @@ struct StageSolve {
         if (Delta == R(0)) Delta = R(1);
         alpha = R(0); nfev = 1; escaped = false; last_ratio = R(0);
         status = (cost < N::inf()) ? ST_RUNNING : ST_NONFINITE;      // false for NaN and inf
+        if (status == ST_RUNNING) plan();
     }
 
     // Singularity escape (optional, SEQIK_FLAG_ESCAPE).  For the Rz(a) Ry(b) stages the end point does not depend on
@@ -386,10 +389,13 @@ struct StageSolve {
         pred = -(take_p ? p_value : take_r ? r_value : ag_value);
     }
 
-    // One function evaluation: one pass of scipy's inner `while actual_reduction <= 0` loop, preceded by
-    // the head of the outer iteration (recomputed from the iterate: it is unchanged after a rejected step).
-    SK_HD void trip() {
-        const R gtol = R(1e-8), ftol = R(1e-8), xtol = R(1e-8);
+    // plan(): the head of scipy's outer iteration for the CURRENT iterate -- scaling, termination tests that need no
+    // evaluation (gtol, max_nfev, skip-confirm), trust-region step -- leaving the step to evaluate in (st0, st1,
+    // step_h_sq, pred).  It runs at the end of init()/restart() and at the end of every trip(), so a solve costs
+    // exactly one loop trip per function evaluation and its termination is known in the trip that produced it.
+    // (After a rejected step the iterate is unchanged and only Delta/alpha differ: plan() recomputes the same head.)
+    SK_HD void plan() {
+        const R gtol = R(1e-8), ftol = R(1e-8);
         Hat h;
         R v0, v1, dv0, dv1; cl_scaling(v0, v1, dv0, dv1);
         const R g_norm = N::max_(N::abs_(g0 * v0), N::abs_(g1 * v1));
@@ -443,16 +449,20 @@ struct StageSolve {
         }
         const R sc = gn_taken ? R(1) : Delta * N::rsqrt_(N::fma_(t1, t1, t0 * t0));
         const R ph0 = -t0 * sc, ph1 = -t1 * sc;
-        R st0, st1, sh0, sh1, pred;
+        R sh0, sh1;
         select_step(h, h.d0 * ph0, h.d1 * ph1, ph0, ph1, st0, st1, sh0, sh1, pred);
-        // Optional: skip the evaluation that would only CONFIRM convergence.  When the model has just been accurate
-        // (previous actual/predicted within 25 % of 1) and now predicts a reduction below ftol * cost for a plain
-        // Gauss-Newton step, the reference evaluates that step, accepts it and stops on ftol; the step is below
-        // sqrt(2 ftol cost) / L ~ 3e-6 rad.  Stopping here saves one of the ~5 evaluations of a warm-started solve.
-        if (skip_confirm && gn_taken && pred < ftol * cost && pred >= R(0) && N::abs_(last_ratio - R(1)) < R(0.25)) {
-            status = ST_FTOL; return;
-        }
+        step_h_sq = N::fma_(sh1, sh1, sh0 * sh0);
+        // Optional (SEQIK_FLAG_SKIP_CONFIRM): do not evaluate a step that would only CONFIRM convergence.  When the model
+        // has just been accurate (previous actual/predicted within 25 % of 1) and now predicts a reduction below
+        // ftol * cost for a plain Gauss-Newton step, the reference evaluates that step, accepts it and stops on ftol;
+        // the step is below sqrt(2 ftol cost) / L ~ 3e-6 rad.  Saves one of the ~5 evaluations of a warm-started solve.
+        if (skip_confirm && gn_taken && pred < ftol * cost && pred >= R(0) && N::abs_(last_ratio - R(1)) < R(0.25)) status = ST_FTOL;
+    }
 
+    // One function evaluation: one pass of scipy's inner `while actual_reduction <= 0` loop on the step plan() left,
+    // then plan() for the next one.
+    SK_HD void trip() {
+        const R ftol = R(1e-8), xtol = R(1e-8);
         // ---- trial point: strictly feasible, evaluated through the step's sin/cos/versine
         R nx0 = x0 + st0, nx1 = x1 + st1;
         R ndl0 = dl0 + st0, ndu0 = du0 - st0, ndl1 = dl1 + st1, ndu1 = du1 - st1;
@@ -476,7 +486,6 @@ struct StageSolve {
         }
         nfev += 1;
         const R actual = -N::fma_(R(0.5), dot(dw, dw), dot(f, dw));
-        const R step_h_sq = N::fma_(sh1, sh1, sh0 * sh0);
         // update_tr_radius
         R ratio;
         if (pred > R(0)) ratio = (actual != R(0)) ? actual * N::rcp_(pred) : R(0); else if (pred == R(0) && actual == R(0)) ratio = R(1); else ratio = R(0);
@@ -500,6 +509,7 @@ struct StageSolve {
             gradient();
         }
         status = term;
+        if (term == ST_RUNNING) plan();
     }
 
     // make_strictly_feasible(x, lb, ub, rstep=0): one fp64 ulp inside the bound `b`
