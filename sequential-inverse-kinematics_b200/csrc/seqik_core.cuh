@@ -44,8 +44,10 @@
 
 #if defined(__CUDACC__)
 #define SK_HD __host__ __device__ __forceinline__
+#define SK_HD_COLD __host__ __device__ __noinline__     // rare paths: one out-of-line copy instead of one per call site
 #else
 #define SK_HD inline
+#define SK_HD_COLD inline
 #endif
 
 namespace seqik {
@@ -328,7 +330,8 @@ struct StageSolve {
     }
 
     // select_step (trf.py:129-203) restricted to the active pair.
-    SK_HD void select_step(const Hat& h, R p0, R p1, R ph0, R ph1, R& st0, R& st1, R& sh0, R& sh1, R& pred) const {
+    static SK_HD void select_step(const Hat& h, R dl0, R du0, R dl1, R du1, R Delta, R p0, R p1, R ph0, R ph1,
+                                  R& st0, R& st1, R& sh0, R& sh1, R& pred) {
         const bool inb = (dl0 + p0 >= R(0)) && (du0 - p0 >= R(0)) && (dl1 + p1 >= R(0)) && (du1 - p1 >= R(0));
         // in_bounds: scipy returns the plain step.  By far the common case once the trust region has adapted; the
         // three-candidate search below is straight-line code that only runs for lanes whose step leaves the box.
@@ -389,35 +392,16 @@ struct StageSolve {
         pred = -(take_p ? p_value : take_r ? r_value : ag_value);
     }
 
-    // plan(): the head of scipy's outer iteration for the CURRENT iterate -- scaling, termination tests that need no
-    // evaluation (gtol, max_nfev, skip-confirm), trust-region step -- leaving the step to evaluate in (st0, st1,
-    // step_h_sq, pred).  It runs at the end of init()/restart() and at the end of every trip(), so a solve costs
-    // exactly one loop trip per function evaluation and its termination is known in the trip that produced it.
-    // (After a rejected step the iterate is unchanged and only Delta/alpha differ: plan() recomputes the same head.)
-    SK_HD void plan() {
-        const R gtol = R(1e-8), ftol = R(1e-8);
-        Hat h;
-        R v0, v1, dv0, dv1; cl_scaling(v0, v1, dv0, dv1);
-        const R g_norm = N::max_(N::abs_(g0 * v0), N::abs_(g1 * v1));
-        if (g_norm < gtol) { status = ST_GTOL; return; }
-        if (nfev >= max_nfev) { status = ST_MAXFEV; return; }
-        h.d0 = N::sqrt_(v0); h.d1 = N::sqrt_(v1);
-        h.gh0 = h.d0 * g0; h.gh1 = h.d1 * g1;
-        h.B0 = N::fma_(v0, ja_sq(), g0 * dv0); h.B1 = N::fma_(v1, L * L, g1 * dv1);   // Jh^T Jh + diag(g dv), diagonal
-        h.theta = N::max_(R(0.995), R(1) - g_norm);
-        // ---- solve_lsq_trust_region, rank-deficient branch; singular values^2 = (B0, B1), V = I
-        // gn_mode: scipy's SVD of the full chain leaves ~1e-17 singular values on the inert slots; the Levenberg
-        // parameter then decays to ~1e-20 and that null-space noise absorbs the trust-region norm, i.e. the active
-        // pair receives the plain Gauss-Newton step whenever it fits in Delta.  Measured against the reference's
-        // shipped angles (6000 frames x 2 legs) this reproduces the reference's evaluation counts and termination
-        // statuses; the literal rank-deficient branch below is kept for the steps that do not fit.
-        const bool one_var = has_a_() == R(0);
-        const R tg0 = one_var ? R(0) : h.gh0 * N::rcp_(h.B0), tg1 = h.gh1 * N::rcp_(h.B1);
-        const bool gn_taken = gn_mode && (one_var || h.B0 > R(0)) && h.B1 > R(0) && (N::fma_(tg1, tg1, tg0 * tg0) <= Delta * Delta);
+    // The general step of plan(): Levenberg iteration when the Gauss-Newton step does not fit the trust region, then
+    // select_step's three-candidate search when the step leaves the box.  Rare once the trust region has adapted
+    // (< 0.1 % of the evaluations of the benchmark workload), so it lives out of line.
+    struct Step { R st0, st1, sh_sq, pred, alpha; };
+    static SK_HD_COLD Step slow_step(Hat h, R tg0, R tg1, bool gn_taken, bool one_var, R Delta, R alpha,
+                                     R dl0, R du0, R dl1, R du1) {
         R t0 = tg0, t1 = tg1;
         if (gn_taken) alpha = R(0);
         if (!gn_taken) {
-            if (has_a_() == R(0)) {
+            if (one_var) {
                 // one variable: whatever the Levenberg parameter, the step is rescaled to the trust radius below,
                 // i.e. p_h = -sign(gh1) Delta (the parameter is never used again for this stage)
                 t0 = R(0); t1 = h.gh1;
@@ -449,9 +433,47 @@ struct StageSolve {
         }
         const R sc = gn_taken ? R(1) : Delta * N::rsqrt_(N::fma_(t1, t1, t0 * t0));
         const R ph0 = -t0 * sc, ph1 = -t1 * sc;
-        R sh0, sh1;
-        select_step(h, h.d0 * ph0, h.d1 * ph1, ph0, ph1, st0, st1, sh0, sh1, pred);
-        step_h_sq = N::fma_(sh1, sh1, sh0 * sh0);
+        Step o; R sh0, sh1;
+        select_step(h, dl0, du0, dl1, du1, Delta, h.d0 * ph0, h.d1 * ph1, ph0, ph1, o.st0, o.st1, sh0, sh1, o.pred);
+        o.sh_sq = N::fma_(sh1, sh1, sh0 * sh0); o.alpha = alpha;
+        return o;
+    }
+
+    // plan(): the head of scipy's outer iteration for the CURRENT iterate -- scaling, termination tests that need no
+    // evaluation (gtol, max_nfev, skip-confirm), trust-region step -- leaving the step to evaluate in (st0, st1,
+    // step_h_sq, pred).  It runs at the end of init()/restart() and at the end of every trip(), so a solve costs
+    // exactly one loop trip per function evaluation and its termination is known in the trip that produced it.
+    // (After a rejected step the iterate is unchanged and only Delta/alpha differ: plan() recomputes the same head.)
+    SK_HD void plan() {
+        const R gtol = R(1e-8), ftol = R(1e-8);
+        Hat h;
+        R v0, v1, dv0, dv1; cl_scaling(v0, v1, dv0, dv1);
+        const R g_norm = N::max_(N::abs_(g0 * v0), N::abs_(g1 * v1));
+        if (g_norm < gtol) { status = ST_GTOL; return; }
+        if (nfev >= max_nfev) { status = ST_MAXFEV; return; }
+        h.d0 = N::sqrt_(v0); h.d1 = N::sqrt_(v1);
+        h.gh0 = h.d0 * g0; h.gh1 = h.d1 * g1;
+        h.B0 = N::fma_(v0, ja_sq(), g0 * dv0); h.B1 = N::fma_(v1, L * L, g1 * dv1);   // Jh^T Jh + diag(g dv), diagonal
+        h.theta = N::max_(R(0.995), R(1) - g_norm);
+        // ---- solve_lsq_trust_region, rank-deficient branch; singular values^2 = (B0, B1), V = I
+        // gn_mode: scipy's SVD of the full chain leaves ~1e-17 singular values on the inert slots; the Levenberg
+        // parameter then decays to ~1e-20 and that null-space noise absorbs the trust-region norm, i.e. the active
+        // pair receives the plain Gauss-Newton step whenever it fits in Delta.  Measured against the reference's
+        // shipped angles (6000 frames x 2 legs) this reproduces the reference's evaluation counts and termination
+        // statuses; the literal rank-deficient branch below is kept for the steps that do not fit.
+        const bool one_var = has_a_() == R(0);
+        const R tg0 = one_var ? R(0) : h.gh0 * N::rcp_(h.B0), tg1 = h.gh1 * N::rcp_(h.B1);
+        const bool gn_taken = gn_mode && (one_var || h.B0 > R(0)) && h.B1 > R(0) && (N::fma_(tg1, tg1, tg0 * tg0) <= Delta * Delta);
+        // fast path: the Gauss-Newton step fits the trust region and stays inside the box (select_step's in_bounds case)
+        const R ph0 = -tg0, ph1 = -tg1, p0 = h.d0 * ph0, p1 = h.d1 * ph1;
+        const bool inb = (dl0 + p0 >= R(0)) && (du0 - p0 >= R(0)) && (dl1 + p1 >= R(0)) && (du1 - p1 >= R(0));
+        if (gn_taken && inb) {
+            alpha = R(0);
+            st0 = p0; st1 = p1; step_h_sq = N::fma_(ph1, ph1, ph0 * ph0); pred = -model(h, ph0, ph1);
+        } else {
+            const Step o = slow_step(h, tg0, tg1, gn_taken, one_var, Delta, alpha, dl0, du0, dl1, du1);
+            st0 = o.st0; st1 = o.st1; step_h_sq = o.sh_sq; pred = o.pred; alpha = o.alpha;
+        }
         // Optional (SEQIK_FLAG_SKIP_CONFIRM): do not evaluate a step that would only CONFIRM convergence.  When the model
         // has just been accurate (previous actual/predicted within 25 % of 1) and now predicts a reduction below
         // ftol * cost for a plain Gauss-Newton step, the reference evaluates that step, accepts it and stops on ftol;
