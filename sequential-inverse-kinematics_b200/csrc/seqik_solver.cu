@@ -307,11 +307,11 @@ extern "C" int seqik_leg_solve_f32(const float* pose, int64_t pose_chain_stride,
         if (forced) cpw = (int)forced;
         if (cpw < 1 || cpw > PIPE_CHAINS) return seqik_fail(SEQIK_EINVAL, "seqik_leg_solve_f32: chains per warp must be 1..8");
         const int64_t grid = (n_chain + cpw - 1) / cpw;
-        // open/close phases every 2nd iteration when a warp hosts several chains: the lanes that finished a solve then
-        // close/open together, which saves more issue slots than the average half-iteration wait costs (measured
-        // -15 % at 6 000 - 60 000 chains, neutral for one chain per warp).  Scheduling only: results are unchanged.
+        // open/close phases only every 2nd iteration: the lanes that finished a solve then close/open together, which
+        // saves more issue slots than the average half-iteration wait costs (measured -9 % at 600 chains, -15 % at
+        // 6 000 - 60 000 chains).  Scheduling only: results are unchanged.
         const uint32_t gate_sel = (flags >> SEQIK_FLAG_GATE_SHIFT) & 3u;      // 0 auto, 1/2/3 = every 1st/2nd/4th iteration
-        const int gate_mask = gate_sel ? (1 << (gate_sel - 1)) - 1 : (cpw >= 2 ? 1 : 0);
+        const int gate_mask = gate_sel ? (1 << (gate_sel - 1)) - 1 : 1;
         leg_solve_pipe_kernel<<<(unsigned)grid, 32, 0, (cudaStream_t)stream>>>(a, cpw, gate_mask);
     }
     return seqik_check_launch("seqik_leg_solve_f32");
