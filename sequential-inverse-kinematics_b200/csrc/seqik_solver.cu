@@ -183,12 +183,12 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, 
     bool carried = false;            // S holds the previous frame's solve of this (chain, stage)
 
     for (int it = 0; __any_sync(full, live && t < n_frame); ++it) {
-        const bool gate = (it & gate_mask) == 0;      // open/close phases only every (gate_mask + 1)-th iteration
+        if ((it & gate_mask) == 0) {                    // open/close phases only every (gate_mask + 1)-th iteration (warp-uniform)
         const int started_next = __shfl_sync(full, started, (lane + 1) & 31);   // consumer's progress (lane + 1)
         // ---- optional singularity escape: a solve that ended on sin b = 0 may continue from a closed-form candidate
-        if (gate && esc && live && solving && !frozen && S.done()) S.escape();
+        if (esc && live && solving && !frozen && S.done()) S.escape();
         // ---- close the converged solve: outputs + hand-off to the next stage (needs a free ring slot)
-        if (gate && live && t < n_frame && solving && S.done() && (s == hi || t < started_next + PIPE_DEPTH)) {
+        if (live && t < n_frame && solving && S.done() && (s == hi || t < started_next + PIPE_DEPTH)) {
             if (!frozen) {
                 xa = S.x0; xb = S.x1; nf += (uint32_t)S.nfev;
                 if (S.status == ST_MAXFEV && worst > ST_MAXFEV) worst = ST_MAXFEV;
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, 
         __syncwarp(full);            // ring writes above are visible to the reads below
         const int done_prev = __shfl_sync(full, done, (lane + 31) & 31);        // producer's progress (lane - 1)
         // ---- open the next solve when the previous stage has published this frame
-        if (gate && live && t < n_frame && !solving && (s == 0 || t < done_prev)) {
+        if (live && t < n_frame && !solving && (s == 0 || t < done_prev)) {
             if (s > 0) {
                 const float (*q)[PIPE_CHAINS] = ring[s - 1][t & (PIPE_DEPTH - 1)];
                 A.c0 = {q[0][cw], q[1][cw], q[2][cw]}; A.c1 = {q[3][cw], q[4][cw], q[5][cw]}; A.c2 = {q[6][cw], q[7][cw], q[8][cw]};
@@ -245,6 +245,7 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, 
             }
             solving = true; started = t + 1;
         }
+        }   // gate
         // ---- one function evaluation
         if (live && solving && !S.done()) S.trip();
     }
