@@ -155,12 +155,14 @@ template <typename R> SK_HD R dot(const Vec3<R>& a, const Vec3<R>& b) {
 // ---------------------------------------------------------------------------------
 // One stage solve: the iterate + one evaluation per trip()
 // ---------------------------------------------------------------------------------
-// KIND / HASA >= 0 fix the rotation kind / the presence of variable `a` at compile time (the stage-pipeline
-// kernel instantiates one solver per stage); -1 = run-time members (one lane walks all four stages).
-template <typename R, int KIND = -1, int HASA = -1>
+// Internally every stage is solved in the Rz(a) Ry(b) form.  Stage 1 (Rx(a) Ry(b)) is mapped onto it by the constant
+// rotation P = Ry(pi/2): Rx(a) Ry(b) (0,0,-L) = P Rz(a) Ry(b - pi/2) (0,0,-L), i.e. target q' = P^T q = (-q.z, q.y, q.x),
+// pitch variable b' = b - pi/2 with its bounds shifted alike (`xy`, `shift`).  One code path for all lanes of a warp.
+template <typename R>
 struct StageSolve {
     // problem
-    int kind_rt; R L, has_a_rt; R span0, span1;   // span = ub - lb (inf if unbounded)
+    bool xy; R shift;                   // stage-1 mapping: b = x1 + shift
+    R L, has_a; R span0, span1;         // span = ub - lb (inf if unbounded)
     R null_sq; int max_nfev;
     bool gn_mode;   // true: take the Gauss-Newton step when it fits the trust region (see trip())
     // iterate
@@ -174,30 +176,27 @@ struct StageSolve {
     bool skip_confirm;                  // SEQIK_FLAG_SKIP_CONFIRM, see trip()
 
     typedef Num<R> N;
-    SK_HD int kind_() const { return KIND >= 0 ? KIND : kind_rt; }
-    SK_HD R has_a_() const { return HASA >= 0 ? R(HASA) : has_a_rt; }
+    SK_HD int kind_() const { return xy ? KIND_XY : KIND_ZY; }
+    SK_HD R has_a_() const { return has_a; }
+    // results in the caller's (un-mapped) terms
+    SK_HD R angle_b() const { return x1 + shift; }
+    SK_HD R sin_b() const { return xy ? cb : sb; }                      // sin(b' + pi/2) = cos b'
+    SK_HD R cos_b() const { return xy ? -sb : cb; }                     // cos(b' + pi/2) = -sin b'
+    SK_HD Vec3<R> res() const { return xy ? Vec3<R>{f.z, f.y, -f.x} : f; }   // residual w - q = P f'
 
     // end point w = Rot_a Ry(b) (0,0,-L) of the solved segment in the pivot frame
     SK_HD Vec3<R> point() const {
         const R Lsb = L * sb, Lcb = L * cb;
-        if (kind_() == KIND_XY) return {-Lsb, Lcb * sa, -Lcb * ca};
         return {-Lsb * ca, -Lsb * sa, -Lcb};
     }
-    // gradient g = J^T f with the two Jacobian columns of w
+    // gradient g = J^T f with the two Jacobian columns of w:  ja = has_a (Lsb sa, -Lsb ca, 0),  jb = (-Lcb ca, -Lcb sa, Lsb)
     SK_HD void gradient() {
         const R Lsb = L * sb, Lcb = L * cb;
-        if (kind_() == KIND_XY) {
-            // ja = (0, Lcb ca, Lcb sa)   jb = (-Lcb, -Lsb sa, Lsb ca)
-            g0 = Lcb * N::fma_(ca, f.y, sa * f.z);
-            g1 = N::fma_(-Lcb, f.x, Lsb * N::fma_(ca, f.z, -(sa * f.y)));
-        } else {
-            // ja = has_a (Lsb sa, -Lsb ca, 0)   jb = (-Lcb ca, -Lcb sa, Lsb)
-            g0 = has_a_() * Lsb * N::fma_(sa, f.x, -(ca * f.y));
-            g1 = N::fma_(Lsb, f.z, -(Lcb * N::fma_(ca, f.x, sa * f.y)));
-        }
+        g0 = has_a * Lsb * N::fma_(sa, f.x, -(ca * f.y));
+        g1 = N::fma_(Lsb, f.z, -(Lcb * N::fma_(ca, f.x, sa * f.y)));
     }
     // |ja|^2 (|jb|^2 = L^2, ja.jb = 0)
-    SK_HD R ja_sq() const { const R m = (kind_() == KIND_XY) ? cb : sb; return has_a_() * (L * m) * (L * m); }
+    SK_HD R ja_sq() const { return has_a * (L * sb) * (L * sb); }
 
     // Coleman-Li scaling (common.py CL_scaling_vector): v = distance to the bound the anti-gradient points at
     SK_HD void cl_scaling(R& v0, R& v1, R& dv0, R& dv1) const {
@@ -222,11 +221,13 @@ struct StageSolve {
     }
 
     // least_squares prologue: x0 made strictly feasible (rstep 1e-10), f, g, Delta0
-    SK_HD void init(int kind_in, R L_, R has_a_in, const Vec3<R>& q, R a, R b,
+    SK_HD void init(int kind_in, R L_, R has_a_in, const Vec3<R>& q_in, R a, R b,
                     R lb0, R ub0, R lb1, R ub1, R null_sq_, int n_full, int mode = 0) {
         gn_mode = (mode & 1) != 0; skip_confirm = (mode & 2) != 0;     // bit 0 Gauss-Newton mode, bit 1 skip-confirm
-        kind_rt = kind_in; L = L_; has_a_rt = has_a_in; null_sq = null_sq_; max_nfev = 100 * n_full;
-        place(a, b, lb0, ub0, lb1, ub1);
+        xy = kind_in == KIND_XY; shift = xy ? R(1.57079632679489661923) : R(0);
+        L = L_; has_a = has_a_in; null_sq = null_sq_; max_nfev = 100 * n_full;
+        const Vec3<R> q = xy ? Vec3<R>{-q_in.z, q_in.y, q_in.x} : q_in;
+        place(a, b - shift, lb0, ub0, lb1 - shift, ub1 - shift);
         R va, vb;
         N::sincosv_(x0, &sa, &ca, &va); N::sincosv_(x1, &sb, &cb, &vb);
         const Vec3<R> w = point();
@@ -236,7 +237,8 @@ struct StageSolve {
         R v0, v1, dv0, dv1; cl_scaling(v0, v1, dv0, dv1);
         // v can be ~1e-38 (an iterate parked on a bound at 0): there x = +-v, the term x^2 / v = v is negligible
         // against null_sq >= 1 and x * x underflows, so it is dropped instead of evaluating 0 * rcp(tiny) = 0 * inf
-        const R q0 = (v0 > R(1e-30)) ? x0 * x0 * N::rcp_(v0) : R(0), q1 = (v1 > R(1e-30)) ? x1 * x1 * N::rcp_(v1) : R(0);
+        const R xb_ = x1 + shift;
+        const R q0 = (v0 > R(1e-30)) ? x0 * x0 * N::rcp_(v0) : R(0), q1 = (v1 > R(1e-30)) ? xb_ * xb_ * N::rcp_(v1) : R(0);
         Delta = N::sqrt_(null_sq + q0 + q1);
         if (Delta == R(0)) Delta = R(1);
         alpha = R(0); nfev = 1; escaped = false; last_ratio = R(0);
@@ -248,14 +250,16 @@ struct StageSolve {
     // carried over and only the bound distances and the residual against the new target is rebuilt (least_squares
     // prologue without the trigonometry).  Callers re-run init() every SEQIK_RESYNC frames so that the carried
     // sin/cos cannot drift from the angle (float32 random walk, < 1e-6 rad over 64 frames).
-    SK_HD void restart(const Vec3<R>& q, R lb0, R ub0, R lb1, R ub1) {
-        place(x0, x1, lb0, ub0, lb1, ub1);      // bound distances re-derived from the angle, exactly as init() would
+    SK_HD void restart(const Vec3<R>& q_in, R lb0, R ub0, R lb1, R ub1) {
+        const Vec3<R> q = xy ? Vec3<R>{-q_in.z, q_in.y, q_in.x} : q_in;
+        place(x0, x1, lb0, ub0, lb1 - shift, ub1 - shift);   // bound distances re-derived from the angle, exactly as init() would
         const Vec3<R> w = point();
         f = {w.x - q.x, w.y - q.y, w.z - q.z};
         cost = R(0.5) * dot(f, f);
         gradient();
         R v0, v1, dv0, dv1; cl_scaling(v0, v1, dv0, dv1);
-        const R q0 = (v0 > R(1e-30)) ? x0 * x0 * N::rcp_(v0) : R(0), q1 = (v1 > R(1e-30)) ? x1 * x1 * N::rcp_(v1) : R(0);
+        const R xb_ = x1 + shift;
+        const R q0 = (v0 > R(1e-30)) ? x0 * x0 * N::rcp_(v0) : R(0), q1 = (v1 > R(1e-30)) ? xb_ * xb_ * N::rcp_(v1) : R(0);
         Delta = N::sqrt_(null_sq + q0 + q1);
         if (Delta == R(0)) Delta = R(1);
         alpha = R(0); nfev = 1; escaped = false; last_ratio = R(0);
@@ -270,7 +274,7 @@ struct StageSolve {
     // closed-form mirror solutions of "point a segment at the target" (SURVEY.md 3.4), clamped to the box, are
     // evaluated; if one is clearly better the solve continues from it.  At most once per solve.
     SK_HD bool escape() {
-        if (escaped || kind_() != KIND_ZY || has_a_() == R(0) || sb * sb > R(1e-8)) return false;
+        if (escaped || xy || has_a == R(0) || sb * sb > R(1e-8)) return false;
         escaped = true;
         const Vec3<R> w = point();
         const Vec3<R> q = {w.x - f.x, w.y - f.y, w.z - f.z};
@@ -294,7 +298,7 @@ struct StageSolve {
         if (!(best < R(0.98) * cost - R(5e-7))) return false;  // clearly better: > 2 % and > (1e-3 mm)^2 / 2
         const R nsq = null_sq; const int mx = max_nfev; const int nf = nfev;
         const int md = (gn_mode ? 1 : 0) | (skip_confirm ? 2 : 0);
-        init(kind_rt, L, has_a_rt, q, ba, bb, lb0, ub0, lb1, ub1, nsq, 1, md);
+        init(KIND_ZY, L, has_a, q, ba, bb, lb0, ub0, lb1, ub1, nsq, 1, md);
         max_nfev = mx; nfev = nf; escaped = true;
         return true;
     }
@@ -500,12 +504,7 @@ struct StageSolve {
         const R dsa = N::fma_(ca, sda, -(sa * va)), dca = -N::fma_(sa, sda, ca * va);   // sin/cos(a + e0) - sin/cos(a)
         const R dsb = N::fma_(cb, sdb, -(sb * vb)), dcb = -N::fma_(sb, sdb, cb * vb);
         const R nsa = sa + dsa, nca = ca + dca, nsb = sb + dsb, ncb = cb + dcb;
-        Vec3<R> dw;   // w(x + e) - w(x)
-        if (kind_() == KIND_XY) {
-            dw = {-L * dsb, L * N::fma_(dcb, nsa, cb * dsa), -L * N::fma_(dcb, nca, cb * dca)};
-        } else {
-            dw = {-L * N::fma_(dsb, nca, sb * dca), -L * N::fma_(dsb, nsa, sb * dsa), -L * dcb};
-        }
+        const Vec3<R> dw = {-L * N::fma_(dsb, nca, sb * dca), -L * N::fma_(dsb, nsa, sb * dsa), -L * dcb};   // w(x + e) - w(x)
         nfev += 1;
         const R actual = -N::fma_(R(0.5), dot(dw, dw), dot(f, dw));
         // update_tr_radius
@@ -517,7 +516,8 @@ struct StageSolve {
         else if (ratio > R(0.75) && step_h_sq > R(0.9025) * Delta * Delta) Delta_new = R(2) * Delta;
         // check_termination
         const R step_sq = N::fma_(st1, st1, st0 * st0);
-        const R x_norm = N::sqrt_(N::fma_(x1, x1, N::fma_(x0, x0, null_sq)));
+        const R xb_ = x1 + shift;
+        const R x_norm = N::sqrt_(N::fma_(xb_, xb_, N::fma_(x0, x0, null_sq)));
         const R xt_rhs = xtol * (xtol + x_norm);
         const bool ft = (actual < ftol * cost) && (ratio > R(0.25));
         const bool xt = step_sq < xt_rhs * xt_rhs;
@@ -640,20 +640,20 @@ struct ChainRunner {
     // close the converged stage, open the next one (possibly of the next frame)
     SK_HD void advance() {
         if (s >= lo) {
-            if (s == 0) { ang0 = S.x0; ang1 = S.x1; nf0 += (uint32_t)S.nfev; }
-            else if (s == 1) { ang2 = S.x0; ang3 = S.x1; nf1 += (uint32_t)S.nfev; }
-            else if (s == 2) { ang4 = S.x0; ang5 = S.x1; nf2 += (uint32_t)S.nfev; }
-            else { ang6 = S.x1; nf3 += (uint32_t)S.nfev; }
+            if (s == 0) { ang0 = S.x0; ang1 = S.angle_b(); nf0 += (uint32_t)S.nfev; }
+            else if (s == 1) { ang2 = S.x0; ang3 = S.angle_b(); nf1 += (uint32_t)S.nfev; }
+            else if (s == 2) { ang4 = S.x0; ang5 = S.angle_b(); nf2 += (uint32_t)S.nfev; }
+            else { ang6 = S.angle_b(); nf3 += (uint32_t)S.nfev; }
             if (S.status == ST_MAXFEV && worst_status > ST_MAXFEV) worst_status = ST_MAXFEV;
             if (S.status == ST_NONFINITE) worst_status = ST_NONFINITE;
         }
         // next pivot = pivot + A w(x) = target + A f   (q = A^T rel, f = w - q)
-        const Vec3<R> Af = mul(A, S.f);
+        const Vec3<R> Af = mul(A, S.res());
         piv = {(piv.x + rel.x) + Af.x, (piv.y + rel.y) + Af.y, (piv.z + rel.z) + Af.z};
         const Vec3<R> jw = {piv.x + o.x, piv.y + o.y, piv.z + o.z};
         if (s == 0) { io.put_fk(t, 4, jw); io.put_fk(t, 5, jw); } else io.put_fk(t, 5 + s, jw);
         if (s < hi) {
-            A = rotate_frame(A, S.kind_(), S.sa, S.ca, S.sb, S.cb);
+            A = rotate_frame(A, S.kind_(), S.sa, S.ca, S.sin_b(), S.cos_b());
             ++s;
             begin_stage();
         } else {
@@ -707,13 +707,13 @@ SK_HD void solve_frame(const ChainParams<R>& P, const R* kp, R* ang, R* fk, Fram
             if ((gn_mask & 16) && S.escape()) while (!S.done()) S.trip();
         }
         if (s != 3) ang[ia] = S.x0;
-        ang[ib] = S.x1;
+        ang[ib] = S.angle_b();
         if (fs) { fs->nfev[s] = S.nfev; fs->status[s] = S.status; }
         // next pivot = pivot + A w = target + A f
-        const Vec3<R> Af = mul(A, S.f);
+        const Vec3<R> Af = mul(A, S.res());
         piv = {(piv.x + rel.x) + Af.x, (piv.y + rel.y) + Af.y, (piv.z + rel.z) + Af.z};
         joint[s] = piv;
-        A = rotate_frame(A, kind, S.sa, S.ca, S.sb, S.cb);
+        A = rotate_frame(A, kind, S.sa, S.ca, S.sin_b(), S.cos_b());
     }
     if (fk) {
         for (int r = 0; r < 4; ++r) { fk[3 * r] = o.x; fk[3 * r + 1] = o.y; fk[3 * r + 2] = o.z; }

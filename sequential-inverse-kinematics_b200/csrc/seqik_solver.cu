@@ -190,14 +190,14 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, 
         // ---- close the converged solve: outputs + hand-off to the next stage (needs a free ring slot)
         if (live && t < n_frame && solving && S.done() && (s == hi || t < started_next + PIPE_DEPTH)) {
             if (!frozen) {
-                xa = S.x0; xb = S.x1; nf += (uint32_t)S.nfev;
+                xa = S.x0; xb = S.angle_b(); nf += (uint32_t)S.nfev;
                 if (S.status == ST_MAXFEV && worst > ST_MAXFEV) worst = ST_MAXFEV;
                 if (S.status == ST_NONFINITE) worst = ST_NONFINITE;
                 if (s != 3) *pa_a = xa;
                 *pa_b = xb;
             }
             // joint position = pivot + A w(x) = target + A f   (q = A^T rel, f = w - q)
-            const Vec3<float> Af = mul(A, S.f);
+            const Vec3<float> Af = mul(A, S.res());
             const Vec3<float> np_ = {(piv.x + rel.x) + Af.x, (piv.y + rel.y) + Af.y, (piv.z + rel.z) + Af.z};
             if (fk) {
                 // rows 0-3 repeat the origin, 4 and 5 are both the Coxa-Femur joint: lane s writes origin row s and its
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, 
             }
             pa_a += a.ang_fs; pa_b += a.ang_fs;
             if (s < hi) {
-                const Mat3<float> B = rotate_frame(A, kind, S.sa, S.ca, S.sb, S.cb);
+                const Mat3<float> B = rotate_frame(A, kind, S.sa, S.ca, S.sin_b(), S.cos_b());
                 float (*q)[PIPE_CHAINS] = ring[s][t & (PIPE_DEPTH - 1)];
                 q[0][cw] = B.c0.x; q[1][cw] = B.c0.y; q[2][cw] = B.c0.z; q[3][cw] = B.c1.x; q[4][cw] = B.c1.y; q[5][cw] = B.c1.z;
                 q[6][cw] = B.c2.x; q[7][cw] = B.c2.y; q[8][cw] = B.c2.z; q[9][cw] = np_.x; q[10][cw] = np_.y; q[11][cw] = np_.z;
