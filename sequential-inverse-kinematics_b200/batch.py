@@ -18,7 +18,7 @@ import numpy as np
 from . import _native as N
 from . import engine
 
-RESYNC_FRAMES = 64      # SEQIK_RESYNC of csrc/seqik_core.cuh
+RESYNC_FRAMES = 32      # SEQIK_RESYNC of csrc/seqik_core.cuh
 
 
 def bind_to_gpu_numa(device_index: int) -> Optional[Sequence[int]]:
@@ -127,7 +127,7 @@ class BatchedLegIK:
         s_in.wait_stream(main)
         s_out.wait_stream(main)
         F = self.n_frame
-        # chunk starts on multiples of 64 frames (the kernel's resync period): then chunking is bit-identical
+        # chunk starts on multiples of 32 frames (the kernel's resync period): then chunking is bit-identical
         # to one launch over all frames
         bounds = sorted({0, F} | {min(F, RESYNC_FRAMES * round(F * k / n_chunks / RESYNC_FRAMES)) for k in range(1, n_chunks)})
 

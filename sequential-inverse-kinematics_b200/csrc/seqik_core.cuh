@@ -138,7 +138,7 @@ template <> struct Num<double> {
     static SK_HD double eps_in() { return 2.220446049250313e-16; }
 };
 
-constexpr int SEQIK_RESYNC = 64;          // frames between full re-initialisations of a carried solve
+constexpr int SEQIK_RESYNC = 32;          // frames between full re-initialisations of a carried solve
 
 enum : int { KIND_XY = 0, KIND_ZY = 1 };   // Rx(a)Ry(b) (stage 1)  |  Rz(a)Ry(b) (stages 2-4)
 
@@ -249,7 +249,7 @@ struct StageSolve {
     // Next frame of the same (chain, stage): the warm start IS the previous solve's final iterate, so its sin/cos are
     // carried over and only the bound distances and the residual against the new target is rebuilt (least_squares
     // prologue without the trigonometry).  Callers re-run init() every SEQIK_RESYNC frames so that the carried
-    // sin/cos cannot drift from the angle (float32 random walk, < 1e-6 rad over 64 frames).
+    // sin/cos cannot drift from the angle (float32 random walk, ~1e-6 rad over 32 frames).
     SK_HD void restart(const Vec3<R>& q_in, R lb0, R ub0, R lb1, R ub1) {
         const Vec3<R> q = xy ? Vec3<R>{-q_in.z, q_in.y, q_in.x} : q_in;
         place(x0, x1, lb0, ub0, lb1 - shift, ub1 - shift);   // bound distances re-derived from the angle, exactly as init() would

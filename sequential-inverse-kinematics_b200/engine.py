@@ -52,7 +52,7 @@ def leg_solve(pose, params, affine=None, stages: Sequence[int] = (1, 2, 3, 4), w
     override the automatic kernel schedule (tuning and tests); results do not depend on them.
     ``frames=(t0, t1)`` solves only that frame range IN PLACE of the full-size pose/angles/fk tensors, warm-started
     from frame t0-1 of ``angles`` (t0 > 0).  Chunked calls over consecutive ranges are bit-identical to one call over
-    all frames when every t0 is a multiple of 64 (the kernel re-derives sin/cos from the angles every 64 frames and at
+    all frames when every t0 is a multiple of 32 (the kernel re-derives sin/cos from the angles every 32 frames and at
     the first frame of a call); otherwise they agree to float32 rounding.
     """
     torch = N.require_cuda()
