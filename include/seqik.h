@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SEQIK_ABI_VERSION 3
+#define SEQIK_ABI_VERSION 4
 #define SEQIK_OK 0
 #define SEQIK_EINVAL (-1)
 #define SEQIK_ECUDA (-3)
@@ -101,6 +101,47 @@ int seqik_leg_solve_f32(const float* pose, int64_t pose_chain_stride, int64_t po
                         const float* warm, int64_t warm_chain_stride,
                         int32_t* status, uint32_t* nfev,
                         int64_t n_chain, int64_t n_frame, uint32_t stage_mask, uint32_t flags, void* stream);
+
+/* Generic (single-target) leg IK: all 7 joints solved at once against ONE target, the claw.
+ * Replaces LegInvKinGeneric.run_ik_and_fk / calculate_ik_stage (seqikpy/leg_inverse_kinematics.py:473-613) together
+ * with KinematicChainGeneric.create_leg_chain (seqikpy/kinematic_chain.py:444-532), ikpy Chain.inverse_kinematics /
+ * forward_kinematics and scipy.optimize.least_squares on that chain.
+ *
+ * JOINT ORDER of this entry point = the link order of the generic chain: ThC_roll, ThC_yaw, ThC_pitch, CTr_pitch,
+ * CTr_roll, FTi_pitch, TiTa_pitch (roll FIRST: kinematic_chain.py:464-488) -- for params, warm and angles alike.
+ *
+ *   pose    [n_chain][n_frame][k][3] key points, k > target_row; row 0 = Thorax-Coxa origin, row target_row = the end
+ *           effector (the reference takes the LAST key point, leg_inverse_kinematics.py:582); other rows are not read
+ *   params  [n_chain][32]: [0..3] segment lengths, [4..10] lower / [11..17] upper bounds, [18..24] seeds (slots 1..7 of
+ *           INITIAL_ANGLES[leg]["stage_4"], applied positionally to the generic chain exactly as the reference does,
+ *           leg_inverse_kinematics.py:583), [25] squared norm of the two inert seed slots (Base link, Claw)
+ *   angles  [n_chain][n_frame][7] out;  fk NULL, or [n_chain][n_frame][9][3] out (rows 0-3 origin, 4-5 Coxa-Femur
+ *           joint, 6 Femur-Tibia, 7 Tibia-Tarsus, 8 Claw);  warm / status / nfev ([n_chain], evaluations summed over
+ *           frames) as in seqik_leg_solve_f32
+ *   flags   bits SEQIK_FLAG_CPW_SHIFT..+5: chains per warp (1..32), 0 = automatic; other bits must be 0
+ *
+ * The reference's generic solve is under-determined (3 equations, 7 unknowns) and its answer depends on rounding noise
+ * (DESIGN.md 5.4): this entry point restates the same iteration, reproduces the reference solve by solve from the same
+ * seed (tests) and reaches the same claw residual, but a free-running recording follows its own path on the
+ * self-motion manifold. */
+int seqik_leg_solve_generic_f32(const float* pose, int64_t pose_chain_stride, int64_t pose_frame_stride, int32_t target_row,
+                                const float* params,
+                                float* angles, int64_t ang_chain_stride, int64_t ang_frame_stride,
+                                float* fk, int64_t fk_chain_stride, int64_t fk_frame_stride,
+                                const float* warm, int64_t warm_chain_stride,
+                                int32_t* status, uint32_t* nfev,
+                                int64_t n_chain, int64_t n_frame, uint32_t flags, void* stream);
+/* Same with FP64 data AND FP64 device arithmetic (B200's FP64 pipe runs at half the FP32 rate; a lane-per-chain solve is
+ * latency-bound, so the cost is ~2x).  The reference's generic iteration amplifies rounding (its candidate-step choice
+ * flips on near-ties): in FP64 the device agrees with scipy solve by solve as often as scipy agrees with itself under
+ * a 1e-12 mm input perturbation (~98 % of solves within 1e-3 rad), in FP32 on ~90 %.  The dict API uses this one. */
+int seqik_leg_solve_generic_f64(const double* pose, int64_t pose_chain_stride, int64_t pose_frame_stride, int32_t target_row,
+                                const double* params,
+                                double* angles, int64_t ang_chain_stride, int64_t ang_frame_stride,
+                                double* fk, int64_t fk_chain_stride, int64_t fk_frame_stride,
+                                const double* warm, int64_t warm_chain_stride,
+                                int32_t* status, uint32_t* nfev,
+                                int64_t n_chain, int64_t n_frame, uint32_t flags, void* stream);
 
 /* Forward kinematics only: angles -> 9x3 joint positions.
  * Replaces LegInvKinBase.calculate_fk (seqikpy/leg_inverse_kinematics.py:71-77) on the stage-4 chain.

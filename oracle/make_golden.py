@@ -19,6 +19,10 @@ Fixtures
   locomotion.npz     bundled data/df3d_pose_result__210902_PR_Fly1 (BASELINE config 1): raw frames 300:400 of the
                      6 legs, reference AlignPose output (== shipped pose3d_aligned.pkl), oracle angles + FK
   synthetic.npz      trials 0-1 x 6 legs x first 250 frames of the synthetic workload: pose, oracle angles + FK
+  generic_leg.npz    generic 7-DOF IK (LegInvKinGeneric) of the oracle on the first 500 frames of the grooming RF/LF legs:
+                     the free-running angles (2,500,9) with status/nfev/cost, and -- because that problem is under-determined and
+                     its free-running answer depends on rounding noise -- the SAME solves repeated with the target
+                     perturbed by 1e-12 mm from the same seeds (the oracle's own reproducibility, frame by frame)
   synthetic_long.npz trial 5, legs RM and LH, 2000 frames: oracle angles (float32) -- a long warm-start chain that spans
                      many of the kernel's 64-frame resync periods
 """
@@ -64,6 +68,18 @@ def _oracle_leg(args):
     return key, stack7(ang, leg), fk[key]
 
 
+def _generic_leg(args):
+    """Free-running generic oracle + the same solves (same seeds) with the target perturbed by 1e-12 mm."""
+    leg, arr, size, bounds, init = args
+    stats = []
+    ja, fk = O.run_generic_leg(leg, arr[:, -1], arr[:, 0], init, size, bounds, stats=stats)
+    teacher = np.vstack([np.asarray(init, dtype=float)[None], ja[:-1]])
+    noise = 1e-12 * np.random.default_rng(7).normal(size=(arr.shape[0], 3))
+    ja2, _ = O.run_generic_leg(leg, arr[:, -1] + noise, arr[:, 0], init, size, bounds, teacher=teacher)
+    st = np.array([(s[2], s[3], s[4]) for s in stats], dtype=float)
+    return ja, fk[:, 8], st, ja2
+
+
 def oracle_legs(pose_dict, size, bounds, init, procs=8):
     """Oracle over several legs in parallel processes (legs are independent)."""
     jobs = [(k, v, size, bounds, init) for k, v in pose_dict.items()]
@@ -75,7 +91,7 @@ def oracle_legs(pose_dict, size, bounds, init, procs=8):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reuse-cache", default=None, help="directory with oracle_full_{RF,LF}.pkl from a previous run")
-    ap.add_argument("--only", default="", help="comma-separated subset: leg,head,align,loco,synth,long")
+    ap.add_argument("--only", default="", help="comma-separated subset: leg,head,align,loco,synth,long,generic")
     args = ap.parse_args()
     only = set(filter(None, args.only.split(",")))
     GOLD.mkdir(parents=True, exist_ok=True)
@@ -192,6 +208,18 @@ def main():
         print(f"synthetic oracle: {time.time() - t0:.1f} s")
         np.savez_compressed(GOLD / "synthetic.npz", trials=np.array(trials), legs=np.array(S.LEGS),
                             pose=np.stack(poses), oracle_angles=np.stack(angs), oracle_fk=np.stack(fks))
+    # ---------------------------------------------------------------- generic 7-DOF IK (LegInvKinGeneric)
+    if not only or "generic" in only:
+        n_frame = 500
+        size = O.calculate_body_size(RD.NMF_TEMPLATE, ["RF", "LF"])
+        t0 = time.time()
+        with Pool(2) as pool:
+            res = pool.map(_generic_leg, [(leg, aligned[f"{leg}_leg"][:n_frame], size, RD.BOUNDS, RD.INITIAL_ANGLES[leg]["stage_4"])
+                                          for leg in ("RF", "LF")])
+        print(f"generic oracle: {time.time() - t0:.1f} s")
+        np.savez_compressed(GOLD / "generic_leg.npz", legs=np.array(["RF", "LF"]), n_frame=np.array(n_frame),
+                            oracle_angles=np.stack([r[0] for r in res]), oracle_fk_claw=np.stack([r[1] for r in res]),
+                            oracle_stats=np.stack([r[2] for r in res]), perturbed_angles=np.stack([r[3] for r in res]))
     # ---------------------------------------------------------------- long warm-start chain (drift check)
     if not only or "long" in only:
         n_frame, trial, legs = 2000, 5, ("RM", "LH")

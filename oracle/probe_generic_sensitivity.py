@@ -1,4 +1,4 @@
-"""Evidence for DESIGN.md section 8: the reference's GENERIC 7-DOF leg IK (LegInvKinGeneric + KinematicChainGeneric,
+"""Evidence for DESIGN.md section 5.4: the reference's GENERIC 7-DOF leg IK (LegInvKinGeneric + KinematicChainGeneric,
 seqikpy/leg_inverse_kinematics.py:406-613, seqikpy/kinematic_chain.py:424-532) has no reproducible answer to be a
 drop-in for.  TEST INFRASTRUCTURE / analysis script; run in the build container:
 
@@ -22,13 +22,7 @@ from seqikpy_b200 import data as D              # noqa: E402
 
 
 def generic_chain(leg, size, bounds):
-    L = lambda s: float(size[f"{leg}_{s}"])
-    b = lambda d: bounds[f"{leg}_{d}"]
-    rev = lambda dof, axis, trans=(0, 0, 0): O.Link(f"{leg}_{dof}", trans, (0, 0, 0), axis, b(dof))
-    return [O.Link("Base link", origin=True), rev("ThC_roll", O.Z_AXIS), rev("ThC_yaw", O.X_AXIS), rev("ThC_pitch", O.Y_AXIS),
-            rev("CTr_pitch", O.Y_AXIS, (0, 0, -L("Coxa"))), rev("CTr_roll", O.Z_AXIS), rev("FTi_pitch", O.Y_AXIS, (0, 0, -L("Femur"))),
-            rev("TiTa_pitch", O.Y_AXIS, (0, 0, -L("Tibia"))),
-            O.Link(f"{leg}_Claw", (0, 0, -L("Tarsus")), (0, 0, 0), (0.0, 0.0, 0.0), (-np.pi, np.pi))]
+    return O.build_generic_chain(leg, size, bounds)
 
 
 def run(links, pose, seed):

@@ -249,6 +249,88 @@ def run_ik_and_fk(aligned_pos, body_size, bounds, initial_angles, stages=(1, 2, 
     return angles, fk
 
 
+# ----------------------------------------------------------------------------
+# KinematicChainGeneric + LegInvKinGeneric  (kinematic_chain.py:424-532, leg_inverse_kinematics.py:406-613)
+# ----------------------------------------------------------------------------
+GENERIC_DOF_ORDER = ("ThC_roll", "ThC_yaw", "ThC_pitch", "CTr_pitch", "CTr_roll", "FTi_pitch", "TiTa_pitch")
+
+
+def build_generic_chain(leg, body_size, bounds):
+    """Links of ``KinematicChainGeneric.create_leg_chain(leg)`` (kinematic_chain.py:464-530): all joints revolute,
+    ThC in roll-yaw-pitch order, the claw as a degenerate last link."""
+    if leg not in LEGS:
+        raise ValueError(f"Unknown leg name ({leg}) is provided!")
+
+    def L(seg):
+        return float(body_size[f"{leg}_{seg}"])
+
+    def rev(dof, axis, trans=(0, 0, 0)):
+        return Link(f"{leg}_{dof}", trans, (0, 0, 0), axis, bounds[f"{leg}_{dof}"])
+
+    return [Link("Base link", origin=True), rev("ThC_roll", Z_AXIS), rev("ThC_yaw", X_AXIS), rev("ThC_pitch", Y_AXIS),
+            rev("CTr_pitch", Y_AXIS, (0, 0, -L("Coxa"))), rev("CTr_roll", Z_AXIS),
+            rev("FTi_pitch", Y_AXIS, (0, 0, -L("Femur"))), rev("TiTa_pitch", Y_AXIS, (0, 0, -L("Tibia"))),
+            Link(f"{leg}_Claw", (0, 0, -L("Tarsus")), (0, 0, 0), (0.0, 0.0, 0.0), (-np.pi, np.pi))]
+
+
+def run_generic_leg(leg, end_effector, origin, init, body_size, bounds, teacher=None, stats=None):
+    """``LegInvKinGeneric.calculate_ik_stage`` (leg_inverse_kinematics.py:473-547): one 9-slot solve per frame against
+    the claw, warm-started from the previous frame.  Returns (joint_angles (N, 9), forward_kinematics (N, 9, 3)).
+    ``teacher`` (N, 9), if given, replaces the warm start of every frame (single solves from prescribed seeds)."""
+    links = build_generic_chain(leg, body_size, bounds)
+    n = end_effector.shape[0]
+    target = end_effector - origin
+    ja = np.empty((n, len(links)))
+    fk = np.empty((n, len(links), 3))
+    x0 = np.asarray(init, dtype=float)
+    for t in range(n):
+        if teacher is not None:
+            x0 = teacher[t]
+        res = inverse_kinematics(links, target[t], x0, return_result=True)
+        ja[t] = res.x
+        if stats is not None:
+            stats.append((leg, t, res.status, res.nfev, res.cost))
+        fk[t] = np.array([m[:3, 3] for m in forward_kinematics(links, ja[t], full=True)]) + origin[t]
+        x0 = ja[t]
+    return ja, fk
+
+
+def run_generic_ik_and_fk(aligned_pos, body_size, bounds, initial_angles):
+    """``LegInvKinGeneric.run_ik_and_fk`` (leg_inverse_kinematics.py:549-613): returns (joint_angles_dict, fk_dict)."""
+    angles, fk = {}, {}
+    for name, arr in aligned_pos.items():
+        if "leg" not in name.lower():
+            continue
+        leg = name.split("_")[0]
+        if leg not in body_size:
+            continue
+        ja, fk[name] = run_generic_leg(leg, arr[:, -1, :], arr[:, 0, :], initial_angles[leg]["stage_4"], body_size, bounds)
+        for i, dof in enumerate(GENERIC_DOF_ORDER):
+            angles[f"Angle_{leg}_{dof}"] = ja[:, 1 + i]
+    return angles, fk
+
+
+def fk_generic(angles7, seg_len, origin):
+    """9-row FK of the generic chain for (N,7) angles in GENERIC_DOF_ORDER (rows: Base, 7 joint origins, claw)."""
+    angles7 = np.asarray(angles7, dtype=float)
+    n = angles7.shape[0]
+    out = np.zeros((n, 9, 3))
+    for t in range(n):
+        r, y, p, cp, cr, fp, tp = angles7[t]
+        R = axis_rotation(Z_AXIS, r) @ axis_rotation(X_AXIS, y) @ axis_rotation(Y_AXIS, p)
+        pos = R @ np.array([0, 0, -seg_len[0]])
+        out[t, 4] = out[t, 5] = pos
+        R = R @ axis_rotation(Y_AXIS, cp) @ axis_rotation(Z_AXIS, cr)
+        pos = pos + R @ np.array([0, 0, -seg_len[1]])
+        out[t, 6] = pos
+        R = R @ axis_rotation(Y_AXIS, fp)
+        pos = pos + R @ np.array([0, 0, -seg_len[2]])
+        out[t, 7] = pos
+        R = R @ axis_rotation(Y_AXIS, tp)
+        out[t, 8] = pos + R @ np.array([0, 0, -seg_len[3]])
+    return out + np.asarray(origin).reshape(-1, 1, 3)
+
+
 def fk_closed_form(angles7, seg_len, origin):
     """Closed-form 9-row FK of the stage-4 chain for (N,7) angles.
 

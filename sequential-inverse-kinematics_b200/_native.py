@@ -12,7 +12,7 @@ import numpy as np
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "csrc" / "libseqik_sm100.so"
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 CHAIN_PARAM_FLOATS = 32
 FLAG_ESCAPE = 1 << 4
 FLAG_SKIP_CONFIRM = 1 << 5
@@ -30,6 +30,10 @@ _SIGNATURES = {
     "seqik_last_error": (ctypes.c_char_p, []),
     "seqik_leg_solve_f32": (_int, [_vp, _i64, _i64, _vp, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64, _vp, _vp,
                                    _i64, _i64, _u32, _u32, _vp]),
+    "seqik_leg_solve_generic_f32": (_int, [_vp, _i64, _i64, ctypes.c_int32, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64,
+                                           _vp, _vp, _i64, _i64, _u32, _vp]),
+    "seqik_leg_solve_generic_f64": (_int, [_vp, _i64, _i64, ctypes.c_int32, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64,
+                                           _vp, _vp, _i64, _i64, _u32, _vp]),
     "seqik_memcpy2d_async": (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _int, _vp]),
     "seqik_fk_f32": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp]),
     "seqik_head_angles_f32": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),

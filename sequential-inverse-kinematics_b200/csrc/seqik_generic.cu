@@ -1,0 +1,158 @@
+// seqik_generic.cu -- the generic (single-target, 7-DOF) leg-IK kernel (sm_100a) behind seqik_leg_solve_generic_f32.
+//
+// Replaces LegInvKinGeneric.run_ik_and_fk / calculate_ik_stage (seqikpy/leg_inverse_kinematics.py:473-613) on the chain of
+// KinematicChainGeneric (seqikpy/kinematic_chain.py:424-532).  A chain = one leg of one trial; its frames are solved
+// serially (the warm start of leg_inverse_kinematics.py:524), chains are independent.
+//
+// Mapping: ONE LANE PER CHAIN.  A generic solve is a 7-variable problem whose trust-region subproblem is eleven
+// symmetric 3x3 solves per evaluation (seqik_generic.cuh); its vectors are short (7) and its many reductions would cost
+// more as warp shuffles than they do as seven dependent FMAs, so a chain is not split across lanes.  All lanes run
+// GenericSolve::trip() -- one function evaluation -- in a warp-convergent loop and sit at different (frame, iteration)
+// positions of their own chains, so a slow solve (the reference needs 25 - 330 evaluations per frame) delays only its
+// own chain.  Chains are first spread over warps (one warp per SM sub-partition while that is possible), then warps are
+// filled: a warp instruction costs the same for 1 or 32 active lanes.  No tensor cores: scalar 3x3 / 7-vector algebra.
+//
+// Two instantiations: float32 (the throughput path) and float64 (B200's FP64 pipe runs at half the FP32 rate, and a lane-
+// per-chain solve is latency-bound anyway).  The reference's generic solve crawls along zig-zagging 1-D minimisations whose
+// candidate choice amplifies rounding; in float64 the device agrees with scipy solve by solve as often as scipy agrees
+// with itself, in float32 a few percent less often.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/seqik.h"
+#include "seqik_common.h"
+#include "seqik_generic.cuh"
+
+using namespace seqik;
+
+template <typename R>
+struct GenArgs {
+    const R* pose; int64_t pose_cs, pose_fs; int target_row;
+    const R* params;
+    R* angles; int64_t ang_cs, ang_fs;
+    R* fk; int64_t fk_cs, fk_fs;
+    const R* warm; int64_t warm_cs;
+    int32_t* status; uint32_t* nfev;
+    int64_t n_chain, n_frame;
+};
+
+template <typename R>
+__global__ void __launch_bounds__(32) leg_solve_generic_kernel(GenArgs<R> a, int cpw) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x;
+    const int64_t c = (int64_t)blockIdx.x * cpw + lane;
+    const bool owner = lane < cpw && c < a.n_chain;
+    const int64_t cc = owner ? c : 0;
+    const R* prm = a.params + cc * SEQIK_CHAIN_PARAM_FLOATS;
+    const R* pk = a.pose + cc * a.pose_cs;                        // key points of the frame to open next
+    R* pa = a.angles + cc * a.ang_cs;
+    R* pf = a.fk ? a.fk + cc * a.fk_cs : nullptr;
+    const int n_frame = (int)a.n_frame;
+    const int trow = 3 * a.target_row;
+    const R null_sq = __ldg(prm + 25);
+
+    GenericSolve<R> S;
+    {
+        const R* seed = a.warm ? a.warm + cc * a.warm_cs : prm + 18;
+#pragma unroll
+        for (int i = 0; i < GEN_DOF; ++i) S.x[i] = seed[i];
+    }
+    S.status = ST_GTOL;
+    int t = owner ? 0 : n_frame;
+    bool solving = false;
+    uint32_t nf = 0; int worst = ST_GTOL;
+    Vec3<R> o = {R(0), R(0), R(0)};
+    // key points of the next frame, loaded one frame ahead (the loads are in flight during the current solve)
+    Vec3<R> ko = o, kt = o;
+    if (t < n_frame) { ko = {__ldg(pk), __ldg(pk + 1), __ldg(pk + 2)}; kt = {__ldg(pk + trow), __ldg(pk + trow + 1), __ldg(pk + trow + 2)}; pk += a.pose_fs; }
+
+    while (__any_sync(full, t < n_frame)) {
+        if (t < n_frame && !solving) {                                   // open frame t
+            o = ko;
+            S.start(prm, Vec3<R>{kt.x - ko.x, kt.y - ko.y, kt.z - ko.z}, null_sq);
+            if (t + 1 < n_frame) { ko = {__ldg(pk), __ldg(pk + 1), __ldg(pk + 2)}; kt = {__ldg(pk + trow), __ldg(pk + trow + 1), __ldg(pk + trow + 2)}; pk += a.pose_fs; }
+            solving = true;
+        }
+        if (solving) S.trip();                                           // one function evaluation
+        if (solving && S.done()) {                                       // close frame t: angles + the 9 joint rows
+            nf += (uint32_t)S.nfev;
+            if (S.status == ST_MAXFEV && worst > ST_MAXFEV) worst = ST_MAXFEV;
+            if (S.status == ST_NONFINITE) worst = ST_NONFINITE;
+#pragma unroll
+            for (int i = 0; i < GEN_DOF; ++i) pa[i] = S.x[i];
+            pa += a.ang_fs;
+            if (pf) {
+                Vec3<R> org[3], claw;
+                S.joints(org, &claw);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { pf[3 * r] = o.x; pf[3 * r + 1] = o.y; pf[3 * r + 2] = o.z; }
+                const Vec3<R> rows[5] = {org[0], org[0], org[1], org[2], claw};
+#pragma unroll
+                for (int r = 0; r < 5; ++r) { pf[12 + 3 * r] = rows[r].x + o.x; pf[13 + 3 * r] = rows[r].y + o.y; pf[14 + 3 * r] = rows[r].z + o.z; }
+                pf += a.fk_fs;
+            }
+            solving = false; ++t;
+        }
+    }
+    if (owner) {
+        if (a.status) a.status[c] = worst == ST_NONFINITE ? -1 : worst;
+        if (a.nfev) a.nfev[c] = nf;
+    }
+}
+
+template <typename R>
+static int launch_generic(const char* me, const R* pose, int64_t pose_chain_stride, int64_t pose_frame_stride, int32_t target_row,
+                          const R* params, R* angles, int64_t ang_chain_stride, int64_t ang_frame_stride,
+                          R* fk, int64_t fk_chain_stride, int64_t fk_frame_stride, const R* warm, int64_t warm_chain_stride,
+                          int32_t* status, uint32_t* nfev, int64_t n_chain, int64_t n_frame, uint32_t flags, void* stream) {
+    if (n_chain < 0 || n_frame < 0) return seqik_fail(SEQIK_EINVAL, "%s: negative size", me);
+    if (n_chain == 0 || n_frame == 0) return SEQIK_OK;
+    if (!pose || !params || !angles) return seqik_fail(SEQIK_EINVAL, "%s: pose, params and angles must not be NULL", me);
+    if (target_row < 1) return seqik_fail(SEQIK_EINVAL, "%s: target_row must be >= 1 (row 0 is the Thorax-Coxa origin)", me);
+    if (pose_frame_stride < 3 * ((int64_t)target_row + 1) || ang_frame_stride < 7 || (fk && fk_frame_stride < 27))
+        return seqik_fail(SEQIK_EINVAL, "%s: frame stride smaller than the innermost block", me);
+    if (n_frame > 2147483647LL) return seqik_fail(SEQIK_EINVAL, "%s: too many frames", me);
+    if (flags & ~(0x3Fu << SEQIK_FLAG_CPW_SHIFT)) return seqik_fail(SEQIK_EINVAL, "%s: unknown flag bits", me);
+    GenArgs<R> a;
+    a.pose = pose; a.pose_cs = pose_chain_stride; a.pose_fs = pose_frame_stride; a.target_row = (int)target_row;
+    a.params = params;
+    a.angles = angles; a.ang_cs = ang_chain_stride; a.ang_fs = ang_frame_stride;
+    a.fk = fk; a.fk_cs = fk_chain_stride; a.fk_fs = fk_frame_stride;
+    a.warm = warm; a.warm_cs = warm_chain_stride;
+    a.status = status; a.nfev = nfev; a.n_chain = n_chain; a.n_frame = n_frame;
+    int dev = 0, n_sm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    int cpw = (int)((n_chain + 4LL * n_sm - 1) / (4LL * n_sm));
+    cpw = cpw < 1 ? 1 : (cpw > 32 ? 32 : cpw);
+    const uint32_t forced = (flags >> SEQIK_FLAG_CPW_SHIFT) & 0x3F;         // tuning / tests
+    if (forced) cpw = (int)forced;
+    if (cpw < 1 || cpw > 32) return seqik_fail(SEQIK_EINVAL, "%s: chains per warp must be 1..32", me);
+    const int64_t grid = (n_chain + cpw - 1) / cpw;
+    leg_solve_generic_kernel<R><<<(unsigned)grid, 32, 0, (cudaStream_t)stream>>>(a, cpw);
+    return seqik_check_launch(me);
+}
+
+extern "C" int seqik_leg_solve_generic_f32(const float* pose, int64_t pose_chain_stride, int64_t pose_frame_stride, int32_t target_row,
+                                           const float* params,
+                                           float* angles, int64_t ang_chain_stride, int64_t ang_frame_stride,
+                                           float* fk, int64_t fk_chain_stride, int64_t fk_frame_stride,
+                                           const float* warm, int64_t warm_chain_stride,
+                                           int32_t* status, uint32_t* nfev,
+                                           int64_t n_chain, int64_t n_frame, uint32_t flags, void* stream) {
+    return launch_generic<float>("seqik_leg_solve_generic_f32", pose, pose_chain_stride, pose_frame_stride, target_row, params,
+                                 angles, ang_chain_stride, ang_frame_stride, fk, fk_chain_stride, fk_frame_stride,
+                                 warm, warm_chain_stride, status, nfev, n_chain, n_frame, flags, stream);
+}
+
+extern "C" int seqik_leg_solve_generic_f64(const double* pose, int64_t pose_chain_stride, int64_t pose_frame_stride, int32_t target_row,
+                                           const double* params,
+                                           double* angles, int64_t ang_chain_stride, int64_t ang_frame_stride,
+                                           double* fk, int64_t fk_chain_stride, int64_t fk_frame_stride,
+                                           const double* warm, int64_t warm_chain_stride,
+                                           int32_t* status, uint32_t* nfev,
+                                           int64_t n_chain, int64_t n_frame, uint32_t flags, void* stream) {
+    return launch_generic<double>("seqik_leg_solve_generic_f64", pose, pose_chain_stride, pose_frame_stride, target_row, params,
+                                  angles, ang_chain_stride, ang_frame_stride, fk, fk_chain_stride, fk_frame_stride,
+                                  warm, warm_chain_stride, status, nfev, n_chain, n_frame, flags, stream);
+}

@@ -101,6 +101,49 @@ def leg_solve(pose, params, affine=None, stages: Sequence[int] = (1, 2, 3, 4), w
     return angles, fk, status, nfev
 
 
+def leg_solve_generic(pose, params, target_row: int = -1, want_fk: bool = True, warm=None, want_stats: bool = True,
+                      chains_per_warp: int = 0):
+    """Generic single-target leg IK (LegInvKinGeneric): pose (n_chain, n_frame, k, 3) with the ThC at row 0 and the end
+    effector at ``target_row`` (default: the last row, like the reference); params (n_chain, 32) from
+    ``KinematicChainGeneric.pack_chain_params``.  float32 tensors run the FP32 kernel, float64 tensors the FP64 one
+    (data and device arithmetic; see include/seqik.h).  Returns (angles (n_chain, n_frame, 7) in GENERIC chain order --
+    ThC_roll, ThC_yaw, ThC_pitch, CTr_pitch, CTr_roll, FTi_pitch, TiTa_pitch --, fk (n_chain, n_frame, 9, 3) | None,
+    status | None, nfev | None).  ``warm`` (n_chain, 7) replaces the seeds of ``params``."""
+    torch = N.require_cuda()
+    lib = N.load_library()
+    if not isinstance(pose, torch.Tensor) or pose.dim() != 4 or pose.shape[-1] != 3:
+        raise ValueError("pose must be a (n_chain, n_frame, k, 3) tensor")
+    dtype = pose.dtype
+    if dtype not in (torch.float32, torch.float64):
+        raise ValueError(f"pose must be float32 or float64, got {dtype}")
+    k = int(pose.shape[2])
+    pose = _check(pose, "pose", (k, 3), dtype)
+    row = target_row if target_row >= 0 else k + target_row
+    if not 1 <= row < k:
+        raise ValueError(f"target_row {target_row} outside the {k} key points (row 0 is the origin)")
+    n_chain, n_frame = int(pose.shape[0]), int(pose.shape[1])
+    params = _check(params, "params", (N.CHAIN_PARAM_FLOATS,), dtype)
+    if params.shape[0] != n_chain:
+        raise ValueError("params must have one row per chain")
+    dev = pose.device
+    if warm is not None:
+        warm = _check(warm, "warm", (7,), dtype)
+        if warm.shape[0] != n_chain:
+            raise ValueError("warm must be (n_chain, 7)")
+    angles = torch.empty((n_chain, n_frame, 7), dtype=dtype, device=dev)
+    fk = torch.empty((n_chain, n_frame, 9, 3), dtype=dtype, device=dev) if want_fk else None
+    status = torch.empty((n_chain,), dtype=torch.int32, device=dev) if want_stats else None
+    nfev = torch.empty((n_chain,), dtype=torch.int32, device=dev) if want_stats else None
+    fn = lib.seqik_leg_solve_generic_f32 if dtype == torch.float32 else lib.seqik_leg_solve_generic_f64
+    with torch.cuda.device(dev):
+        rc = fn(pose.data_ptr(), n_frame * k * 3, k * 3, row, N.ptr(params),
+                angles.data_ptr(), n_frame * 7, 7, N.ptr(fk), n_frame * 27, 27,
+                N.ptr(warm), 7, N.ptr(status), N.ptr(nfev), n_chain, n_frame, (chains_per_warp & 0x3F) << 12,
+                N.stream_ptr(torch, dev))
+    N.check(rc, "seqik_leg_solve_generic")
+    return angles, fk, status, nfev
+
+
 def forward_kinematics(angles, origin, params):
     """angles (n_chain, n_frame, 7) + origin (n_chain, n_frame, 3) or (n_chain, 3) -> fk (n_chain, n_frame, 9, 3)."""
     torch = N.require_cuda()

@@ -195,3 +195,62 @@ class KinematicChainSeq(KinematicChainBase):
             inert = np.delete(seed, act)
             row[25 + stage - 1] = float(np.dot(inert, inert))
         return row
+
+
+# link order of the generic chain (reference kinematic_chain.py:464-530): roll comes FIRST
+GENERIC_DOF_ORDER = ("ThC_roll", "ThC_yaw", "ThC_pitch", "CTr_pitch", "CTr_roll", "FTi_pitch", "TiTa_pitch")
+_GENERIC_LINKS = (
+    ("ThC_roll", Axes.Z_AXIS, None), ("ThC_yaw", Axes.X_AXIS, None), ("ThC_pitch", Axes.Y_AXIS, None),
+    ("CTr_pitch", Axes.Y_AXIS, "Coxa"), ("CTr_roll", Axes.Z_AXIS, None), ("FTi_pitch", Axes.Y_AXIS, "Femur"),
+    ("TiTa_pitch", Axes.Y_AXIS, "Tibia"),
+)
+
+
+class KinematicChainGeneric(KinematicChainBase):
+    """One chain for the entire leg, every joint revolute (reference kinematic_chain.py:424-532)."""
+
+    def __call__(self):
+        print("Generic kinematic chain is called.")
+
+    def create_leg_chain(self, leg_name: str, **kwargs) -> Chain:
+        """Base link, ThC roll/yaw/pitch, CTr pitch/roll, FTi pitch, TiTa pitch, Claw.  ValueError on an unknown leg."""
+        if leg_name not in LEG_NAMES:
+            raise ValueError(f"Unknown leg name ({leg_name}) is provided!")
+        links = [Link("Base link", joint_type="fixed")]
+        for dof, axis, seg in _GENERIC_LINKS:
+            offset = (0, 0, 0) if seg is None else (0, 0, -self.body_size[f"{leg_name}_{seg}"])
+            links.append(Link(f"{leg_name}_{dof}", offset, (0, 0, 0), axis, "revolute", self.bounds_dof[f"{leg_name}_{dof}"]))
+        links.append(Link(f"{leg_name}_Claw", (0, 0, -self.body_size[f"{leg_name}_Tarsus"]), (0, 0, 0), [0, 0, 0],
+                          "revolute", (-np.pi, np.pi)))
+        return Chain(name="chain", links=links)
+
+    def chain_bounds(self, leg: str):
+        """(lb, ub) over the 9 chain slots -- the arrays scipy's feasibility check sees."""
+        lb = [-np.inf] + [self.bounds_dof[f"{leg}_{d}"][0] for d in GENERIC_DOF_ORDER] + [-np.pi]
+        ub = [np.inf] + [self.bounds_dof[f"{leg}_{d}"][1] for d in GENERIC_DOF_ORDER] + [np.pi]
+        return np.asarray(lb, dtype=float), np.asarray(ub, dtype=float)
+
+    def check_seed(self, leg: str, seed) -> None:
+        """Raises the ValueError scipy raises when ANY slot of the 9-vector seed is outside its bounds."""
+        lb, ub = self.chain_bounds(leg)
+        seed = np.asarray(seed, dtype=float)
+        if seed.shape != lb.shape:
+            raise ValueError(f"Inconsistent shapes between bounds and `x0`: the generic chain of {leg} needs {lb.size} "
+                             f"initial angles, got {seed.size}.")
+        if not np.all((seed >= lb) & (seed <= ub)):
+            raise ValueError("Initial guess is outside of provided bounds")
+
+    def pack_chain_params(self, leg: str, seed) -> np.ndarray:
+        """The 32-float constants row of ``seqik_leg_solve_generic_f32`` (include/seqik.h) for one leg.  ``seed`` is the
+        9-vector the reference hands to the generic chain POSITIONALLY (``initial_angles[leg]["stage_4"]``,
+        leg_inverse_kinematics.py:583): slot i seeds link i whatever DOF the stage-4 vector meant it for."""
+        seed = np.asarray(seed, dtype=float)
+        self.check_seed(leg, seed)
+        lb, ub = self.chain_bounds(leg)
+        row = np.zeros(32, dtype=np.float64)
+        row[0:4] = [self.body_size[f"{leg}_{s}"] for s in SEGMENTS]
+        row[4:11] = lb[1:8]
+        row[11:18] = ub[1:8]
+        row[18:25] = seed[1:8]
+        row[25] = seed[0] ** 2 + seed[8] ** 2
+        return row

@@ -18,7 +18,8 @@ import numpy as np
 from . import _native as N
 from . import engine
 from .data import INITIAL_ANGLES
-from .kinematic_chain import (DOF_ORDER, STAGE_ACTIVE_DOFS, KinematicChainBase, KinematicChainSeq)
+from .kinematic_chain import (DOF_ORDER, GENERIC_DOF_ORDER, STAGE_ACTIVE_DOFS, KinematicChainBase, KinematicChainGeneric,
+                              KinematicChainSeq)
 from .utils import save_file
 
 logging.basicConfig(format=" %(asctime)s - %(levelname)s- %(message)s", handlers=[logging.StreamHandler()])
@@ -221,6 +222,143 @@ class LegInvKinSeq(LegInvKinBase):
         # restore the reference's insertion order (aligned_pos order)
         forward_kinematics_dict = {n: forward_kinematics_dict[n] for n in names}
 
+        self.logger.debug("Joint angles and forward kinematics are computed.")
+        if export_path is not None:
+            save_file(Path(export_path) / "forward_kinematics.pkl", forward_kinematics_dict)
+            save_file(Path(export_path) / "leg_joint_angles.pkl", self.joint_angles_dict)
+            self.logger.info("Joint angles and forward kinematics are saved at %s", export_path)
+        return self.joint_angles_dict, forward_kinematics_dict
+
+
+class LegInvKinGeneric(LegInvKinBase):
+    """Generic leg IK: all seven joints solved at once against ONE target, the claw (drop-in for the reference's
+    ``LegInvKinGeneric``, seqikpy/leg_inverse_kinematics.py:406-613).
+
+    One kernel launch solves every leg: frames serial inside a leg (warm start, :524), legs in parallel.  The device
+    solver restates the reference's optimiser (scipy TRF on the chain of ``KinematicChainGeneric``) and reaches the same
+    claw residual, but the problem is under-determined -- 3 equations, 7 unknowns -- and the reference's own answer
+    depends on rounding noise: solve by solve from the same seed the two agree, a free-running recording
+    follows its own path along the self-motion manifold.  There is no CPU path.
+
+    Extra, optional arguments over the reference: ``device`` (default ``"cuda"``) and ``precision`` -- ``"float64"``
+    (default: FP64 data and device arithmetic, which agrees with scipy solve by solve as often as scipy agrees with
+    itself) or ``"float32"`` (faster, agrees a few percent less often; same claw residual bound).
+    """
+
+    def __init__(
+        self,
+        aligned_pos: Dict[str, np.ndarray],
+        kinematic_chain_class: KinematicChainGeneric,
+        initial_angles: Optional[Dict[str, np.ndarray]] = None,
+        log_level: Literal["DEBUG", "INFO", "WARNING", "ERROR"] = "INFO",
+        device: str = "cuda",
+        precision: Literal["float64", "float32"] = "float64",
+    ) -> None:
+        super().__init__(aligned_pos, kinematic_chain_class, initial_angles, log_level)
+        if precision not in ("float64", "float32"):
+            raise ValueError(f"precision must be 'float64' or 'float32', got {precision!r}")
+        self.joint_angles_dict = {}
+        self.device = device
+        self.precision = precision
+        #: solver statistics of the last call: {leg: {"nfev": evaluations summed over frames, "status": int}}
+        self.solver_stats = {}
+
+    def _solve(self, legs, pose2, seeds):
+        """legs: names; pose2 (n_leg, N, 2, 3) = ThC origin + end effector; seeds: 9-vector per leg.
+        Returns float64 angles (n_leg, N, 7) in generic chain order and fk (n_leg, N, 9, 3)."""
+        torch = N.require_cuda()
+        N.load_library()
+        chain = self.kinematic_chain_class
+        params = np.stack([chain.pack_chain_params(leg, seeds[i]) for i, leg in enumerate(legs)])
+        dev = torch.device(self.device)
+        npdt = np.float64 if self.precision == "float64" else np.float32
+        d_pose = torch.from_numpy(np.ascontiguousarray(pose2, dtype=npdt)).to(dev)
+        d_params = torch.from_numpy(params.astype(npdt)).to(dev)
+        d_angles, d_fk, d_status, d_nfev = engine.leg_solve_generic(d_pose, d_params, target_row=1, want_fk=True)
+        angles = d_angles.cpu().numpy().astype(np.float64)
+        fk = d_fk.cpu().numpy().astype(np.float64)
+        status, nfev = d_status.cpu().numpy(), d_nfev.cpu().numpy()
+        for i, leg in enumerate(legs):
+            self.solver_stats[leg] = {"nfev": int(nfev[i]), "status": int(status[i])}
+            if status[i] < 0:       # what scipy.optimize.least_squares raises inside the reference's frame loop
+                raise ValueError(f"Residuals are not finite in the initial point (leg {leg}: NaN/inf key points).")
+            if status[i] == 0:
+                self.logger.warning("Leg %s: at least one solve stopped at the evaluation limit", leg)
+        return angles, fk
+
+    def _store(self, leg, angles):
+        for i, dof in enumerate(GENERIC_DOF_ORDER):          # the reference's link order (Base and Claw skipped, :537-544)
+            self.joint_angles_dict[f"Angle_{leg}_{dof}"] = angles[:, i].copy()
+
+    def calculate_ik_stage(
+        self,
+        end_effector_pos: np.ndarray,
+        origin: np.ndarray,
+        initial_angles: np.ndarray,
+        segment_name: str,
+        **kwargs
+    ) -> np.ndarray:
+        """Generic IK of one leg over all frames (reference :473-547): ``end_effector_pos`` (N, 3) claw positions,
+        ``origin`` (N, 3) or (3,) Thorax-Coxa joint, ``initial_angles`` the 9-vector seed of the chain.  Stores the
+        joint angles in ``self.joint_angles_dict`` and returns the joint positions, shape (N, 9, 3)."""
+        if segment_name not in _LEGS:
+            raise ValueError(f"Segment name ({segment_name}) is not valid.")
+        end_effector_pos = np.asarray(end_effector_pos, dtype=float).reshape(-1, 3)
+        n_frames = end_effector_pos.shape[0]
+        origin = np.asarray(origin, dtype=float)
+        if origin.size == 3:
+            origin = np.tile(origin.reshape(1, 3), (n_frames, 1))
+        pose2 = np.stack([origin, end_effector_pos], axis=1)[None]
+        if n_frames == 0:
+            self.kinematic_chain_class.check_seed(segment_name, initial_angles)
+            angles, fk = np.zeros((1, 0, 7)), np.zeros((1, 0, 9, 3))
+        else:
+            angles, fk = self._solve([segment_name], pose2, [np.asarray(initial_angles, dtype=float)])
+        self._store(segment_name, angles[0])
+        return fk[0]
+
+    def run_ik_and_fk(
+        self,
+        export_path: Union[Path, str] = None,
+        **kwargs
+    ) -> Tuple[Dict[str, np.ndarray], Dict[str, np.ndarray]]:
+        """Joint angles and forward kinematics of every ``*_leg`` entry (reference :549-613).  The end effector is the
+        LAST key point of each leg array, the seed is ``initial_angles[leg]["stage_4"]`` (:582-583).  kwargs:
+        ``hide_progress_bar`` (accepted for compatibility).  With ``export_path`` both dictionaries are pickled as
+        ``leg_joint_angles.pkl`` / ``forward_kinematics.pkl``."""
+        forward_kinematics_dict = {}
+        self.logger.info("Computing joint angles and forward kinematics...")
+        names, legs, arrays = [], [], []
+        for segment_name, segment_array in self.aligned_pos.items():
+            if "leg" not in segment_name.lower():
+                self.logger.debug("Segment %s is not a leg, continuing...", segment_name)
+                continue
+            leg_name = segment_name.split("_")[0]
+            if leg_name not in self.kinematic_chain_class.body_size:
+                self.logger.warning("Leg %s is not in the kinematic chain, continuing...", leg_name)
+                continue
+            if leg_name not in _LEGS:
+                raise ValueError(f"Segment name ({leg_name}) is not valid.")
+            arr = np.asarray(segment_array)
+            if arr.ndim != 3 or arr.shape[1] < 2 or arr.shape[2] != 3:
+                raise ValueError(f"{segment_name}: expected (N, >=2, 3), got {arr.shape}")
+            names.append(segment_name)
+            legs.append(leg_name)
+            arrays.append(arr)
+        by_len = {}
+        for i, arr in enumerate(arrays):
+            by_len.setdefault(arr.shape[0], []).append(i)
+        for n_frames, idx in by_len.items():
+            pose2 = np.stack([arrays[i][:, (0, -1), :] for i in idx]).astype(float)
+            seeds = [np.asarray(self.initial_angles[legs[i]]["stage_4"], dtype=float) for i in idx]
+            if n_frames == 0:
+                angles, fk = np.zeros((len(idx), 0, 7)), np.zeros((len(idx), 0, 9, 3))
+            else:
+                angles, fk = self._solve([legs[i] for i in idx], pose2, seeds)
+            for j, i in enumerate(idx):
+                self._store(legs[i], angles[j])
+                forward_kinematics_dict[names[i]] = fk[j]
+        forward_kinematics_dict = {n: forward_kinematics_dict[n] for n in names}
         self.logger.debug("Joint angles and forward kinematics are computed.")
         if export_path is not None:
             save_file(Path(export_path) / "forward_kinematics.pkl", forward_kinematics_dict)

@@ -50,3 +50,8 @@ def synthetic_gold():
 @pytest.fixture(scope="session")
 def synthetic_long():
     return _npz("synthetic_long.npz")
+
+
+@pytest.fixture(scope="session")
+def generic_gold():
+    return _npz("generic_leg.npz")

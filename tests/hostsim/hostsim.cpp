@@ -2,6 +2,7 @@
 // TEST INFRASTRUCTURE: compiled by tests/hostsim_build.py with g++, loaded via ctypes by
 // tests; the product package never loads it.
 #include "seqik_core.cuh"
+#include "seqik_generic.cuh"
 #include <cstdint>
 
 using namespace seqik;
@@ -62,5 +63,42 @@ void hostsim_chain_f64(const double* pose, int64_t n_frame, const double* seg, c
                        const double* null_sq, const double* seed, double* angles, double* fk, int32_t* nfev,
                        int32_t* status, int stage_mask, int gn_mask) {
     run_chain<double>(pose, n_frame, seg, lb, ub, null_sq, seed, angles, fk, nfev, status, stage_mask, gn_mask);
+}
+}
+
+// ---- generic 7-DOF solve (csrc/seqik_generic.cuh): pose (N,2,3) = ThC origin + claw per frame; prm = 32-float row
+// (seg 0..3, lb 4..10, ub 11..17, seed 18..24, null_sq 25; joints in generic chain order).  teacher: NULL, or (N,7)
+// seeds that replace the warm start of every frame (teacher-forced single solves).
+template <typename R>
+static void run_generic(const R* pose, int64_t n_frame, const R* prm, const R* teacher, R* angles, R* fk,
+                        int32_t* nfev, int32_t* status) {
+    GenericSolve<R> S;
+    for (int i = 0; i < 7; ++i) S.x[i] = prm[18 + i];
+    for (int64_t t = 0; t < n_frame; ++t) {
+        const R* p = pose + t * 6;
+        if (teacher) for (int i = 0; i < 7; ++i) S.x[i] = teacher[t * 7 + i];
+        S.start(prm, Vec3<R>{p[3] - p[0], p[4] - p[1], p[5] - p[2]}, prm[25]);
+        while (!S.done()) S.trip();
+        for (int i = 0; i < 7; ++i) angles[t * 7 + i] = S.x[i];
+        nfev[t] = S.nfev; status[t] = S.status;
+        if (fk) {
+            Vec3<R> org[3], claw;
+            S.joints(org, &claw);
+            R* o = fk + t * 27;
+            for (int r = 0; r < 4; ++r) { o[3 * r] = p[0]; o[3 * r + 1] = p[1]; o[3 * r + 2] = p[2]; }
+            const Vec3<R> rows[5] = {org[0], org[0], org[1], org[2], claw};
+            for (int r = 0; r < 5; ++r) { o[12 + 3 * r] = rows[r].x + p[0]; o[13 + 3 * r] = rows[r].y + p[1]; o[14 + 3 * r] = rows[r].z + p[2]; }
+        }
+    }
+}
+
+extern "C" {
+void hostsim_generic_f32(const float* pose, int64_t n_frame, const float* prm, const float* teacher, float* angles,
+                         float* fk, int32_t* nfev, int32_t* status) {
+    run_generic<float>(pose, n_frame, prm, teacher, angles, fk, nfev, status);
+}
+void hostsim_generic_f64(const double* pose, int64_t n_frame, const double* prm, const double* teacher, double* angles,
+                         double* fk, int32_t* nfev, int32_t* status) {
+    run_generic<double>(pose, n_frame, prm, teacher, angles, fk, nfev, status);
 }
 }

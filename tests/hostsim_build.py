@@ -18,7 +18,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    deps = [SRC, CSRC / "seqik_core.cuh"]
+    deps = [SRC, CSRC / "seqik_core.cuh", CSRC / "seqik_generic.cuh"]
     if not OUT.exists() or any(d.stat().st_mtime > OUT.stat().st_mtime for d in deps):
         # -ffp-contract=off: no FMA contraction, so the f64 build tracks the Python model closely
         cmd = ["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-std=c++17", "-x", "c++", str(SRC),
@@ -64,3 +64,24 @@ def run_runner_f32(pose, seg, lb, ub, null_sq, seed, stage_mask=0xF, gn_mask=0):
     steps = fn(pose.ctypes.data, n, *(a.ctypes.data for a in args), angles.ctypes.data, fk.ctypes.data,
                nfev_sum.ctypes.data, stage_mask, gn_mask)
     return angles, fk, nfev_sum, steps
+
+
+def solve_generic(pose2, prm, teacher=None, dtype=np.float32, want_fk=True):
+    """Generic 7-DOF chain on the host build: pose2 (N,2,3) = ThC origin + claw, prm (32,) generic constants row,
+    teacher (N,7) optional per-frame seeds -> angles (N,7) in generic chain order, fk (N,9,3), nfev (N,), status (N,)."""
+    lib = load()
+    fn = lib.hostsim_generic_f32 if dtype == np.float32 else lib.hostsim_generic_f64
+    pose2 = np.ascontiguousarray(pose2, dtype=dtype)
+    n = pose2.shape[0]
+    prm = np.ascontiguousarray(prm, dtype=dtype)
+    teacher = None if teacher is None else np.ascontiguousarray(teacher, dtype=dtype)
+    angles = np.zeros((n, 7), dtype=dtype)
+    fk = np.zeros((n, 9, 3), dtype=dtype)
+    nfev = np.zeros(n, dtype=np.int32)
+    status = np.zeros(n, dtype=np.int32)
+    P = ctypes.c_void_p
+    fn.argtypes = [P, ctypes.c_int64, P, P, P, P, P, P]
+    fn.restype = None
+    fn(pose2.ctypes.data, n, prm.ctypes.data, None if teacher is None else teacher.ctypes.data, angles.ctypes.data,
+       fk.ctypes.data if want_fk else None, nfev.ctypes.data, status.ctypes.data)
+    return angles, fk, nfev, status
