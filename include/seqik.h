@@ -212,6 +212,19 @@ int seqik_head_affine_f32(const float* stats, const float* consts, float* affine
 int seqik_head_apply_f32(const float* head, const float* affine, float* out, int64_t n_trial, int64_t n_frame,
                          void* stream);
 
+/* Shape-preserving cubic (pchip) resampling of uniformly sampled series onto a finer or coarser uniform grid: the hand-off
+ * of joint angles to a simulation time step.  Replaces utils.interpolate_signal / interpolate_joint_angles
+ * (seqikpy/utils.py:332-359) = scipy.interpolate.pchip_interpolate(arange(0, n*ts, ts), y, arange(0, n*ts, new_ts)),
+ * including the extrapolation of the last cubic piece over the samples of the new grid that lie past the last knot.
+ *   in  [n_block][n][width], out [n_block][m][width], m = ceil(n * original_ts / new_ts) (the length of numpy's arange);
+ *   width = interleaved channels (7 for an angles tensor [n_chain][n_frame][7], 1 for plain series [n_series][n]).
+ * Values must be finite (scipy raises otherwise; the reference's retry zeroes +-inf samples and the last sample first:
+ * the host wrapper does the same). */
+int seqik_pchip_resample_f32(const float* in, float* out, int64_t n_block, int64_t n, int64_t m, int64_t width,
+                             double original_ts, double new_ts, void* stream);
+int seqik_pchip_resample_f64(const double* in, double* out, int64_t n_block, int64_t n, int64_t m, int64_t width,
+                             double original_ts, double new_ts, void* stream);
+
 /* Strided copy between host (pinned) and device buffers: `height` rows of `width_bytes`, row pitches in bytes.
  * direction 1 = host to device, 2 = device to host.  Plumbing for the chunked host pipeline (a frame range of a
  * chain-major array is a 2-D block); a thin wrapper over cudaMemcpy2DAsync so that callers need no CUDA binding. */

@@ -19,7 +19,10 @@ n_frame = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 counts = [int(a) for a in sys.argv[2:]] or [6, 600, 6000, 60000]
 size, bounds, init = S.chain_constants()
 chain = KinematicChainGeneric(bounds, list(S.LEGS), size)
-rows6 = np.stack([chain.pack_chain_params(leg, init[leg]["stage_4"]) for leg in S.LEGS])
+# the stage-4 seed vector is in yaw, pitch, roll order; the reference hands it to the generic chain positionally, which for the
+# locomotion constants puts some slots outside their bounds (scipy raises, and so do we) -- permute it into chain order here
+perm = [0, 3, 1, 2, 4, 5, 6, 7, 8]
+rows6 = np.stack([chain.pack_chain_params(leg, np.asarray(init[leg]["stage_4"], dtype=float)[perm]) for leg in S.LEGS])
 n_unique = 8
 pose = np.stack([S.make_trial(tr, 1000)[:n_frame] for tr in range(n_unique)]).transpose(0, 2, 1, 3, 4)   # (trial, leg, frame, 5, 3)
 pose = pose.reshape(n_unique * 6, n_frame, 5, 3)

@@ -57,5 +57,12 @@ report("head_kernel", timeit(lambda: engine.head_angles(r, l, neck, rest)), nf *
 th = torch.randn((n_trial, 6 * n_frame, 3, 3), device="cuda", generator=g); hc = torch.rand((n_trial, 5), device="cuda", generator=g) + 0.5
 report("head_affine (series fp64 + radix select + affine)", timeit(lambda: engine.head_affine(r, th, hc)), nf * (24 + 36 + 20 + 20), nf, "frames")
 report("head_apply_kernel", timeit(lambda: engine.head_apply(r, torch.rand((n_trial, 8), device="cuda") + 0.5)), nf * 48, nf, "frames")
+# pchip resampler: the 6000 x 1000 x 7 angles of this workload from 100 Hz onto a 1 kHz grid (42e6 in, 420e6 out)
+for dt, nb in ((torch.float32, 4), (torch.float64, 8)):
+    a = angles.to(dt)
+    n_out = n_chain * 10 * n_frame * 7
+    report(f"pchip_kernel ({str(dt).split('.')[1]}, x10 upsampling of the angles tensor)", timeit(lambda: engine.pchip_resample(a, 0.01, 0.001), reps=5),
+           (angles.numel() + n_out) * nb, n_out, "samples")
+    del a
 x = torch.empty(1 << 28, device="cuda"); y = torch.empty_like(x)
 report("torch copy (reference point)", timeit(lambda: y.copy_(x)), 2 * x.numel() * 4, x.numel(), "elements")

@@ -34,6 +34,8 @@ _SIGNATURES = {
                                            _vp, _vp, _i64, _i64, _u32, _vp]),
     "seqik_leg_solve_generic_f64": (_int, [_vp, _i64, _i64, ctypes.c_int32, _vp, _vp, _i64, _i64, _vp, _i64, _i64, _vp, _i64,
                                            _vp, _vp, _i64, _i64, _u32, _vp]),
+    "seqik_pchip_resample_f32": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, ctypes.c_double, ctypes.c_double, _vp]),
+    "seqik_pchip_resample_f64": (_int, [_vp, _vp, _i64, _i64, _i64, _i64, ctypes.c_double, ctypes.c_double, _vp]),
     "seqik_memcpy2d_async": (_int, [_vp, _i64, _vp, _i64, _i64, _i64, _int, _vp]),
     "seqik_fk_f32": (_int, [_vp, _vp, _i64, _vp, _vp, _i64, _i64, _vp]),
     "seqik_head_angles_f32": (_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i64, _vp]),

@@ -507,3 +507,82 @@ extern "C" int seqik_head_apply_f32(const float* head, const float* affine, floa
     head_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(head, affine, out, n_trial, n_frame);
     return check_launch("seqik_head_apply_f32");
 }
+
+// ---------------------------------------------------------------------------------------------
+// pchip resampling of joint-angle series (the hand-off to a simulation time step)
+// ---------------------------------------------------------------------------------------------
+// utils.interpolate_signal (seqikpy/utils.py:332-349) = scipy.interpolate.pchip_interpolate(arange(0, n ts, ts), y,
+// arange(0, n ts, new_ts)): Fritsch-Carlson derivatives (harmonic mean of the neighbouring secant slopes, 0 at a local
+// extremum, the three-point rule with its two clamps at the ends), cubic Hermite pieces evaluated in the power basis
+// about the left knot, and -- because the new grid runs past the last sample -- the last piece extrapolated.
+// One thread per output sample; `width` interleaved channels ([block][sample][width], e.g. the 7 DOFs of an angles
+// tensor) so that loads and stores of neighbouring threads are contiguous.  HBM-bound: (n + m) * width values per block.
+template <typename T> __device__ __forceinline__ T pchip_sign(T v) { return (T)((v > T(0)) - (v < T(0))); }
+template <typename T> __device__ __forceinline__ T pchip_edge(T h0, T h1, T m0, T m1) {      // scipy PchipInterpolator._edge_case
+    T d = ((T(2) * h0 + h1) * m0 - h0 * m1) / (h0 + h1);
+    if (pchip_sign(d) != pchip_sign(m0)) d = T(0);
+    else if (pchip_sign(m0) != pchip_sign(m1) && fabs(d) > T(3) * fabs(m0)) d = T(3) * m0;
+    return d;
+}
+template <typename T> __device__ __forceinline__ T pchip_inner(T h, T ma, T mb) {            // _find_derivatives, interior point
+    if (pchip_sign(ma) != pchip_sign(mb) || ma == T(0) || mb == T(0)) return T(0);
+    const T w = T(3) * h;                                                                     // w1 = w2 = 3 h on a uniform grid
+    return T(1) / ((w / ma + w / mb) / (w + w));
+}
+template <typename T>
+__global__ void __launch_bounds__(256) pchip_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t n_block, int64_t n,
+                                                    int64_t m, int64_t width, double ts, double new_ts) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_block * m * width) return;
+    const int64_t j = idx % width, u = (idx / width) % m, b = idx / (width * m);
+    // interval: the largest k with k ts <= x, at most n - 2 (the last piece also serves x beyond the last knot)
+    const double x = (double)u * new_ts;
+    int64_t k = (int64_t)floor(x / ts);
+    while ((double)(k + 1) * ts <= x) ++k;
+    while (k > 0 && (double)k * ts > x) --k;
+    if (k > n - 2) k = n - 2;
+    if (k < 0) k = 0;
+    const T s = (T)(x - (double)k * ts);
+    const T h = (T)ts;
+    const T* y = in + b * n * width + j;
+    const T y0 = __ldg(y + k * width), y1 = __ldg(y + (k + 1) * width);
+    const T slope = (y1 - y0) / h;
+    T d0, d1;
+    if (n == 2) { d0 = slope; d1 = slope; }
+    else {
+        // secant slopes of the neighbouring intervals (where they exist)
+        const T m_prev = (k > 0) ? (y0 - __ldg(y + (k - 1) * width)) / h : T(0);
+        const T m_next = (k + 2 < n) ? (__ldg(y + (k + 2) * width) - y1) / h : T(0);
+        d0 = (k > 0) ? pchip_inner(h, m_prev, slope) : pchip_edge(h, h, slope, m_next);
+        d1 = (k + 2 < n) ? pchip_inner(h, slope, m_next) : pchip_edge(h, h, slope, m_prev);
+    }
+    // CubicHermiteSpline coefficients (power basis about the left knot), summed in ascending powers like PPoly
+    const T t_ = (d0 + d1 - T(2) * slope) / h;
+    const T c0 = t_ / h, c1 = (slope - d0) / h - t_;
+    T res = y0, z = s;
+    res += d0 * z; z *= s;
+    res += c1 * z; z *= s;
+    res += c0 * z;
+    out[idx] = res;
+}
+template <typename T>
+static int pchip_launch(const char* me, const T* in, T* out, int64_t n_block, int64_t n, int64_t m, int64_t width,
+                        double original_ts, double new_ts, void* stream) {
+    if (n_block < 0 || n < 0 || m < 0 || width < 0) return seqik_fail(SEQIK_EINVAL, "%s: negative size", me);
+    if (n_block == 0 || m == 0 || width == 0) return SEQIK_OK;
+    if (n < 2) return seqik_fail(SEQIK_EINVAL, "%s: at least 2 samples are needed", me);
+    if (!in || !out) return seqik_fail(SEQIK_EINVAL, "%s: NULL pointer", me);
+    if (!(original_ts > 0.0) || !(new_ts > 0.0)) return seqik_fail(SEQIK_EINVAL, "%s: time steps must be positive", me);
+    const int64_t total = n_block * m * width;
+    if (total > 2147483647LL * 256) return seqik_fail(SEQIK_EINVAL, "%s: too many output samples for one launch", me);
+    pchip_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, out, n_block, n, m, width, original_ts, new_ts);
+    return seqik_check_launch(me);
+}
+extern "C" int seqik_pchip_resample_f32(const float* in, float* out, int64_t n_block, int64_t n, int64_t m, int64_t width,
+                                        double original_ts, double new_ts, void* stream) {
+    return pchip_launch<float>("seqik_pchip_resample_f32", in, out, n_block, n, m, width, original_ts, new_ts, stream);
+}
+extern "C" int seqik_pchip_resample_f64(const double* in, double* out, int64_t n_block, int64_t n, int64_t m, int64_t width,
+                                        double original_ts, double new_ts, void* stream) {
+    return pchip_launch<double>("seqik_pchip_resample_f64", in, out, n_block, n, m, width, original_ts, new_ts, stream);
+}

@@ -289,3 +289,43 @@ def head_apply(head, affine):
         rc = lib.seqik_head_apply_f32(N.ptr(head), N.ptr(affine), N.ptr(out), n_trial, n_frame, N.stream_ptr(torch, head.device))
     N.check(rc, "seqik_head_apply_f32")
     return out
+
+
+def pchip_resample(series, original_ts: float, new_ts: float):
+    """Shape-preserving cubic resampling (``utils.interpolate_signal``, reference utils.py:332-349) of uniformly sampled
+    series on the device: ``series`` (n_block, n, width) -- e.g. an angles tensor (n_chain, n_frame, 7) -- or (n_series, n);
+    float32 or float64.  Returns the same layout with ``m = len(np.arange(0, n * original_ts, new_ts))`` samples.
+    Like the reference's retry, +-inf samples are zeroed together with the last sample of that series; NaN raises."""
+    import numpy as np
+    torch = N.require_cuda()
+    lib = N.load_library()
+    if not isinstance(series, torch.Tensor) or not series.is_cuda:
+        raise N.SeqIKNativeError("series must be a CUDA tensor (there is no CPU path)")
+    if series.dtype not in (torch.float32, torch.float64):
+        raise ValueError(f"series must be float32 or float64, got {series.dtype}")
+    if series.dim() not in (2, 3):
+        raise ValueError("series must be (n_series, n) or (n_block, n, width)")
+    flat = series.dim() == 2
+    x = series.unsqueeze(-1) if flat else series
+    if not x.is_contiguous():
+        raise ValueError("series must be contiguous")
+    n_block, n, width = (int(v) for v in x.shape)
+    if n < 2:
+        raise ValueError("at least 2 samples are needed")
+    if not (original_ts > 0 and new_ts > 0):
+        raise ValueError("time steps must be positive")
+    m = int(np.ceil((n * original_ts) / new_ts))                # length of np.arange(0, n * original_ts, new_ts)
+    finite = torch.isfinite(x)
+    if not bool(finite.all()):
+        if bool(torch.isnan(x).any()):
+            raise ValueError("`y` must contain only finite values.")
+        x = torch.where(finite, x, torch.zeros_like(x))
+        hit = (~finite).any(dim=1)                                # (n_block, width): series that held an inf
+        x[:, -1, :] = torch.where(hit, torch.zeros_like(x[:, -1, :]), x[:, -1, :])
+    out = torch.empty((n_block, m, width), dtype=x.dtype, device=x.device)
+    fn = lib.seqik_pchip_resample_f32 if x.dtype == torch.float32 else lib.seqik_pchip_resample_f64
+    with torch.cuda.device(x.device):
+        rc = fn(x.data_ptr(), out.data_ptr(), n_block, n, m, width, float(original_ts), float(new_ts),
+                N.stream_ptr(torch, x.device))
+    N.check(rc, "seqik_pchip_resample")
+    return out.squeeze(-1) if flat else out

@@ -45,6 +45,16 @@ def test_argument_validation_without_gpu():
     assert lib.seqik_head_angles_f32(8, 8, 8, 5, 0, 0, 8, 8, 1, 1, 0) == -1                              # bad neck stride
     assert lib.seqik_memcpy2d_async(8, 4, 8, 16, 8, 2, 1, 0) == -1                                       # pitch < width
     assert lib.seqik_memcpy2d_async(8, 16, 8, 16, 8, 2, 3, 0) == -1                                      # bad direction
+    gen = [0, 0, 15, 4, 0, 0, 0, 7, 0, 0, 27, 0, 0, 0, 0]
+    assert lib.seqik_leg_solve_generic_f32(*gen, -1, 10, 0, 0) == -1                                       # negative size
+    assert lib.seqik_leg_solve_generic_f64(*gen, 0, 10, 0, 0) == 0                                         # empty: ok
+    assert lib.seqik_leg_solve_generic_f32(*gen, 4, 10, 0, 0) == -1                                        # NULL pose
+    assert lib.seqik_leg_solve_generic_f32(8, 150, 15, 0, 8, 8, 70, 7, 0, 0, 27, 0, 0, 0, 0, 4, 10, 0, 0) == -1   # target_row 0
+    assert lib.seqik_leg_solve_generic_f32(8, 150, 15, 5, 8, 8, 70, 7, 0, 0, 27, 0, 0, 0, 0, 4, 10, 0, 0) == -1   # row outside the stride
+    assert lib.seqik_leg_solve_generic_f64(8, 150, 15, 4, 8, 8, 70, 7, 0, 0, 27, 0, 0, 0, 0, 4, 10, 1, 0) == -1   # unknown flag bit
+    assert lib.seqik_pchip_resample_f32(8, 8, 1, 1, 10, 1, 0.01, 0.001, 0) == -1                          # fewer than 2 samples
+    assert lib.seqik_pchip_resample_f64(8, 8, 1, 5, 10, 1, 0.01, 0.0, 0) == -1                            # non-positive step
+    assert lib.seqik_pchip_resample_f64(8, 8, 0, 5, 10, 1, 0.01, 0.001, 0) == 0                           # empty: ok
     with pytest.raises(ValueError):
         N.check(-1, "x")
 
