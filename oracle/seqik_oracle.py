@@ -31,6 +31,12 @@ The chain topology follows /root/reference/seqikpy/kinematic_chain.py:152-421
 (stage builders) and the frame loop / warm start / column extraction follow
 /root/reference/seqikpy/leg_inverse_kinematics.py:239-322.
 
+The generic single-target path (``LegInvKinGeneric`` / ``KinematicChainGeneric``,
+leg_inverse_kinematics.py:406-613, kinematic_chain.py:424-532) is restated by
+``build_generic_chain`` / ``run_generic_leg`` / ``run_generic_ik_and_fk`` on the same ikpy
+glue.  The reference ships no output for it; its fixture (tests/golden/generic_leg.npz) is
+this oracle's own output together with a measurement of how reproducible that output is.
+
 Parity pinning
 --------------
 The reference's own tests hold no numeric check for this path

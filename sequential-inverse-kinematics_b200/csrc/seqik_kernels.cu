@@ -517,53 +517,101 @@ extern "C" int seqik_head_apply_f32(const float* head, const float* affine, floa
 // about the left knot, and -- because the new grid runs past the last sample -- the last piece extrapolated.
 // One thread per output sample; `width` interleaved channels ([block][sample][width], e.g. the 7 DOFs of an angles
 // tensor) so that loads and stores of neighbouring threads are contiguous.  HBM-bound: (n + m) * width values per block.
+__device__ __forceinline__ float pchip_div(float a, float b) { return __fdividef(a, b); }     // <= 2 ulp; |b| < 2^126 here
+__device__ __forceinline__ double pchip_div(double a, double b) { return a / b; }
 template <typename T> __device__ __forceinline__ T pchip_sign(T v) { return (T)((v > T(0)) - (v < T(0))); }
 template <typename T> __device__ __forceinline__ T pchip_edge(T h0, T h1, T m0, T m1) {      // scipy PchipInterpolator._edge_case
-    T d = ((T(2) * h0 + h1) * m0 - h0 * m1) / (h0 + h1);
+    T d = pchip_div((T(2) * h0 + h1) * m0 - h0 * m1, h0 + h1);
     if (pchip_sign(d) != pchip_sign(m0)) d = T(0);
     else if (pchip_sign(m0) != pchip_sign(m1) && fabs(d) > T(3) * fabs(m0)) d = T(3) * m0;
     return d;
 }
-template <typename T> __device__ __forceinline__ T pchip_inner(T h, T ma, T mb) {            // _find_derivatives, interior point
+template <typename T> __device__ __forceinline__ T pchip_inner(T ma, T mb) {                 // _find_derivatives, interior point
+    // uniform grid: w1 = w2 = 3 h, so 1 / ((w1 / ma + w2 / mb) / (w1 + w2)) is the harmonic mean 2 ma mb / (ma + mb)
     if (pchip_sign(ma) != pchip_sign(mb) || ma == T(0) || mb == T(0)) return T(0);
-    const T w = T(3) * h;                                                                     // w1 = w2 = 3 h on a uniform grid
-    return T(1) / ((w / ma + w / mb) / (w + w));
+    return pchip_div(T(2) * ma * mb, ma + mb);
 }
-template <typename T>
-__global__ void __launch_bounds__(256) pchip_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t n_block, int64_t n,
-                                                    int64_t m, int64_t width, double ts, double new_ts) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_block * m * width) return;
-    const int64_t j = idx % width, u = (idx / width) % m, b = idx / (width * m);
-    // interval: the largest k with k ts <= x, at most n - 2 (the last piece also serves x beyond the last knot)
-    const double x = (double)u * new_ts;
-    int64_t k = (int64_t)floor(x / ts);
-    while ((double)(k + 1) * ts <= x) ++k;
-    while (k > 0 && (double)k * ts > x) --k;
-    if (k > n - 2) k = n - 2;
-    if (k < 0) k = 0;
-    const T s = (T)(x - (double)k * ts);
-    const T h = (T)ts;
-    const T* y = in + b * n * width + j;
-    const T y0 = __ldg(y + k * width), y1 = __ldg(y + (k + 1) * width);
-    const T slope = (y1 - y0) / h;
-    T d0, d1;
-    if (n == 2) { d0 = slope; d1 = slope; }
-    else {
-        // secant slopes of the neighbouring intervals (where they exist)
-        const T m_prev = (k > 0) ? (y0 - __ldg(y + (k - 1) * width)) / h : T(0);
-        const T m_next = (k + 2 < n) ? (__ldg(y + (k + 2) * width) - y1) / h : T(0);
-        d0 = (k > 0) ? pchip_inner(h, m_prev, slope) : pchip_edge(h, h, slope, m_next);
-        d1 = (k + 2 < n) ? pchip_inner(h, slope, m_next) : pchip_edge(h, h, slope, m_prev);
+// W = compile-time channel count (1 or 7: index arithmetic by multiply-shift), 0 = run-time `width` (<= 256).
+// One thread per (interval k, channel j): the derivatives and the cubic's coefficients are computed once per interval and
+// every sample of the new grid that falls into it is evaluated from them (10 samples per interval for 100 Hz -> 1 kHz);
+// the samples past the last knot belong to the last interval.  A CTA owns floor(256 / width) whole intervals, hence one
+// CONTIGUOUS range of the output, which it assembles in shared memory and writes with coalesced (128-bit) stores; ranges
+// too long for the buffer (extreme up-sampling) are stored directly.  grid.x tiles the n - 1 intervals of one block row,
+// grid.y strides over the block rows (the FP64 interval bounds are computed once per thread): no 64-bit division.
+constexpr int PCHIP_STAGE_BYTES = 32768;
+template <typename T, int W>
+__global__ void __launch_bounds__(256) pchip_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t n_block, int n,
+                                                    int m, int width_rt, double ts, double new_ts, double inv_new_ts) {
+    constexpr int CAP = PCHIP_STAGE_BYTES / (int)sizeof(T);
+    __shared__ __align__(16) T stage[CAP];
+    __shared__ int s_first, s_end;
+    const int width = W ? W : width_rt;
+    const int kpc = 256 / width;                                 // intervals per CTA
+    const int kl = (int)threadIdx.x / width, j = (int)threadIdx.x - kl * width;
+    const int k0 = (int)blockIdx.x * kpc, k1 = min(k0 + kpc, n - 1) - 1;     // this CTA's intervals
+    const int k = k0 + kl;
+    const bool active = kl < kpc && k <= k1;
+    // samples u of the new grid with k ts <= u new_ts < (k + 1) ts  (same comparisons as scipy's interval search)
+    const double xk = (double)k * ts, xk1 = (double)(k + 1) * ts;
+    int u_lo = 0, u_hi = 0;
+    if (active) {
+        u_lo = (int)ceil(xk * inv_new_ts); u_hi = (int)ceil(xk1 * inv_new_ts);
+        while (u_lo > 0 && (double)(u_lo - 1) * new_ts >= xk) --u_lo;
+        while ((double)u_lo * new_ts < xk) ++u_lo;
+        while (u_hi > 0 && (double)(u_hi - 1) * new_ts >= xk1) --u_hi;
+        while ((double)u_hi * new_ts < xk1) ++u_hi;
+        if (k == n - 2) u_hi = m;                               // the last piece is extrapolated over the rest of the grid
+        u_hi = min(u_hi, m); u_lo = min(u_lo, u_hi);
+        if (j == 0 && k == k0) s_first = u_lo;
+        if (j == 0 && k == k1) s_end = u_hi;
     }
-    // CubicHermiteSpline coefficients (power basis about the left knot), summed in ascending powers like PPoly
-    const T t_ = (d0 + d1 - T(2) * slope) / h;
-    const T c0 = t_ / h, c1 = (slope - d0) / h - t_;
-    T res = y0, z = s;
-    res += d0 * z; z *= s;
-    res += c1 * z; z *= s;
-    res += c0 * z;
-    out[idx] = res;
+    __syncthreads();
+    const int first = s_first, n_out = (s_end - first) * width;  // the CTA's output range [first, s_end) x width
+    if (n_out <= 0) return;                                      // down-sampling: no sample in these intervals
+    const bool staged = n_out <= CAP;
+    const T h = (T)ts, rh = (T)(1.0 / ts);
+    for (int64_t b = blockIdx.y; b < n_block; b += gridDim.y) {
+        T* dst = out + (b * m + first) * width;
+        if (active && u_lo < u_hi) {
+            const T* y = in + (b * n + k) * width + j;
+            const T y0 = __ldg(y), y1 = __ldg(y + width);
+            const T slope = (y1 - y0) * rh;
+            T d0, d1;
+            if (n == 2) { d0 = slope; d1 = slope; }
+            else {
+                // secant slopes of the neighbouring intervals (where they exist)
+                const T m_prev = (k > 0) ? (y0 - __ldg(y - width)) * rh : T(0);
+                const T m_next = (k + 2 < n) ? (__ldg(y + 2 * width) - y1) * rh : T(0);
+                d0 = (k > 0) ? pchip_inner(m_prev, slope) : pchip_edge(h, h, slope, m_next);
+                d1 = (k + 2 < n) ? pchip_inner(slope, m_next) : pchip_edge(h, h, slope, m_prev);
+            }
+            // CubicHermiteSpline coefficients (power basis about the left knot), summed in ascending powers like PPoly
+            const T t_ = (d0 + d1 - T(2) * slope) * rh;
+            const T c0 = t_ * rh, c1 = (slope - d0) * rh - t_;
+            T* o = (staged ? stage : dst) + (u_lo - first) * width + j;
+            for (int u = u_lo; u < u_hi; ++u, o += width) {
+                const T s = (T)((double)u * new_ts - xk);
+                T res = y0, z = s;
+                res += d0 * z; z *= s;
+                res += c1 * z; z *= s;
+                res += c0 * z;
+                *o = res;
+            }
+        }
+        if (staged) {
+            __syncthreads();
+            // coalesced copy-out; 128-bit when the destination allows it
+            constexpr int V = 16 / (int)sizeof(T);
+            const int head = (int)(((16 - ((uintptr_t)dst & 15)) & 15) / sizeof(T));    // elements up to the first 16-byte boundary
+            if (head == 0 && (n_out % V) == 0) {
+                const float4* s4 = reinterpret_cast<const float4*>(stage); float4* d4 = reinterpret_cast<float4*>(dst);
+                for (int i = threadIdx.x; i < n_out / V; i += blockDim.x) __stcs(d4 + i, s4[i]);
+            } else {
+                for (int i = threadIdx.x; i < n_out; i += blockDim.x) dst[i] = stage[i];
+            }
+            __syncthreads();
+        }
+    }
 }
 template <typename T>
 static int pchip_launch(const char* me, const T* in, T* out, int64_t n_block, int64_t n, int64_t m, int64_t width,
@@ -573,9 +621,20 @@ static int pchip_launch(const char* me, const T* in, T* out, int64_t n_block, in
     if (n < 2) return seqik_fail(SEQIK_EINVAL, "%s: at least 2 samples are needed", me);
     if (!in || !out) return seqik_fail(SEQIK_EINVAL, "%s: NULL pointer", me);
     if (!(original_ts > 0.0) || !(new_ts > 0.0)) return seqik_fail(SEQIK_EINVAL, "%s: time steps must be positive", me);
-    const int64_t total = n_block * m * width;
-    if (total > 2147483647LL * 256) return seqik_fail(SEQIK_EINVAL, "%s: too many output samples for one launch", me);
-    pchip_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(in, out, n_block, n, m, width, original_ts, new_ts);
+    if (n * width > 2147483647LL || m * width > 2147483647LL) return seqik_fail(SEQIK_EINVAL, "%s: series too long for one launch", me);
+    // ~1 M threads fill the machine; beyond that a thread walks over block rows (its interval bounds are computed once)
+    if (width > 256) return seqik_fail(SEQIK_EINVAL, "%s: at most 256 interleaved channels", me);
+    const int64_t kpc = 256 / width;
+    const int64_t gx = (n - 1 + kpc - 1) / kpc;
+    int64_t gy = (1LL << 20) / (gx * 256);
+    gy = gy < 1 ? 1 : (gy > n_block ? n_block : gy);
+    if (gy > 65535) gy = 65535;
+    const dim3 grid((unsigned)gx, (unsigned)gy);
+    const double inv_new = 1.0 / new_ts;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (width == 7) pchip_kernel<T, 7><<<grid, 256, 0, st>>>(in, out, n_block, (int)n, (int)m, 7, original_ts, new_ts, inv_new);
+    else if (width == 1) pchip_kernel<T, 1><<<grid, 256, 0, st>>>(in, out, n_block, (int)n, (int)m, 1, original_ts, new_ts, inv_new);
+    else pchip_kernel<T, 0><<<grid, 256, 0, st>>>(in, out, n_block, (int)n, (int)m, (int)width, original_ts, new_ts, inv_new);
     return seqik_check_launch(me);
 }
 extern "C" int seqik_pchip_resample_f32(const float* in, float* out, int64_t n_block, int64_t n, int64_t m, int64_t width,

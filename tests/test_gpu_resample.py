@@ -37,9 +37,9 @@ def test_resample_grooming_angles(eng, grooming_leg, dtype, tol):
 def test_resample_shapes_and_edge_cases(eng):
     torch, engine = eng
     rng = np.random.default_rng(3)
-    for case in range(24):
+    for case in range(36):
         n = int(rng.integers(2, 50))
-        ts, new_ts = [(0.01, 0.001), (1.0, 0.5), (0.005, 0.0007), (1 / 30, 1 / 100), (0.01, 0.025)][case % 5]
+        ts, new_ts = [(0.01, 0.001), (1.0, 0.5), (0.005, 0.0007), (1 / 30, 1 / 100), (0.01, 0.025), (0.1, 0.3)][case % 6]
         y = rng.normal(size=(3, n)).cumsum(axis=1)
         if case % 3 == 0:
             y[:, n // 3:n // 2 + 1] = y[:, n // 3:n // 3 + 1]            # plateaus: zero secant slopes
