@@ -19,6 +19,8 @@ Fixtures
   locomotion.npz     bundled data/df3d_pose_result__210902_PR_Fly1 (BASELINE config 1): raw frames 300:400 of the
                      6 legs, reference AlignPose output (== shipped pose3d_aligned.pkl), oracle angles + FK
   synthetic.npz      trials 0-1 x 6 legs x first 250 frames of the synthetic workload: pose, oracle angles + FK
+  synthetic_wide.npz trials 2-7 x 6 legs x all 1000 frames of the synthetic workload: oracle angles (float32) and the
+                     oracle's FK residual per joint (float32) -- with synthetic.npz the "trials 0-7" parity run of SURVEY.md 8d
   generic_leg.npz    generic 7-DOF IK (LegInvKinGeneric) of the oracle on the first 500 frames of the grooming RF/LF legs:
                      the free-running angles (2,500,9) with status/nfev/cost, and -- because that problem is under-determined and
                      its free-running answer depends on rounding noise -- the SAME solves repeated with the target
@@ -91,7 +93,7 @@ def oracle_legs(pose_dict, size, bounds, init, procs=8):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reuse-cache", default=None, help="directory with oracle_full_{RF,LF}.pkl from a previous run")
-    ap.add_argument("--only", default="", help="comma-separated subset: leg,head,align,loco,synth,long,generic")
+    ap.add_argument("--only", default="", help="comma-separated subset: leg,head,align,loco,synth,wide,long,generic")
     args = ap.parse_args()
     only = set(filter(None, args.only.split(",")))
     GOLD.mkdir(parents=True, exist_ok=True)
@@ -208,6 +210,25 @@ def main():
         print(f"synthetic oracle: {time.time() - t0:.1f} s")
         np.savez_compressed(GOLD / "synthetic.npz", trials=np.array(trials), legs=np.array(S.LEGS),
                             pose=np.stack(poses), oracle_angles=np.stack(angs), oracle_fk=np.stack(fks))
+    # ---------------------------------------------------------------- synthetic trials 2-7, all 1000 frames (SURVEY.md 8d parity run)
+    if not only or "wide" in only:
+        trials, n_frame = [2, 3, 4, 5, 6, 7], 1000
+        size, bounds, init = S.chain_constants()
+        t0 = time.time()
+        jobs = {}
+        for tr in trials:
+            pose = S.make_trial(tr, n_frame)
+            for li, leg in enumerate(S.LEGS):
+                jobs[(tr, leg)] = (f"{leg}_leg", np.ascontiguousarray(pose[:, li]), size, bounds, init)
+        with Pool(8) as pool:
+            res = pool.map(_oracle_leg, list(jobs.values()))
+        ang = np.stack([r[1] for r in res]).reshape(len(trials), 6, n_frame, 7)
+        fk = np.stack([r[2] for r in res]).reshape(len(trials), 6, n_frame, 9, 3)
+        poses = np.stack([S.make_trial(tr, n_frame) for tr in trials]).transpose(0, 2, 1, 3, 4)      # (trial, leg, frame, 5, 3)
+        resid = np.linalg.norm(fk[:, :, :, [5, 6, 7, 8]] - poses[:, :, :, 1:5], axis=-1)
+        print(f"wide synthetic oracle: {time.time() - t0:.1f} s, mean FK error {resid.mean():.5f} mm")
+        np.savez_compressed(GOLD / "synthetic_wide.npz", trials=np.array(trials), legs=np.array(S.LEGS), n_frame=np.array(n_frame),
+                            oracle_angles=ang.astype(np.float32), oracle_fk_residual=resid.astype(np.float32))
     # ---------------------------------------------------------------- generic 7-DOF IK (LegInvKinGeneric)
     if not only or "generic" in only:
         n_frame = 500

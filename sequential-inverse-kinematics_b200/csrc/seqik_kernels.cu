@@ -285,7 +285,7 @@ __device__ __forceinline__ void quantile_pos(double q, int64_t n, int64_t& lo, f
 __global__ void __launch_bounds__(SEL_BLOCK) mid_quantile_kernel(const float* __restrict__ series, const int32_t* __restrict__ counts,
                                                                  int64_t n, float* __restrict__ out) {
     __shared__ unsigned int hist[4][256];
-    __shared__ uint32_t s_prefix[4]; __shared__ unsigned long long s_rank[4];
+    __shared__ uint32_t s_prefix[4]; __shared__ unsigned long long s_rank[4]; __shared__ int s_hist[4];
     __shared__ uint32_t cache[SEL_CACHE];
     const int64_t sidx = blockIdx.x;
     const float* v = series + sidx * n;
@@ -305,21 +305,41 @@ __global__ void __launch_bounds__(SEL_BLOCK) mid_quantile_kernel(const float* __
         for (int k = threadIdx.x; k < 4 * 256; k += SEL_BLOCK) (&hist[0][0])[k] = 0;
         __syncthreads();
         const uint32_t p0 = s_prefix[0], p1 = s_prefix[1], p2 = s_prefix[2], p3 = s_prefix[3];
+        // ranks that still share a prefix share a histogram (the four ranks are two adjacent pairs: they separate only in
+        // the last passes), which removes most of the shared-memory atomics
+        const int h1 = (p1 == p0) ? 0 : 1, h2 = (p2 == p0) ? 0 : (p2 == p1) ? 1 : 2;
+        const int h3 = (p3 == p0) ? 0 : (p3 == p1) ? 1 : (p3 == p2) ? 2 : 3;
+        if (threadIdx.x == 0) { s_hist[0] = 0; s_hist[1] = h1; s_hist[2] = h2; s_hist[3] = h3; }
         for (int64_t i = threadIdx.x; i < n; i += SEL_BLOCK) {
             const uint32_t k = cached ? cache[i] : order_key(__ldg(v + i));
             const uint32_t km = k & mask, d = (k >> shift) & 0xFF;
             if (km == p0) atomicAdd(&hist[0][d], 1u);
-            if (km == p1) atomicAdd(&hist[1][d], 1u);
-            if (km == p2) atomicAdd(&hist[2][d], 1u);
-            if (km == p3) atomicAdd(&hist[3][d], 1u);
+            if (h1 == 1 && km == p1) atomicAdd(&hist[1][d], 1u);
+            if (h2 == 2 && km == p2) atomicAdd(&hist[2][d], 1u);
+            if (h3 == 3 && km == p3) atomicAdd(&hist[3][d], 1u);
         }
         __syncthreads();
-        if (threadIdx.x < 4) {
-            const int w = threadIdx.x;
-            unsigned long long r = s_rank[w], acc = 0; int d = 0;
-            for (; d < 256; ++d) { if (acc + hist[w][d] > r) break; acc += hist[w][d]; }
-            if (d > 255) d = 255;
-            s_prefix[w] |= ((uint32_t)d << shift); s_rank[w] = r - acc;
+        if (threadIdx.x < 4 * 32) {
+            // warp w locates the bin of rank s_rank[w] in hist[w]: each lane sums 8 bins, a warp scan finds the lane whose
+            // cumulative count first exceeds the rank, that lane walks its 8 bins (a serial 256-bin walk per pass was 4/5
+            // of this kernel's time)
+            const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+            const unsigned int* hrow = &hist[s_hist[w]][8 * lane];
+            unsigned int own = 0;
+#pragma unroll
+            for (int d = 0; d < 8; ++d) own += hrow[d];
+            unsigned int incl = own;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { const unsigned int t = __shfl_up_sync(0xffffffffu, incl, off); if (lane >= off) incl += t; }
+            const unsigned long long r = s_rank[w];
+            const unsigned int hit = __ballot_sync(0xffffffffu, (unsigned long long)incl > r);
+            const int sel = hit ? __ffs(hit) - 1 : 31;                     // first lane whose cumulative count exceeds the rank
+            if (lane == sel) {
+                unsigned long long acc = (unsigned long long)(incl - own); int d = 0;
+                for (; d < 8; ++d) { if (acc + hrow[d] > r) break; acc += hrow[d]; }
+                if (d > 7) d = 7;
+                s_prefix[w] |= ((uint32_t)(8 * lane + d) << shift); s_rank[w] = r - acc;
+            }
         }
         mask |= 0xFFu << shift;
         __syncthreads();

@@ -184,6 +184,7 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, 
 
     for (int it = 0; __any_sync(full, live && t < n_frame); ++it) {
         if ((it & gate_mask) == 0) {                    // open/close phases only every (gate_mask + 1)-th iteration (warp-uniform)
+        __syncwarp(full);            // ring reads of the previous open phase are complete before a slot is written again
         const int started_next = __shfl_sync(full, started, (lane + 1) & 31);   // consumer's progress (lane + 1)
         // ---- optional singularity escape: a solve that ended on sin b = 0 may continue from a closed-form candidate
         if (esc && live && solving && !frozen && S.done()) S.escape();

@@ -55,3 +55,8 @@ def synthetic_long():
 @pytest.fixture(scope="session")
 def generic_gold():
     return _npz("generic_leg.npz")
+
+
+@pytest.fixture(scope="session")
+def synthetic_wide():
+    return _npz("synthetic_wide.npz")

@@ -230,6 +230,62 @@ def test_synthetic_vs_oracle_and_shard_invariance(api, synthetic_gold):
     assert (a1 - ang).abs().max() < 2e-4 and (f1 - fk).abs().max() < 1e-4 and int(s1.min()) == 1
 
 
+def test_synthetic_trials_2_to_7_all_frames_vs_oracle(api, synthetic_wide):
+    """SURVEY.md 8d parity run, second half: trials 2-7 x 6 legs x all 1000 frames (36 000 leg-frames) against the
+    oracle: angles within 1e-3 rad, FK residual per joint never worse than the oracle's by more than 1e-4 mm, and the
+    same mean FK error."""
+    S, t = api.synthetic, api.torch
+    trials = [int(x) for x in synthetic_wide["trials"]]
+    n_frame = int(synthetic_wide["n_frame"])
+    pose = S.make_trials(trials, n_frame)
+    size, bounds, init = S.chain_constants()
+    chain = api.Chain(bounds, list(S.LEGS), size)
+    row = np.stack([chain.pack_chain_params(leg, init[leg]) for leg in S.LEGS]).astype(np.float32)
+    params = t.from_numpy(np.tile(row, (len(trials), 1))).cuda()
+    chains = S.to_chains(t.from_numpy(np.ascontiguousarray(pose)).cuda())
+    ang, fk, status, nfev = api.engine.leg_solve(chains, params)
+    a = ang.cpu().numpy().reshape(len(trials), 6, n_frame, 7)
+    dev = np.abs(a - synthetic_wide["oracle_angles"])
+    assert dev.max() < ANGLE_TOL and np.median(dev) < 5e-6
+    f = fk.cpu().numpy().reshape(len(trials), 6, n_frame, 9, 3)
+    pose_c = pose.transpose(0, 2, 1, 3, 4)
+    r_ours = np.linalg.norm(f[:, :, :, [5, 6, 7, 8]] - pose_c[:, :, :, 1:5], axis=-1)
+    assert (r_ours - synthetic_wide["oracle_fk_residual"]).max() < FK_TOL + F32_FK_NOISE
+    assert abs(r_ours.mean() - synthetic_wide["oracle_fk_residual"].mean()) < 1e-5
+    assert int(status.min()) == 1 and int(status.max()) == 1
+
+
+def test_full_size_properties(api):
+    """BASELINE config 3 at full size (1000 trials x 1000 frames x 6 legs = 6e6 leg-frames), through size-independent
+    properties: every chain converges, every angle is inside its limits, the FK rows the solver carries equal the
+    standalone FK kernel applied to the angles it returns, rows 0-3 repeat the origin and row 4 = row 5, the mean FK
+    error equals the oracle's on this workload (0.0264 mm), trials that hold the same data give bit-identical
+    results wherever they sit in the batch, and the result does not depend on the launch's frame chunking."""
+    S, t = api.synthetic, api.torch
+    from seqikpy_b200.batch import BatchedLegIK
+    n_trial, n_frame, n_unique = 1000, 1000, 20
+    size, bounds, init = S.chain_constants()
+    chain = api.Chain(bounds, list(S.LEGS), size)
+    uniq = t.from_numpy(np.ascontiguousarray(S.make_trials(range(n_unique), n_frame).transpose(0, 2, 1, 3, 4))).cuda()
+    sess = BatchedLegIK(chain, init, S.LEGS, n_trial, n_frame)
+    sess.d_pose.copy_(uniq.repeat(n_trial // n_unique, 1, 1, 1, 1).reshape(sess.n_chain, n_frame, 5, 3))
+    ang, fk = sess.solve_device()
+    assert int(sess.status.min()) == 1 and int(sess.status.max()) == 1
+    lb, ub = sess.params[:, None, 4:11], sess.params[:, None, 11:18]
+    assert bool(((ang >= lb - 1e-6) & (ang <= ub + 1e-6)).all())
+    fk2 = api.engine.forward_kinematics(ang, sess.d_pose[:, :, 0].contiguous(), sess.params)
+    assert float((fk2 - fk).abs().max()) < 1e-5
+    assert t.equal(fk[:, :, :4], sess.d_pose[:, :, :1].expand(-1, -1, 4, -1)) and t.equal(fk[:, :, 4], fk[:, :, 5])
+    err = (fk[:, :, 5:9] - sess.d_pose[:, :, 1:5]).norm(dim=-1).mean().item()
+    assert abs(err - 0.0264) < 5e-4, err
+    a5 = ang.view(n_trial // n_unique, n_unique * 6, n_frame, 7)
+    assert t.equal(a5[0], a5[-1]) and t.equal(a5[0], a5[17])
+    ref = ang.clone()
+    api.engine.leg_solve(sess.d_pose, sess.params, angles=sess.d_angles, fk=sess.d_fk, frames=(0, 512))
+    api.engine.leg_solve(sess.d_pose, sess.params, angles=sess.d_angles, fk=sess.d_fk, frames=(512, 1000))
+    assert t.equal(sess.d_angles, ref)
+
+
 def test_long_warm_start_chain_vs_oracle(api, synthetic_long):
     """2000 serially warm-started frames (62 of the kernel's 32-frame resync periods) against the oracle: the carried
     solver state does not drift."""

@@ -79,6 +79,21 @@ def test_long_warm_start_chain_vs_oracle(synthetic_long):
         assert (status > 0).all()
 
 
+def test_synthetic_trials_2_to_7_vs_oracle(synthetic_wide):
+    """Trials 2-7 x 6 legs x all 1000 frames of the synthetic workload (36 000 leg-frames) against the oracle."""
+    from seqikpy_b200 import synthetic as S
+    size, bounds, init = S.chain_constants()
+    n_frame = int(synthetic_wide["n_frame"])
+    for ti, tr in enumerate(synthetic_wide["trials"]):
+        pose = S.make_trial(int(tr), n_frame)
+        for li, leg in enumerate(S.LEGS):
+            seg, lb, ub, nsq, seed = leg_consts(size, bounds, init, leg)
+            ang, fk, _, status = H.solve_chain(pose[:, li], seg, lb, ub, nsq, seed, gn_mask=GN)
+            assert np.abs(ang - synthetic_wide["oracle_angles"][ti, li]).max() < ANGLE_TOL, (tr, leg)
+            assert (fk_residual(fk, pose[:, li]) - synthetic_wide["oracle_fk_residual"][ti, li]).max() < FK_TOL + 2e-6
+            assert (status > 0).all()
+
+
 def test_runner_state_machine_equals_serial_composition(grooming_leg):
     """ChainRunner::step() (what a lane executes) gives bit-identical results to the serial frame solve."""
     from seqikpy_b200 import data as D
