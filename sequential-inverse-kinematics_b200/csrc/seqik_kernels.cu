@@ -509,6 +509,78 @@ __global__ void __launch_bounds__(SEL_BLOCK) mid_quantile_kernel(const float* __
     }
 }
 
+// Short series (n <= WQ_N, e.g. the 1000-frame trials of the benchmark configurations): ONE WARP per series.  Same 4-pass
+// radix select, but the histograms are private to the warp, so there is no block barrier and no idle thread: 8 warps
+// x ~600 instructions per series become 1 warp x ~1000 (measured 0.52 -> see profiles/r01_stream_kernels.jsonl).
+constexpr int WQ_N = 1024, WQ_WARPS = 4;
+__global__ void __launch_bounds__(32 * WQ_WARPS) mid_quantile_warp_kernel(const float* __restrict__ series, const int32_t* __restrict__ counts,
+                                                                          int64_t n_series, int n, float* __restrict__ out) {
+    __shared__ uint32_t cache[WQ_WARPS][WQ_N];
+    __shared__ unsigned int hist[WQ_WARPS][4][256];
+    const unsigned full = 0xffffffffu;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t sidx = (int64_t)blockIdx.x * WQ_WARPS + w;
+    if (sidx >= n_series) return;                                 // whole warps leave: no block-level barrier below
+    const float* v = series + sidx * n;
+    const int64_t m = counts ? (int64_t)counts[sidx] : n;
+    if (m <= 0) { if (lane == 0) out[sidx] = __int_as_float(0x7fc00000); return; }
+    uint32_t* key = cache[w];
+    for (int i = lane; i < n; i += 32) key[i] = order_key(__ldg(v + i));
+    int64_t lo45, lo55; float f45, f55;
+    quantile_pos(0.45, m, lo45, f45); quantile_pos(0.55, m, lo55, f55);
+    unsigned int rank[4]; uint32_t prefix[4] = {0u, 0u, 0u, 0u};   // warp-uniform
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const int64_t r = (k < 2 ? lo45 : lo55) + (k & 1); rank[k] = (unsigned int)(r > m - 1 ? m - 1 : r); }
+    uint32_t mask = 0;
+#pragma unroll 1
+    for (int pass = 3; pass >= 0; --pass) {
+        const int shift = 8 * pass;
+        // ranks that still share a prefix share a histogram
+        int h[4];
+        h[0] = 0; h[1] = (prefix[1] == prefix[0]) ? 0 : 1;
+        h[2] = (prefix[2] == prefix[0]) ? 0 : (prefix[2] == prefix[1]) ? 1 : 2;
+        h[3] = (prefix[3] == prefix[0]) ? 0 : (prefix[3] == prefix[1]) ? 1 : (prefix[3] == prefix[2]) ? 2 : 3;
+        for (int k = lane; k < 4 * 256; k += 32) (&hist[w][0][0])[k] = 0;
+        __syncwarp(full);
+        for (int i = lane; i < n; i += 32) {
+            const uint32_t k = key[i];
+            const uint32_t km = k & mask, d = (k >> shift) & 0xFF;
+            if (km == prefix[0]) atomicAdd(&hist[w][0][d], 1u);
+            if (h[1] == 1 && km == prefix[1]) atomicAdd(&hist[w][1][d], 1u);
+            if (h[2] == 2 && km == prefix[2]) atomicAdd(&hist[w][2][d], 1u);
+            if (h[3] == 3 && km == prefix[3]) atomicAdd(&hist[w][3][d], 1u);
+        }
+        __syncwarp(full);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            // the bin of rank[k] in hist[h[k]]: each lane sums 8 bins, a warp scan finds the lane whose cumulative count first
+            // exceeds the rank, that lane walks its 8 bins and broadcasts (bin, count below)
+            const unsigned int* hrow = &hist[w][h[k]][8 * lane];
+            unsigned int own = 0;
+#pragma unroll
+            for (int d = 0; d < 8; ++d) own += hrow[d];
+            unsigned int incl = own;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) { const unsigned int t = __shfl_up_sync(full, incl, off); if (lane >= off) incl += t; }
+            const unsigned int hit = __ballot_sync(full, incl > rank[k]);
+            const int sel = hit ? __ffs(hit) - 1 : 31;
+            unsigned int acc = incl - own; int d = 0;
+            for (; d < 8; ++d) { if (acc + hrow[d] > rank[k]) break; acc += hrow[d]; }
+            if (d > 7) d = 7;
+            const int bin = __shfl_sync(full, 8 * lane + d, sel);
+            const unsigned int below = __shfl_sync(full, acc, sel);
+            prefix[k] |= ((uint32_t)bin << shift); rank[k] -= below;
+        }
+        mask |= 0xFFu << shift;
+        __syncwarp(full);
+    }
+    if (lane == 0) {
+        const float a0 = key_value(prefix[0]), a1 = key_value(prefix[1]), b0 = key_value(prefix[2]), b1 = key_value(prefix[3]);
+        const float q0 = a0 + (a1 - a0) * f45, q1 = b0 + (b1 - b0) * f55;
+        out[sidx] = 0.5f * (q0 + q1);
+    }
+}
+
 extern "C" int seqik_mid_quantile_f32(const float* series, const int32_t* counts, float* scratch, float* out,
                                       int64_t n_series, int64_t n, void* stream) {
     (void)scratch;   // kept in the signature (ABI): the single-kernel select needs no scratch
@@ -517,7 +589,10 @@ extern "C" int seqik_mid_quantile_f32(const float* series, const int32_t* counts
     if (n == 0) return fail(SEQIK_EINVAL, "seqik_mid_quantile_f32: empty series");
     if (!series || !out) return fail(SEQIK_EINVAL, "seqik_mid_quantile_f32: NULL pointer");
     if (n_series > 2147483647LL) return fail(SEQIK_EINVAL, "seqik_mid_quantile_f32: too many series");
-    mid_quantile_kernel<<<(unsigned)n_series, SEL_BLOCK, 0, (cudaStream_t)stream>>>(series, counts, n, out);
+    if (n <= WQ_N)
+        mid_quantile_warp_kernel<<<(unsigned)((n_series + WQ_WARPS - 1) / WQ_WARPS), 32 * WQ_WARPS, 0, (cudaStream_t)stream>>>(series, counts, n_series, (int)n, out);
+    else
+        mid_quantile_kernel<<<(unsigned)n_series, SEL_BLOCK, 0, (cudaStream_t)stream>>>(series, counts, n, out);
     return check_launch("seqik_mid_quantile_f32");
 }
 
