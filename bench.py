@@ -274,6 +274,15 @@ def run_ours(args):
         sess.solve_host(host_pose, n_chunks=args.chunks)
     ms_e2e = timed(lambda: sess.solve_host(host_pose, synchronize=False, n_chunks=args.chunks), args.steps) / args.steps
     clocks = sampler.stop() if sampler else None
+    # ---- the same call with the joints-only FK layout (rows 5..8: the rows that carry information); a secondary figure,
+    #      the headline `e2e` above keeps the reference's 9-row layout
+    ms_e2e_joints = None
+    if not args.no_joints_e2e:
+        sess_j = BatchedLegIK(chain, init, S.LEGS, T, F, device=dev, schedule=args.schedule, chains_per_warp=args.cpw, fk_layout="joints")
+        for _ in range(2):
+            sess_j.solve_host(host_pose, n_chunks=args.chunks)
+        ms_e2e_joints = timed(lambda: sess_j.solve_host(host_pose, synchronize=False, n_chunks=args.chunks), args.steps) / args.steps
+        del sess_j
 
     sess.solve_device()
     torch.cuda.synchronize()
@@ -312,6 +321,10 @@ def run_ours(args):
             "e2e": {"value": leg_frames / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": leg_frames_rank * 60, "d2h_bytes_per_step": leg_frames_rank * (28 + 108),
                     "bytes_are": "per GPU", "frame_chunks": args.chunks, "gpu_launches": args.steps * sess.launches_per_call},
+            "e2e_joints_only": None if ms_e2e_joints is None else {
+                "value": leg_frames / (ms_e2e_joints * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_joints,
+                "h2d_bytes_per_step": leg_frames_rank * 60, "d2h_bytes_per_step": leg_frames_rank * (28 + 48),
+                "note": "fk_layout='joints': FK rows 5..8 only (rows 0-3 of the reference layout repeat the input origin, row 4 repeats row 5)"},
             "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                          "traffic": traffic, "kernel": "leg_solve", "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback",
@@ -351,6 +364,7 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=100, help="frames per chain and step of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin each rank to its GPU's local CPUs")
+    ap.add_argument("--no-joints-e2e", action="store_true", help="skip the secondary end-to-end figure with the joints-only FK layout")
     ap.add_argument("--cpu-baseline-only", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--cpu-procs", type=int, default=6, help=argparse.SUPPRESS)
     args = ap.parse_args()

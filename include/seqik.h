@@ -49,6 +49,11 @@ extern "C" {
                                                 1 = one lane per chain, 2 = stage pipeline (four lanes per chain) */
 #define SEQIK_FLAG_SCHED_MASK (0xFu << SEQIK_FLAG_SCHED_SHIFT)
 #define SEQIK_FLAG_GATE_SHIFT 18             /* bits 18..19: open/close phases of schedule 2 every 1st/2nd/4th iteration (1/2/3), 0 = automatic */
+#define SEQIK_FLAG_FK_JOINTS (1u << 20)      /* fk holds only the four joint rows that carry information: [n_chain][n_frame][4][3] =
+                                                rows 5..8 of the full layout (Coxa-Femur, Femur-Tibia, Tibia-Tarsus, Claw).  Rows 0-3
+                                                of the full layout repeat the input origin and row 4 repeats row 5; leaving them out
+                                                cuts the result from 136 to 76 bytes per leg-frame, which is what an end-to-end
+                                                call over PCIe is bound by */
 #define SEQIK_FLAG_CPW_SHIFT 12              /* bits 12..17: chains per warp of schedule 2 (1..8), 0 = automatic */
 
 int seqik_abi_version(void);
@@ -82,7 +87,8 @@ const char* seqik_last_error(void);
  *           `angles=self.joint_angles_dict, t=t` of kinematic_chain.py:99-150
  *   fk      NULL, or [n_chain][n_frame][9][3] out (rows 0-3 origin, 4-5 Coxa-Femur joint,
  *           6 Femur-Tibia, 7 Tibia-Tarsus, 8 Claw: leg_inverse_kinematics.py:71-77,279-282);
- *           rows of stages after the last solved one are left untouched
+ *           rows of stages after the last solved one are left untouched.  With SEQIK_FLAG_FK_JOINTS:
+ *           [n_chain][n_frame][4][3], the joint rows only
  *   warm    NULL, or 7 angles per chain (addressed warm + c*warm_chain_stride) that replace the seeds of `params`:
  *           pass the last solved frame of the same chains (angles + (t0-1)*ang_frame_stride) to continue a
  *           recording in frame chunks -- bit-identical to one call over all frames, which is what lets the host

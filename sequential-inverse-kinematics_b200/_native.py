@@ -17,6 +17,7 @@ CHAIN_PARAM_FLOATS = 32
 FLAG_ESCAPE = 1 << 4
 FLAG_SKIP_CONFIRM = 1 << 5
 FLAG_DEFAULT = 0x3F                     # SEQIK_FLAG_DEFAULT: Gauss-Newton mode in all four stages + escape + skip-confirm
+FLAG_FK_JOINTS = 1 << 20
 FLAG_SCHED_SHIFT = 8
 SCHED_AUTO, SCHED_LANE_PER_CHAIN, SCHED_STAGE_PIPELINE = 0, 1, 2
 

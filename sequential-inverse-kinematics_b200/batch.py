@@ -66,7 +66,10 @@ class BatchedLegIK:
 
     def __init__(self, kinematic_chain_class, initial_angles, legs: Sequence[str], n_trial: int, n_frame: int,
                  device="cuda", want_fk: bool = True, schedule: int = N.SCHED_AUTO, host_buffers: bool = True,
-                 chains_per_warp: int = 0):
+                 chains_per_warp: int = 0, fk_layout: str = "full"):
+        """``fk_layout``: "full" = the reference's 9 rows per leg-frame; "joints" = only the four rows that carry
+        information (rows 5..8: rows 0-3 of the full layout repeat the input origin, row 4 repeats row 5), which cuts
+        the device->host result from 136 to 76 bytes per leg-frame -- the end-to-end call is bound by that copy."""
         torch = N.require_cuda()
         N.load_library()
         self.torch = torch
@@ -80,11 +83,15 @@ class BatchedLegIK:
         f32 = dict(dtype=torch.float32, device=self.device)
         self.d_pose = torch.empty((self.n_chain, self.n_frame, 5, 3), **f32)
         self.d_angles = torch.empty((self.n_chain, self.n_frame, 7), **f32)
-        self.d_fk = torch.empty((self.n_chain, self.n_frame, 9, 3), **f32) if want_fk else None
+        if fk_layout not in ("full", "joints"):
+            raise ValueError(f"fk_layout must be 'full' or 'joints', got {fk_layout!r}")
+        self.fk_layout = fk_layout
+        self.fk_rows = 9 if fk_layout == "full" else 4
+        self.d_fk = torch.empty((self.n_chain, self.n_frame, self.fk_rows, 3), **f32) if want_fk else None
         self.h_angles = self.h_fk = None
         if host_buffers:
             self.h_angles = torch.empty((self.n_chain, self.n_frame, 7), dtype=torch.float32, pin_memory=True)
-            self.h_fk = torch.empty((self.n_chain, self.n_frame, 9, 3), dtype=torch.float32, pin_memory=True) if want_fk else None
+            self.h_fk = torch.empty((self.n_chain, self.n_frame, self.fk_rows, 3), dtype=torch.float32, pin_memory=True) if want_fk else None
         self.status = self.nfev = None
         self._copy_streams = None
         self.default_chunks = 8
@@ -101,7 +108,7 @@ class BatchedLegIK:
         _, _, self.status, self.nfev = engine.leg_solve(pose, self.params, affine=affine, angles=self.d_angles, fk=self.d_fk,
                                                         want_fk=self.d_fk is not None, schedule=self.schedule,
                                                         chains_per_warp=self.chains_per_warp,
-                                                        want_stats=want_stats)
+                                                        want_stats=want_stats, fk_layout=self.fk_layout)
         return self.d_angles, self.d_fk
 
     def solve_host(self, pose_host, synchronize: bool = True, n_chunks: Optional[int] = None):
@@ -146,13 +153,14 @@ class BatchedLegIK:
                 ev_in.record(s_in)
                 main.wait_event(ev_in)
                 engine.leg_solve(self.d_pose, self.params, angles=self.d_angles, fk=self.d_fk, want_fk=self.d_fk is not None,
-                                 schedule=self.schedule, chains_per_warp=self.chains_per_warp, want_stats=False, frames=(t0, t1))
+                                 schedule=self.schedule, chains_per_warp=self.chains_per_warp, want_stats=False, frames=(t0, t1),
+                                 fk_layout=self.fk_layout)
                 ev_k = torch.cuda.Event()
                 ev_k.record(main)
                 s_out.wait_event(ev_k)
                 copy2d(self.h_angles, self.d_angles, 7, t0, t1, 2, s_out)
                 if self.h_fk is not None:
-                    copy2d(self.h_fk, self.d_fk, 27, t0, t1, 2, s_out)
+                    copy2d(self.h_fk, self.d_fk, 3 * self.fk_rows, t0, t1, 2, s_out)
             main.wait_stream(s_out)
         self.launches_per_call = len(bounds) - 1
         if synchronize:
@@ -163,7 +171,8 @@ class BatchedLegIK:
         """Mean over chains, frames and the 4 distal joints of |fk[5..8] - pose[1..4]| in mm.
         Reduction of RESULTS for reporting (torch ops on the device tensors), not part of the solve."""
         pose = self.d_pose if pose is None else pose.reshape(self.n_chain, self.n_frame, 5, 3)
-        d = self.d_fk[:, :, 5:9, :] - pose[:, :, 1:5, :]
+        joints = self.d_fk if self.fk_layout == "joints" else self.d_fk[:, :, 5:9, :]
+        d = joints - pose[:, :, 1:5, :]
         return float(d.square().sum(-1).sqrt().mean())
 
 

@@ -35,6 +35,7 @@ struct LegArgs {
     int32_t* status; uint32_t* nfev;
     int64_t n_chain, n_frame;
     int stage_mask, gn_mask;
+    int fk_joints;                          // SEQIK_FLAG_FK_JOINTS: fk holds the 4 joint rows only ([4][3] per leg-frame)
 };
 
 // alignment map applied on load (AlignPose.align_leg, alignment.py:471-485)
@@ -62,7 +63,7 @@ struct DevIO {
     const float* pose; int64_t fs;          // base of this chain, frame stride
     const float* prm;                       // 32 floats
     float* ang; int64_t ang_fs;
-    float* fk; int64_t fk_fs;
+    float* fk; int64_t fk_fs; bool fk_joints;
     LoadMap map;
 
     __device__ __forceinline__ Vec3<float> kp(int64_t t, int row) const {
@@ -76,6 +77,7 @@ struct DevIO {
     }
     __device__ __forceinline__ float angle_in(int64_t t, int i) const { return ang[t * ang_fs + i]; }
     __device__ __forceinline__ void put_fk(int64_t t, int row, const Vec3<float>& v) const {
+        if (fk_joints) { if (row < 5) return; row -= 5; }       // joints-only layout: rows 5..8 of the full one
         if (fk) { float* p = fk + t * fk_fs + row * 3; p[0] = v.x; p[1] = v.y; p[2] = v.z; }
     }
     __device__ __forceinline__ float seg(int i) const { return __ldg(prm + i); }
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(32) leg_solve_lane_kernel(LegArgs a) {
     io.pose = a.pose + c * a.pose_cs; io.fs = a.pose_fs;
     io.prm = a.params + c * SEQIK_CHAIN_PARAM_FLOATS;
     io.ang = a.angles + c * a.ang_cs; io.ang_fs = a.ang_fs;
-    io.fk = a.fk ? a.fk + c * a.fk_cs : nullptr; io.fk_fs = a.fk_fs;
+    io.fk = a.fk ? a.fk + c * a.fk_cs : nullptr; io.fk_fs = a.fk_fs; io.fk_joints = a.fk_joints != 0;
     io.map.init(a.affine, c);
     float seed[7];
 #pragma unroll
@@ -204,10 +206,14 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, 
                 // rows 0-3 repeat the origin, 4 and 5 are both the Coxa-Femur joint: lane s writes origin row s and its
                 // own joint row(s), which spreads the 27 floats of a frame over the four lanes
                 const Vec3<float> jw = {np_.x + o.x, np_.y + o.y, np_.z + o.z};
-                pf[0] = o.x; pf[1] = o.y; pf[2] = o.z;                                   // row s
-                pf[15] = jw.x; pf[16] = jw.y; pf[17] = jw.z;                             // row 5 + s
-                if (s == 0) { pf[12] = jw.x; pf[13] = jw.y; pf[14] = jw.z; }             // row 4
-                if (s == hi && hi < 3) for (int r = 1; r < 4 - hi; ++r) { pf[3 * r] = o.x; pf[3 * r + 1] = o.y; pf[3 * r + 2] = o.z; }
+                if (a.fk_joints) {                                                       // joints-only layout: row s = this lane's joint
+                    pf[0] = jw.x; pf[1] = jw.y; pf[2] = jw.z;
+                } else {
+                    pf[0] = o.x; pf[1] = o.y; pf[2] = o.z;                               // row s
+                    pf[15] = jw.x; pf[16] = jw.y; pf[17] = jw.z;                         // row 5 + s
+                    if (s == 0) { pf[12] = jw.x; pf[13] = jw.y; pf[14] = jw.z; }         // row 4
+                    if (s == hi && hi < 3) for (int r = 1; r < 4 - hi; ++r) { pf[3 * r] = o.x; pf[3 * r + 1] = o.y; pf[3 * r + 2] = o.z; }
+                }
                 pf += a.fk_fs;
             }
             pa_a += a.ang_fs; pa_b += a.ang_fs;
@@ -278,7 +284,8 @@ extern "C" int seqik_leg_solve_f32(const float* pose, int64_t pose_chain_stride,
         if (stage_mask == 0 || stage_mask > 0xF || (m & (m + 1)) != 0)
             return seqik_fail(SEQIK_EINVAL, "seqik_leg_solve_f32: stage_mask must be a contiguous run of bits within 0xF");
     }
-    if (pose_frame_stride < 15 || ang_frame_stride < 7 || (fk && fk_frame_stride < 27))
+    const bool fk_joints = (flags & SEQIK_FLAG_FK_JOINTS) != 0;
+    if (pose_frame_stride < 15 || ang_frame_stride < 7 || (fk && fk_frame_stride < (fk_joints ? 12 : 27)))
         return seqik_fail(SEQIK_EINVAL, "seqik_leg_solve_f32: frame stride smaller than the innermost block");
     if (n_frame > 2147483647LL) return seqik_fail(SEQIK_EINVAL, "seqik_leg_solve_f32: too many frames");
     uint32_t sched = (flags & SEQIK_FLAG_SCHED_MASK) >> SEQIK_FLAG_SCHED_SHIFT;
@@ -292,6 +299,7 @@ extern "C" int seqik_leg_solve_f32(const float* pose, int64_t pose_chain_stride,
     a.fk = fk; a.fk_cs = fk_chain_stride; a.fk_fs = fk_frame_stride;
     a.warm = warm; a.warm_cs = warm_chain_stride;
     a.status = status; a.nfev = nfev; a.n_chain = n_chain; a.n_frame = n_frame;
+    a.fk_joints = fk_joints ? 1 : 0;
     a.stage_mask = (int)stage_mask; a.gn_mask = (int)(flags & 0x3F);   // bits 0-3 Gauss-Newton mode per stage, bit 4 escape, bit 5 skip-confirm
     if (sched == 1) {
         const int64_t grid = (n_chain + 31) / 32;

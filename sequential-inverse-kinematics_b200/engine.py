@@ -44,7 +44,7 @@ def stages_to_mask(stages: Sequence[int]) -> int:
 
 def leg_solve(pose, params, affine=None, stages: Sequence[int] = (1, 2, 3, 4), want_fk: bool = True,
               angles=None, fk=None, flags: int = N.FLAG_DEFAULT, schedule: int = N.SCHED_AUTO,
-              want_stats: bool = True, chains_per_warp: int = 0, frames=None, gate: int = 0):
+              want_stats: bool = True, chains_per_warp: int = 0, frames=None, gate: int = 0, fk_layout: str = "full"):
     """4-stage sequential IK (+FK) of every chain.  Returns (angles, fk|None, status|None, nfev|None).
 
     ``angles`` must be given (and is updated in place) when ``stages`` does not start at 1:
@@ -54,6 +54,8 @@ def leg_solve(pose, params, affine=None, stages: Sequence[int] = (1, 2, 3, 4), w
     from frame t0-1 of ``angles`` (t0 > 0).  Chunked calls over consecutive ranges are bit-identical to one call over
     all frames when every t0 is a multiple of 32 (the kernel re-derives sin/cos from the angles every 32 frames and at
     the first frame of a call); otherwise they agree to float32 rounding.
+    ``fk_layout="joints"``: ``fk`` is (n_chain, n_frame, 4, 3), the joint rows 5..8 of the full layout only (rows 0-3
+    repeat the origin, row 4 repeats row 5) -- 76 instead of 136 result bytes per leg-frame.
     """
     torch = N.require_cuda()
     lib = N.load_library()
@@ -74,10 +76,15 @@ def leg_solve(pose, params, affine=None, stages: Sequence[int] = (1, 2, 3, 4), w
         _check(angles, "angles", (7,))
         if tuple(angles.shape) != (n_chain, n_frame, 7):
             raise ValueError("angles must be (n_chain, n_frame, 7)")
+    if fk_layout not in ("full", "joints"):
+        raise ValueError(f"fk_layout must be 'full' or 'joints', got {fk_layout!r}")
+    fk_rows = 9 if fk_layout == "full" else 4
     if want_fk and fk is None:
-        fk = torch.empty((n_chain, n_frame, 9, 3), dtype=torch.float32, device=dev)
+        fk = torch.empty((n_chain, n_frame, fk_rows, 3), dtype=torch.float32, device=dev)
     if fk is not None:
-        _check(fk, "fk", (9, 3))
+        _check(fk, "fk", (fk_rows, 3))
+        if tuple(fk.shape[:2]) != (n_chain, n_frame):
+            raise ValueError(f"fk must be (n_chain, n_frame, {fk_rows}, 3)")
     if affine is not None:
         _check(affine, "affine", (8,))
     status = torch.empty((n_chain,), dtype=torch.int32, device=dev) if want_stats else None
@@ -87,15 +94,17 @@ def leg_solve(pose, params, affine=None, stages: Sequence[int] = (1, 2, 3, 4), w
         raise ValueError(f"frames {frames} outside [0, {n_frame}]")
     if t0 > 0 and not mask & 1:
         raise ValueError("a frame range that does not start at 0 needs stages starting at 1")
-    p_fk = 0 if fk is None else fk.data_ptr() + 4 * 27 * t0
+    fk_floats = 3 * fk_rows
+    p_fk = 0 if fk is None else fk.data_ptr() + 4 * fk_floats * t0
     warm = 0 if t0 == 0 else angles.data_ptr() + 4 * 7 * (t0 - 1)
     with torch.cuda.device(dev):
         rc = lib.seqik_leg_solve_f32(
             pose.data_ptr() + 4 * 15 * t0, n_frame * 15, 15, N.ptr(affine), N.ptr(params),
-            angles.data_ptr() + 4 * 7 * t0, n_frame * 7, 7, p_fk, n_frame * 27, 27,
+            angles.data_ptr() + 4 * 7 * t0, n_frame * 7, 7, p_fk, n_frame * fk_floats, fk_floats,
             warm, n_frame * 7,
             N.ptr(status), N.ptr(nfev), n_chain, t1 - t0, mask,
-            (flags & 0xFF) | ((schedule & 0xF) << N.FLAG_SCHED_SHIFT) | ((chains_per_warp & 0x3F) << 12) | ((gate & 3) << 18),
+            (flags & 0xFF) | ((schedule & 0xF) << N.FLAG_SCHED_SHIFT) | ((chains_per_warp & 0x3F) << 12) | ((gate & 3) << 18)
+            | (N.FLAG_FK_JOINTS if fk_layout == "joints" else 0),
             N.stream_ptr(torch, dev))
     N.check(rc, "seqik_leg_solve_f32")
     return angles, fk, status, nfev

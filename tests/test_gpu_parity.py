@@ -335,6 +335,36 @@ def test_frame_chunks_and_host_pipeline_equal_one_launch(api):
         api.engine.leg_solve(sess.d_pose, sess.params, angles=ang, fk=fk, frames=(5, 200))
 
 
+def test_joints_only_fk_layout(api):
+    """fk_layout="joints" returns exactly rows 5..8 of the full layout (bitwise), through the tensor API, both kernel
+    schedules, frame chunks and the pipelined host call; angles are unaffected."""
+    S, t = api.synthetic, api.torch
+    from seqikpy_b200.batch import BatchedLegIK
+    n_trial, n_frame = 3, 160
+    size, bounds, init = S.chain_constants()
+    chain = api.Chain(bounds, list(S.LEGS), size)
+    pose = S.make_trials(range(n_trial), 1000)[:, :n_frame]
+    host = t.from_numpy(np.ascontiguousarray(pose.transpose(0, 2, 1, 3, 4))).pin_memory()
+    full = BatchedLegIK(chain, init, S.LEGS, n_trial, n_frame)
+    full.d_pose.copy_(host.reshape(full.n_chain, n_frame, 5, 3))
+    a_ref, f_ref = (x.clone() for x in full.solve_device())
+    slim = BatchedLegIK(chain, init, S.LEGS, n_trial, n_frame, fk_layout="joints")
+    slim.d_pose.copy_(full.d_pose)
+    a_j, f_j = slim.solve_device()
+    assert tuple(f_j.shape) == (slim.n_chain, n_frame, 4, 3)
+    assert t.equal(a_j, a_ref) and t.equal(f_j, f_ref[:, :, 5:9])
+    assert abs(slim.mean_fk_error() - full.mean_fk_error()) < 1e-9
+    h_a, h_f = slim.solve_host(host, n_chunks=3)
+    assert t.equal(h_a, a_ref.cpu()) and t.equal(h_f, f_ref[:, :, 5:9].cpu())
+    _, f_lane, _, _ = api.engine.leg_solve(full.d_pose, full.params, schedule=api.native.SCHED_LANE_PER_CHAIN, fk_layout="joints")
+    _, f_lane_full, _, _ = api.engine.leg_solve(full.d_pose, full.params, schedule=api.native.SCHED_LANE_PER_CHAIN)
+    assert t.equal(f_lane, f_lane_full[:, :, 5:9])
+    with pytest.raises(ValueError):
+        api.engine.leg_solve(full.d_pose, full.params, fk=f_ref, fk_layout="joints")        # a 9-row buffer for the 4-row layout
+    with pytest.raises(ValueError):
+        api.engine.leg_solve(full.d_pose, full.params, fk_layout="rows")
+
+
 def test_fk_kernel_matches_solver_and_oracle(api, synthetic_gold):
     S, t = api.synthetic, api.torch
     size, bounds, init = S.chain_constants()
