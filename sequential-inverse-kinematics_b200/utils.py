@@ -2,7 +2,8 @@
 
 Mirrors the functions of the reference's ``seqikpy/utils.py`` that the hot path and its input converters use:
 ``calculate_body_size`` (:89-123), ``save_file`` (:235-238), ``load_file`` (:241-245), ``dict_to_nparray_pose`` /
-``dict_to_nparray_angle`` (:293-329).  The video / stimulus helpers of that module are outside the path.
+``dict_to_nparray_angle`` (:293-329), ``interpolate_signal`` / ``interpolate_joint_angles`` (:332-359, on the device).
+The video / stimulus helpers of that module are outside the path.
 """
 import pickle
 from typing import Dict, List
@@ -66,18 +67,40 @@ def load_file(output_fname):
 
 def interpolate_signal(signal, original_ts, new_ts):
     """Resamples a signal sampled every ``original_ts`` onto a ``new_ts`` grid with a shape-preserving cubic (pchip)
-    -- the hand-off of joint angles to a simulation time step (reference utils.py:332-349).  Host-side, after the path."""
-    from scipy.interpolate import pchip_interpolate
-    signal = np.array(signal, dtype=float)
-    total_time = signal.shape[0] * original_ts
-    original_x = np.arange(0, total_time, original_ts)
-    new_x = np.arange(0, total_time, new_ts)
-    if not np.all(np.isfinite(signal)):          # the reference zeroes non-finite samples (and the last one) and retries
-        signal[~np.isfinite(signal)] = 0
-        signal[-1] = 0
-    return np.array(pchip_interpolate(original_x, signal, new_x))
+    -- the hand-off of joint angles to a simulation time step (reference utils.py:332-349, which calls
+    ``scipy.interpolate.pchip_interpolate``).  ``signal``: (n,) or (n, k) along axis 0.  Runs the FP64 device kernel
+    (``seqik_pchip_resample_f64``, equal to scipy's result to ~1e-12 relative); like every compute path of this package
+    it needs the CUDA library and raises without it.  +-inf samples are zeroed together with the last sample, as the
+    reference's retry does; NaN raises ``ValueError`` like scipy."""
+    from . import _native as N
+    from . import engine
+    torch = N.require_cuda()
+    arr = np.array(signal, dtype=np.float64)
+    if arr.ndim not in (1, 2):
+        raise ValueError("signal must be (n,) or (n, k)")
+    x = torch.from_numpy(np.ascontiguousarray(arr.reshape(1, arr.shape[0], -1))).cuda()
+    out = engine.pchip_resample(x, original_ts, new_ts).cpu().numpy()[0]
+    return out[:, 0] if arr.ndim == 1 else out
 
 
 def interpolate_joint_angles(joint_angles_dict, **kwargs):
-    """``interpolate_signal`` over every entry of a joint-angle dictionary (reference utils.py:352-359)."""
-    return {dof: interpolate_signal(signal=values, **kwargs) for dof, values in joint_angles_dict.items()}
+    """``interpolate_signal`` over every entry of a joint-angle dictionary (reference utils.py:352-359); entries of equal
+    length are resampled by one kernel launch."""
+    from . import _native as N
+    from . import engine
+    torch = N.require_cuda()
+    original_ts, new_ts = kwargs["original_ts"], kwargs["new_ts"]
+    arrays = {dof: np.array(values, dtype=np.float64) for dof, values in joint_angles_dict.items()}
+    out = {}
+    by_len = {}
+    for dof, arr in arrays.items():
+        if arr.ndim != 1:
+            out[dof] = interpolate_signal(arr, original_ts, new_ts)
+        else:
+            by_len.setdefault(arr.shape[0], []).append(dof)
+    for n, dofs in by_len.items():
+        x = torch.from_numpy(np.stack([arrays[d] for d in dofs])).cuda()
+        res = engine.pchip_resample(x, original_ts, new_ts).cpu().numpy()
+        for i, d in enumerate(dofs):
+            out[d] = res[i]
+    return {dof: out[dof] for dof in joint_angles_dict}

@@ -72,3 +72,25 @@ def test_resample_shapes_and_edge_cases(eng):
         engine.pchip_resample(torch.tensor(y, dtype=torch.float64, device="cuda"), 0.01, 0.002)
     with pytest.raises(ValueError):
         engine.pchip_resample(torch.zeros((2, 1), dtype=torch.float64, device="cuda"), 0.01, 0.002)
+
+
+def test_utils_interpolate_like_the_reference(eng, grooming_leg):
+    """utils.interpolate_signal / interpolate_joint_angles (reference utils.py:332-359) on the device kernel: same keys,
+    lengths and values as the reference's scipy call."""
+    from seqikpy_b200.utils import interpolate_joint_angles, interpolate_signal
+    keys = [str(k) for k in grooming_leg["angle_keys"]]
+    ang = {k: grooming_leg["ref_angles"].reshape(-1, 7)[:6000, i % 7].copy() if i < 7 else grooming_leg["ref_angles"][1][:, i - 7].copy()
+           for i, k in enumerate(keys)}
+    ang["short"] = np.cos(np.arange(0, 3.0, 0.01))                       # a second length in the same dictionary
+    out = interpolate_joint_angles(ang, original_ts=0.01, new_ts=0.001)
+    assert list(out.keys()) == list(ang.keys())
+    for k, v in ang.items():
+        ref = reference_resample(v, 0.01, 0.001)
+        assert out[k].shape == ref.shape and out[k].dtype == np.float64
+        assert np.abs(out[k] - ref).max() < 1e-12 * max(1.0, np.abs(ref).max()), k
+    assert np.allclose(interpolate_signal(np.arange(5.0), 1.0, 0.5)[:8], np.arange(0, 4.0, 0.5))
+    two = np.stack([np.sin(np.arange(50) * 0.3), np.arange(50) ** 1.5], axis=1)             # (n, k) along axis 0
+    got = interpolate_signal(two, 0.02, 0.005)
+    assert got.shape == (200, 2)
+    for j in range(2):
+        assert np.abs(got[:, j] - reference_resample(two[:, j], 0.02, 0.005)).max() < 1e-10
