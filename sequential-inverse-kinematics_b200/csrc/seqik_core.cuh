@@ -115,6 +115,22 @@ template <> struct Num<float> {
         *c = ((q + 1) & 2) ? -cc : cc;
         *v = (q == 0) ? vr : 1.0f - *c;
     }
+    // the same for two angles at once: ONE branch for the pair (both in quadrant 0, the usual case for a step), and the
+    // two polynomial chains in one basic block so that they interleave.  Bitwise equal to two sincosv_ calls.
+    static SK_HD void sincosv2_(float x, float y, float* sx, float* cx, float* vx, float* sy, float* cy, float* vy) {
+        if (fmaxf(fabsf(x), fabsf(y)) < 0.78f) {
+            const float zx = x * x, zy = y * y;
+            float spx = fmaf(zx, -1.9515295891e-4f, 8.3321608736e-3f), spy = fmaf(zy, -1.9515295891e-4f, 8.3321608736e-3f);
+            spx = fmaf(spx, zx, -1.6666654611e-1f); spy = fmaf(spy, zy, -1.6666654611e-1f);
+            float cpx = fmaf(zx, 2.443315711809948e-5f, -1.388731625493765e-3f), cpy = fmaf(zy, 2.443315711809948e-5f, -1.388731625493765e-3f);
+            cpx = fmaf(cpx, zx, 4.166664568298827e-2f); cpy = fmaf(cpy, zy, 4.166664568298827e-2f);
+            *sx = fmaf(spx * zx, x, x); *sy = fmaf(spy * zy, y, y);
+            *vx = fmaf(-cpx * zx, zx, 0.5f * zx); *vy = fmaf(-cpy * zy, zy, 0.5f * zy);
+            *cx = 1.0f - *vx; *cy = 1.0f - *vy;
+            return;
+        }
+        sincosv_(x, sx, cx, vx); sincosv_(y, sy, cy, vy);
+    }
     static SK_HD float inf() { return INFINITY; }
     static SK_HD float tiny() { return 1.17549435e-38f; }     // stands in for nextafter(0, .)
     static SK_HD float eps_in() { return 2.220446e-16f; }     // fp64 ulp: strict-feasibility gap
@@ -132,6 +148,9 @@ template <> struct Num<double> {
         *s = sin(x); *c = cos(x);
         const double h = sin(0.5 * x);
         *v = 2.0 * h * h;
+    }
+    static SK_HD void sincosv2_(double x, double y, double* sx, double* cx, double* vx, double* sy, double* cy, double* vy) {
+        sincosv_(x, sx, cx, vx); sincosv_(y, sy, cy, vy);
     }
     static SK_HD double inf() { return (double)INFINITY; }
     static SK_HD double tiny() { return 4.9406564584124654e-324; }
@@ -220,16 +239,32 @@ struct StageSolve {
         }
     }
 
-    // least_squares prologue: x0 made strictly feasible (rstep 1e-10), f, g, Delta0
-    SK_HD void init(int kind_in, R L_, R has_a_in, const Vec3<R>& q_in, R a, R b,
-                    R lb0, R ub0, R lb1, R ub1, R null_sq_, int n_full, int mode = 0) {
+    // the constants of a (chain, stage) problem / the seed of a new solve in the caller's terms
+    SK_HD void set_problem(int kind_in, R L_, R has_a_in, R null_sq_, int n_full, int mode) {
         gn_mode = (mode & 1) != 0; skip_confirm = (mode & 2) != 0;     // bit 0 Gauss-Newton mode, bit 1 skip-confirm
         xy = kind_in == KIND_XY; shift = xy ? R(1.57079632679489661923) : R(0);
         L = L_; has_a = has_a_in; null_sq = null_sq_; max_nfev = 100 * n_full;
+    }
+    SK_HD void set_iterate(R a, R b) { x0 = a; x1 = b - shift; }
+
+    // least_squares prologue: x0 made strictly feasible (rstep 1e-10), f, g, Delta0
+    SK_HD void init(int kind_in, R L_, R has_a_in, const Vec3<R>& q_in, R a, R b,
+                    R lb0, R ub0, R lb1, R ub1, R null_sq_, int n_full, int mode = 0) {
+        set_problem(kind_in, L_, has_a_in, null_sq_, n_full, mode);
+        set_iterate(a, b);
+        restart(q_in, lb0, ub0, lb1, ub1, true);
+    }
+
+    // The prologue proper.  `fresh`: the sin/cos of the iterate are derived from the angles (a new solve, init()).
+    // Otherwise this is the next frame of the same (chain, stage): the warm start IS the previous solve's final iterate,
+    // so its sin/cos are carried over and only the bound distances and the residual against the new target are rebuilt
+    // (least_squares prologue without the trigonometry).  Callers pass fresh = true every SEQIK_RESYNC frames so that the
+    // carried sin/cos cannot drift from the angle (float32 random walk, ~1e-6 rad over 32 frames).  One code path for
+    // both, so that lanes of a warp that re-derive and lanes that carry run the same instructions but the trigonometry.
+    SK_HD void restart(const Vec3<R>& q_in, R lb0, R ub0, R lb1, R ub1, bool fresh = false) {
         const Vec3<R> q = xy ? Vec3<R>{-q_in.z, q_in.y, q_in.x} : q_in;
-        place(a, b - shift, lb0, ub0, lb1 - shift, ub1 - shift);
-        R va, vb;
-        N::sincosv_(x0, &sa, &ca, &va); N::sincosv_(x1, &sb, &cb, &vb);
+        place(x0, x1, lb0, ub0, lb1 - shift, ub1 - shift);   // bound distances (re-)derived from the angle
+        if (fresh) { R va, vb; N::sincosv_(x0, &sa, &ca, &va); N::sincosv_(x1, &sb, &cb, &vb); }
         const Vec3<R> w = point();
         f = {w.x - q.x, w.y - q.y, w.z - q.z};
         cost = R(0.5) * dot(f, f);
@@ -243,28 +278,7 @@ struct StageSolve {
         if (Delta == R(0)) Delta = R(1);
         alpha = R(0); nfev = 1; escaped = false; last_ratio = R(0);
         status = (cost < N::inf()) ? ST_RUNNING : ST_NONFINITE;      // false for NaN and inf
-        if (status == ST_RUNNING) plan();
-    }
-
-    // Next frame of the same (chain, stage): the warm start IS the previous solve's final iterate, so its sin/cos are
-    // carried over and only the bound distances and the residual against the new target is rebuilt (least_squares
-    // prologue without the trigonometry).  Callers re-run init() every SEQIK_RESYNC frames so that the carried
-    // sin/cos cannot drift from the angle (float32 random walk, ~1e-6 rad over 32 frames).
-    SK_HD void restart(const Vec3<R>& q_in, R lb0, R ub0, R lb1, R ub1) {
-        const Vec3<R> q = xy ? Vec3<R>{-q_in.z, q_in.y, q_in.x} : q_in;
-        place(x0, x1, lb0, ub0, lb1 - shift, ub1 - shift);   // bound distances re-derived from the angle, exactly as init() would
-        const Vec3<R> w = point();
-        f = {w.x - q.x, w.y - q.y, w.z - q.z};
-        cost = R(0.5) * dot(f, f);
-        gradient();
-        R v0, v1, dv0, dv1; cl_scaling(v0, v1, dv0, dv1);
-        const R xb_ = x1 + shift;
-        const R q0 = (v0 > R(1e-30)) ? x0 * x0 * N::rcp_(v0) : R(0), q1 = (v1 > R(1e-30)) ? xb_ * xb_ * N::rcp_(v1) : R(0);
-        Delta = N::sqrt_(null_sq + q0 + q1);
-        if (Delta == R(0)) Delta = R(1);
-        alpha = R(0); nfev = 1; escaped = false; last_ratio = R(0);
-        status = (cost < N::inf()) ? ST_RUNNING : ST_NONFINITE;      // false for NaN and inf
-        if (status == ST_RUNNING) plan();
+        plan(status == ST_RUNNING);
     }
 
     // Singularity escape (optional, SEQIK_FLAG_ESCAPE).  For the Rz(a) Ry(b) stages the end point does not depend on
@@ -273,8 +287,9 @@ struct StageSolve {
     // its finite-difference Jacobian (SURVEY.md finding 4), i.e. frames later and irreproducibly.  Here the two
     // closed-form mirror solutions of "point a segment at the target" (SURVEY.md 3.4), clamped to the box, are
     // evaluated; if one is clearly better the solve continues from it.  At most once per solve.
+    SK_HD bool escape_possible() const { return !(escaped || xy || has_a == R(0) || sb * sb > R(1e-8)); }
     SK_HD bool escape() {
-        if (escaped || xy || has_a == R(0) || sb * sb > R(1e-8)) return false;
+        if (!escape_possible()) return false;
         escaped = true;
         const Vec3<R> w = point();
         const Vec3<R> q = {w.x - f.x, w.y - f.y, w.z - f.z};
@@ -448,13 +463,14 @@ struct StageSolve {
     // step_h_sq, pred).  It runs at the end of init()/restart() and at the end of every trip(), so a solve costs
     // exactly one loop trip per function evaluation and its termination is known in the trip that produced it.
     // (After a rejected step the iterate is unchanged and only Delta/alpha differ: plan() recomputes the same head.)
-    SK_HD void plan() {
+    SK_HD void plan(bool active = true) {
         const R gtol = R(1e-8), ftol = R(1e-8);
         Hat h;
         R v0, v1, dv0, dv1; cl_scaling(v0, v1, dv0, dv1);
         const R g_norm = N::max_(N::abs_(g0 * v0), N::abs_(g1 * v1));
-        if (g_norm < gtol) { status = ST_GTOL; return; }
-        if (nfev >= max_nfev) { status = ST_MAXFEV; return; }
+        // straight-line code: the termination tests that need no evaluation are folded into selects at the end, so that
+        // a trip is one basic block but for the rare general step (lanes that are not `active` change nothing)
+        const bool stop_g = g_norm < gtol, stop_n = nfev >= max_nfev;
         h.d0 = N::sqrt_(v0); h.d1 = N::sqrt_(v1);
         h.gh0 = h.d0 * g0; h.gh1 = h.d1 * g1;
         h.B0 = N::fma_(v0, ja_sq(), g0 * dv0); h.B1 = N::fma_(v1, L * L, g1 * dv1);   // Jh^T Jh + diag(g dv), diagonal
@@ -471,18 +487,21 @@ struct StageSolve {
         // fast path: the Gauss-Newton step fits the trust region and stays inside the box (select_step's in_bounds case)
         const R ph0 = -tg0, ph1 = -tg1, p0 = h.d0 * ph0, p1 = h.d1 * ph1;
         const bool inb = (dl0 + p0 >= R(0)) && (du0 - p0 >= R(0)) && (dl1 + p1 >= R(0)) && (du1 - p1 >= R(0));
-        if (gn_taken && inb) {
-            alpha = R(0);
-            st0 = p0; st1 = p1; step_h_sq = N::fma_(ph1, ph1, ph0 * ph0); pred = -model(h, ph0, ph1);
-        } else {
+        const bool run = active && !stop_g && !stop_n;
+        R n_st0 = p0, n_st1 = p1, n_sh = N::fma_(ph1, ph1, ph0 * ph0), n_pred = -model(h, ph0, ph1), n_alpha = R(0);
+        if (run && !(gn_taken && inb)) {
             const Step o = slow_step(h, tg0, tg1, gn_taken, one_var, Delta, alpha, dl0, du0, dl1, du1);
-            st0 = o.st0; st1 = o.st1; step_h_sq = o.sh_sq; pred = o.pred; alpha = o.alpha;
+            n_st0 = o.st0; n_st1 = o.st1; n_sh = o.sh_sq; n_pred = o.pred; n_alpha = o.alpha;
         }
+        st0 = run ? n_st0 : st0; st1 = run ? n_st1 : st1; step_h_sq = run ? n_sh : step_h_sq; pred = run ? n_pred : pred;
+        alpha = run ? n_alpha : alpha;
         // Optional (SEQIK_FLAG_SKIP_CONFIRM): do not evaluate a step that would only CONFIRM convergence.  When the model
         // has just been accurate (previous actual/predicted within 25 % of 1) and now predicts a reduction below
         // ftol * cost for a plain Gauss-Newton step, the reference evaluates that step, accepts it and stops on ftol;
         // the step is below sqrt(2 ftol cost) / L ~ 3e-6 rad.  Saves one of the ~5 evaluations of a warm-started solve.
-        if (skip_confirm && gn_taken && pred < ftol * cost && pred >= R(0) && N::abs_(last_ratio - R(1)) < R(0.25)) status = ST_FTOL;
+        const bool confirm_only = skip_confirm && gn_taken && n_pred < ftol * cost && n_pred >= R(0) && N::abs_(last_ratio - R(1)) < R(0.25);
+        const int st_new = stop_g ? ST_GTOL : stop_n ? ST_MAXFEV : confirm_only ? ST_FTOL : ST_RUNNING;
+        status = active ? st_new : status;
     }
 
     // One function evaluation: one pass of scipy's inner `while actual_reduction <= 0` loop on the step plan() left,
@@ -500,7 +519,7 @@ struct StageSolve {
             if (ndu1 <= R(0)) { const R gap = inner_gap(nx1 + ndu1); e1 = du1 - gap; ndu1 = gap; ndl1 = span1 - gap; nx1 = x1 + e1; }
         }
         R sda, cda, va, sdb, cdb, vb;
-        N::sincosv_(e0, &sda, &cda, &va); N::sincosv_(e1, &sdb, &cdb, &vb);
+        N::sincosv2_(e0, e1, &sda, &cda, &va, &sdb, &cdb, &vb);
         const R dsa = N::fma_(ca, sda, -(sa * va)), dca = -N::fma_(sa, sda, ca * va);   // sin/cos(a + e0) - sin/cos(a)
         const R dsb = N::fma_(cb, sdb, -(sb * vb)), dcb = -N::fma_(sb, sdb, cb * vb);
         const R nsa = sa + dsa, nca = ca + dca, nsb = sb + dsb, ncb = cb + dcb;
@@ -508,12 +527,11 @@ struct StageSolve {
         nfev += 1;
         const R actual = -N::fma_(R(0.5), dot(dw, dw), dot(f, dw));
         // update_tr_radius
-        R ratio;
-        if (pred > R(0)) ratio = (actual != R(0)) ? actual * N::rcp_(pred) : R(0); else if (pred == R(0) && actual == R(0)) ratio = R(1); else ratio = R(0);
+        const R ratio_pos = (actual != R(0)) ? actual * N::rcp_(pred) : R(0);
+        const R ratio = (pred > R(0)) ? ratio_pos : ((pred == R(0) && actual == R(0)) ? R(1) : R(0));
         last_ratio = ratio;
-        R Delta_new = Delta;
-        if (ratio < R(0.25)) Delta_new = R(0.25) * N::sqrt_(step_h_sq);
-        else if (ratio > R(0.75) && step_h_sq > R(0.9025) * Delta * Delta) Delta_new = R(2) * Delta;
+        const bool shrink = ratio < R(0.25), grow = !shrink && ratio > R(0.75) && step_h_sq > R(0.9025) * Delta * Delta;
+        const R Delta_new = shrink ? R(0.25) * N::sqrt_(step_h_sq) : grow ? R(2) * Delta : Delta;
         // check_termination
         const R step_sq = N::fma_(st1, st1, st0 * st0);
         const R xb_ = x1 + shift;
@@ -522,16 +540,18 @@ struct StageSolve {
         const bool ft = (actual < ftol * cost) && (ratio > R(0.25));
         const bool xt = step_sq < xt_rhs * xt_rhs;
         const int term = (ft && xt) ? ST_BOTH : ft ? ST_FTOL : xt ? ST_XTOL : ST_RUNNING;
-        if (term == ST_RUNNING) { alpha *= Delta * N::rcp_(Delta_new); Delta = Delta_new; }
-        if (actual > R(0)) {
-            x0 = nx0; x1 = nx1; dl0 = ndl0; du0 = ndu0; dl1 = ndl1; du1 = ndu1;
-            sa = nsa; ca = nca; sb = nsb; cb = ncb;
-            f = {f.x + dw.x, f.y + dw.y, f.z + dw.z};
-            cost = cost - actual;
-            gradient();
-        }
+        const bool go_on = term == ST_RUNNING;
+        alpha = go_on ? alpha * (Delta * N::rcp_(Delta_new)) : alpha; Delta = go_on ? Delta_new : Delta;
+        // accept / reject by selects (the gradient of an unchanged iterate is recomputed to the same bits)
+        const bool acc = actual > R(0);
+        x0 = acc ? nx0 : x0; x1 = acc ? nx1 : x1;
+        dl0 = acc ? ndl0 : dl0; du0 = acc ? ndu0 : du0; dl1 = acc ? ndl1 : dl1; du1 = acc ? ndu1 : du1;
+        sa = acc ? nsa : sa; ca = acc ? nca : ca; sb = acc ? nsb : sb; cb = acc ? ncb : cb;
+        f = {acc ? f.x + dw.x : f.x, acc ? f.y + dw.y : f.y, acc ? f.z + dw.z : f.z};
+        cost = acc ? cost - actual : cost;
+        gradient();
         status = term;
-        if (term == ST_RUNNING) plan();
+        plan(go_on);
     }
 
     // make_strictly_feasible(x, lb, ub, rstep=0): one fp64 ulp inside the bound `b`

@@ -117,19 +117,25 @@ constexpr int PIPE_DEPTH = 4;               // frames a stage may run ahead of t
 constexpr int PIPE_SLOT = 12;               // 3x3 frame (columns) + pivot
 constexpr int PIPE_CHAINS = 8;              // chains per warp (maximum)
 
+// kFull: all four stages solved and the nine-row FK layout written (the benchmark configurations and the dict API):
+// the frozen-stage, partial-stage and output-layout decisions are compiled out.  Same arithmetic either way.
+template <bool kFull>
 __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, int gate_mask) {
-    __shared__ float ring[3][PIPE_DEPTH][PIPE_SLOT][PIPE_CHAINS];      // chain innermost: conflict-free per stage
+    __shared__ float ring[4][PIPE_DEPTH][PIPE_SLOT][PIPE_CHAINS];      // chain innermost: conflict-free per stage; [3] = identity (stage 1's input)
     __shared__ float kpbuf[6][32];                                     // prefetched key points, one column per lane
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x;
     const int s = lane & 3;                                   // this lane's stage (0..3)
     const int cw = lane >> 2;                                 // chain within the warp
     const int64_t c = (int64_t)blockIdx.x * cpw + cw;
-    int lo = 0; while (lo < 3 && !((a.stage_mask >> lo) & 1)) ++lo;
-    int hi = 3; while (hi > 0 && !((a.stage_mask >> hi) & 1)) --hi;
+    int lo = 0, hi = 3;
+    if (!kFull) {
+        while (lo < 3 && !((a.stage_mask >> lo) & 1)) ++lo;
+        while (hi > 0 && !((a.stage_mask >> hi) & 1)) --hi;
+    }
     const bool owner = cw < cpw && c < a.n_chain;
     const bool live = owner && s <= hi;                       // lanes of stages after the last requested one idle
-    const bool frozen = s < lo;                               // DOFs read from the angles buffer, not solved
+    const bool frozen = !kFull && s < lo;                     // DOFs read from the angles buffer, not solved
     const int n_frame = (int)a.n_frame;
 
     // per-lane constants of (chain, stage)
@@ -137,7 +143,8 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, 
     const float* prm = a.params + cc * SEQIK_CHAIN_PARAM_FLOATS;
     const float* pose = a.pose + cc * a.pose_cs;
     float* ang = a.angles + cc * a.ang_cs;
-    float* fk = a.fk ? a.fk + cc * a.fk_cs : nullptr;
+    float* fk = (kFull || a.fk) ? a.fk + cc * a.fk_cs : nullptr;
+    const bool fk_joints = !kFull && a.fk_joints;
     LoadMap map; map.init(a.affine, cc);
     const int kind = (s == 0) ? KIND_XY : KIND_ZY;
     const float seg = __ldg(prm + s);
@@ -154,11 +161,12 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, 
     float xa = (s == 3) ? 0.f : seed[ia], xb = seed[ib];                           // warm start, frame to frame
 
     // running output / input pointers of the frame this lane works on (advanced per frame: no 64-bit index math per access)
-    float* pa_a = ang + ia; float* pa_b = ang + ib;
+    float* pa_a = ang + ((s == 3) ? 6 : ia); float* pa_b = ang + ib;             // stage 4 has one DOF: both point at it
     float* pf = fk ? fk + 3 * s : nullptr;
     const float* pnext = pose;       // frame whose key points are prefetched next
 
     StageSolve<float> S;
+    S.set_problem(kind, seg, has_a, null_sq, n_full, gn);
     Mat3<float> A = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
     Vec3<float> piv = {0.f, 0.f, 0.f}, o = {0.f, 0.f, 0.f}, rel = {0.f, 0.f, 0.f};
     int t = 0;                       // frame this lane works on
@@ -166,6 +174,13 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, 
     bool solving = false;
     uint32_t nf = 0; int worst = ST_GTOL;
     S.status = ST_GTOL;
+    // stage 1 starts every frame from the identity frame at the origin: it reads them from a constant ring slot like
+    // the other stages read their producer's, so that the hand-off read is the same instruction for all lanes
+    if (lane < PIPE_CHAINS)
+        for (int d = 0; d < PIPE_DEPTH; ++d)
+            for (int k = 0; k < PIPE_SLOT; ++k) ring[3][d][k][lane] = (k == 0 || k == 4 || k == 8) ? 1.f : 0.f;
+    __syncwarp(full);
+    const int sp = (s + 3) & 3;      // ring this lane reads from
     // key points of frame t (origin + this stage's target, 6 floats), fetched one frame ahead with cp.async into
     // shared memory: the copy is in flight during the previous solve and does not hold a register scoreboard
     // (plain loads made the first dependent instruction of every open wait a full DRAM latency)
@@ -189,30 +204,30 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, 
         __syncwarp(full);            // ring reads of the previous open phase are complete before a slot is written again
         const int started_next = __shfl_sync(full, started, (lane + 1) & 31);   // consumer's progress (lane + 1)
         // ---- optional singularity escape: a solve that ended on sin b = 0 may continue from a closed-form candidate
-        if (esc && live && solving && !frozen && S.done()) S.escape();
+        if (esc && live && solving && !frozen && S.done() && S.escape_possible()) S.escape();
         // ---- close the converged solve: outputs + hand-off to the next stage (needs a free ring slot)
         if (live && t < n_frame && solving && S.done() && (s == hi || t < started_next + PIPE_DEPTH)) {
             if (!frozen) {
                 xa = S.x0; xb = S.angle_b(); nf += (uint32_t)S.nfev;
-                if (S.status == ST_MAXFEV && worst > ST_MAXFEV) worst = ST_MAXFEV;
-                if (S.status == ST_NONFINITE) worst = ST_NONFINITE;
-                if (s != 3) *pa_a = xa;
+                worst = (S.status == ST_MAXFEV && worst > ST_MAXFEV) ? ST_MAXFEV : worst;
+                worst = (S.status == ST_NONFINITE) ? ST_NONFINITE : worst;
+                *pa_a = (s == 3) ? xb : xa;
                 *pa_b = xb;
             }
             // joint position = pivot + A w(x) = target + A f   (q = A^T rel, f = w - q)
             const Vec3<float> Af = mul(A, S.res());
             const Vec3<float> np_ = {(piv.x + rel.x) + Af.x, (piv.y + rel.y) + Af.y, (piv.z + rel.z) + Af.z};
-            if (fk) {
+            if (kFull || fk) {
                 // rows 0-3 repeat the origin, 4 and 5 are both the Coxa-Femur joint: lane s writes origin row s and its
                 // own joint row(s), which spreads the 27 floats of a frame over the four lanes
                 const Vec3<float> jw = {np_.x + o.x, np_.y + o.y, np_.z + o.z};
-                if (a.fk_joints) {                                                       // joints-only layout: row s = this lane's joint
+                if (fk_joints) {                                                         // joints-only layout: row s = this lane's joint
                     pf[0] = jw.x; pf[1] = jw.y; pf[2] = jw.z;
                 } else {
                     pf[0] = o.x; pf[1] = o.y; pf[2] = o.z;                               // row s
                     pf[15] = jw.x; pf[16] = jw.y; pf[17] = jw.z;                         // row 5 + s
                     if (s == 0) { pf[12] = jw.x; pf[13] = jw.y; pf[14] = jw.z; }         // row 4
-                    if (s == hi && hi < 3) for (int r = 1; r < 4 - hi; ++r) { pf[3 * r] = o.x; pf[3 * r + 1] = o.y; pf[3 * r + 2] = o.z; }
+                    if (!kFull && s == hi && hi < 3) for (int r = 1; r < 4 - hi; ++r) { pf[3 * r] = o.x; pf[3 * r + 1] = o.y; pf[3 * r + 2] = o.z; }
                 }
                 pf += a.fk_fs;
             }
@@ -229,8 +244,8 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, 
         const int done_prev = __shfl_sync(full, done, (lane + 31) & 31);        // producer's progress (lane - 1)
         // ---- open the next solve when the previous stage has published this frame
         if (live && t < n_frame && !solving && (s == 0 || t < done_prev)) {
-            if (s > 0) {
-                const float (*q)[PIPE_CHAINS] = ring[s - 1][t & (PIPE_DEPTH - 1)];
+            {
+                const float (*q)[PIPE_CHAINS] = ring[sp][t & (PIPE_DEPTH - 1)];
                 A.c0 = {q[0][cw], q[1][cw], q[2][cw]}; A.c1 = {q[3][cw], q[4][cw], q[5][cw]}; A.c2 = {q[6][cw], q[7][cw], q[8][cw]};
                 piv = {q[9][cw], q[10][cw], q[11][cw]};
             }
@@ -242,14 +257,16 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, 
             const Vec3<float> k = map.apply(kt, s + 1);
             rel = {(k.x - o.x) - piv.x, (k.y - o.y) - piv.y, (k.z - o.z) - piv.z};
             const Vec3<float> q3 = mulT(A, rel);
-            if (carried && !frozen && (t & (SEQIK_RESYNC - 1)) != 0) {
-                S.restart(q3, lb0, ub0, lb1, ub1);
-            } else {
+            // a carried solve continues from its own final iterate; every SEQIK_RESYNC frames (and at the first frame of
+            // a call) the iterate is re-derived from the angles.  Same code but for the trigonometry (restart's `fresh`).
+            const bool fresh = !(carried && !frozen && (t & (SEQIK_RESYNC - 1)) != 0);
+            if (fresh) {
                 if (frozen) { xa = (s == 3) ? 0.f : *pa_a; xb = *pa_b; }
-                S.init(kind, seg, has_a, q3, xa, xb, lb0, ub0, lb1, ub1, null_sq, n_full, gn);
-                if (frozen) S.status = ST_GTOL;
+                S.set_iterate(xa, xb);
                 carried = true;
             }
+            S.restart(q3, lb0, ub0, lb1, ub1, fresh);
+            if (frozen) S.status = ST_GTOL;
             solving = true; started = t + 1;
         }
         }   // gate
@@ -322,7 +339,8 @@ extern "C" int seqik_leg_solve_f32(const float* pose, int64_t pose_chain_stride,
         // 6 000 - 60 000 chains).  Scheduling only: results are unchanged.
         const uint32_t gate_sel = (flags >> SEQIK_FLAG_GATE_SHIFT) & 3u;      // 0 auto, 1/2/3 = every 1st/2nd/4th iteration
         const int gate_mask = gate_sel ? (1 << (gate_sel - 1)) - 1 : 1;
-        leg_solve_pipe_kernel<<<(unsigned)grid, 32, 0, (cudaStream_t)stream>>>(a, cpw, gate_mask);
+        if (stage_mask == 0xF && fk && !fk_joints) leg_solve_pipe_kernel<true><<<(unsigned)grid, 32, 0, (cudaStream_t)stream>>>(a, cpw, gate_mask);
+        else leg_solve_pipe_kernel<false><<<(unsigned)grid, 32, 0, (cudaStream_t)stream>>>(a, cpw, gate_mask);
     }
     return seqik_check_launch("seqik_leg_solve_f32");
 }

@@ -66,6 +66,60 @@ void hostsim_chain_f64(const double* pose, int64_t n_frame, const double* seg, c
 }
 }
 
+// ---- the stage-pipeline kernel's per-lane arithmetic, run serially: the solve of (stage, frame) is carried from
+// (stage, frame - 1) by StageSolve::restart and re-derived by init every SEQIK_RESYNC frames, exactly as
+// leg_solve_pipe_kernel does (csrc/seqik_solver.cu); scheduling does not change the arithmetic.
+static void run_carried(const float* pose, int64_t n_frame, const float* prm, float* angles, float* fk, int32_t* nfev,
+                        int gn_mask) {
+    typedef float R;
+    StageSolve<R> S[4];
+    bool carried[4] = {false, false, false, false};
+    R xa[4], xb[4];
+    for (int s = 0; s < 4; ++s) { xa[s] = (s == 3) ? 0.f : prm[18 + 2 * s]; xb[s] = prm[18 + ((s == 3) ? 6 : 2 * s + 1)]; }
+    const R inf = Num<R>::inf();
+    const bool esc = (gn_mask >> 4) & 1;
+    for (int64_t t = 0; t < n_frame; ++t) {
+        const R* kp = pose + t * 15;
+        const Vec3<R> o = {kp[0], kp[1], kp[2]};
+        Mat3<R> A = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
+        Vec3<R> piv = {0.f, 0.f, 0.f};
+        R* f9 = fk + t * 27;
+        for (int s = 0; s < 4; ++s) {
+            const int kind = (s == 0) ? KIND_XY : KIND_ZY;
+            const int ia = 2 * s, ib = (s == 3) ? 6 : 2 * s + 1;
+            const R lb0 = (s == 3) ? -inf : prm[4 + ia], ub0 = (s == 3) ? inf : prm[11 + ia];
+            const R lb1 = prm[4 + ib], ub1 = prm[11 + ib];
+            const int n_full = (s == 0) ? 4 : (s == 1) ? 6 : (s == 2) ? 8 : 9;
+            const int gn = ((gn_mask >> s) & 1) | (((gn_mask >> 5) & 1) << 1);
+            const Vec3<R> k = {kp[3 * (s + 1)], kp[3 * (s + 1) + 1], kp[3 * (s + 1) + 2]};
+            const Vec3<R> rel = {(k.x - o.x) - piv.x, (k.y - o.y) - piv.y, (k.z - o.z) - piv.z};
+            const Vec3<R> q3 = mulT(A, rel);
+            if (carried[s] && (t & (SEQIK_RESYNC - 1)) != 0) S[s].restart(q3, lb0, ub0, lb1, ub1);
+            else { S[s].init(kind, prm[s], (s == 3) ? 0.f : 1.f, q3, xa[s], xb[s], lb0, ub0, lb1, ub1, prm[25 + s], n_full, gn); carried[s] = true; }
+            for (;;) {
+                while (!S[s].done()) S[s].trip();
+                if (!(esc && S[s].escape())) break;
+            }
+            xa[s] = S[s].x0; xb[s] = S[s].angle_b();
+            if (s != 3) angles[t * 7 + ia] = xa[s];
+            angles[t * 7 + ib] = xb[s];
+            nfev[t * 4 + s] = S[s].nfev;
+            const Vec3<R> Af = mul(A, S[s].res());
+            const Vec3<R> np_ = {(piv.x + rel.x) + Af.x, (piv.y + rel.y) + Af.y, (piv.z + rel.z) + Af.z};
+            const Vec3<R> jw = {np_.x + o.x, np_.y + o.y, np_.z + o.z};
+            f9[3 * s] = o.x; f9[3 * s + 1] = o.y; f9[3 * s + 2] = o.z;
+            f9[15 + 3 * s] = jw.x; f9[16 + 3 * s] = jw.y; f9[17 + 3 * s] = jw.z;
+            if (s == 0) { f9[12] = jw.x; f9[13] = jw.y; f9[14] = jw.z; }
+            A = rotate_frame(A, kind, S[s].sa, S[s].ca, S[s].sin_b(), S[s].cos_b());
+            piv = np_;
+        }
+    }
+}
+extern "C" void hostsim_carried_f32(const float* pose, int64_t n_frame, const float* prm, float* angles, float* fk,
+                                    int32_t* nfev, int gn_mask) {
+    run_carried(pose, n_frame, prm, angles, fk, nfev, gn_mask);
+}
+
 // ---- generic 7-DOF solve (csrc/seqik_generic.cuh): pose (N,2,3) = ThC origin + claw per frame; prm = 32-float row
 // (seg 0..3, lb 4..10, ub 11..17, seed 18..24, null_sq 25; joints in generic chain order).  teacher: NULL, or (N,7)
 // seeds that replace the warm start of every frame (teacher-forced single solves).

@@ -66,6 +66,25 @@ def run_runner_f32(pose, seg, lb, ub, null_sq, seed, stage_mask=0xF, gn_mask=0):
     return angles, fk, nfev_sum, steps
 
 
+def run_carried_f32(pose, prm, gn_mask=0x3F):
+    """The stage-pipeline kernel's per-lane arithmetic (solves carried frame to frame by StageSolve::restart, re-derived
+    every SEQIK_RESYNC frames), run serially on the host build: pose (N,5,3), prm (32,) -> angles (N,7), fk (N,9,3),
+    nfev (N,4)."""
+    lib = load()
+    pose = np.ascontiguousarray(pose, dtype=np.float32)
+    prm = np.ascontiguousarray(prm, dtype=np.float32)
+    n = pose.shape[0]
+    angles = np.zeros((n, 7), dtype=np.float32)
+    fk = np.zeros((n, 9, 3), dtype=np.float32)
+    nfev = np.zeros((n, 4), dtype=np.int32)
+    P = ctypes.c_void_p
+    fn = lib.hostsim_carried_f32
+    fn.argtypes = [P, ctypes.c_int64, P, P, P, P, ctypes.c_int]
+    fn.restype = None
+    fn(pose.ctypes.data, n, prm.ctypes.data, angles.ctypes.data, fk.ctypes.data, nfev.ctypes.data, gn_mask)
+    return angles, fk, nfev
+
+
 def solve_generic(pose2, prm, teacher=None, dtype=np.float32, want_fk=True):
     """Generic 7-DOF chain on the host build: pose2 (N,2,3) = ThC origin + claw, prm (32,) generic constants row,
     teacher (N,7) optional per-frame seeds -> angles (N,7) in generic chain order, fk (N,9,3), nfev (N,), status (N,)."""
