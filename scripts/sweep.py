@@ -36,7 +36,7 @@ def run(n_trial, n_frame, sched, cpw, reps=3, gate=0):
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "gate":
         for n_trial in (100, 1000, 1250, 10000):
-            for gate in (1, 2, 3):
+            for gate in (1, 2, 3, 4, 5, 6, 8):
                 run(n_trial, 500, 2, 0, gate=gate)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "cpw":

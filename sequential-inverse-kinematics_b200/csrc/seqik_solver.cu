@@ -120,7 +120,7 @@ constexpr int PIPE_CHAINS = 8;              // chains per warp (maximum)
 // kFull: all four stages solved and the nine-row FK layout written (the benchmark configurations and the dict API):
 // the frozen-stage, partial-stage and output-layout decisions are compiled out.  Same arithmetic either way.
 template <bool kFull>
-__global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, int gate_mask) {
+__global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, int gate_period) {
     __shared__ float ring[4][PIPE_DEPTH][PIPE_SLOT][PIPE_CHAINS];      // chain innermost: conflict-free per stage; [3] = identity (stage 1's input)
     __shared__ float kpbuf[6][32];                                     // prefetched key points, one column per lane
     const unsigned full = 0xffffffffu;
@@ -199,8 +199,9 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, 
     if (live && n_frame > 0) prefetch();
     bool carried = false;            // S holds the previous frame's solve of this (chain, stage)
 
-    for (int it = 0; __any_sync(full, live && t < n_frame); ++it) {
-        if ((it & gate_mask) == 0) {                    // open/close phases only every (gate_mask + 1)-th iteration (warp-uniform)
+    for (int gate_ctr = 1; __any_sync(full, live && t < n_frame);) {
+        if (--gate_ctr == 0) {                          // open/close phases only every gate_period-th iteration (warp-uniform)
+        gate_ctr = gate_period;
         __syncwarp(full);            // ring reads of the previous open phase are complete before a slot is written again
         const int started_next = __shfl_sync(full, started, (lane + 1) & 31);   // consumer's progress (lane + 1)
         // ---- optional singularity escape: a solve that ended on sin b = 0 may continue from a closed-form candidate
@@ -334,13 +335,14 @@ extern "C" int seqik_leg_solve_f32(const float* pose, int64_t pose_chain_stride,
         if (forced) cpw = (int)forced;
         if (cpw < 1 || cpw > PIPE_CHAINS) return seqik_fail(SEQIK_EINVAL, "seqik_leg_solve_f32: chains per warp must be 1..8");
         const int64_t grid = (n_chain + cpw - 1) / cpw;
-        // open/close phases only every 2nd iteration: the lanes that finished a solve then close/open together, which
-        // saves more issue slots than the average half-iteration wait costs (measured -9 % at 600 chains, -15 % at
-        // 6 000 - 60 000 chains).  Scheduling only: results are unchanged.
-        const uint32_t gate_sel = (flags >> SEQIK_FLAG_GATE_SHIFT) & 3u;      // 0 auto, 1/2/3 = every 1st/2nd/4th iteration
-        const int gate_mask = gate_sel ? (1 << (gate_sel - 1)) - 1 : 1;
-        if (stage_mask == 0xF && fk && !fk_joints) leg_solve_pipe_kernel<true><<<(unsigned)grid, 32, 0, (cudaStream_t)stream>>>(a, cpw, gate_mask);
-        else leg_solve_pipe_kernel<false><<<(unsigned)grid, 32, 0, (cudaStream_t)stream>>>(a, cpw, gate_mask);
+        // open/close phases only every 6th iteration: a phase costs the warp about two trips whatever the number of lanes
+        // that take part, so it pays to let nearly all lanes of the warp finish their solves (3 - 6 trips) and then close /
+        // open together (config 3, ms per 1000 frames: period 1 / 2 / 4 / 6 / 8 = 5.8 / 4.4 / 3.9 / 3.6 / 3.6).
+        // Scheduling only: results are unchanged.
+        const uint32_t gate_sel = (flags >> SEQIK_FLAG_GATE_SHIFT) & 0xFu;    // 0 auto, else the period in iterations
+        const int gate_period = gate_sel ? (int)gate_sel : 6;
+        if (stage_mask == 0xF && fk && !fk_joints) leg_solve_pipe_kernel<true><<<(unsigned)grid, 32, 0, (cudaStream_t)stream>>>(a, cpw, gate_period);
+        else leg_solve_pipe_kernel<false><<<(unsigned)grid, 32, 0, (cudaStream_t)stream>>>(a, cpw, gate_period);
     }
     return seqik_check_launch("seqik_leg_solve_f32");
 }

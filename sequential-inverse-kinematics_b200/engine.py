@@ -103,7 +103,7 @@ def leg_solve(pose, params, affine=None, stages: Sequence[int] = (1, 2, 3, 4), w
             angles.data_ptr() + 4 * 7 * t0, n_frame * 7, 7, p_fk, n_frame * fk_floats, fk_floats,
             warm, n_frame * 7,
             N.ptr(status), N.ptr(nfev), n_chain, t1 - t0, mask,
-            (flags & 0xFF) | ((schedule & 0xF) << N.FLAG_SCHED_SHIFT) | ((chains_per_warp & 0x3F) << 12) | ((gate & 3) << 18)
+            (flags & 0xFF) | ((schedule & 0xF) << N.FLAG_SCHED_SHIFT) | ((chains_per_warp & 0x3F) << 12) | ((gate & 0xF) << 21)
             | (N.FLAG_FK_JOINTS if fk_layout == "joints" else 0),
             N.stream_ptr(torch, dev))
     N.check(rc, "seqik_leg_solve_f32")

@@ -223,7 +223,7 @@ def test_synthetic_vs_oracle_and_shard_invariance(api, synthetic_gold):
         assert t.equal(a_s, ang[lo:hi]) and t.equal(f_s, fk[lo:hi])
     # results do not depend on how chains are packed into warps (bit-identical); the one-lane-per-chain schedule
     # re-derives sin/cos from the angle at every frame instead of every 64 and agrees to float32 rounding
-    for cpw, gate in ((1, 0), (2, 1), (3, 2), (8, 3), (8, 1)):
+    for cpw, gate in ((1, 0), (2, 1), (3, 2), (8, 3), (8, 1), (4, 7), (8, 15)):
         a2, f2, s2, n2 = api.engine.leg_solve(chains, params, schedule=api.native.SCHED_STAGE_PIPELINE, chains_per_warp=cpw, gate=gate)
         assert t.equal(ang, a2) and t.equal(fk, f2) and t.equal(nfev, n2) and t.equal(status, s2), (cpw, gate)
     a1, f1, s1, n1 = api.engine.leg_solve(chains, params, schedule=api.native.SCHED_LANE_PER_CHAIN)
