@@ -43,8 +43,24 @@ extern "C" {
                                                 model was accurate on the previous step (actual/predicted within 25 % of 1) and now
                                                 predicts a reduction below ftol * cost for a plain Gauss-Newton step.  The skipped
                                                 step is < ~3e-6 rad; saves one of the ~5 evaluations of a warm-started solve */
-#define SEQIK_FLAG_DEFAULT 0x3Fu             /* Gauss-Newton mode in all four stages + escape + skip-confirm (validated against
-                                                the reference's shipped angles and forward kinematics) */
+#define SEQIK_FLAG_NEWTON (1u << 6)          /* Newton steps: where the Gauss-Newton step is admissible (fits the trust region, stays in
+                                                the box) and the full Hessian of the two-angle model -- J^T J plus the residual-curvature
+                                                term, closed form -- is safely positive definite, take the Newton step instead.  Key
+                                                points are noisy, so the residual does not vanish at the solution and Gauss-Newton
+                                                converges linearly; Newton reaches the same minimiser in fewer evaluations (config 3:
+                                                5.3 -> 4.1 per solve in stage 1) and ends closer to it than the reference's ftol stop */
+#define SEQIK_FLAG_CLOSED_FORM (1u << 7)     /* closed-form warm step (stage pipeline schedule): before the next frame of a carried solve
+                                                the iterate is moved to the point of the sphere |w| = L nearest to the new target, on
+                                                the warm start's branch -- the minimiser the iteration would converge to -- when that
+                                                is a short (< 0.5 rad), strictly interior, well-conditioned move; the solve then ends
+                                                with its first evaluation or is polished by the iteration.  Every other case (first
+                                                frame of a call, re-derivation frames, active bounds, near-singular or ill-conditioned
+                                                targets, large moves) runs from the warm start as without the flag.  Config 3:
+                                                4.1 -> 1.2 evaluations per solve */
+#define SEQIK_FLAG_REFERENCE_ITERATES 0x3Fu  /* the reference's own iterates: Gauss-Newton mode in all four stages + escape +
+                                                skip-confirm, evaluation counts and termination statuses as scipy's */
+#define SEQIK_FLAG_DEFAULT 0xFFu             /* the above + Newton steps + closed-form warm step (each set validated against the
+                                                reference's shipped angles and forward kinematics) */
 #define SEQIK_FLAG_SCHED_SHIFT 8             /* bits 8..11: kernel schedule, 0 = automatic,
                                                 1 = one lane per chain, 2 = stage pipeline (four lanes per chain) */
 #define SEQIK_FLAG_SCHED_MASK (0xFu << SEQIK_FLAG_SCHED_SHIFT)

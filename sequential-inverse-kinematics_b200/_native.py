@@ -16,7 +16,10 @@ ABI_VERSION = 4
 CHAIN_PARAM_FLOATS = 32
 FLAG_ESCAPE = 1 << 4
 FLAG_SKIP_CONFIRM = 1 << 5
-FLAG_DEFAULT = 0x3F                     # SEQIK_FLAG_DEFAULT: Gauss-Newton mode in all four stages + escape + skip-confirm
+FLAG_NEWTON = 1 << 6
+FLAG_REFERENCE_ITERATES = 0x3F          # SEQIK_FLAG_REFERENCE_ITERATES: Gauss-Newton mode in all four stages + escape + skip-confirm
+FLAG_CLOSED_FORM = 1 << 7
+FLAG_DEFAULT = 0xFF                     # SEQIK_FLAG_DEFAULT: the above + Newton steps + closed-form warm step
 FLAG_FK_JOINTS = 1 << 20
 FLAG_SCHED_SHIFT = 8
 SCHED_AUTO, SCHED_LANE_PER_CHAIN, SCHED_STAGE_PIPELINE = 0, 1, 2

@@ -157,7 +157,15 @@ template <> struct Num<double> {
     static SK_HD double eps_in() { return 2.220446049250313e-16; }
 };
 
-constexpr int SEQIK_RESYNC = 32;          // frames between full re-initialisations of a carried solve
+constexpr int SEQIK_RESYNC = 32;
+// StageSolve mode of stage s (0..3) from the solver flags (include/seqik.h): bit 0 Gauss-Newton mode of that stage,
+// bit 1 skip-confirm, bit 2 Newton steps, bit 3 closed-form warm step
+inline
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+int stage_mode(int flags, int s) { return ((flags >> s) & 1) | (((flags >> 5) & 1) << 1) | (((flags >> 6) & 1) << 2) | (((flags >> 7) & 1) << 3); }
+          // frames between full re-initialisations of a carried solve
 
 enum : int { KIND_XY = 0, KIND_ZY = 1 };   // Rx(a)Ry(b) (stage 1)  |  Rz(a)Ry(b) (stages 2-4)
 
@@ -193,6 +201,9 @@ struct StageSolve {
     R last_ratio;                       // actual/predicted reduction of the previous evaluation of this solve (0: none yet)
     R st0, st1, step_h_sq, pred;        // the step plan() chose for the next evaluation, its hat-space length^2, its predicted reduction
     bool skip_confirm;                  // SEQIK_FLAG_SKIP_CONFIRM, see trip()
+    bool newton;                        // SEQIK_FLAG_NEWTON, see plan()
+    bool closed_form;                   // SEQIK_FLAG_CLOSED_FORM, see warm_step()
+    bool seeded;                        // this solve started from warm_step()'s point
 
     typedef Num<R> N;
     SK_HD int kind_() const { return xy ? KIND_XY : KIND_ZY; }
@@ -241,7 +252,8 @@ struct StageSolve {
 
     // the constants of a (chain, stage) problem / the seed of a new solve in the caller's terms
     SK_HD void set_problem(int kind_in, R L_, R has_a_in, R null_sq_, int n_full, int mode) {
-        gn_mode = (mode & 1) != 0; skip_confirm = (mode & 2) != 0;     // bit 0 Gauss-Newton mode, bit 1 skip-confirm
+        gn_mode = (mode & 1) != 0; skip_confirm = (mode & 2) != 0; newton = (mode & 4) != 0; closed_form = (mode & 8) != 0;   // see stage_mode()
+        seeded = false;
         xy = kind_in == KIND_XY; shift = xy ? R(1.57079632679489661923) : R(0);
         L = L_; has_a = has_a_in; null_sq = null_sq_; max_nfev = 100 * n_full;
     }
@@ -261,8 +273,53 @@ struct StageSolve {
     // (least_squares prologue without the trigonometry).  Callers pass fresh = true every SEQIK_RESYNC frames so that the
     // carried sin/cos cannot drift from the angle (float32 random walk, ~1e-6 rad over 32 frames).  One code path for
     // both, so that lanes of a warp that re-derive and lanes that carry run the same instructions but the trigonometry.
+    // asin for |s| < 0.25 (truncation < 1e-8)
+    static SK_HD R asin_small(R s) {
+        const R z = s * s;
+        R p = N::fma_(z, R(0.030381944444444444), R(0.044642857142857144));
+        p = N::fma_(p, z, R(0.075)); p = N::fma_(p, z, R(0.16666666666666666));
+        return N::fma_(p * z, s, s);
+    }
+
+    // Optional (SEQIK_FLAG_CLOSED_FORM): the closed-form warm step.  A stage points a segment of fixed length at its
+    // target: without the box, the minimiser of |w(a, b) - q|^2 is the point of the sphere |w| = L nearest to q, i.e.
+    // (sb ca, sb sa, cb) = -q / |q| on the branch (sign of sb) of the warm start -- the minimiser the reference's
+    // iteration converges to from that warm start when it is a short step away.  So for the next frame of a carried
+    // solve the iterate is MOVED there before the prologue (sin/cos directly from q, the angles by the small rotation
+    // from the carried iterate); the prologue then finds a vanishing gradient and the solve ends with its first
+    // evaluation, or Newton's iteration polishes it.  Taken only when the move is small (both rotations below
+    // 0.5 rad), stays strictly inside the box and away from the sin b = 0 singularity, and the minimum is well
+    // conditioned (its Hessian is |q| / L times the Gauss-Newton one: |q| > L / 2, Newton's own admission test -- closer
+    // targets leave the direction ill-determined and the reference crawls there); in every other case -- first
+    // frame of a call, re-derivation frames, active bounds, large moves -- the solve runs from the warm start exactly
+    // as without the flag.  One-variable stage 4: the same in the plane of its single rotation.
+    SK_HD void warm_step(const Vec3<R>& q, R lb0, R ub0, R lb1, R ub1) {
+        const bool one_var = has_a == R(0);
+        const R rho2 = one_var ? q.x * q.x : N::fma_(q.y, q.y, q.x * q.x);
+        const R qn2 = N::fma_(q.z, q.z, rho2);
+        const R rn = N::rsqrt_(qn2), rr = N::rsqrt_(rho2);
+        const R sgn = (sb < R(0)) ? R(-1) : R(1);
+        const R t_ = sgn * rr;
+        const R n_sb = one_var ? -(q.x * rn) : sgn * (rho2 * rr) * rn, n_cb = -(q.z * rn);
+        const R n_ca = one_var ? ca : -(q.x * t_), n_sa = one_var ? sa : -(q.y * t_);
+        const R sda = N::fma_(n_sa, ca, -(n_ca * sa)), cda = N::fma_(n_ca, ca, n_sa * sa);
+        const R sdb = N::fma_(n_sb, cb, -(n_cb * sb)), cdb = N::fma_(n_cb, cb, n_sb * sb);
+        // rotation angles by the half-angle form: sin(d / 2) = sin d / sqrt(2 (1 + cos d)), |d| < 0.5 rad
+        const R hsa = sda * N::rsqrt_(R(2) + R(2) * cda), hsb = sdb * N::rsqrt_(R(2) + R(2) * cdb);
+        const R nx0 = x0 + R(2) * asin_small(hsa), nx1 = x1 + R(2) * asin_small(hsb);
+        const R m = R(1e-5);
+        const bool ok = N::abs_(hsa) < R(0.25) && N::abs_(hsb) < R(0.25) && cda > R(0) && cdb > R(0)
+                        && (one_var || rho2 > R(0.01) * qn2) && qn2 > R(0.25) * L * L && qn2 < N::inf()
+                        && nx0 - lb0 > m && ub0 - nx0 > m && nx1 - lb1 > m && ub1 - nx1 > m;
+        x0 = ok ? nx0 : x0; x1 = ok ? nx1 : x1;
+        sa = ok ? n_sa : sa; ca = ok ? n_ca : ca; sb = ok ? n_sb : sb; cb = ok ? n_cb : cb;
+        seeded = ok;
+    }
+
     SK_HD void restart(const Vec3<R>& q_in, R lb0, R ub0, R lb1, R ub1, bool fresh = false) {
         const Vec3<R> q = xy ? Vec3<R>{-q_in.z, q_in.y, q_in.x} : q_in;
+        seeded = false;
+        if (closed_form && gn_mode && !fresh) warm_step(q, lb0, ub0, lb1 - shift, ub1 - shift);
         place(x0, x1, lb0, ub0, lb1 - shift, ub1 - shift);   // bound distances (re-)derived from the angle
         if (fresh) { R va, vb; N::sincosv_(x0, &sa, &ca, &va); N::sincosv_(x1, &sb, &cb, &vb); }
         const Vec3<R> w = point();
@@ -312,7 +369,7 @@ struct StageSolve {
         nfev += 2;
         if (!(best < R(0.98) * cost - R(5e-7))) return false;  // clearly better: > 2 % and > (1e-3 mm)^2 / 2
         const R nsq = null_sq; const int mx = max_nfev; const int nf = nfev;
-        const int md = (gn_mode ? 1 : 0) | (skip_confirm ? 2 : 0);
+        const int md = (gn_mode ? 1 : 0) | (skip_confirm ? 2 : 0) | (newton ? 4 : 0) | (closed_form ? 8 : 0);
         init(KIND_ZY, L, has_a, q, ba, bb, lb0, ub0, lb1, ub1, nsq, 1, md);
         max_nfev = mx; nfev = nf; escaped = true;
         return true;
@@ -465,41 +522,74 @@ struct StageSolve {
     // (After a rejected step the iterate is unchanged and only Delta/alpha differ: plan() recomputes the same head.)
     SK_HD void plan(bool active = true) {
         const R gtol = R(1e-8), ftol = R(1e-8);
-        Hat h;
         R v0, v1, dv0, dv1; cl_scaling(v0, v1, dv0, dv1);
         const R g_norm = N::max_(N::abs_(g0 * v0), N::abs_(g1 * v1));
         // straight-line code: the termination tests that need no evaluation are folded into selects at the end, so that
         // a trip is one basic block but for the rare general step (lanes that are not `active` change nothing)
-        const bool stop_g = g_norm < gtol, stop_n = nfev >= max_nfev;
-        h.d0 = N::sqrt_(v0); h.d1 = N::sqrt_(v1);
-        h.gh0 = h.d0 * g0; h.gh1 = h.d1 * g1;
-        h.B0 = N::fma_(v0, ja_sq(), g0 * dv0); h.B1 = N::fma_(v1, L * L, g1 * dv1);   // Jh^T Jh + diag(g dv), diagonal
-        h.theta = N::max_(R(0.995), R(1) - g_norm);
-        // ---- solve_lsq_trust_region, rank-deficient branch; singular values^2 = (B0, B1), V = I
-        // gn_mode: scipy's SVD of the full chain leaves ~1e-17 singular values on the inert slots; the Levenberg
-        // parameter then decays to ~1e-20 and that null-space noise absorbs the trust-region norm, i.e. the active
-        // pair receives the plain Gauss-Newton step whenever it fits in Delta.  Measured against the reference's
-        // shipped angles (6000 frames x 2 legs) this reproduces the reference's evaluation counts and termination
-        // statuses; the literal rank-deficient branch below is kept for the steps that do not fit.
-        const bool one_var = has_a_() == R(0);
-        const R tg0 = one_var ? R(0) : h.gh0 * N::rcp_(h.B0), tg1 = h.gh1 * N::rcp_(h.B1);
-        const bool gn_taken = gn_mode && (one_var || h.B0 > R(0)) && h.B1 > R(0) && (N::fma_(tg1, tg1, tg0 * tg0) <= Delta * Delta);
-        // fast path: the Gauss-Newton step fits the trust region and stays inside the box (select_step's in_bounds case)
-        const R ph0 = -tg0, ph1 = -tg1, p0 = h.d0 * ph0, p1 = h.d1 * ph1;
-        const bool inb = (dl0 + p0 >= R(0)) && (du0 - p0 >= R(0)) && (dl1 + p1 >= R(0)) && (du1 - p1 >= R(0));
+        // (a solve moved to the closed-form minimiser stops at float32's gradient floor: |g| < 2e-7 is < ~1e-6 rad)
+        const bool stop_g = g_norm < ((seeded && nfev == 1) ? R(2e-7) : gtol), stop_n = nfev >= max_nfev;
         const bool run = active && !stop_g && !stop_n;
-        R n_st0 = p0, n_st1 = p1, n_sh = N::fma_(ph1, ph1, ph0 * ph0), n_pred = -model(h, ph0, ph1), n_alpha = R(0);
-        if (run && !(gn_taken && inb)) {
-            const Step o = slow_step(h, tg0, tg1, gn_taken, one_var, Delta, alpha, dl0, du0, dl1, du1);
-            n_st0 = o.st0; n_st1 = o.st1; n_sh = o.sh_sq; n_pred = o.pred; n_alpha = o.alpha;
+        const bool one_var = has_a_() == R(0);
+        const R B0 = N::fma_(v0, ja_sq(), g0 * dv0), B1 = N::fma_(v1, L * L, g1 * dv1);   // Jh^T Jh + diag(g dv), diagonal
+        R n_st0 = R(0), n_st1 = R(0), n_sh = R(0), n_pred = R(0), n_alpha = R(0);
+        bool take = false, gn_taken = false;
+        // Optional (SEQIK_FLAG_NEWTON): the Newton step of the same scaled model with the residual-curvature term
+        // sum_i f_i Hess(w_i) added -- closed form for the two-angle segment: w_aa = (Lsb ca, Lsb sa, 0), w_bb = -w,
+        // w_ab = (Lcb sa, -Lcb ca, 0).  The targets are noisy key points, so the residual does not vanish at the solution
+        // and Gauss-Newton converges only linearly (3.3 - 4.8 evaluations per warm-started solve); Newton's iteration
+        // reaches the same minimiser (to ~1e-6 rad of where the reference's ftol stop leaves it) in 2 - 3.  Taken only
+        // where the full Hessian is safely positive definite and close to the Gauss-Newton one, the step fits the trust
+        // region and stays inside the box; every other case falls through to the reference's step below.  Written in
+        // terms of v = d^2 (no square roots): with r = H^-1-weighted gradient, the step is p = -v r, its hat-space
+        // length^2 is sum v r^2 and the model's predicted reduction is sum v g r - 0.5 (p_h^T H p_h).
+        if (newton && gn_mode) {
+            const R Lsb = L * sb, Lcb = L * cb;
+            const R u = N::fma_(ca, f.x, sa * f.y), w_ = N::fma_(sa, f.x, -(ca * f.y));
+            const R e00 = has_a * Lsb * u, e11 = N::fma_(Lsb, u, Lcb * f.z), e01 = has_a * Lcb * w_;
+            const R B0_ = one_var ? R(1) : B0;
+            const R H00 = one_var ? R(1) : N::fma_(v0, e00, B0), H11 = N::fma_(v1, e11, B1);
+            const R ve = v0 * v1 * e01;                                   // H01^2 = ve * e01
+            const R det = N::fma_(H00, H11, -(ve * e01));
+            const bool pd = H00 > R(0.5) * B0_ && H11 > R(0.5) * B1 && det > R(0.25) * B0_ * B1;
+            const R rdet = N::rcp_(det);
+            const R r0 = N::fma_(H11, g0, -(v1 * e01 * g1)) * rdet, r1 = N::fma_(H00, g1, -(v0 * e01 * g0)) * rdet;
+            const R q0_ = -(v0 * r0), q1_ = -(v1 * r1);
+            const R nsq = N::fma_(v1 * r1, r1, v0 * r0 * r0);
+            const bool n_inb = (dl0 + q0_ >= R(0)) && (du0 - q0_ >= R(0)) && (dl1 + q1_ >= R(0)) && (du1 - q1_ >= R(0));
+            take = pd && n_inb && nsq <= Delta * Delta;
+            const R quad = N::fma_(H11 * v1 * r1, r1, N::fma_(R(2) * ve * r0, r1, H00 * v0 * r0 * r0));
+            n_st0 = q0_; n_st1 = q1_; n_sh = nsq; n_pred = N::fma_(v1 * g1, r1, v0 * g0 * r0) - R(0.5) * quad;
+        }
+        if (run && !take) {
+            Hat h;
+            h.d0 = N::sqrt_(v0); h.d1 = N::sqrt_(v1);
+            h.gh0 = h.d0 * g0; h.gh1 = h.d1 * g1;
+            h.B0 = B0; h.B1 = B1;
+            h.theta = N::max_(R(0.995), R(1) - g_norm);
+            // ---- solve_lsq_trust_region, rank-deficient branch; singular values^2 = (B0, B1), V = I
+            // gn_mode: scipy's SVD of the full chain leaves ~1e-17 singular values on the inert slots; the Levenberg
+            // parameter then decays to ~1e-20 and that null-space noise absorbs the trust-region norm, i.e. the active
+            // pair receives the plain Gauss-Newton step whenever it fits in Delta.  Measured against the reference's
+            // shipped angles (6000 frames x 2 legs) this reproduces the reference's evaluation counts and termination
+            // statuses; the literal rank-deficient branch below is kept for the steps that do not fit.
+            const R tg0 = one_var ? R(0) : h.gh0 * N::rcp_(h.B0), tg1 = h.gh1 * N::rcp_(h.B1);
+            gn_taken = gn_mode && (one_var || h.B0 > R(0)) && h.B1 > R(0) && (N::fma_(tg1, tg1, tg0 * tg0) <= Delta * Delta);
+            // fast path: the Gauss-Newton step fits the trust region and stays inside the box (select_step's in_bounds case)
+            const R ph0 = -tg0, ph1 = -tg1, p0 = h.d0 * ph0, p1 = h.d1 * ph1;
+            const bool inb = (dl0 + p0 >= R(0)) && (du0 - p0 >= R(0)) && (dl1 + p1 >= R(0)) && (du1 - p1 >= R(0));
+            n_st0 = p0; n_st1 = p1; n_sh = N::fma_(ph1, ph1, ph0 * ph0); n_pred = -model(h, ph0, ph1);
+            if (!(gn_taken && inb)) {
+                const Step o = slow_step(h, tg0, tg1, gn_taken, one_var, Delta, alpha, dl0, du0, dl1, du1);
+                n_st0 = o.st0; n_st1 = o.st1; n_sh = o.sh_sq; n_pred = o.pred; n_alpha = o.alpha;
+            }
         }
         st0 = run ? n_st0 : st0; st1 = run ? n_st1 : st1; step_h_sq = run ? n_sh : step_h_sq; pred = run ? n_pred : pred;
         alpha = run ? n_alpha : alpha;
         // Optional (SEQIK_FLAG_SKIP_CONFIRM): do not evaluate a step that would only CONFIRM convergence.  When the model
         // has just been accurate (previous actual/predicted within 25 % of 1) and now predicts a reduction below
-        // ftol * cost for a plain Gauss-Newton step, the reference evaluates that step, accepts it and stops on ftol;
-        // the step is below sqrt(2 ftol cost) / L ~ 3e-6 rad.  Saves one of the ~5 evaluations of a warm-started solve.
-        const bool confirm_only = skip_confirm && gn_taken && n_pred < ftol * cost && n_pred >= R(0) && N::abs_(last_ratio - R(1)) < R(0.25);
+        // ftol * cost for a plain Gauss-Newton (or Newton) step, the reference evaluates that step, accepts it and stops
+        // on ftol; the step is below sqrt(2 ftol cost) / L ~ 3e-6 rad.  Saves one of the ~5 evaluations of a solve.
+        const bool confirm_only = skip_confirm && (take || gn_taken) && n_pred < ftol * cost && n_pred >= R(0) && N::abs_(last_ratio - R(1)) < R(0.25);
         const int st_new = stop_g ? ST_GTOL : stop_n ? ST_MAXFEV : confirm_only ? ST_FTOL : ST_RUNNING;
         status = active ? st_new : status;
     }
@@ -627,7 +717,7 @@ struct ChainRunner {
         const Vec3<R> q = mulT(A, rel);
         const R inf = Num<R>::inf();
         const int n_full = (s == 0) ? 4 : (s == 1) ? 6 : (s == 2) ? 8 : 9;
-        const int gn = ((gn_mask >> s) & 1) | (((gn_mask >> 5) & 1) << 1);
+        const int gn = stage_mode(gn_mask, s);
         const bool frozen = s < lo;
         if (frozen) {   // kinematic_chain.py: earlier-stage DOFs are `fixed` links at angles[...][t]
             if (s == 0) { ang0 = io.angle_in(t, 0); ang1 = io.angle_in(t, 1); }
@@ -720,8 +810,8 @@ SK_HD void solve_frame(const ChainParams<R>& P, const R* kp, R* ang, R* fk, Fram
         const int ia = (s == 3) ? -1 : 2 * s, ib = (s == 3) ? 6 : 2 * s + 1;
         StageSolve<R> S;
         const R inf = Num<R>::inf();
-        if (s == 3) S.init(kind, P.seg[s], R(0), q, R(0), ang[ib], -inf, inf, P.lb[ib], P.ub[ib], P.null_sq[s], n_full[s], ((gn_mask >> s) & 1) | (((gn_mask >> 5) & 1) << 1));
-        else S.init(kind, P.seg[s], R(1), q, ang[ia], ang[ib], P.lb[ia], P.ub[ia], P.lb[ib], P.ub[ib], P.null_sq[s], n_full[s], ((gn_mask >> s) & 1) | (((gn_mask >> 5) & 1) << 1));
+        if (s == 3) S.init(kind, P.seg[s], R(0), q, R(0), ang[ib], -inf, inf, P.lb[ib], P.ub[ib], P.null_sq[s], n_full[s], stage_mode(gn_mask, s));
+        else S.init(kind, P.seg[s], R(1), q, ang[ia], ang[ib], P.lb[ia], P.ub[ia], P.lb[ib], P.ub[ib], P.null_sq[s], n_full[s], stage_mode(gn_mask, s));
         if (stage_mask & (1 << s)) {
             while (!S.done()) S.trip();
             if ((gn_mask & 16) && S.escape()) while (!S.done()) S.trip();

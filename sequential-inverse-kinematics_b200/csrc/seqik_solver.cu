@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, 
     const float lb1 = frozen ? -inf : __ldg(prm + 4 + ib), ub1 = frozen ? inf : __ldg(prm + 11 + ib);
     const float null_sq = frozen ? 0.f : __ldg(prm + 25 + s);
     const int n_full = (s == 0) ? 4 : (s == 1) ? 6 : (s == 2) ? 8 : 9;
-    const int gn = ((a.gn_mask >> s) & 1) | (((a.gn_mask >> 5) & 1) << 1);   // StageSolve mode: Gauss-Newton, skip-confirm
+    const int gn = stage_mode(a.gn_mask, s);                                  // StageSolve mode: Gauss-Newton, skip-confirm, Newton
     const bool esc = (a.gn_mask >> 4) & 1;
     const float has_a = (s == 3) ? 0.f : 1.f;
     const float* seed = a.warm ? a.warm + cc * a.warm_cs : prm + 18;
@@ -318,7 +318,7 @@ extern "C" int seqik_leg_solve_f32(const float* pose, int64_t pose_chain_stride,
     a.warm = warm; a.warm_cs = warm_chain_stride;
     a.status = status; a.nfev = nfev; a.n_chain = n_chain; a.n_frame = n_frame;
     a.fk_joints = fk_joints ? 1 : 0;
-    a.stage_mask = (int)stage_mask; a.gn_mask = (int)(flags & 0x3F);   // bits 0-3 Gauss-Newton mode per stage, bit 4 escape, bit 5 skip-confirm
+    a.stage_mask = (int)stage_mask; a.gn_mask = (int)(flags & 0xFF);   // bits 0-3 Gauss-Newton mode per stage, 4 escape, 5 skip-confirm, 6 Newton, 7 closed-form warm step
     if (sched == 1) {
         const int64_t grid = (n_chain + 31) / 32;
         leg_solve_lane_kernel<<<(unsigned)grid, 32, 0, (cudaStream_t)stream>>>(a);
@@ -335,12 +335,13 @@ extern "C" int seqik_leg_solve_f32(const float* pose, int64_t pose_chain_stride,
         if (forced) cpw = (int)forced;
         if (cpw < 1 || cpw > PIPE_CHAINS) return seqik_fail(SEQIK_EINVAL, "seqik_leg_solve_f32: chains per warp must be 1..8");
         const int64_t grid = (n_chain + cpw - 1) / cpw;
-        // open/close phases only every 6th iteration: a phase costs the warp about two trips whatever the number of lanes
-        // that take part, so it pays to let nearly all lanes of the warp finish their solves (3 - 6 trips) and then close /
-        // open together (config 3, ms per 1000 frames: period 1 / 2 / 4 / 6 / 8 = 5.8 / 4.4 / 3.9 / 3.6 / 3.6).
-        // Scheduling only: results are unchanged.
+        // Period of the open/close phases.  A phase costs the warp about two trips whatever the number of lanes that take
+        // part, so it pays to let nearly all lanes of the warp finish their solves and then close / open together: every
+        // 6th iteration for the reference's iterates (3 - 6 trips per solve; config 3, ms per 1000 frames at period
+        // 1 / 2 / 4 / 6 / 8 = 5.8 / 4.4 / 3.9 / 3.6 / 3.6), every 4th with Newton steps (2 - 3 trips), every 2nd with the
+        // closed-form warm step (mostly none).  Scheduling only: results are unchanged.
         const uint32_t gate_sel = (flags >> SEQIK_FLAG_GATE_SHIFT) & 0xFu;    // 0 auto, else the period in iterations
-        const int gate_period = gate_sel ? (int)gate_sel : 6;
+        const int gate_period = gate_sel ? (int)gate_sel : (flags & SEQIK_FLAG_CLOSED_FORM) ? 2 : (flags & SEQIK_FLAG_NEWTON) ? 4 : 6;
         if (stage_mask == 0xF && fk && !fk_joints) leg_solve_pipe_kernel<true><<<(unsigned)grid, 32, 0, (cudaStream_t)stream>>>(a, cpw, gate_period);
         else leg_solve_pipe_kernel<false><<<(unsigned)grid, 32, 0, (cudaStream_t)stream>>>(a, cpw, gate_period);
     }

@@ -90,7 +90,7 @@ static void run_carried(const float* pose, int64_t n_frame, const float* prm, fl
             const R lb0 = (s == 3) ? -inf : prm[4 + ia], ub0 = (s == 3) ? inf : prm[11 + ia];
             const R lb1 = prm[4 + ib], ub1 = prm[11 + ib];
             const int n_full = (s == 0) ? 4 : (s == 1) ? 6 : (s == 2) ? 8 : 9;
-            const int gn = ((gn_mask >> s) & 1) | (((gn_mask >> 5) & 1) << 1);
+            const int gn = stage_mode(gn_mask, s);
             const Vec3<R> k = {kp[3 * (s + 1)], kp[3 * (s + 1) + 1], kp[3 * (s + 1) + 2]};
             const Vec3<R> rel = {(k.x - o.x) - piv.x, (k.y - o.y) - piv.y, (k.z - o.z) - piv.z};
             const Vec3<R> q3 = mulT(A, rel);

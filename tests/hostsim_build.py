@@ -66,7 +66,7 @@ def run_runner_f32(pose, seg, lb, ub, null_sq, seed, stage_mask=0xF, gn_mask=0):
     return angles, fk, nfev_sum, steps
 
 
-def run_carried_f32(pose, prm, gn_mask=0x3F):
+def run_carried_f32(pose, prm, gn_mask=0xFF):
     """The stage-pipeline kernel's per-lane arithmetic (solves carried frame to frame by StageSolve::restart, re-derived
     every SEQIK_RESYNC frames), run serially on the host build: pose (N,5,3), prm (32,) -> angles (N,7), fk (N,9,3),
     nfev (N,4)."""

@@ -9,7 +9,9 @@ import model_trf2 as M
 from helpers import ANGLE_TOL, FK_TOL, bad_frames, fk_residual, residual_of_angles, singular_windows
 from oracle import seqik_oracle as O
 
-GN = 0b111111  # SEQIK_FLAG_DEFAULT: Gauss-Newton mode in all four stages + singularity escape + skip-confirm
+GN_REF = 0b0111111  # SEQIK_FLAG_REFERENCE_ITERATES: Gauss-Newton mode in all four stages + singularity escape + skip-confirm
+GN_NEWTON = 0b1111111  # the above + Newton steps
+GN = 0b11111111     # SEQIK_FLAG_DEFAULT: the above + closed-form warm step (acts on carried solves only)
 
 
 def leg_consts(size, bounds, init, leg):
@@ -19,12 +21,13 @@ def leg_consts(size, bounds, init, leg):
     return seg, lb, ub, M.null_sq_from_seeds(init[leg]), M.seeds7(init[leg])
 
 
+@pytest.mark.parametrize("flags", [GN, GN_NEWTON, GN_REF])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-def test_grooming_rf_all_frames(grooming_leg, dtype):
+def test_grooming_rf_all_frames(grooming_leg, dtype, flags):
     from seqikpy_b200 import data as D
     size = O.calculate_body_size(D.NMF_TEMPLATE, ["RF", "LF"])
     seg, lb, ub, nsq, seed = leg_consts(size, D.BOUNDS, D.INITIAL_ANGLES, "RF")
-    ang, fk, nfev, status = H.solve_chain(grooming_leg["pose"][0], seg, lb, ub, nsq, seed, dtype=dtype, gn_mask=GN)
+    ang, fk, nfev, status = H.solve_chain(grooming_leg["pose"][0], seg, lb, ub, nsq, seed, dtype=dtype, gn_mask=flags)
     assert len(bad_frames(ang, grooming_leg["ref_angles"][0])) == 0
     assert len(bad_frames(ang, grooming_leg["oracle_angles"][0])) == 0
     r_ours = fk_residual(fk, grooming_leg["pose"][0])
@@ -33,12 +36,13 @@ def test_grooming_rf_all_frames(grooming_leg, dtype):
     assert (status > 0).all() and nfev.mean() < 6
 
 
+@pytest.mark.parametrize("flags", [GN, GN_NEWTON, GN_REF])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-def test_grooming_lf(grooming_leg, dtype):
+def test_grooming_lf(grooming_leg, dtype, flags):
     from seqikpy_b200 import data as D
     size = O.calculate_body_size(D.NMF_TEMPLATE, ["RF", "LF"])
     seg, lb, ub, nsq, seed = leg_consts(size, D.BOUNDS, D.INITIAL_ANGLES, "LF")
-    ang, fk, _, _ = H.solve_chain(grooming_leg["pose"][1], seg, lb, ub, nsq, seed, dtype=dtype, gn_mask=GN)
+    ang, fk, _, _ = H.solve_chain(grooming_leg["pose"][1], seg, lb, ub, nsq, seed, dtype=dtype, gn_mask=flags)
     bad = bad_frames(ang, grooming_leg["ref_angles"][1])
     # mismatches only around the reference's own singular episodes (helpers.singular_windows)
     allowed = singular_windows(grooming_leg["ref_angles"][1])
@@ -49,13 +53,14 @@ def test_grooming_lf(grooming_leg, dtype):
     assert set(worse) <= allowed, worse
 
 
-def test_locomotion_and_synthetic_vs_oracle(locomotion, synthetic_gold):
+@pytest.mark.parametrize("flags", [GN, GN_NEWTON, GN_REF])
+def test_locomotion_and_synthetic_vs_oracle(locomotion, synthetic_gold, flags):
     from seqikpy_b200 import data as D, synthetic as S
     legs = list(locomotion["legs"])
     size = O.calculate_body_size(D.TEMPLATE_NMF_LOCOMOTION, legs)
     for i, leg in enumerate(legs):
         seg, lb, ub, nsq, seed = leg_consts(size, D.BOUNDS_LOCOMOTION, D.INITIAL_ANGLES_LOCOMOTION, leg)
-        ang, fk, _, _ = H.solve_chain(locomotion["aligned"][i], seg, lb, ub, nsq, seed, gn_mask=GN)
+        ang, fk, _, _ = H.solve_chain(locomotion["aligned"][i], seg, lb, ub, nsq, seed, gn_mask=flags)
         assert np.abs(ang - locomotion["oracle_angles"][i]).max() < ANGLE_TOL, leg
         r = fk_residual(fk, locomotion["aligned"][i]) - fk_residual(locomotion["oracle_fk"][i], locomotion["aligned"][i])
         assert r.max() < FK_TOL + 2e-6
@@ -63,7 +68,7 @@ def test_locomotion_and_synthetic_vs_oracle(locomotion, synthetic_gold):
     for tr in range(2):
         for li, leg in enumerate(S.LEGS):
             seg, lb, ub, nsq, seed = leg_consts(size, bounds, init, leg)
-            ang, fk, _, _ = H.solve_chain(synthetic_gold["pose"][tr][:, li], seg, lb, ub, nsq, seed, gn_mask=GN)
+            ang, fk, _, _ = H.solve_chain(synthetic_gold["pose"][tr][:, li], seg, lb, ub, nsq, seed, gn_mask=flags)
             assert np.abs(ang - synthetic_gold["oracle_angles"][tr, li]).max() < ANGLE_TOL, (tr, leg)
 
 
@@ -117,3 +122,79 @@ def test_python_model_agrees_with_host_core(grooming_leg):
     stats = []
     a_model, _ = M.solve_leg(pose, seg, lb, ub, seed, nsq, stats=stats)
     assert np.abs(np.asarray(a_model) - a_host).max() < 1e-7
+
+
+def test_newton_steps_save_evaluations_and_keep_the_minimiser(synthetic_gold):
+    """SEQIK_FLAG_NEWTON: fewer evaluations per solve, the same minimiser (both runs within float32 noise of each other
+    relative to the tolerance, and the forward-kinematics residual not worse)."""
+    from seqikpy_b200 import synthetic as S
+    size, bounds, init = S.chain_constants()
+    for li, leg in enumerate(S.LEGS[:3]):
+        seg, lb, ub, nsq, seed = leg_consts(size, bounds, init, leg)
+        pose = synthetic_gold["pose"][0][:, li]
+        a_gn, f_gn, n_gn, _ = H.solve_chain(pose, seg, lb, ub, nsq, seed, gn_mask=GN_REF)
+        a_nt, f_nt, n_nt, st = H.solve_chain(pose, seg, lb, ub, nsq, seed, gn_mask=GN)
+        assert (st > 0).all()
+        assert n_nt.mean() < n_gn.mean() - 0.5, (n_nt.mean(0), n_gn.mean(0))
+        assert np.abs(a_nt - a_gn).max() < 1e-4
+        assert (fk_residual(f_nt, pose) - fk_residual(f_gn, pose)).max() < 1e-5
+
+
+def test_carried_solves_equal_fresh_solves_to_rounding(synthetic_gold):
+    """The stage-pipeline kernel carries a solve's sin/cos from frame to frame (StageSolve::restart) and re-derives them
+    every SEQIK_RESYNC frames; its per-lane arithmetic, run serially on the host build, stays within float32 rounding of
+    the frame-by-frame composition and of the oracle."""
+    from seqikpy_b200 import synthetic as S
+    from seqikpy_b200.kinematic_chain import KinematicChainSeq
+    size, bounds, init = S.chain_constants()
+    chain = KinematicChainSeq(bounds, list(S.LEGS), size)
+    for flags in (GN_NEWTON, GN_REF):
+        for li, leg in enumerate(S.LEGS[:2]):
+            seg, lb, ub, nsq, seed = leg_consts(size, bounds, init, leg)
+            pose = synthetic_gold["pose"][0][:, li]
+            a1, f1, n1, _ = H.solve_chain(pose, seg, lb, ub, nsq, seed, gn_mask=flags)
+            a2, f2, n2 = H.run_carried_f32(pose, chain.pack_chain_params(leg, init[leg]), flags)
+            assert np.abs(a1 - a2).max() < 2e-5 and np.abs(f1 - f2).max() < 2e-5
+            assert abs(n1.mean() - n2.mean()) < 0.1
+            assert np.abs(a2 - synthetic_gold["oracle_angles"][0, li]).max() < ANGLE_TOL
+
+
+@pytest.mark.parametrize("flags", [GN, GN_NEWTON, GN_REF])
+def test_carried_solves_on_the_grooming_trial(grooming_leg, flags):
+    """The pipeline kernel's arithmetic (carried solves; with SEQIK_FLAG_CLOSED_FORM the closed-form warm step) over all
+    6000 frames of both legs against the reference's shipped angles: same acceptance as the frame-by-frame solves."""
+    from seqikpy_b200 import data as D
+    from seqikpy_b200.kinematic_chain import KinematicChainSeq
+    size = O.calculate_body_size(D.NMF_TEMPLATE, ["RF", "LF"])
+    chain = KinematicChainSeq(D.BOUNDS, ["RF", "LF"], size)
+    for li, leg in enumerate(["RF", "LF"]):
+        seg = [size[f"{leg}_{s}"] for s in O.SEGMENTS]
+        pose = grooming_leg["pose"][li]
+        ang, fk, nfev = H.run_carried_f32(pose, chain.pack_chain_params(leg, D.INITIAL_ANGLES[leg]), flags)
+        allowed = singular_windows(grooming_leg["ref_angles"][li])
+        bad = bad_frames(ang, grooming_leg["ref_angles"][li])
+        assert set(bad) <= allowed and len(bad) <= 30, (leg, bad)
+        r_ours = fk_residual(fk, pose)
+        r_ref = residual_of_angles(grooming_leg["ref_angles"][li], seg, pose)
+        worse = np.where(((r_ours - r_ref) > FK_TOL + 2e-6).any(axis=1))[0]
+        assert set(worse) <= allowed, (leg, worse)
+        # the FK rows are those of the returned angles
+        assert np.abs(r_ours - residual_of_angles(ang.astype(np.float64), seg, pose)).max() < 1e-5
+        if flags == GN:
+            assert nfev.mean() < 1.5        # most solves end with their first evaluation
+
+
+def test_closed_form_warm_step_on_synthetic_trials(synthetic_wide):
+    """Default flags on the carried path, trials 2-4 x 6 legs x 1000 frames against the oracle."""
+    from seqikpy_b200 import synthetic as S
+    from seqikpy_b200.kinematic_chain import KinematicChainSeq
+    size, bounds, init = S.chain_constants()
+    chain = KinematicChainSeq(bounds, list(S.LEGS), size)
+    n_frame = int(synthetic_wide["n_frame"])
+    for ti, tr in enumerate(synthetic_wide["trials"][:3]):
+        pose = S.make_trial(int(tr), n_frame)
+        for li, leg in enumerate(S.LEGS):
+            ang, fk, nfev = H.run_carried_f32(pose[:, li], chain.pack_chain_params(leg, init[leg]), GN)
+            assert np.abs(ang - synthetic_wide["oracle_angles"][ti, li]).max() < ANGLE_TOL, (tr, leg)
+            assert (fk_residual(fk, pose[:, li]) - synthetic_wide["oracle_fk_residual"][ti, li]).max() < FK_TOL + 2e-6
+            assert nfev.mean() < 1.6
