@@ -66,6 +66,8 @@ extern "C" {
 #define SEQIK_FLAG_SCHED_MASK (0xFu << SEQIK_FLAG_SCHED_SHIFT)
 #define SEQIK_FLAG_GATE_SHIFT 21             /* bits 21..24: period (1..15 loop iterations) of the open/close phases of schedule 2, 0 = automatic.
                                                 Scheduling only: results do not depend on it */
+#define SEQIK_FLAG_TRIP_SHIFT 25             /* bits 25..27: period (1..7 loop iterations) of the evaluation block of schedule 2, 0 = automatic.
+                                                Scheduling only */
 #define SEQIK_FLAG_FK_JOINTS (1u << 20)      /* fk holds only the four joint rows that carry information: [n_chain][n_frame][4][3] =
                                                 rows 5..8 of the full layout (Coxa-Femur, Femur-Tibia, Tibia-Tarsus, Claw).  Rows 0-3
                                                 of the full layout repeat the input origin and row 4 repeats row 5; leaving them out

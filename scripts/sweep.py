@@ -13,7 +13,7 @@ chain = KinematicChainSeq(bounds, list(S.LEGS), size)
 base = S.to_chains(torch.from_numpy(S.make_trials(range(16), 1000)).cuda())          # 96 chains x 1000 frames
 
 
-def run(n_trial, n_frame, sched, cpw, reps=3, gate=0, flags=None):
+def run(n_trial, n_frame, sched, cpw, reps=3, gate=0, flags=None, trip=0):
     kw = {} if flags is None else {"flags": flags}
     n_chain = n_trial * 6
     reps_c = (n_chain + 95) // 96
@@ -22,15 +22,15 @@ def run(n_trial, n_frame, sched, cpw, reps=3, gate=0, flags=None):
     params = torch.from_numpy(chain_param_table(chain, init, S.LEGS, reps_c * 16)[:n_chain]).cuda()
     ang = torch.empty((n_chain, n_frame, 7), device="cuda"); fk = torch.empty((n_chain, n_frame, 9, 3), device="cuda")
     for _ in range(2):
-        engine.leg_solve(pose, params, angles=ang, fk=fk, schedule=sched, chains_per_warp=cpw, want_stats=False, gate=gate, **kw)
+        engine.leg_solve(pose, params, angles=ang, fk=fk, schedule=sched, chains_per_warp=cpw, want_stats=False, gate=gate, trip_period=trip, **kw)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        engine.leg_solve(pose, params, angles=ang, fk=fk, schedule=sched, chains_per_warp=cpw, want_stats=False, gate=gate, **kw)
+        engine.leg_solve(pose, params, angles=ang, fk=fk, schedule=sched, chains_per_warp=cpw, want_stats=False, gate=gate, trip_period=trip, **kw)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    print(json.dumps({"trials": n_trial, "chains": n_chain, "frames": n_frame, "sched": sched, "cpw": cpw, "gate": gate, "flags": flags, "ms": round(ms, 3),
+    print(json.dumps({"trials": n_trial, "chains": n_chain, "frames": n_frame, "sched": sched, "cpw": cpw, "gate": gate, "trip": trip, "flags": flags, "ms": round(ms, 3),
                       "Mlf_s": round(n_chain * n_frame / ms / 1e3, 1)}), flush=True)
 
 
@@ -45,6 +45,11 @@ if __name__ == "__main__":
             for flags in (0x7F, 0xFF):
                 for gate in (1, 2, 3, 4):
                     run(n_trial, 500, 2, 0, gate=gate, flags=flags)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "trip":
+        for n_trial in (100, 1000, 1250, 10000):
+            for gate, trip in ((2, 1), (1, 1), (1, 2), (1, 3), (2, 2), (2, 3), (3, 2), (3, 3), (2, 4), (1, 4)):
+                run(n_trial, 500, 2, 0, gate=gate, trip=trip)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "cpw":
         for n_trial in (100, 200, 400, 1000, 1250, 2500):

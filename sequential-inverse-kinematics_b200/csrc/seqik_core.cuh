@@ -264,7 +264,7 @@ struct StageSolve {
                     R lb0, R ub0, R lb1, R ub1, R null_sq_, int n_full, int mode = 0) {
         set_problem(kind_in, L_, has_a_in, null_sq_, n_full, mode);
         set_iterate(a, b);
-        restart(q_in, lb0, ub0, lb1, ub1, true);
+        restart(q_in, lb0, ub0, lb1, ub1, true, false);
     }
 
     // The prologue proper.  `fresh`: the sin/cos of the iterate are derived from the angles (a new solve, init()).
@@ -316,12 +316,17 @@ struct StageSolve {
         seeded = ok;
     }
 
-    SK_HD void restart(const Vec3<R>& q_in, R lb0, R ub0, R lb1, R ub1, bool fresh = false) {
+    // `warm`: the iterate is a previous frame's solution (false only for the seed of a recording's first frame), i.e.
+    // the closed-form warm step may be taken.
+    SK_HD void restart(const Vec3<R>& q_in, R lb0, R ub0, R lb1, R ub1, bool fresh = false, bool warm = true) {
         const Vec3<R> q = xy ? Vec3<R>{-q_in.z, q_in.y, q_in.x} : q_in;
-        seeded = false;
-        if (closed_form && gn_mode && !fresh) warm_step(q, lb0, ub0, lb1 - shift, ub1 - shift);
         place(x0, x1, lb0, ub0, lb1 - shift, ub1 - shift);   // bound distances (re-)derived from the angle
         if (fresh) { R va, vb; N::sincosv_(x0, &sa, &ca, &va); N::sincosv_(x1, &sb, &cb, &vb); }
+        seeded = false;
+        if (closed_form && gn_mode && warm) {
+            warm_step(q, lb0, ub0, lb1 - shift, ub1 - shift);
+            dl0 = x0 - lb0; du0 = ub0 - x0; dl1 = x1 - (lb1 - shift); du1 = (ub1 - shift) - x1;   // strictly inside: no nudge
+        }
         const Vec3<R> w = point();
         f = {w.x - q.x, w.y - q.y, w.z - q.z};
         cost = R(0.5) * dot(f, f);

@@ -120,7 +120,7 @@ constexpr int PIPE_CHAINS = 8;              // chains per warp (maximum)
 // kFull: all four stages solved and the nine-row FK layout written (the benchmark configurations and the dict API):
 // the frozen-stage, partial-stage and output-layout decisions are compiled out.  Same arithmetic either way.
 template <bool kFull>
-__global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, int gate_period) {
+__global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, int gate_period, int trip_period) {
     __shared__ float ring[4][PIPE_DEPTH][PIPE_SLOT][PIPE_CHAINS];      // chain innermost: conflict-free per stage; [3] = identity (stage 1's input)
     __shared__ float kpbuf[6][32];                                     // prefetched key points, one column per lane
     const unsigned full = 0xffffffffu;
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, 
     if (live && n_frame > 0) prefetch();
     bool carried = false;            // S holds the previous frame's solve of this (chain, stage)
 
-    for (int gate_ctr = 1; __any_sync(full, live && t < n_frame);) {
+    for (int gate_ctr = 1, trip_ctr = trip_period; __any_sync(full, live && t < n_frame);) {
         if (--gate_ctr == 0) {                          // open/close phases only every gate_period-th iteration (warp-uniform)
         gate_ctr = gate_period;
         __syncwarp(full);            // ring reads of the previous open phase are complete before a slot is written again
@@ -266,13 +266,16 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, 
                 S.set_iterate(xa, xb);
                 carried = true;
             }
-            S.restart(q3, lb0, ub0, lb1, ub1, fresh);
+            S.restart(q3, lb0, ub0, lb1, ub1, fresh, !frozen && (t > 0 || a.warm != nullptr));   // frozen DOFs stay where they are
             if (frozen) S.status = ST_GTOL;
             solving = true; started = t + 1;
         }
         }   // gate
-        // ---- one function evaluation
-        if (live && solving && !S.done()) S.trip();
+        // ---- one function evaluation (every trip_period-th iteration, warp-uniform)
+        if (--trip_ctr == 0) {
+            trip_ctr = trip_period;
+            if (live && solving && !S.done()) S.trip();
+        }
     }
     // per-chain statistics
     const int w1 = min(worst, __shfl_xor_sync(full, worst, 1));
@@ -342,8 +345,10 @@ extern "C" int seqik_leg_solve_f32(const float* pose, int64_t pose_chain_stride,
         // closed-form warm step (mostly none).  Scheduling only: results are unchanged.
         const uint32_t gate_sel = (flags >> SEQIK_FLAG_GATE_SHIFT) & 0xFu;    // 0 auto, else the period in iterations
         const int gate_period = gate_sel ? (int)gate_sel : (flags & SEQIK_FLAG_CLOSED_FORM) ? 2 : (flags & SEQIK_FLAG_NEWTON) ? 4 : 6;
-        if (stage_mask == 0xF && fk && !fk_joints) leg_solve_pipe_kernel<true><<<(unsigned)grid, 32, 0, (cudaStream_t)stream>>>(a, cpw, gate_period);
-        else leg_solve_pipe_kernel<false><<<(unsigned)grid, 32, 0, (cudaStream_t)stream>>>(a, cpw, gate_period);
+        const uint32_t trip_sel = (flags >> SEQIK_FLAG_TRIP_SHIFT) & 0x7u;
+        const int trip_period = trip_sel ? (int)trip_sel : 1;
+        if (stage_mask == 0xF && fk && !fk_joints) leg_solve_pipe_kernel<true><<<(unsigned)grid, 32, 0, (cudaStream_t)stream>>>(a, cpw, gate_period, trip_period);
+        else leg_solve_pipe_kernel<false><<<(unsigned)grid, 32, 0, (cudaStream_t)stream>>>(a, cpw, gate_period, trip_period);
     }
     return seqik_check_launch("seqik_leg_solve_f32");
 }

@@ -44,7 +44,7 @@ def stages_to_mask(stages: Sequence[int]) -> int:
 
 def leg_solve(pose, params, affine=None, stages: Sequence[int] = (1, 2, 3, 4), want_fk: bool = True,
               angles=None, fk=None, flags: int = N.FLAG_DEFAULT, schedule: int = N.SCHED_AUTO,
-              want_stats: bool = True, chains_per_warp: int = 0, frames=None, gate: int = 0, fk_layout: str = "full"):
+              want_stats: bool = True, chains_per_warp: int = 0, frames=None, gate: int = 0, fk_layout: str = "full", trip_period: int = 0):
     """4-stage sequential IK (+FK) of every chain.  Returns (angles, fk|None, status|None, nfev|None).
 
     ``angles`` must be given (and is updated in place) when ``stages`` does not start at 1:
@@ -103,7 +103,7 @@ def leg_solve(pose, params, affine=None, stages: Sequence[int] = (1, 2, 3, 4), w
             angles.data_ptr() + 4 * 7 * t0, n_frame * 7, 7, p_fk, n_frame * fk_floats, fk_floats,
             warm, n_frame * 7,
             N.ptr(status), N.ptr(nfev), n_chain, t1 - t0, mask,
-            (flags & 0xFF) | ((schedule & 0xF) << N.FLAG_SCHED_SHIFT) | ((chains_per_warp & 0x3F) << 12) | ((gate & 0xF) << 21)
+            (flags & 0xFF) | ((schedule & 0xF) << N.FLAG_SCHED_SHIFT) | ((chains_per_warp & 0x3F) << 12) | ((gate & 0xF) << 21) | ((trip_period & 7) << 25)
             | (N.FLAG_FK_JOINTS if fk_layout == "joints" else 0),
             N.stream_ptr(torch, dev))
     N.check(rc, "seqik_leg_solve_f32")

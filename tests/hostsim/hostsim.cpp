@@ -94,8 +94,9 @@ static void run_carried(const float* pose, int64_t n_frame, const float* prm, fl
             const Vec3<R> k = {kp[3 * (s + 1)], kp[3 * (s + 1) + 1], kp[3 * (s + 1) + 2]};
             const Vec3<R> rel = {(k.x - o.x) - piv.x, (k.y - o.y) - piv.y, (k.z - o.z) - piv.z};
             const Vec3<R> q3 = mulT(A, rel);
-            if (carried[s] && (t & (SEQIK_RESYNC - 1)) != 0) S[s].restart(q3, lb0, ub0, lb1, ub1);
-            else { S[s].init(kind, prm[s], (s == 3) ? 0.f : 1.f, q3, xa[s], xb[s], lb0, ub0, lb1, ub1, prm[25 + s], n_full, gn); carried[s] = true; }
+            const bool fresh = !(carried[s] && (t & (SEQIK_RESYNC - 1)) != 0);
+            if (fresh) { S[s].set_problem(kind, prm[s], (s == 3) ? 0.f : 1.f, prm[25 + s], n_full, gn); S[s].set_iterate(xa[s], xb[s]); carried[s] = true; }
+            S[s].restart(q3, lb0, ub0, lb1, ub1, fresh, t > 0);
             for (;;) {
                 while (!S[s].done()) S[s].trip();
                 if (!(esc && S[s].escape())) break;
