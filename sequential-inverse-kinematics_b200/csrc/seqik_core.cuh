@@ -203,7 +203,8 @@ struct StageSolve {
     bool skip_confirm;                  // SEQIK_FLAG_SKIP_CONFIRM, see trip()
     bool newton;                        // SEQIK_FLAG_NEWTON, see plan()
     bool closed_form;                   // SEQIK_FLAG_CLOSED_FORM, see warm_step()
-    bool seeded;                        // this solve started from warm_step()'s point
+    bool seeded;                        // this solve started (and ended) at warm_step()'s point
+    Vec3<R> seed_f;                     // residual at that point
 
     typedef Num<R> N;
     SK_HD int kind_() const { return xy ? KIND_XY : KIND_ZY; }
@@ -314,6 +315,9 @@ struct StageSolve {
         x0 = ok ? nx0 : x0; x1 = ok ? nx1 : x1;
         sa = ok ? n_sa : sa; ca = ok ? n_ca : ca; sb = ok ? n_sb : sb; cb = ok ? n_cb : cb;
         seeded = ok;
+        // residual there: w = L q / |q| (in the rotation's plane for one variable), f = w - q
+        const R k = N::fma_(L, rn, R(-1));
+        seed_f = {q.x * k, one_var ? -q.y : q.y * k, q.z * k};
     }
 
     // `warm`: the iterate is a previous frame's solution (false only for the seed of a recording's first frame), i.e.
@@ -327,6 +331,14 @@ struct StageSolve {
             warm_step(q, lb0, ub0, lb1 - shift, ub1 - shift);
             dl0 = x0 - lb0; du0 = ub0 - x0; dl1 = x1 - (lb1 - shift); du1 = (ub1 - shift) - x1;   // strictly inside: no nudge
         }
+        alpha = R(0); nfev = 1; escaped = false; last_ratio = R(0);
+        if (seeded) {
+            // the minimiser itself: the gradient vanishes by construction (w is parallel to q, both Jacobian columns are
+            // orthogonal to w), so the solve ends with this evaluation -- no model, no step
+            f = seed_f; cost = R(0.5) * dot(f, f); g0 = R(0); g1 = R(0);
+            status = (cost < N::inf()) ? ST_GTOL : ST_NONFINITE;
+            return;
+        }
         const Vec3<R> w = point();
         f = {w.x - q.x, w.y - q.y, w.z - q.z};
         cost = R(0.5) * dot(f, f);
@@ -338,7 +350,6 @@ struct StageSolve {
         const R q0 = (v0 > R(1e-30)) ? x0 * x0 * N::rcp_(v0) : R(0), q1 = (v1 > R(1e-30)) ? xb_ * xb_ * N::rcp_(v1) : R(0);
         Delta = N::sqrt_(null_sq + q0 + q1);
         if (Delta == R(0)) Delta = R(1);
-        alpha = R(0); nfev = 1; escaped = false; last_ratio = R(0);
         status = (cost < N::inf()) ? ST_RUNNING : ST_NONFINITE;      // false for NaN and inf
         plan(status == ST_RUNNING);
     }
@@ -531,8 +542,7 @@ struct StageSolve {
         const R g_norm = N::max_(N::abs_(g0 * v0), N::abs_(g1 * v1));
         // straight-line code: the termination tests that need no evaluation are folded into selects at the end, so that
         // a trip is one basic block but for the rare general step (lanes that are not `active` change nothing)
-        // (a solve moved to the closed-form minimiser stops at float32's gradient floor: |g| < 2e-7 is < ~1e-6 rad)
-        const bool stop_g = g_norm < ((seeded && nfev == 1) ? R(2e-7) : gtol), stop_n = nfev >= max_nfev;
+        const bool stop_g = g_norm < gtol, stop_n = nfev >= max_nfev;
         const bool run = active && !stop_g && !stop_n;
         const bool one_var = has_a_() == R(0);
         const R B0 = N::fma_(v0, ja_sq(), g0 * dv0), B1 = N::fma_(v1, L * L, g1 * dv1);   // Jh^T Jh + diag(g dv), diagonal
