@@ -284,13 +284,24 @@ def run_ours(args):
         ms_e2e_joints = timed(lambda: sess_j.solve_host(host_pose, synchronize=False, n_chunks=args.chunks), args.steps) / args.steps
         del sess_j
 
+    # ---- the same kernel walking the reference's own iterates (SEQIK_FLAG_REFERENCE_ITERATES: no Newton steps, no
+    #      closed-form warm step): a secondary figure that shows what the default flags save
+    sess.flags = _native.FLAG_REFERENCE_ITERATES
+    for _ in range(3):
+        sess.solve_device()
+    ms_ref_it = timed(lambda: sess.solve_device(want_stats=False), args.steps) / args.steps
+    sess.solve_device()
+    torch.cuda.synchronize()
+    nfev_ref_it = sess.nfev.to(torch.float64).sum(0)
+    sess.flags = _native.FLAG_DEFAULT
+
     sess.solve_device()
     torch.cuda.synchronize()
     nfev = sess.nfev.to(torch.float64).sum(0)                     # evaluations per stage, this rank
     fk_err = torch.tensor([sess.mean_fk_error()], dtype=torch.float64, device=dev)
     maxfev = (sess.status == 0).sum().to(torch.float64).reshape(1)
     if world > 1:
-        dist.all_reduce(nfev); dist.all_reduce(fk_err); dist.all_reduce(maxfev)
+        dist.all_reduce(nfev); dist.all_reduce(fk_err); dist.all_reduce(maxfev); dist.all_reduce(nfev_ref_it)
     leg_frames_rank = sess.leg_frames
     leg_frames = leg_frames_rank * world
     nfev_per_lf = (nfev / leg_frames).tolist()
@@ -326,13 +337,19 @@ def run_ours(args):
                 "h2d_bytes_per_step": leg_frames_rank * 60, "d2h_bytes_per_step": leg_frames_rank * (28 + 48),
                 "note": "fk_layout='joints': FK rows 5..8 only (rows 0-3 of the reference layout repeat the input origin, row 4 repeats row 5)"},
             "gpu_launches": args.steps,
+            "solver_flags": {"value": "SEQIK_FLAG_DEFAULT (0xFF): Gauss-Newton mode, escape, skip-confirm, Newton steps, closed-form warm step",
+                             "reference_iterates": {"flags": "SEQIK_FLAG_REFERENCE_ITERATES (0x3F)", "ms_per_step": ms_ref_it,
+                                                    "value": leg_frames / (ms_ref_it * 1e-3), "unit": UNIT,
+                                                    "nfev_per_leg_frame_by_stage": (nfev_ref_it / leg_frames).tolist()}},
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                          "traffic": traffic, "kernel": "leg_solve", "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback",
-                         "note": "the solver is FP32-latency bound, not HBM bound; see fp32",
+                         "note": "the solver is bound by dependent-issue latency, neither by HBM nor by the FP32 pipe; see fp32 and DESIGN.md 5.1",
                          "fp32": {"achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_tf / fp32_peak,
-                                  "flop_model": "nominal 14.5 kFLOP per leg-frame (SURVEY.md 8d: the reference's full-chain, "
-                                                "finite-difference evaluation count; the kernel's closed-form 2-variable "
-                                                "formulation executes far fewer, see ncu_*)",
+                                  "flop_model": "nominal 14.5 kFLOP per leg-frame = the REFERENCE's work (SURVEY.md 8d: full-chain, "
+                                                "finite-difference evaluations x its iteration counts).  The kernel does not do "
+                                                "that work (two-variable closed forms, ~1.1 evaluations per solve), so `achieved`/"
+                                                "`frac` here say how fast the reference's work is retired, NOT how busy the FP32 "
+                                                "pipe is: that is ncu_frac",
                                   "ncu_flop_per_leg_frame": ncu_flop,
                                   "ncu_achieved": None if not ncu_flop else leg_frames_rank * ncu_flop / (ms_step * 1e-3) / 1e12,
                                   "ncu_frac": None if not ncu_flop else leg_frames_rank * ncu_flop / (ms_step * 1e-3) / 1e12 / fp32_peak,

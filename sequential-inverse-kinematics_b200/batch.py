@@ -66,8 +66,9 @@ class BatchedLegIK:
 
     def __init__(self, kinematic_chain_class, initial_angles, legs: Sequence[str], n_trial: int, n_frame: int,
                  device="cuda", want_fk: bool = True, schedule: int = N.SCHED_AUTO, host_buffers: bool = True,
-                 chains_per_warp: int = 0, fk_layout: str = "full"):
-        """``fk_layout``: "full" = the reference's 9 rows per leg-frame; "joints" = only the four rows that carry
+                 chains_per_warp: int = 0, fk_layout: str = "full", flags: int = N.FLAG_DEFAULT):
+        """``flags``: solver flags (include/seqik.h; ``N.FLAG_REFERENCE_ITERATES`` walks the reference's own iterates).
+        ``fk_layout``: "full" = the reference's 9 rows per leg-frame; "joints" = only the four rows that carry
         information (rows 5..8: rows 0-3 of the full layout repeat the input origin, row 4 repeats row 5), which cuts
         the device->host result from 136 to 76 bytes per leg-frame -- the end-to-end call is bound by that copy."""
         torch = N.require_cuda()
@@ -79,6 +80,7 @@ class BatchedLegIK:
         self.device = torch.device(device)
         self.schedule = schedule
         self.chains_per_warp = chains_per_warp
+        self.flags = int(flags)
         self.params = torch.from_numpy(chain_param_table(kinematic_chain_class, initial_angles, self.legs, n_trial)).to(self.device)
         f32 = dict(dtype=torch.float32, device=self.device)
         self.d_pose = torch.empty((self.n_chain, self.n_frame, 5, 3), **f32)
@@ -107,7 +109,7 @@ class BatchedLegIK:
         pose = self.d_pose if pose is None else pose.reshape(self.n_chain, self.n_frame, 5, 3)
         _, _, self.status, self.nfev = engine.leg_solve(pose, self.params, affine=affine, angles=self.d_angles, fk=self.d_fk,
                                                         want_fk=self.d_fk is not None, schedule=self.schedule,
-                                                        chains_per_warp=self.chains_per_warp,
+                                                        chains_per_warp=self.chains_per_warp, flags=self.flags,
                                                         want_stats=want_stats, fk_layout=self.fk_layout)
         return self.d_angles, self.d_fk
 
@@ -154,7 +156,7 @@ class BatchedLegIK:
                 main.wait_event(ev_in)
                 engine.leg_solve(self.d_pose, self.params, angles=self.d_angles, fk=self.d_fk, want_fk=self.d_fk is not None,
                                  schedule=self.schedule, chains_per_warp=self.chains_per_warp, want_stats=False, frames=(t0, t1),
-                                 fk_layout=self.fk_layout)
+                                 fk_layout=self.fk_layout, flags=self.flags)
                 ev_k = torch.cuda.Event()
                 ev_k.record(main)
                 s_out.wait_event(ev_k)
