@@ -205,6 +205,8 @@ struct StageSolve {
     bool closed_form;                   // SEQIK_FLAG_CLOSED_FORM, see warm_step()
     bool seeded;                        // this solve started (and ended) at warm_step()'s point
     Vec3<R> seed_f;                     // residual at that point
+    int seed_at;                        // 0 interior, 1 / 2: first angle on its lower / upper limit
+    bool have_bt; R sl0, cl0, su0, cu0; // sin/cos of the first angle's limits (set_limit_trig)
 
     typedef Num<R> N;
     SK_HD int kind_() const { return xy ? KIND_XY : KIND_ZY; }
@@ -257,6 +259,7 @@ struct StageSolve {
         seeded = false;
         xy = kind_in == KIND_XY; shift = xy ? R(1.57079632679489661923) : R(0);
         L = L_; has_a = has_a_in; null_sq = null_sq_; max_nfev = 100 * n_full;
+        have_bt = false; seed_at = 0; sl0 = cl0 = su0 = cu0 = R(0);
     }
     SK_HD void set_iterate(R a, R b) { x0 = a; x1 = b - shift; }
 
@@ -312,12 +315,41 @@ struct StageSolve {
         const bool ok = N::abs_(hsa) < R(0.25) && N::abs_(hsb) < R(0.25) && cda > R(0) && cdb > R(0)
                         && (one_var || rho2 > R(0.01) * qn2) && qn2 > R(0.25) * L * L && qn2 < N::inf()
                         && nx0 - lb0 > m && ub0 - nx0 > m && nx1 - lb1 > m && ub1 - nx1 > m;
-        x0 = ok ? nx0 : x0; x1 = ok ? nx1 : x1;
-        sa = ok ? n_sa : sa; ca = ok ? n_ca : ca; sb = ok ? n_sb : sb; cb = ok ? n_cb : cb;
-        seeded = ok;
         // residual there: w = L q / |q| (in the rotation's plane for one variable), f = w - q
         const R k = N::fma_(L, rn, R(-1));
         seed_f = {q.x * k, one_var ? -q.y : q.y * k, q.z * k};
+        // ---- the same with the first angle ON its limit: when the free minimiser lies beyond a limit of `a` (and only
+        // then), the box-constrained minimiser has a = that limit and b the minimiser in the plane of the b rotation
+        // at that a: (sb, cb) = -(q_e, q_z) / |.|, q_e = q . (ca, sa, 0).  Admitted under the same tests (small moves,
+        // same branch, conditioning in that plane, b strictly interior) plus the KKT sign of the a-gradient there.
+        const bool lo = nx0 - lb0 <= m, hi_ = ub0 - nx0 <= m;
+        const R b_sa = lo ? sl0 : su0, b_ca = lo ? cl0 : cu0, b_x0 = lo ? lb0 : ub0;
+        const R qe = N::fma_(q.y, b_sa, q.x * b_ca), pn2 = N::fma_(q.z, q.z, qe * qe);
+        const R rp = N::rsqrt_(pn2);
+        const R c_sb = -(qe * rp), c_cb = -(q.z * rp);
+        const R sdb2 = N::fma_(c_sb, cb, -(c_cb * sb)), cdb2 = N::fma_(c_cb, cb, c_sb * sb);
+        const R hsb2 = sdb2 * N::rsqrt_(R(2) + R(2) * cdb2);
+        const R cx1 = x1 + R(2) * asin_small(hsb2);
+        const R ga = c_sb * N::fma_(b_ca, q.y, -(b_sa * q.x));          // sign of d cost / d a at the candidate (times L > 0)
+        const bool ok_b = have_bt && !one_var && !ok && (lo != hi_) && N::abs_(b_x0 - x0) < R(0.5)
+                          && N::abs_(hsa) < R(0.25) && cda > R(0)          // the free minimiser is a short move away, too
+                          && N::abs_(hsb2) < R(0.25) && cdb2 > R(0) && c_sb * sgn > R(0.1) && pn2 > R(0.25) * L * L && pn2 < N::inf()
+                          && cx1 - lb1 > m && ub1 - cx1 > m && (lo ? ga > R(0) : ga < R(0));
+        x0 = ok ? nx0 : ok_b ? b_x0 : x0; x1 = ok ? nx1 : ok_b ? cx1 : x1;
+        sa = ok ? n_sa : ok_b ? b_sa : sa; ca = ok ? n_ca : ok_b ? b_ca : ca;
+        sb = ok ? n_sb : ok_b ? c_sb : sb; cb = ok ? n_cb : ok_b ? c_cb : cb;
+        seeded = ok || ok_b;
+        seed_at = ok_b ? (lo ? 1 : 2) : 0;
+        if (ok_b) {
+            const R Lsb = L * c_sb;
+            seed_f = {-(Lsb * b_ca) - q.x, -(Lsb * b_sa) - q.y, -(L * c_cb) - q.z};
+        }
+    }
+    // sin/cos of the first angle's limits, for warm_step()'s on-the-limit case (once per (chain, stage))
+    SK_HD void set_limit_trig(R lb0, R ub0) {
+        R v_;
+        have_bt = lb0 > -N::inf() && ub0 < N::inf();
+        if (have_bt) { N::sincosv_(lb0, &sl0, &cl0, &v_); N::sincosv_(ub0, &su0, &cu0, &v_); }
     }
 
     // `warm`: the iterate is a previous frame's solution (false only for the seed of a recording's first frame), i.e.
@@ -330,6 +362,10 @@ struct StageSolve {
         if (closed_form && gn_mode && warm) {
             warm_step(q, lb0, ub0, lb1 - shift, ub1 - shift);
             dl0 = x0 - lb0; du0 = ub0 - x0; dl1 = x1 - (lb1 - shift); du1 = (ub1 - shift) - x1;   // strictly inside: no nudge
+            if (seeded && seed_at != 0) {        // on a limit: one fp64 ulp inside, like the iterates that land there
+                const R gap = inner_gap(x0);
+                dl0 = (seed_at == 1) ? gap : span0 - gap; du0 = (seed_at == 1) ? span0 - gap : gap;
+            }
         }
         alpha = R(0); nfev = 1; escaped = false; last_ratio = R(0);
         if (seeded) {

@@ -167,6 +167,7 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, 
 
     StageSolve<float> S;
     S.set_problem(kind, seg, has_a, null_sq, n_full, gn);
+    if (live && !frozen) S.set_limit_trig(lb0, ub0);
     Mat3<float> A = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
     Vec3<float> piv = {0.f, 0.f, 0.f}, o = {0.f, 0.f, 0.f}, rel = {0.f, 0.f, 0.f};
     int t = 0;                       // frame this lane works on

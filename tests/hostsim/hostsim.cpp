@@ -95,7 +95,14 @@ static void run_carried(const float* pose, int64_t n_frame, const float* prm, fl
             const Vec3<R> rel = {(k.x - o.x) - piv.x, (k.y - o.y) - piv.y, (k.z - o.z) - piv.z};
             const Vec3<R> q3 = mulT(A, rel);
             const bool fresh = !(carried[s] && (t & (SEQIK_RESYNC - 1)) != 0);
-            if (fresh) { S[s].set_problem(kind, prm[s], (s == 3) ? 0.f : 1.f, prm[25 + s], n_full, gn); S[s].set_iterate(xa[s], xb[s]); carried[s] = true; }
+            if (fresh) {
+                const bool had = S[s].have_bt && carried[s];
+                const float l0 = S[s].sl0, l1 = S[s].cl0, u0 = S[s].su0, u1 = S[s].cu0;
+                S[s].set_problem(kind, prm[s], (s == 3) ? 0.f : 1.f, prm[25 + s], n_full, gn);
+                if (!carried[s]) S[s].set_limit_trig(lb0, ub0);          // once per (chain, stage), like the kernel
+                else { S[s].have_bt = had; S[s].sl0 = l0; S[s].cl0 = l1; S[s].su0 = u0; S[s].cu0 = u1; }
+                S[s].set_iterate(xa[s], xb[s]); carried[s] = true;
+            }
             S[s].restart(q3, lb0, ub0, lb1, ub1, fresh, t > 0);
             for (;;) {
                 while (!S[s].done()) S[s].trip();

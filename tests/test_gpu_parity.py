@@ -221,13 +221,20 @@ def test_synthetic_vs_oracle_and_shard_invariance(api, synthetic_gold):
     for lo, hi in ((0, 6), (6, 24), (5, 7)):
         a_s, f_s, _, _ = api.engine.leg_solve(chains[lo:hi].contiguous(), params[lo:hi].contiguous())
         assert t.equal(a_s, ang[lo:hi]) and t.equal(f_s, fk[lo:hi])
-    # results do not depend on how chains are packed into warps (bit-identical); the one-lane-per-chain schedule
-    # re-derives sin/cos from the angle at every frame instead of every 64 and agrees to float32 rounding
+    # results do not depend on how chains are packed into warps (bit-identical).  The one-lane-per-chain schedule starts
+    # every solve afresh from the warm start (no carried state, hence no closed-form warm step): it iterates to the
+    # same minimisers and stops where the ftol test says, up to a few 1e-4 rad from them on flat (bound-active) solves
     for cpw, gate in ((1, 0), (2, 1), (3, 2), (8, 3), (8, 1), (4, 7), (8, 15)):
         a2, f2, s2, n2 = api.engine.leg_solve(chains, params, schedule=api.native.SCHED_STAGE_PIPELINE, chains_per_warp=cpw, gate=gate)
         assert t.equal(ang, a2) and t.equal(fk, f2) and t.equal(nfev, n2) and t.equal(status, s2), (cpw, gate)
     a1, f1, s1, n1 = api.engine.leg_solve(chains, params, schedule=api.native.SCHED_LANE_PER_CHAIN)
-    assert (a1 - ang).abs().max() < 2e-4 and (f1 - fk).abs().max() < 1e-4 and int(s1.min()) == 1
+    assert (a1 - ang).abs().max() < 5e-4 and (f1 - fk).abs().max() < 1e-4 and int(s1.min()) == 1
+    # with the reference's iterates in both schedules the agreement is float32 rounding
+    ref_it = api.native.FLAG_REFERENCE_ITERATES
+    a3, f3, _, _ = api.engine.leg_solve(chains, params, flags=ref_it)
+    a4, f4, _, _ = api.engine.leg_solve(chains, params, flags=ref_it, schedule=api.native.SCHED_LANE_PER_CHAIN)
+    assert (a3 - a4).abs().max() < 2e-4 and (f3 - f4).abs().max() < 1e-4
+    assert (a3 - ang).abs().max() < 5e-4 and (f3 - fk).abs().max() < 1e-4
 
 
 def test_synthetic_trials_2_to_7_all_frames_vs_oracle(api, synthetic_wide):
