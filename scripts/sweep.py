@@ -51,6 +51,11 @@ if __name__ == "__main__":
             for gate, trip in ((2, 1), (1, 1), (1, 2), (1, 3), (2, 2), (2, 3), (3, 2), (3, 3), (2, 4), (1, 4)):
                 run(n_trial, 500, 2, 0, gate=gate, trip=trip)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "big":
+        for n_trial in (3000, 5000, 10000):
+            for cpw in (4, 5, 6, 8):
+                run(n_trial, 500, 2, cpw)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "cpw":
         for n_trial in (100, 200, 400, 1000, 1250, 2500):
             for cpw in (1, 2, 3, 4, 5, 6, 7, 8):

@@ -328,13 +328,18 @@ extern "C" int seqik_leg_solve_f32(const float* pose, int64_t pose_chain_stride,
         leg_solve_lane_kernel<<<(unsigned)grid, 32, 0, (cudaStream_t)stream>>>(a);
     } else {
         // chains per warp (measured): spread the chains over one warp per SM sub-partition (4 x 148) while
-        // that is possible, then fill the warps up to 8 chains (all 32 lanes).  Small batches run at pure chain latency
-        // whatever the packing; large ones are fastest fully packed.
+        // that is possible, then fill the warps -- up to 5 chains (20 lanes) while the warps still fit the SMs in about two
+        // waves (a warp runs the iteration block for all its lanes whenever ONE lane needs it, so less-than-full warps
+        // execute fewer instructions per chain: 6 000 / 7 500 / 15 000 chains are 3 / 6 / 18 % faster at 4 - 5 chains per
+        // warp than at 8), 6 beyond that (18 000 - 60 000 chains: 6 is 15 - 22 % faster than 8; `scripts/sweep.py big`).
+        // Small batches run at pure chain latency whatever the packing.
         int dev = 0, n_sm = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         int cpw = (int)((n_chain + 4LL * n_sm - 1) / (4LL * n_sm));
-        cpw = cpw < 1 ? 1 : (cpw > PIPE_CHAINS ? PIPE_CHAINS : cpw);
+        // (with the iterating flag sets nearly every lane needs the iteration block anyway: full warps are best there)
+        const int cap = !(flags & SEQIK_FLAG_CLOSED_FORM) ? PIPE_CHAINS : (n_chain <= 27LL * 4 * n_sm) ? 5 : 6;
+        cpw = cpw < 1 ? 1 : (cpw > cap ? cap : cpw);
         const uint32_t forced = (flags >> SEQIK_FLAG_CPW_SHIFT) & 0x3F;     // tuning / tests
         if (forced) cpw = (int)forced;
         if (cpw < 1 || cpw > PIPE_CHAINS) return seqik_fail(SEQIK_EINVAL, "seqik_leg_solve_f32: chains per warp must be 1..8");
