@@ -118,6 +118,10 @@ const char* seqik_last_error(void);
  *   nfev    NULL, or [n_chain][4] out: function evaluations summed over frames, per stage
  *   stage_mask  bit s set = solve stage s+1; the set bits must be contiguous
  *           (stages=[a..b] of run_ik_and_fk, leg_inverse_kinematics.py:350-353)
+ *   flags   SEQIK_FLAG_* above: SEQIK_FLAG_DEFAULT for production use; SEQIK_FLAG_REFERENCE_ITERATES to walk the
+ *           reference's own iterates (evaluation counts and termination statuses as scipy's); scheduling fields
+ *           (schedule, chains per warp, phase periods: tuning and tests) never change results; SEQIK_FLAG_FK_JOINTS
+ *           selects the compact fk layout
  */
 int seqik_leg_solve_f32(const float* pose, int64_t pose_chain_stride, int64_t pose_frame_stride,
                         const float* affine, const float* params,
