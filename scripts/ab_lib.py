@@ -58,5 +58,5 @@ for cpw in (1, 3, 8):
     out[f"cpw{cpw}_equals_full"] = bool(torch.equal(a8, ang) and torch.equal(f8, fk))
 print(json.dumps(out))
 for n_trial in (100, 1000, 1250, 10000):
-    for gate in (2, 3, 4, 5, 6, 8):
+    for gate in (0, 1, 2, 3):
         ns["run"](n_trial, 1000 if n_trial == 1000 else 500, 2, 0, gate=gate)

@@ -297,7 +297,7 @@ struct StageSolve {
     // targets leave the direction ill-determined and the reference crawls there); in every other case -- first
     // frame of a call, re-derivation frames, active bounds, large moves -- the solve runs from the warm start exactly
     // as without the flag.  One-variable stage 4: the same in the plane of its single rotation.
-    SK_HD void warm_step(const Vec3<R>& q, R lb0, R ub0, R lb1, R ub1) {
+    SK_HD void warm_step(const Vec3<R>& q, R lb0, R ub0, R lb1, R ub1, bool enable = true) {
         const bool one_var = has_a == R(0);
         const R rho2 = one_var ? q.x * q.x : N::fma_(q.y, q.y, q.x * q.x);
         const R qn2 = N::fma_(q.z, q.z, rho2);
@@ -312,7 +312,7 @@ struct StageSolve {
         const R hsa = sda * N::rsqrt_(R(2) + R(2) * cda), hsb = sdb * N::rsqrt_(R(2) + R(2) * cdb);
         const R nx0 = x0 + R(2) * asin_small(hsa), nx1 = x1 + R(2) * asin_small(hsb);
         const R m = R(1e-5);
-        const bool ok = N::abs_(hsa) < R(0.25) && N::abs_(hsb) < R(0.25) && cda > R(0) && cdb > R(0)
+        const bool ok = enable && N::abs_(hsa) < R(0.25) && N::abs_(hsb) < R(0.25) && cda > R(0) && cdb > R(0)
                         && (one_var || rho2 > R(0.01) * qn2) && qn2 > R(0.25) * L * L && qn2 < N::inf()
                         && nx0 - lb0 > m && ub0 - nx0 > m && nx1 - lb1 > m && ub1 - nx1 > m;
         // residual there: w = L q / |q| (in the rotation's plane for one variable), f = w - q
@@ -331,7 +331,7 @@ struct StageSolve {
         const R hsb2 = sdb2 * N::rsqrt_(R(2) + R(2) * cdb2);
         const R cx1 = x1 + R(2) * asin_small(hsb2);
         const R ga = c_sb * N::fma_(b_ca, q.y, -(b_sa * q.x));          // sign of d cost / d a at the candidate (times L > 0)
-        const bool ok_b = have_bt && !one_var && !ok && (lo != hi_) && N::abs_(b_x0 - x0) < R(0.5)
+        const bool ok_b = enable && have_bt && !one_var && !ok && (lo != hi_) && N::abs_(b_x0 - x0) < R(0.5)
                           && N::abs_(hsa) < R(0.25) && cda > R(0)          // the free minimiser is a short move away, too
                           && N::abs_(hsb2) < R(0.25) && cdb2 > R(0) && c_sb * sgn > R(0.1) && pn2 > R(0.25) * L * L && pn2 < N::inf()
                           && cx1 - lb1 > m && ub1 - cx1 > m && (lo ? ga > R(0) : ga < R(0));
@@ -355,22 +355,30 @@ struct StageSolve {
     // `warm`: the iterate is a previous frame's solution (false only for the seed of a recording's first frame), i.e.
     // the closed-form warm step may be taken.
     SK_HD void restart(const Vec3<R>& q_in, R lb0, R ub0, R lb1, R ub1, bool fresh = false, bool warm = true) {
+        const Vec3<R> q = restart_a(q_in, lb0, ub0, lb1, ub1, fresh);
+        warm_step(q, lb0, ub0, lb1 - shift, ub1 - shift, closed_form && gn_mode && warm);
+        restart_b(q, lb0, ub0, lb1, ub1);
+    }
+    // The same in three pieces, so that a kernel can put independent work of its own next to the straight-line middle
+    // one (warm_step) and have the two instruction streams interleave:
+    // (a) target into the solve's own frame, bound distances, trigonometry of a fresh iterate
+    SK_HD Vec3<R> restart_a(const Vec3<R>& q_in, R lb0, R ub0, R lb1, R ub1, bool fresh) {
         const Vec3<R> q = xy ? Vec3<R>{-q_in.z, q_in.y, q_in.x} : q_in;
         place(x0, x1, lb0, ub0, lb1 - shift, ub1 - shift);   // bound distances (re-)derived from the angle
         if (fresh) { R va, vb; N::sincosv_(x0, &sa, &ca, &va); N::sincosv_(x1, &sb, &cb, &vb); }
-        seeded = false;
-        if (closed_form && gn_mode && warm) {
-            warm_step(q, lb0, ub0, lb1 - shift, ub1 - shift);
-            dl0 = x0 - lb0; du0 = ub0 - x0; dl1 = x1 - (lb1 - shift); du1 = (ub1 - shift) - x1;   // strictly inside: no nudge
-            if (seeded && seed_at != 0) {        // on a limit: one fp64 ulp inside, like the iterates that land there
-                const R gap = inner_gap(x0);
-                dl0 = (seed_at == 1) ? gap : span0 - gap; du0 = (seed_at == 1) ? span0 - gap : gap;
-            }
-        }
+        return q;
+    }
+    // (b) after warm_step(): the solve ends at the seeded point, or the least_squares prologue runs
+    SK_HD void restart_b(const Vec3<R>& q, R lb0, R ub0, R lb1, R ub1) {
         alpha = R(0); nfev = 1; escaped = false; last_ratio = R(0);
         if (seeded) {
             // the minimiser itself: the gradient vanishes by construction (w is parallel to q, both Jacobian columns are
-            // orthogonal to w), so the solve ends with this evaluation -- no model, no step
+            // orthogonal to w; on a limit the first one points out of the box), so the solve ends with this evaluation
+            dl0 = x0 - lb0; du0 = ub0 - x0; dl1 = x1 - (lb1 - shift); du1 = (ub1 - shift) - x1;   // strictly inside: no nudge
+            if (seed_at != 0) {                  // on a limit: one fp64 ulp inside, like the iterates that land there
+                const R gap = inner_gap(x0);
+                dl0 = (seed_at == 1) ? gap : span0 - gap; du0 = (seed_at == 1) ? span0 - gap : gap;
+            }
             f = seed_f; cost = R(0.5) * dot(f, f); g0 = R(0); g1 = R(0);
             status = (cost < N::inf()) ? ST_GTOL : ST_NONFINITE;
             return;
@@ -730,6 +738,17 @@ template <typename R> SK_HD Mat3<R> rotate_frame(const Mat3<R>& A, int kind, R s
     return C;
 }
 
+// the same without a branch on `kind` (selects on the columns; identical arithmetic): for callers whose lanes mix kinds
+template <typename R> SK_HD Mat3<R> rotate_frame_sel(const Mat3<R>& A, int kind, R sa, R ca, R sb, R cb) {
+    const bool xy = kind == KIND_XY;
+    const Vec3<R> U = xy ? A.c1 : A.c0, V = xy ? A.c2 : A.c1, W = xy ? A.c0 : A.c2;
+    const Vec3<R> P = lin(U, ca, V, sa), Q = lin(U, -sa, V, ca);
+    Mat3<R> B;
+    B.c0 = xy ? W : P; B.c1 = xy ? P : Q; B.c2 = xy ? Q : W;
+    Mat3<R> C;
+    C.c0 = lin(B.c0, cb, B.c2, -sb); C.c1 = B.c1; C.c2 = lin(B.c0, sb, B.c2, cb);
+    return C;
+}
 
 // ---------------------------------------------------------------------------------
 // ChainRunner: one (trial, leg) chain advanced ONE function evaluation per step().
