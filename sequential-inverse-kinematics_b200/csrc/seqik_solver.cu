@@ -348,9 +348,12 @@ extern "C" int seqik_leg_solve_f32(const float* pose, int64_t pose_chain_stride,
         // part, so it pays to let nearly all lanes of the warp finish their solves and then close / open together: every
         // 6th iteration for the reference's iterates (3 - 6 trips per solve; config 3, ms per 1000 frames at period
         // 1 / 2 / 4 / 6 / 8 = 5.8 / 4.4 / 3.9 / 3.6 / 3.6), every 4th with Newton steps (2 - 3 trips), every 2nd with the
-        // closed-form warm step (mostly none).  Scheduling only: results are unchanged.
+        // closed-form warm step every iteration for up to 7 000 chains (latency regime: a lane then handles one frame per
+        // iteration) and every 3rd beyond (throughput regime: fewer instructions; 60 000 chains: 6.1 / 5.7 / 5.2 ms at
+        // period 1 / 2 / 3, `profiles/r01_ab_merged_phase.txt`).  Scheduling only: results are unchanged.
         const uint32_t gate_sel = (flags >> SEQIK_FLAG_GATE_SHIFT) & 0xFu;    // 0 auto, else the period in iterations
-        const int gate_period = gate_sel ? (int)gate_sel : (flags & SEQIK_FLAG_CLOSED_FORM) ? 2 : (flags & SEQIK_FLAG_NEWTON) ? 4 : 6;
+        const int gate_period = gate_sel ? (int)gate_sel
+                              : (flags & SEQIK_FLAG_CLOSED_FORM) ? (n_chain <= 7000 ? 1 : 3) : (flags & SEQIK_FLAG_NEWTON) ? 4 : 6;
         const uint32_t trip_sel = (flags >> SEQIK_FLAG_TRIP_SHIFT) & 0x7u;
         const int trip_period = trip_sel ? (int)trip_sel : 1;
         if (stage_mask == 0xF && fk && !fk_joints) leg_solve_pipe_kernel<true><<<(unsigned)grid, 32, 0, (cudaStream_t)stream>>>(a, cpw, gate_period, trip_period);
