@@ -36,6 +36,18 @@
 // the scaling / model quantities are recomputed from it (they are cheap and it makes a trip
 // one straight-line block, which is what a warp of lanes at different positions needs).
 //
+// On top of that restatement (flags of include/seqik.h, all optional):
+//   * Newton steps (plan()): the residual-curvature term of the two-angle segment is closed
+//     form, so the Newton step of the same scaled model is a 2x2 solve -- taken where the full
+//     Hessian is safely positive definite and the step is admissible, else the step above;
+//   * closed-form warm step (warm_step()): a stage points a segment at its target, so the
+//     box-free minimiser is the point of the sphere |w| = L nearest to the target (on the
+//     warm start's branch), and with the first angle on a limit it is the nearest point of a
+//     circle; for the next frame of a carried solve the iterate is moved there when that is a
+//     short, interior, well-conditioned move and the solve ends with that one evaluation.
+// The reference's own iterates are what runs when the flags are off and wherever the
+// admission tests fail.
+//
 // The same header is compiled by nvcc for the kernels and by g++ for the host-side
 // test harness in tests/hostsim (test infrastructure; never loaded by the product).
 #pragma once

@@ -14,8 +14,10 @@
 //                                       benchmark configurations (6 000 - 7 500 chains per GPU leave a B200 mostly
 //                                       idle under schedule 1, whose run time is one chain's latency).
 //
-// Both run the same per-lane arithmetic (seqik_core.cuh: StageSolve::init / trip), one function evaluation per
-// loop trip, in a warp-convergent loop; lanes sit at different (frame, stage) positions ("decoupled" trips).
+// Both run the same per-lane arithmetic (seqik_core.cuh: StageSolve::init / restart / trip), one function evaluation
+// per loop trip, in a warp-convergent loop; lanes sit at different (frame, stage) positions ("decoupled" trips).
+// Schedule 2 carries a solve from frame to frame (restart: no trigonometry), which is also what lets the closed-form
+// warm step end most solves with their first evaluation (SEQIK_FLAG_CLOSED_FORM); schedule 1 starts every solve afresh.
 // No tensor cores: the work is scalar FP32 2x2 / 3x3 algebra (BASELINE.json north_star).
 #include <cuda_runtime.h>
 #include <stdint.h>
