@@ -324,9 +324,11 @@ struct StageSolve {
         const R hsa = sda * N::rsqrt_(R(2) + R(2) * cda), hsb = sdb * N::rsqrt_(R(2) + R(2) * cdb);
         const R nx0 = x0 + R(2) * asin_small(hsa), nx1 = x1 + R(2) * asin_small(hsb);
         const R m = R(1e-5);
-        const bool ok = enable && N::abs_(hsa) < R(0.25) && N::abs_(hsb) < R(0.25) && cda > R(0) && cdb > R(0)
-                        && (one_var || rho2 > R(0.01) * qn2) && qn2 > R(0.25) * L * L && qn2 < N::inf()
-                        && nx0 - lb0 > m && ub0 - nx0 > m && nx1 - lb1 > m && ub1 - nx1 > m;
+        // (bitwise &: every test is evaluated, no short-circuit branches in this block)
+        const bool in_a = (nx0 - lb0 > m) & (ub0 - nx0 > m), in_b = (nx1 - lb1 > m) & (ub1 - nx1 > m);
+        const bool small_a = (N::abs_(hsa) < R(0.25)) & (cda > R(0)), small_b = (N::abs_(hsb) < R(0.25)) & (cdb > R(0));
+        const bool ok = enable & small_a & small_b & (one_var | (rho2 > R(0.01) * qn2)) & (qn2 > R(0.25) * L * L) & (qn2 < N::inf())
+                        & in_a & in_b;
         // residual there: w = L q / |q| (in the rotation's plane for one variable), f = w - q
         const R k = N::fma_(L, rn, R(-1));
         seed_f = {q.x * k, one_var ? -q.y : q.y * k, q.z * k};
@@ -334,27 +336,32 @@ struct StageSolve {
         // then), the box-constrained minimiser has a = that limit and b the minimiser in the plane of the b rotation
         // at that a: (sb, cb) = -(q_e, q_z) / |.|, q_e = q . (ca, sa, 0).  Admitted under the same tests (small moves,
         // same branch, conditioning in that plane, b strictly interior) plus the KKT sign of the a-gradient there.
-        const bool lo = nx0 - lb0 <= m, hi_ = ub0 - nx0 <= m;
-        const R b_sa = lo ? sl0 : su0, b_ca = lo ? cl0 : cu0, b_x0 = lo ? lb0 : ub0;
-        const R qe = N::fma_(q.y, b_sa, q.x * b_ca), pn2 = N::fma_(q.z, q.z, qe * qe);
-        const R rp = N::rsqrt_(pn2);
-        const R c_sb = -(qe * rp), c_cb = -(q.z * rp);
-        const R sdb2 = N::fma_(c_sb, cb, -(c_cb * sb)), cdb2 = N::fma_(c_cb, cb, c_sb * sb);
-        const R hsb2 = sdb2 * N::rsqrt_(R(2) + R(2) * cdb2);
-        const R cx1 = x1 + R(2) * asin_small(hsb2);
-        const R ga = c_sb * N::fma_(b_ca, q.y, -(b_sa * q.x));          // sign of d cost / d a at the candidate (times L > 0)
-        const bool ok_b = enable && have_bt && !one_var && !ok && (lo != hi_) && N::abs_(b_x0 - x0) < R(0.5)
-                          && N::abs_(hsa) < R(0.25) && cda > R(0)          // the free minimiser is a short move away, too
-                          && N::abs_(hsb2) < R(0.25) && cdb2 > R(0) && c_sb * sgn > R(0.1) && pn2 > R(0.25) * L * L && pn2 < N::inf()
-                          && cx1 - lb1 > m && ub1 - cx1 > m && (lo ? ga > R(0) : ga < R(0));
-        x0 = ok ? nx0 : ok_b ? b_x0 : x0; x1 = ok ? nx1 : ok_b ? cx1 : x1;
-        sa = ok ? n_sa : ok_b ? b_sa : sa; ca = ok ? n_ca : ok_b ? b_ca : ca;
-        sb = ok ? n_sb : ok_b ? c_sb : sb; cb = ok ? n_cb : ok_b ? c_cb : cb;
-        seeded = ok || ok_b;
-        seed_at = ok_b ? (lo ? 1 : 2) : 0;
-        if (ok_b) {
-            const R Lsb = L * c_sb;
-            seed_f = {-(Lsb * b_ca) - q.x, -(Lsb * b_sa) - q.y, -(L * c_cb) - q.z};
+        // One block behind one branch: only lanes whose free minimiser left the box through a limit of `a` enter it
+        // (a few per cent of the solves of the benchmark workload, none on most recordings).
+        x0 = ok ? nx0 : x0; x1 = ok ? nx1 : x1;
+        sa = ok ? n_sa : sa; ca = ok ? n_ca : ca; sb = ok ? n_sb : sb; cb = ok ? n_cb : cb;
+        seeded = ok; seed_at = 0;
+        const bool below = nx0 - lb0 <= m, above = ub0 - nx0 <= m;
+        if (enable & have_bt & !one_var & !ok & (below != above) & small_a) {
+            const bool lo = below;
+            const R b_sa = lo ? sl0 : su0, b_ca = lo ? cl0 : cu0, b_x0 = lo ? lb0 : ub0;
+            const R qe = N::fma_(q.y, b_sa, q.x * b_ca), pn2 = N::fma_(q.z, q.z, qe * qe);
+            const R rp = N::rsqrt_(pn2);
+            const R c_sb = -(qe * rp), c_cb = -(q.z * rp);
+            const R sdb2 = N::fma_(c_sb, cb, -(c_cb * sb)), cdb2 = N::fma_(c_cb, cb, c_sb * sb);
+            const R hsb2 = sdb2 * N::rsqrt_(R(2) + R(2) * cdb2);
+            const R cx1 = x1 + R(2) * asin_small(hsb2);
+            const R ga = c_sb * N::fma_(b_ca, q.y, -(b_sa * q.x));      // sign of d cost / d a at the candidate (times L > 0)
+            const bool kkt = lo ? (ga > R(0)) : (ga < R(0));
+            const bool ok_b = (N::abs_(b_x0 - x0) < R(0.5))
+                              & (N::abs_(hsb2) < R(0.25)) & (cdb2 > R(0)) & (c_sb * sgn > R(0.1)) & (pn2 > R(0.25) * L * L) & (pn2 < N::inf())
+                              & (cx1 - lb1 > m) & (ub1 - cx1 > m) & kkt;
+            if (ok_b) {
+                x0 = b_x0; x1 = cx1; sa = b_sa; ca = b_ca; sb = c_sb; cb = c_cb;
+                seeded = true; seed_at = lo ? 1 : 2;
+                const R Lsb_c = L * c_sb;
+                seed_f = {-(Lsb_c * b_ca) - q.x, -(Lsb_c * b_sa) - q.y, -(L * c_cb) - q.z};
+            }
         }
     }
     // sin/cos of the first angle's limits, for warm_step()'s on-the-limit case (once per (chain, stage))

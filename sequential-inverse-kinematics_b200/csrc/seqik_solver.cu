@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, 
             }
             pa_a += a.ang_fs; pa_b += a.ang_fs;
             if (s < hi) {
-                const Mat3<float> B = rotate_frame(A, kind, S.sa, S.ca, S.sin_b(), S.cos_b());
+                const Mat3<float> B = rotate_frame_sel(A, kind, S.sa, S.ca, S.sin_b(), S.cos_b());   // lanes mix kinds: no branch
                 float (*q)[PIPE_CHAINS] = ring[s][t & (PIPE_DEPTH - 1)];
                 q[0][cw] = B.c0.x; q[1][cw] = B.c0.y; q[2][cw] = B.c0.z; q[3][cw] = B.c1.x; q[4][cw] = B.c1.y; q[5][cw] = B.c1.z;
                 q[6][cw] = B.c2.x; q[7][cw] = B.c2.y; q[8][cw] = B.c2.z; q[9][cw] = np_.x; q[10][cw] = np_.y; q[11][cw] = np_.z;
