@@ -123,7 +123,12 @@ constexpr int PIPE_CHAINS = 8;              // chains per warp (maximum)
 // the frozen-stage, partial-stage and output-layout decisions are compiled out.  Same arithmetic either way.
 template <bool kFull>
 __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, int gate_period, int trip_period) {
-    __shared__ float ring[4][PIPE_DEPTH][PIPE_SLOT][PIPE_CHAINS];      // chain innermost: conflict-free per stage; [3] = identity (stage 1's input)
+    // hand-off ring: [stage][frame slot x 12 floats (+ 1 pad row)][chain].  Bank of an element = (8 (k + stage) + chain) mod 32:
+    // the pad row shifts each stage's plane by 8 banks, so the 4 x 8 lanes of a warp, which all touch the same k at once,
+    // hit 32 different banks (without it the four stage lanes of a chain collided: half of the kernel's shared-memory
+    // wavefronts were bank-conflict replays, ncu l1tex__data_bank_conflicts_pipe_lsu_mem_shared).  [3] = identity
+    // (stage 1's input)
+    __shared__ float ring[4][PIPE_DEPTH * PIPE_SLOT + 1][PIPE_CHAINS];
     __shared__ float kpbuf[6][32];                                     // prefetched key points, one column per lane
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x;
@@ -181,7 +186,7 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, 
     // the other stages read their producer's, so that the hand-off read is the same instruction for all lanes
     if (lane < PIPE_CHAINS)
         for (int d = 0; d < PIPE_DEPTH; ++d)
-            for (int k = 0; k < PIPE_SLOT; ++k) ring[3][d][k][lane] = (k == 0 || k == 4 || k == 8) ? 1.f : 0.f;
+            for (int k = 0; k < PIPE_SLOT; ++k) ring[3][d * PIPE_SLOT + k][lane] = (k == 0 || k == 4 || k == 8) ? 1.f : 0.f;
     __syncwarp(full);
     const int sp = (s + 3) & 3;      // ring this lane reads from
     // key points of frame t (origin + this stage's target, 6 floats), fetched one frame ahead with cp.async into
@@ -238,7 +243,7 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, 
             pa_a += a.ang_fs; pa_b += a.ang_fs;
             if (s < hi) {
                 const Mat3<float> B = rotate_frame_sel(A, kind, S.sa, S.ca, S.sin_b(), S.cos_b());   // lanes mix kinds: no branch
-                float (*q)[PIPE_CHAINS] = ring[s][t & (PIPE_DEPTH - 1)];
+                float (*q)[PIPE_CHAINS] = &ring[s][(t & (PIPE_DEPTH - 1)) * PIPE_SLOT];
                 q[0][cw] = B.c0.x; q[1][cw] = B.c0.y; q[2][cw] = B.c0.z; q[3][cw] = B.c1.x; q[4][cw] = B.c1.y; q[5][cw] = B.c1.z;
                 q[6][cw] = B.c2.x; q[7][cw] = B.c2.y; q[8][cw] = B.c2.z; q[9][cw] = np_.x; q[10][cw] = np_.y; q[11][cw] = np_.z;
             }
@@ -249,7 +254,7 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, 
         // ---- open the next solve when the previous stage has published this frame
         if (live && t < n_frame && !solving && (s == 0 || t < done_prev)) {
             {
-                const float (*q)[PIPE_CHAINS] = ring[sp][t & (PIPE_DEPTH - 1)];
+                const float (*q)[PIPE_CHAINS] = &ring[sp][(t & (PIPE_DEPTH - 1)) * PIPE_SLOT];
                 A.c0 = {q[0][cw], q[1][cw], q[2][cw]}; A.c1 = {q[3][cw], q[4][cw], q[5][cw]}; A.c2 = {q[6][cw], q[7][cw], q[8][cw]};
                 piv = {q[9][cw], q[10][cw], q[11][cw]};
             }
