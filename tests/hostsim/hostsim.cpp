@@ -164,3 +164,33 @@ void hostsim_generic_f64(const double* pose, int64_t n_frame, const double* prm,
     run_generic<double>(pose, n_frame, prm, teacher, angles, fk, nfev, status);
 }
 }
+
+// ---- self-checks of refactors that are otherwise only visible on the GPU: the select-based frame rotation equals the
+// branching one bit for bit, and restart() equals its three pieces.  Returns the number of mismatches.
+extern "C" int hostsim_selfcheck(const float* rnd, int n) {
+    int bad = 0;
+    for (int i = 0; i + 16 <= n; i += 16) {
+        const float* r = rnd + i;
+        const Mat3<float> A = {{r[0], r[1], r[2]}, {r[3], r[4], r[5]}, {r[6], r[7], r[8]}};
+        for (int kind = 0; kind < 2; ++kind) {
+            const Mat3<float> X = rotate_frame(A, kind, r[9], r[10], r[11], r[12]);
+            const Mat3<float> Y = rotate_frame_sel(A, kind, r[9], r[10], r[11], r[12]);
+            const float* x = &X.c0.x; const float* y = &Y.c0.x;
+            for (int k = 0; k < 9; ++k) bad += !(x[k] == y[k]);
+        }
+        for (int fresh = 0; fresh < 2; ++fresh) {
+            StageSolve<float> S1, S2;
+            const Vec3<float> q0 = {0.3f * r[0], 0.3f * r[1], -0.4f + 0.1f * r[2]};
+            S1.init(KIND_ZY, 0.4f, 1.f, q0, 0.2f * r[3], -0.8f + 0.2f * r[4], -1.f, 1.f, -2.f, 0.f, 1.5f, 6, 15);
+            while (!S1.done()) S1.trip();
+            S2 = S1;
+            const Vec3<float> q1 = {q0.x + 0.02f * r[5], q0.y + 0.02f * r[6], q0.z + 0.02f * r[7]};
+            S1.restart(q1, -1.f, 1.f, -2.f, 0.f, fresh != 0, true);
+            const Vec3<float> q = S2.restart_a(q1, -1.f, 1.f, -2.f, 0.f, fresh != 0);
+            S2.warm_step(q, -1.f, 1.f, -2.f - S2.shift, 0.f - S2.shift, S2.closed_form && S2.gn_mode);
+            S2.restart_b(q, -1.f, 1.f, -2.f, 0.f);
+            bad += !(S1.x0 == S2.x0 && S1.x1 == S2.x1 && S1.status == S2.status && S1.cost == S2.cost && S1.sa == S2.sa && S1.cb == S2.cb);
+        }
+    }
+    return bad;
+}

@@ -198,3 +198,13 @@ def test_closed_form_warm_step_on_synthetic_trials(synthetic_wide):
             assert np.abs(ang - synthetic_wide["oracle_angles"][ti, li]).max() < ANGLE_TOL, (tr, leg)
             assert (fk_residual(fk, pose[:, li]) - synthetic_wide["oracle_fk_residual"][ti, li]).max() < FK_TOL + 2e-6
             assert nfev.mean() < 1.6
+
+
+def test_refactored_pieces_equal_their_originals():
+    """rotate_frame_sel == rotate_frame and restart() == restart_a + warm_step + restart_b, bit for bit (host build)."""
+    import ctypes
+    lib = H.load()
+    rnd = np.random.default_rng(5).uniform(-1, 1, 16 * 400).astype(np.float32)
+    lib.hostsim_selfcheck.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.hostsim_selfcheck.restype = ctypes.c_int
+    assert lib.hostsim_selfcheck(rnd.ctypes.data, rnd.size) == 0
