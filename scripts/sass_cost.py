@@ -1,6 +1,7 @@
 """Static cost sheet of a kernel's SASS: per region (source-line ranges) instruction counts, branch counts and the
 sum of the compiler's stall counts (the issue cycles one warp alone needs when no scoreboard wait fires).
-Usage: python scripts/sass_cost.py <lib.so|cubin> <kernel-name-substring>
+Usage: python scripts/sass_cost.py <lib.so|cubin> <kernel-name-substring> [region=hexaddr ...]   (regions split the loop body
+by address; SASS_COLD="file:lo-hi,..." marks source ranges as cold)
 Reads `nvdisasm -g -hex` style output (line info needs -lineinfo).  A development aid: the numbers only rank variants
 of the same kernel before spending GPU time."""
 import re
@@ -94,11 +95,17 @@ if __name__ == "__main__":
     lo, hi = (votes[0], votes[-1]) if len(votes) >= 2 else (0, len(real))
     body = real[lo:hi + 2]
     # split the body at the BSSY that opens the trip (the last top-level region): find by source line of `S.trip()` call
+    # optional cold source ranges (rare paths excluded from the hot sums): SASS_COLD="seqik_core.cuh:100-127,seqik_core.cuh:540-590"
+    import os
+    cold_ranges = []
+    for item in filter(None, os.environ.get("SASS_COLD", "").split(",")):
+        f_, r_ = item.split(":")
+        lo_, hi_ = r_.split("-")
+        cold_ranges.append((f_, int(lo_), int(hi_)))
+
     def is_cold(i):
         f, n = i["line"] or ("", 0)
-        if f.endswith("seqik_core.cuh"):
-            return (100 <= n <= 117) or (214 <= n <= 220 and False) or (276 <= n <= 304) or (403 <= n <= 444)
-        return False
+        return any(f.endswith(cf) and lo_ <= n <= hi_ for cf, lo_, hi_ in cold_ranges)
     # region boundaries: name=hexaddr ... (sorted); default: whole body
     marks = sorted((int(a.split("=")[1], 16), a.split("=")[0]) for a in sys.argv[3:])
     if not marks:

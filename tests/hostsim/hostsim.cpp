@@ -194,3 +194,15 @@ extern "C" int hostsim_selfcheck(const float* rnd, int n) {
     }
     return bad;
 }
+
+// ---- the closed-form warm step on its own: a Rz(a) Ry(b) stage (two variables, or one with has_a = 0) carried at
+// (a, b) meets target q; out = (a', b', seeded, seed_at, cost at the new point).
+extern "C" void hostsim_warm_step_f64(double L, double has_a, const double* ab, const double* q, const double* lbub, double* out) {
+    StageSolve<double> S;
+    S.set_problem(KIND_ZY, L, has_a, 1.0, 6, 15);
+    S.set_limit_trig(lbub[0], lbub[1]);
+    S.set_iterate(ab[0], ab[1]);
+    const Vec3<double> qq = {q[0], q[1], q[2]};
+    S.restart(qq, lbub[0], lbub[1], lbub[2], lbub[3], true, true);
+    out[0] = S.x0; out[1] = S.angle_b(); out[2] = S.seeded ? 1.0 : 0.0; out[3] = S.seed_at; out[4] = S.cost;
+}

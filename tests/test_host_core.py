@@ -208,3 +208,46 @@ def test_refactored_pieces_equal_their_originals():
     lib.hostsim_selfcheck.argtypes = [ctypes.c_void_p, ctypes.c_int]
     lib.hostsim_selfcheck.restype = ctypes.c_int
     assert lib.hostsim_selfcheck(rnd.ctypes.data, rnd.size) == 0
+
+
+def test_closed_form_warm_step_is_the_box_constrained_minimiser():
+    """warm_step() against scipy's TRF on the same two-variable problem min |w(a, b) - q|^2, w = -L (sb ca, sb sa, cb),
+    lb <= (a, b) <= ub, started at the same point: wherever the closed form is admitted -- interior or with `a` on a
+    limit -- it lands on the minimiser scipy converges to (float64 build, 1e-6 rad / 1e-10 in cost)."""
+    import ctypes
+    from scipy.optimize import least_squares
+    lib = H.load()
+    fn = lib.hostsim_warm_step_f64
+    fn.argtypes = [ctypes.c_double, ctypes.c_double] + [ctypes.c_void_p] * 4
+    fn.restype = None
+    rng = np.random.default_rng(11)
+    L = 0.54
+    lbub = np.array([-0.6, 0.9, -2.4, -0.2])
+
+    def w(x):
+        a, b = x
+        return -L * np.array([np.sin(b) * np.cos(a), np.sin(b) * np.sin(a), np.cos(b)])
+    n_interior = n_limit = n_rejected = 0
+    for _ in range(400):
+        x_prev = np.array([rng.uniform(-0.55, 0.85), rng.uniform(-2.2, -0.4)])
+        # the next frame's target: the previous end point moved and scaled a little (noise leaves it off the sphere);
+        # every fourth case pushes `a` towards / beyond one of its limits
+        x_new = x_prev + rng.normal(0, 0.12, 2)
+        if rng.uniform() < 0.25:
+            x_new[0] = rng.choice([lbub[0] - rng.uniform(0, 0.2), lbub[1] + rng.uniform(0, 0.2)])
+            x_prev[0] = np.clip(x_new[0], lbub[0] + 0.05, lbub[1] - 0.05)
+        q = w(x_new) * rng.uniform(0.8, 1.25) + rng.normal(0, 0.01, 3)
+        out = np.zeros(5)
+        fn(L, 1.0, x_prev.ctypes.data, q.ctypes.data, lbub.ctypes.data, out.ctypes.data)
+        if out[2] == 0:
+            n_rejected += 1
+            continue
+        ref = least_squares(lambda x: w(x) - q, x_prev, bounds=(lbub[[0, 2]], lbub[[1, 3]]), xtol=1e-14, ftol=1e-14, gtol=1e-14)
+        assert abs(out[4] - ref.cost) < 1e-10, (out, ref.x, ref.cost)
+        assert np.abs(out[:2] - ref.x).max() < 1e-6, (out, ref.x)
+        if out[3] == 0:
+            n_interior += 1
+        else:
+            n_limit += 1
+            assert out[0] in (lbub[0], lbub[1])
+    assert n_interior > 150 and n_limit > 20 and n_rejected < 200, (n_interior, n_limit, n_rejected)
