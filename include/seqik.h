@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SEQIK_ABI_VERSION 4
+#define SEQIK_ABI_VERSION 5   /* 5: solver flag bits 6-7 (Newton steps, closed-form warm step), phase periods in bits 21-27 */
 #define SEQIK_OK 0
 #define SEQIK_EINVAL (-1)
 #define SEQIK_ECUDA (-3)

@@ -12,7 +12,7 @@ import numpy as np
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "csrc" / "libseqik_sm100.so"
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 CHAIN_PARAM_FLOATS = 32
 FLAG_ESCAPE = 1 << 4
 FLAG_SKIP_CONFIRM = 1 << 5
