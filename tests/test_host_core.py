@@ -251,3 +251,31 @@ def test_closed_form_warm_step_is_the_box_constrained_minimiser():
             n_limit += 1
             assert out[0] in (lbub[0], lbub[1])
     assert n_interior > 150 and n_limit > 20 and n_rejected < 200, (n_interior, n_limit, n_rejected)
+
+
+def test_closed_form_warm_step_one_variable_stage():
+    """The same for the one-variable stage (TiTa pitch only, has_a = 0): the minimiser in the plane of its rotation."""
+    import ctypes
+    from scipy.optimize import least_squares
+    lib = H.load()
+    fn = lib.hostsim_warm_step_f64
+    fn.argtypes = [ctypes.c_double, ctypes.c_double] + [ctypes.c_void_p] * 4
+    fn.restype = None
+    rng = np.random.default_rng(12)
+    L = 0.63
+    lbub = np.array([-np.inf, np.inf, -2.6, -0.05])
+    w = lambda b: -L * np.array([np.sin(b), 0.0, np.cos(b)])
+    n_seeded = 0
+    for _ in range(300):
+        b_prev = rng.uniform(-2.4, -0.3)
+        q = w(b_prev + rng.normal(0, 0.15)) * rng.uniform(0.7, 1.3) + rng.normal(0, 0.02, 3)
+        ab = np.array([0.0, b_prev])
+        out = np.zeros(5)
+        fn(L, 0.0, ab.ctypes.data, q.ctypes.data, lbub.ctypes.data, out.ctypes.data)
+        if out[2] == 0:
+            continue
+        n_seeded += 1
+        ref = least_squares(lambda x: w(x[0]) - q, [b_prev], bounds=([lbub[2]], [lbub[3]]), xtol=1e-14, ftol=1e-14, gtol=1e-14)
+        assert abs(out[1] - ref.x[0]) < 1e-6 and abs(out[4] - ref.cost) < 1e-10, (out, ref.x, ref.cost)
+        assert out[0] == 0.0 and out[3] == 0
+    assert n_seeded > 200
