@@ -206,3 +206,12 @@ extern "C" void hostsim_warm_step_f64(double L, double has_a, const double* ab, 
     S.restart(qq, lbub[0], lbub[1], lbub[2], lbub[3], true, true);
     out[0] = S.x0; out[1] = S.angle_b(); out[2] = S.seeded ? 1.0 : 0.0; out[3] = S.seed_at; out[4] = S.cost;
 }
+
+// ---- one solve step on its own: init at (a, b) against q, then `n_trip` evaluations; out = (a', b', cost, nfev, status)
+extern "C" void hostsim_trips_f64(double L, const double* ab, const double* q, const double* lbub, int mode, int n_trip, double* out) {
+    StageSolve<double> S;
+    const Vec3<double> qq = {q[0], q[1], q[2]};
+    S.init(KIND_ZY, L, 1.0, qq, ab[0], ab[1], lbub[0], lbub[1], lbub[2], lbub[3], 1.0, 6, mode);
+    for (int i = 0; i < n_trip && !S.done(); ++i) S.trip();
+    out[0] = S.x0; out[1] = S.angle_b(); out[2] = S.cost; out[3] = S.nfev; out[4] = S.status;
+}

@@ -279,3 +279,57 @@ def test_closed_form_warm_step_one_variable_stage():
         assert abs(out[1] - ref.x[0]) < 1e-6 and abs(out[4] - ref.cost) < 1e-10, (out, ref.x, ref.cost)
         assert out[0] == 0.0 and out[3] == 0
     assert n_seeded > 200
+
+
+def test_newton_step_is_the_newton_step():
+    """SEQIK_FLAG_NEWTON: the first step of a solve equals -(H + C)^-1 g with H the exact Hessian of 0.5 |w(a, b) - q|^2
+    (finite differences of the analytic gradient) and C = diag(|g_i| / v_i) the Coleman-Li term of scipy's model; with
+    the flag off it equals the Gauss-Newton step -(J^T J + C)^-1 g.  Newton converges to the minimiser in fewer trips."""
+    import ctypes
+    lib = H.load()
+    fn = lib.hostsim_trips_f64
+    fn.argtypes = [ctypes.c_double] + [ctypes.c_void_p] * 3 + [ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    fn.restype = None
+    rng = np.random.default_rng(13)
+    L = 0.69
+    lbub = np.array([-0.9, 2.2, -3.0, -0.1])
+
+    def w(x):
+        a, b = x
+        return -L * np.array([np.sin(b) * np.cos(a), np.sin(b) * np.sin(a), np.cos(b)])
+
+    def jac(x):
+        a, b = x
+        return -L * np.array([[-np.sin(b) * np.sin(a), np.cos(b) * np.cos(a)],
+                              [np.sin(b) * np.cos(a), np.cos(b) * np.sin(a)],
+                              [0.0, -np.sin(b)]])
+
+    def grad(x, q):
+        return jac(x).T @ (w(x) - q)
+    n_newton = 0
+    for _ in range(200):
+        x = np.array([rng.uniform(-0.5, 1.8), rng.uniform(-2.5, -0.6)])
+        q = w(x + rng.normal(0, 0.04, 2)) * rng.uniform(0.85, 1.2) + rng.normal(0, 0.02, 3)
+        g = grad(x, q)
+        v = np.where(g < 0, lbub[[1, 3]] - x, x - lbub[[0, 2]])              # distance to the bound the anti-gradient heads for
+        C = np.diag(np.abs(g) / v)
+        h = 1e-6
+        Hx = np.column_stack([(grad(x + h * e, q) - grad(x - h * e, q)) / (2 * h) for e in np.eye(2)])
+        JTJ = jac(x).T @ jac(x)
+        out_n, out_g = np.zeros(5), np.zeros(5)
+        fn(L, x.ctypes.data, q.ctypes.data, lbub.ctypes.data, 1 | 4, 1, out_n.ctypes.data)      # Gauss-Newton mode + Newton
+        fn(L, x.ctypes.data, q.ctypes.data, lbub.ctypes.data, 1, 1, out_g.ctypes.data)          # Gauss-Newton mode
+        p_g = -np.linalg.solve(JTJ + C, g)
+        assert np.abs(out_g[:2] - (x + p_g)).max() < 1e-9
+        p_n = -np.linalg.solve(Hx + C, g)
+        pd = np.all(np.linalg.eigvalsh(Hx + C) > 0)
+        if pd and np.abs(out_n[:2] - (x + p_n)).max() < 1e-7:
+            n_newton += 1
+        else:                                                               # not admitted: the Gauss-Newton step instead
+            assert np.abs(out_n[:2] - (x + p_g)).max() < 1e-9
+        # both converge to the same point; Newton needs no more evaluations
+        end_n, end_g = np.zeros(5), np.zeros(5)
+        fn(L, x.ctypes.data, q.ctypes.data, lbub.ctypes.data, 1 | 4, 200, end_n.ctypes.data)
+        fn(L, x.ctypes.data, q.ctypes.data, lbub.ctypes.data, 1, 200, end_g.ctypes.data)
+        assert np.abs(end_n[:2] - end_g[:2]).max() < 2e-5 and end_n[3] <= end_g[3]
+    assert n_newton > 150, n_newton
