@@ -317,9 +317,10 @@ def run_ours(args):
         fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12           # TFLOP/s at max clock
         ach_gbs = leg_frames_rank * ALG_BYTES_PER_LEG_FRAME / (ms_step * 1e-3) / 1e9
         ach_tf = leg_frames_rank * ALG_FLOP_PER_LEG_FRAME / (ms_step * 1e-3) / 1e12
-        traffic = ncu_flop = None
+        traffic = ncu_flop = ncu_issue = None
         try:
             prof = json.loads((ROOT / "profiles" / "solver_traffic.json").read_text())
+            ncu_issue = prof.get("issue_active_per_smsp")
             if args.trials == 1000 and args.frames == 1000:          # the capture is of the default configuration
                 traffic = prof.get("dram_bytes_per_launch")
             ncu_flop = prof.get("fp32_flop_per_launch", 0) / 6e6     # measured FP32 FLOP per leg-frame (ffma x2 + fmul + fadd)
@@ -353,6 +354,7 @@ def run_ours(args):
                                   "ncu_flop_per_leg_frame": ncu_flop,
                                   "ncu_achieved": None if not ncu_flop else leg_frames_rank * ncu_flop / (ms_step * 1e-3) / 1e12,
                                   "ncu_frac": None if not ncu_flop else leg_frames_rank * ncu_flop / (ms_step * 1e-3) / 1e12 / fp32_peak,
+                                  "ncu_issue_slots_per_cycle_per_smsp": ncu_issue,
                                   "peak_is": "148 SMs x 128 FMA lanes x 2 x sm_max_mhz",
                                   "nfev_per_leg_frame_by_stage": nfev_per_lf}},
             "cpu_baseline": cpu,
