@@ -449,8 +449,10 @@ struct StageSolve {
         if (!(best < R(0.98) * cost - R(5e-7))) return false;  // clearly better: > 2 % and > (1e-3 mm)^2 / 2
         const R nsq = null_sq; const int mx = max_nfev; const int nf = nfev;
         const int md = (gn_mode ? 1 : 0) | (skip_confirm ? 2 : 0) | (newton ? 4 : 0) | (closed_form ? 8 : 0);
+        const bool bt = have_bt; const R t0 = sl0, t1 = cl0, t2 = su0, t3 = cu0;    // per-(chain, stage) constants survive
         init(KIND_ZY, L, has_a, q, ba, bb, lb0, ub0, lb1, ub1, nsq, 1, md);
         max_nfev = mx; nfev = nf; escaped = true;
+        have_bt = bt; sl0 = t0; cl0 = t1; su0 = t2; cu0 = t3;
         return true;
     }
 
