@@ -71,6 +71,9 @@ def leg_solve(pose, params, affine=None, stages: Sequence[int] = (1, 2, 3, 4), w
     if angles is None:
         if not mask & 1:
             raise ValueError("stages do not start at 1: pass the angles tensor holding the earlier stages' DOFs")
+        if frames is not None and int(frames[0]) > 0:
+            raise ValueError("a frame range that does not start at 0 is warm-started from frame t0-1 of `angles`: "
+                             "pass the angles tensor that already holds that frame")
         angles = torch.empty((n_chain, n_frame, 7), dtype=torch.float32, device=dev)
     else:
         _check(angles, "angles", (7,))
@@ -304,7 +307,8 @@ def pchip_resample(series, original_ts: float, new_ts: float):
     """Shape-preserving cubic resampling (``utils.interpolate_signal``, reference utils.py:332-349) of uniformly sampled
     series on the device: ``series`` (n_block, n, width) -- e.g. an angles tensor (n_chain, n_frame, 7) -- or (n_series, n);
     float32 or float64.  Returns the same layout with ``m = len(np.arange(0, n * original_ts, new_ts))`` samples.
-    Like the reference's retry, +-inf samples are zeroed together with the last sample of that series; NaN raises."""
+    Like the reference's retry (utils.py:343-347: ``signal[np.isinf(signal)] = 0; signal[-1] = 0`` on the WHOLE array of one
+    call), +-inf samples are zeroed and, in every block that held one, the last sample of ALL its channels; NaN raises."""
     import numpy as np
     torch = N.require_cuda()
     lib = N.load_library()
@@ -329,7 +333,7 @@ def pchip_resample(series, original_ts: float, new_ts: float):
         if bool(torch.isnan(x).any()):
             raise ValueError("`y` must contain only finite values.")
         x = torch.where(finite, x, torch.zeros_like(x))
-        hit = (~finite).any(dim=1)                                # (n_block, width): series that held an inf
+        hit = (~finite).any(dim=1).any(dim=1, keepdim=True)       # (n_block, 1): blocks (= one reference call) that held an inf
         x[:, -1, :] = torch.where(hit, torch.zeros_like(x[:, -1, :]), x[:, -1, :])
     out = torch.empty((n_block, m, width), dtype=x.dtype, device=x.device)
     fn = lib.seqik_pchip_resample_f32 if x.dtype == torch.float32 else lib.seqik_pchip_resample_f64

@@ -99,7 +99,8 @@ class HeadInverseKinematics:
         dev = torch.device(self.device)
         d_r = torch.from_numpy(np.ascontiguousarray(two_points(r), dtype=np.float32)[None]).to(dev)
         d_l = torch.from_numpy(np.ascontiguousarray(two_points(l), dtype=np.float32)[None]).to(dev)
-        neck = neck.reshape(-1, 3)
+        # the reference takes aligned_pos["Neck"][:, 0, :] (head_inverse_kinematics.py:156-161): first key point per frame
+        neck = neck[:, 0, :] if neck.ndim == 3 else neck.reshape(-1, 3)
         if neck.shape[0] == 1:
             d_neck = torch.from_numpy(neck.astype(np.float32)).to(dev)                 # (1, 3): one point per trial
         elif neck.shape[0] == n:
@@ -140,15 +141,29 @@ class HeadInverseKinematics:
     def compute_head_yaw(self) -> np.ndarray:
         return self._all_angles()[2].copy()
 
+    def _check_head_roll(self, head_roll) -> None:
+        """The kernel de-rotates the antenna vectors by the head roll IT computes (what ``compute_head_angles`` hands
+        to these methods in the reference, head_inverse_kinematics.py:127-134).  A caller-supplied roll that differs
+        from it cannot be honoured by the fused kernel: refuse loudly instead of returning angles for another roll."""
+        if head_roll is None:
+            return
+        roll = np.asarray(head_roll, dtype=float)
+        own = self._all_angles()[0]
+        if roll.shape != own.shape or not np.allclose(roll, own, rtol=0.0, atol=1e-5):
+            raise ValueError("head_roll differs from the head roll computed from aligned_pos; the device kernel "
+                             "de-rotates by the computed roll (pass compute_head_roll() or None)")
+
     def compute_antenna_yaw(self, side: Literal["R", "L"], head_roll: np.ndarray = None) -> np.ndarray:
-        """``head_roll`` is accepted for signature compatibility; the kernel de-rotates by the roll it computes."""
+        """``head_roll``: None, or the roll of ``compute_head_roll()`` (anything else raises, see _check_head_roll)."""
         side = side.upper()
         if side not in {"R", "L"}:
             raise ValueError("Side should be either R or L")
+        self._check_head_roll(head_roll)
         return self._all_angles()[3 if side == "L" else 5].copy()
 
     def compute_antenna_pitch(self, side: Literal["R", "L"], head_roll: np.ndarray = None) -> np.ndarray:
         side = side.upper()
         if side not in {"R", "L"}:
             raise ValueError("Side should be either R or L")
+        self._check_head_roll(head_roll)
         return self._all_angles()[4 if side == "L" else 6].copy()

@@ -185,6 +185,8 @@ class KinematicChainSeq(KinematicChainBase):
         for stage in (1, 2, 3, 4):
             key = f"stage_{stage}"
             if key not in initial_angles:
+                if stage in stages:      # the reference indexes initial_angles[leg][f"stage_{stage}"]: KeyError
+                    raise KeyError(key)
                 continue
             seed = np.asarray(initial_angles[key], dtype=float)
             if stage in stages:

@@ -61,7 +61,13 @@ class LegInvKinBase(ABC):
 class LegInvKinSeq(LegInvKinBase):
     """Sequential (coxa -> femur -> tibia -> tarsus) leg IK, see the module docstring.
 
-    Extra, optional argument over the reference: ``device`` (default ``"cuda"``).
+    Extra, optional arguments over the reference: ``device`` (default ``"cuda"``) and the solver mode --
+    ``reference_iterates=True`` (or an explicit ``flags`` word of include/seqik.h) makes the kernel walk the
+    reference's own TRF iterates (``SEQIK_FLAG_REFERENCE_ITERATES``: same evaluation counts and termination
+    statuses as scipy's).  The default, ``SEQIK_FLAG_DEFAULT``, adds Newton steps and the closed-form warm step:
+    it ends at the box-constrained minimiser the reference's iteration converges to and stays within 1e-3 rad of
+    the reference's shipped angles everywhere except inside the reference's own singular episodes (CTr_pitch = 0,
+    where its path is driven by finite-difference rounding noise), max 1e-4 rad elsewhere.
     """
 
     def __init__(
@@ -71,10 +77,14 @@ class LegInvKinSeq(LegInvKinBase):
         initial_angles: Optional[Dict[str, np.ndarray]] = None,
         log_level: Literal["DEBUG", "INFO", "WARNING", "ERROR"] = "INFO",
         device: str = "cuda",
+        reference_iterates: bool = False,
+        flags: Optional[int] = None,
     ) -> None:
         super().__init__(aligned_pos, kinematic_chain_class, initial_angles, log_level)
         self.joint_angles_dict = {}
         self.device = device
+        #: solver flags handed to seqik_leg_solve_f32 (include/seqik.h)
+        self.flags = int(flags) if flags is not None else (N.FLAG_REFERENCE_ITERATES if reference_iterates else N.FLAG_DEFAULT)
         #: solver statistics of the last call: {leg: {"nfev": (4,) evaluations per stage, "status": int}}
         self.solver_stats = {}
 
@@ -92,7 +102,8 @@ class LegInvKinSeq(LegInvKinBase):
         d_angles = None
         if angles_in is not None:
             d_angles = torch.from_numpy(np.ascontiguousarray(angles_in, dtype=np.float32)).to(dev)
-        d_angles, d_fk, d_status, d_nfev = engine.leg_solve(d_pose, d_params, stages=stages, angles=d_angles, want_fk=True)
+        d_angles, d_fk, d_status, d_nfev = engine.leg_solve(d_pose, d_params, stages=stages, angles=d_angles, want_fk=True,
+                                                              flags=self.flags)
         angles = d_angles.cpu().numpy().astype(np.float64)
         fk = d_fk.cpu().numpy().astype(np.float64)
         status, nfev = d_status.cpu().numpy(), d_nfev.cpu().numpy()

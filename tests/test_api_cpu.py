@@ -199,3 +199,25 @@ def test_interpolate_joint_angles_needs_the_device():
     with pytest.raises(SeqIKNativeError):
         interpolate_joint_angles({"Angle_RF_ThC_yaw": np.arange(5.0)}, original_ts=0.01, new_ts=0.001)
 
+
+
+def test_missing_stage_seed_raises_keyerror(chain):
+    """A stage that is solved needs its seed vector: the reference indexes initial_angles[leg]["stage_k"] (KeyError,
+    leg_inverse_kinematics.py:376); only stages that are NOT solved may be absent."""
+    seeds = dict(D.INITIAL_ANGLES["RF"])
+    del seeds["stage_3"]
+    with pytest.raises(KeyError):
+        chain.pack_chain_params("RF", seeds)
+    row = chain.pack_chain_params("RF", seeds, stages=(1, 2))          # stage 3 not solved: allowed
+    assert row[18 + 4] == 0.0 and row[18 + 2] == D.INITIAL_ANGLES["RF"]["stage_2"][3]
+
+
+def test_leg_ik_class_exposes_the_solver_mode():
+    """LegInvKinSeq(reference_iterates=True) / flags= select the validated flag sets of include/seqik.h."""
+    from seqikpy_b200 import _native as N
+    from seqikpy_b200.leg_inverse_kinematics import LegInvKinSeq
+    ch = KinematicChainSeq(bounds_dof=D.BOUNDS, legs_list=["RF"], body_size=None)
+    pose = {"RF_leg": np.zeros((2, 5, 3))}
+    assert LegInvKinSeq(pose, ch, D.INITIAL_ANGLES, log_level="ERROR").flags == N.FLAG_DEFAULT
+    assert LegInvKinSeq(pose, ch, D.INITIAL_ANGLES, log_level="ERROR", reference_iterates=True).flags == N.FLAG_REFERENCE_ITERATES
+    assert LegInvKinSeq(pose, ch, D.INITIAL_ANGLES, log_level="ERROR", flags=0x7F).flags == 0x7F
