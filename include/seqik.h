@@ -62,7 +62,10 @@ extern "C" {
 #define SEQIK_FLAG_DEFAULT 0xFFu             /* the above + Newton steps + closed-form warm step (each set validated against the
                                                 reference's shipped angles and forward kinematics) */
 #define SEQIK_FLAG_SCHED_SHIFT 8             /* bits 8..11: kernel schedule, 0 = automatic,
-                                                1 = one lane per chain, 2 = stage pipeline (four lanes per chain) */
+                                                1 = one lane per chain, 2 = stage pipeline (four lanes per chain),
+                                                3 = frame-parallel blocks (a warp per chain, 32 frames per pass; needs all four
+                                                stages and the closed-form warm step in every stage, i.e. the default flags;
+                                                results are bit-identical to schedule 2) */
 #define SEQIK_FLAG_SCHED_MASK (0xFu << SEQIK_FLAG_SCHED_SHIFT)
 #define SEQIK_FLAG_GATE_SHIFT 21             /* bits 21..24: period (1..15 loop iterations) of the open/close phases of schedule 2, 0 = automatic.
                                                 Scheduling only: results do not depend on it */
@@ -73,7 +76,8 @@ extern "C" {
                                                 of the full layout repeat the input origin and row 4 repeats row 5; leaving them out
                                                 cuts the result from 136 to 76 bytes per leg-frame, which is what an end-to-end
                                                 call over PCIe is bound by */
-#define SEQIK_FLAG_CPW_SHIFT 12              /* bits 12..17: chains per warp of schedule 2 (1..8), 0 = automatic */
+#define SEQIK_FLAG_CPW_SHIFT 12              /* bits 12..17: chains per warp of schedule 2 (1..8) / resident warps per SM of schedule 3
+                                                (1..32), 0 = automatic */
 
 int seqik_abi_version(void);
 const char* seqik_last_error(void);

@@ -22,7 +22,7 @@ FLAG_CLOSED_FORM = 1 << 7
 FLAG_DEFAULT = 0xFF                     # SEQIK_FLAG_DEFAULT: the above + Newton steps + closed-form warm step
 FLAG_FK_JOINTS = 1 << 20
 FLAG_SCHED_SHIFT = 8
-SCHED_AUTO, SCHED_LANE_PER_CHAIN, SCHED_STAGE_PIPELINE = 0, 1, 2
+SCHED_AUTO, SCHED_LANE_PER_CHAIN, SCHED_STAGE_PIPELINE, SCHED_FRAME_BLOCKS = 0, 1, 2, 3
 
 _lib = None
 

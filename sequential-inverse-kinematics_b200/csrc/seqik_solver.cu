@@ -25,6 +25,8 @@
 #include "../../include/seqik.h"
 #include "seqik_common.h"
 #include "seqik_core.cuh"
+#include "seqik_block.cuh"
+#include "seqik_tma.cuh"
 
 using namespace seqik;
 
@@ -295,6 +297,380 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, 
 }
 
 // ---------------------------------------------------------------------------------------------
+// schedule 3: frame-parallel blocks -- one warp per chain, 32 consecutive frames per pass (lane = frame)
+// ---------------------------------------------------------------------------------------------
+// The algorithm and why its results are bit-identical to schedule 2 are described in seqik_block.cuh.  Per warp:
+//   * the 32 x 60 B of key points of the NEXT block arrive by one bulk copy (cp.async.bulk -> mbarrier) while the current
+//     block is solved; angles (32 x 28 B) and forward kinematics (32 x 108 B) are staged in shared memory and leave by two
+//     bulk stores: every byte of the chain crosses the memory system once, in 128-byte lines (BASELINE.json north_star 2);
+//   * pass / accumulate / verify / replay loop over the block; a block without a replay costs ~1 100 warp instructions
+//     for 32 leg-frames, a replay one serial frame (StageSolve) and a recomputation of the lanes after it.
+// A CTA is one warp (no block-level barrier); the launch shapes the number of resident warps per SM with dynamic shared
+// memory so that the chains of a batch run in whole waves (seqik_leg_solve_f32).
+constexpr int BLK = 32;
+enum : int { KC_L, KC_LB0, KC_UB0, KC_LB1S, KC_UB1S, KC_SL0, KC_CL0, KC_SU0, KC_CU0, KC_LB0P, KC_UB0P, KC_NSQ, KC_LB1, KC_UB1, KC_N = 16 };
+struct BlockShared {
+    float pose[2][BLK * 15];           // key points of the current / next block (bulk-copy destination)
+    float out_ang[BLK * 7];            // staged results (bulk-store source)
+    float out_fk[BLK * 27];
+    float2 acc_vk[7][BLK + 1];         // per angle series and frame: (v, k) of x <- k x + v   (+1: bank padding)
+    float acc_x[7][BLK + 1];           // [l][t]: placed angle BEFORE frame t of series l; [l][t + 1] after it
+    float kc[4][KC_N];                 // per-stage constants of the chain
+    float P[4][4];                     // sin/cos (sa, ca, sb, cb) per stage of the state before the first lane of a pass
+    uint64_t bar[2];
+};
+
+template <int kFk>                     // 0: no forward kinematics, 1: nine rows, 2: the four joint rows only
+__global__ void __launch_bounds__(BLK) leg_solve_block_kernel(LegArgs a, int bulk_in, int bulk_out) {
+    __shared__ __align__(128) BlockShared sh;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x;
+    const int64_t c = blockIdx.x;
+    const float* prm = a.params + c * SEQIK_CHAIN_PARAM_FLOATS;
+    const float* pose = a.pose + c * a.pose_cs;
+    float* ang = a.angles + c * a.ang_cs;
+    float* fk = kFk ? a.fk + c * a.fk_cs : nullptr;
+    constexpr int FKF = kFk == 1 ? 27 : 12;                        // floats per leg-frame of the fk layout
+    const int n_frame = (int)a.n_frame;
+    const float inf = Num<float>::inf();
+    const float half_pi = 1.57079632679489661923f;
+    LoadMap map; map.init(a.affine, c);
+    const bool esc = (a.gn_mask >> 4) & 1;
+    const bool warm_given = a.warm != nullptr;
+    const bool cf_all = (a.gn_mask & 0x8F) == 0x8F;                // closed-form warm step enabled in all four stages
+
+    if (lane < 4) {                                                // per-(chain, stage) constants
+        const int s = lane, ia = 2 * s, ib = (s == 3) ? 6 : 2 * s + 1;
+        const float shift = (s == 0) ? half_pi : 0.f;
+        const float lb0 = (s == 3) ? -inf : __ldg(prm + 4 + ia), ub0 = (s == 3) ? inf : __ldg(prm + 11 + ia);
+        const float lb1 = __ldg(prm + 4 + ib), ub1 = __ldg(prm + 11 + ib);
+        float* K = sh.kc[s];
+        K[KC_L] = __ldg(prm + s); K[KC_LB0] = lb0; K[KC_UB0] = ub0; K[KC_LB1S] = lb1 - shift; K[KC_UB1S] = ub1 - shift;
+        K[KC_LB1] = lb1; K[KC_UB1] = ub1; K[KC_NSQ] = __ldg(prm + 25 + s);
+        float sl = 0.f, cl = 0.f, su = 0.f, cu = 0.f, v_;
+        if (lb0 > -inf && ub0 < inf) { Num<float>::sincosv_(lb0, &sl, &cl, &v_); Num<float>::sincosv_(ub0, &su, &cu, &v_); }
+        K[KC_SL0] = sl; K[KC_CL0] = cl; K[KC_SU0] = su; K[KC_CU0] = cu;           // all zero: no limit case (warm_guess says interior)
+        K[KC_LB0P] = place1(lb0, lb0, ub0); K[KC_UB0P] = place1(ub0, lb0, ub0);
+    }
+    if (lane == 0) {
+        mbar_init(&sh.bar[0], 1); mbar_init(&sh.bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp(full);
+    // angle series: lanes 0..2 carry the first angle of stages 1..3, lanes 3..6 the second angle of stages 1..4
+    const bool is_ser = lane < 7, is_a = lane < 3;
+    const int sl_ = is_a ? lane : (is_ser ? lane - 3 : 0);
+    const float ser_lb = sh.kc[sl_][is_a ? KC_LB0 : KC_LB1S], ser_ub = sh.kc[sl_][is_a ? KC_UB0 : KC_UB1S];
+    const float ser_shift = (lane == 3) ? half_pi : 0.f;
+    float xcar = 0.f;                                              // carried angle of this lane's series, caller's terms
+    {
+        const float* seed = warm_given ? a.warm + c * a.warm_cs : prm + 18;
+        if (is_ser) xcar = seed[is_a ? 2 * sl_ : (sl_ == 3 ? 6 : 2 * sl_ + 1)];
+    }
+    uint32_t nf[4] = {0u, 0u, 0u, 0u}; int worst = ST_GTOL;
+    const int n_blk = (n_frame + BLK - 1) / BLK;
+    auto frames_of = [&](int b) { const int r = n_frame - b * BLK; return r < BLK ? r : BLK; };
+    auto bulk_load_ok = [&](int b) { return bulk_in && (frames_of(b) & 3) == 0; };
+    auto issue_load = [&](int b) {                                 // lane 0
+        const uint32_t bytes = (uint32_t)frames_of(b) * 60u;
+        mbar_expect_tx(&sh.bar[b & 1], bytes);
+        tma_load_1d(sh.pose[b & 1], pose + (int64_t)b * (BLK * 15), bytes, &sh.bar[b & 1]);
+    };
+    if (lane == 0 && bulk_load_ok(0)) issue_load(0);
+
+    for (int b = 0; b < n_blk; ++b) {
+        const int cur = b & 1, nv = frames_of(b), t_abs0 = b * BLK;
+        const float* kp = sh.pose[cur] + lane * 15;
+        if (bulk_load_ok(b)) mbar_wait(&sh.bar[cur], (uint32_t)(b >> 1) & 1u);
+        else {
+            const float* src = pose + (int64_t)t_abs0 * a.pose_fs;
+            for (int i = lane; i < nv * 15; i += BLK) sh.pose[cur][i] = __ldg(src + (int64_t)(i / 15) * a.pose_fs + i % 15);
+        }
+        __syncwarp(full);
+        if (lane == 0 && b + 1 < n_blk && bulk_load_ok(b + 1)) issue_load(b + 1);
+        // ---- entry: the carried angles re-enter like set_iterate + place; their sin/cos are re-derived (SEQIK_RESYNC = 32)
+        if (is_ser) {
+            const float x = place1(xcar - ser_shift, ser_lb, ser_ub);
+            float es, ec, v_;
+            Num<float>::sincosv_(x, &es, &ec, &v_);
+            sh.acc_x[lane][0] = x;
+            if (is_a) { sh.P[sl_][0] = es; sh.P[sl_][1] = ec; } else { sh.P[sl_][2] = es; sh.P[sl_][3] = ec; }
+            if (lane == 6) { sh.P[3][0] = 0.f; sh.P[3][1] = 1.f; }            // one-variable stage: first angle fixed at 0
+        }
+        __syncwarp(full);
+        bool staged = false;
+        int j0 = 0;
+        for (;;) {
+            const bool act = lane >= j0 && lane < nv;
+            // ================= pass =================
+            float Tsa[4], Tca[4], Tsb[4], Tcb[4];                  // this lane's final sin/cos per stage (speculated)
+            float dA[4], dB[4], dB2[4]; uint32_t bits = 0u;        // per stage: bit 0 small_a, 1 small_b, 2 small_b2, 3 cond, 4 lim ok_q, 5-6 guess
+            Vec3<float> jw[4];
+            const Vec3<float> o = map.apply({kp[0], kp[1], kp[2]}, 0);
+            {
+                Mat3<float> A = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
+                Vec3<float> piv = {0.f, 0.f, 0.f};
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const bool xy = s == 0, one_var = s == 3;
+                    const float* K = sh.kc[s];
+                    const float L = K[KC_L];
+                    const float Psa = sh.P[s][0], Pca = sh.P[s][1], Psb = sh.P[s][2], Pcb = sh.P[s][3];
+                    const float sgn = (Psb < 0.f) ? -1.f : 1.f;
+                    const Vec3<float> kt = map.apply({kp[3 * s + 3], kp[3 * s + 4], kp[3 * s + 5]}, s + 1);
+                    const Vec3<float> rel = {(kt.x - o.x) - piv.x, (kt.y - o.y) - piv.y, (kt.z - o.z) - piv.z};
+                    const Vec3<float> q3 = mulT(A, rel);
+                    const Vec3<float> q = xy ? Vec3<float>{-q3.z, q3.y, q3.x} : q3;
+                    const WarmCand<float> cd = warm_interior(q, L, one_var, sgn, Psa, Pca);
+                    int g = WC_INTERIOR;
+                    if (!one_var) g = warm_guess(cd.n_sa, cd.n_ca, K[KC_SL0], K[KC_CL0], K[KC_SU0], K[KC_CU0]);
+                    float tsa = cd.n_sa, tca = cd.n_ca, tsb = cd.n_sb, tcb = cd.n_cb;
+                    Vec3<float> f = cd.f;
+                    bool limq = false;
+                    const bool any_lim = !one_var && __any_sync(full, act && g != WC_INTERIOR);
+                    if (any_lim && g != WC_INTERIOR) {             // (warp-uniform outer test: the block is skipped when no lane needs it)
+                        const bool lo = g == WC_LO;
+                        tsa = lo ? K[KC_SL0] : K[KC_SU0]; tca = lo ? K[KC_CL0] : K[KC_CU0];
+                        const WarmLimit<float> lc = warm_limit(q, L, lo, tsa, tca, sgn);
+                        tsb = lc.c_sb; tcb = lc.c_cb; f = lc.f; limq = lc.ok_q;
+                    }
+                    Tsa[s] = tsa; Tca[s] = tca; Tsb[s] = tsb; Tcb[s] = tcb;
+                    // the previous lane's state (the first lane of the pass: the state the pass starts from)
+                    float psa = __shfl_up_sync(full, tsa, 1), pca = __shfl_up_sync(full, tca, 1);
+                    float psb = __shfl_up_sync(full, tsb, 1), pcb = __shfl_up_sync(full, tcb, 1);
+                    if (lane == j0) { psa = Psa; pca = Pca; psb = Psb; pcb = Pcb; }
+                    const WarmMove<float> mv = warm_move(cd.n_sa, cd.n_ca, cd.n_sb, cd.n_cb, psa, pca, psb, pcb);
+                    float d2 = 0.f; bool sm2 = false;
+                    if (any_lim && g != WC_INTERIOR) warm_limit_move(tsb, tcb, psb, pcb, d2, sm2);
+                    dA[s] = mv.dA; dB[s] = mv.dB; dB2[s] = d2;
+                    bits |= ((mv.small_a ? 1u : 0u) | (mv.small_b ? 2u : 0u) | (sm2 ? 4u : 0u) | (cd.cond ? 8u : 0u) | (limq ? 16u : 0u)
+                             | ((uint32_t)g << 5)) << (8 * s);
+                    if (act) {
+                        const bool lim = g != WC_INTERIOR;
+                        if (!one_var) sh.acc_vk[s][lane] = make_float2(lim ? (g == WC_LO ? K[KC_LB0P] : K[KC_UB0P]) : mv.dA, lim ? 0.f : 1.f);
+                        sh.acc_vk[3 + s][lane] = make_float2(lim ? d2 : mv.dB, 1.f);
+                    }
+                    // end point, joint position, frame of the next stage
+                    const Vec3<float> res = xy ? Vec3<float>{f.z, f.y, -f.x} : f;
+                    const Vec3<float> Af = mul(A, res);
+                    const Vec3<float> np_ = {(piv.x + rel.x) + Af.x, (piv.y + rel.y) + Af.y, (piv.z + rel.z) + Af.z};
+                    jw[s] = {np_.x + o.x, np_.y + o.y, np_.z + o.z};
+                    if (s < 3) {
+                        A = rotate_frame(A, xy ? KIND_XY : KIND_ZY, tsa, tca, xy ? tcb : tsb, xy ? -tsb : tcb);
+                        piv = np_;
+                    }
+                }
+            }
+            __syncwarp(full);
+            // ================= accumulate (frame order, one series per lane) =================
+            if (is_ser) {
+                float x = sh.acc_x[lane][j0];
+#pragma unroll 4
+                for (int t = j0; t < nv; ++t) {
+                    const float2 vk = sh.acc_vk[lane][t];
+                    x = fmaf(vk.y, x, vk.x);
+                    sh.acc_x[lane][t + 1] = x;
+                }
+            }
+            __syncwarp(full);
+            // ================= verify =================
+            float ox0[4], ox1[4];
+            bool pass_ok = true;
+            {
+                const bool enable_t = cf_all && (t_abs0 + lane > 0 || warm_given);
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const float* K = sh.kc[s];
+                    const uint32_t bs = bits >> (8 * s);
+                    const int g = (int)((bs >> 5) & 3u);
+                    const float xp0 = (s < 3) ? sh.acc_x[s < 3 ? s : 0][lane] : 0.f, xp1 = sh.acc_x[3 + s][lane];
+                    WarmMove<float> mv; mv.dA = dA[s]; mv.dB = dB[s]; mv.small_a = bs & 1u; mv.small_b = bs & 2u;
+                    const int wc = warm_case(enable_t, s < 3 && K[KC_CL0] * K[KC_CL0] + K[KC_SL0] * K[KC_SL0] > 0.f, s == 3, xp0, xp1, mv,
+                                             (bs & 8u) != 0u, K[KC_LB0], K[KC_UB0], K[KC_LB1S], K[KC_UB1S], g, dB2[s], (bs & 4u) != 0u,
+                                             (bs & 16u) != 0u, ox0[s], ox1[s]);
+                    pass_ok = pass_ok && wc == g;
+                }
+            }
+            const unsigned failed = __ballot_sync(full, act && !pass_ok);
+            const int j = failed ? __ffs((int)failed) - 1 : nv;              // first lane whose speculation does not hold
+            // ================= commit lanes j0 .. j-1 =================
+            if (!staged) {                                                     // the previous block's bulk stores have read the staging area
+                if (lane == 0) tma_store_wait_read<0>();
+                __syncwarp(full);
+                staged = true;
+            }
+            if (act && lane < j) {
+                float* oa = sh.out_ang + lane * 7;
+                oa[0] = ox0[0]; oa[1] = ox1[0] + half_pi; oa[2] = ox0[1]; oa[3] = ox1[1]; oa[4] = ox0[2]; oa[5] = ox1[2]; oa[6] = ox1[3];
+                nf[0] += 1u; nf[1] += 1u; nf[2] += 1u; nf[3] += 1u;
+                if (kFk == 1) {
+                    float* of = sh.out_fk + lane * 27;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) { of[3 * r] = o.x; of[3 * r + 1] = o.y; of[3 * r + 2] = o.z; }
+                    of[12] = jw[0].x; of[13] = jw[0].y; of[14] = jw[0].z;
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) { of[15 + 3 * s] = jw[s].x; of[16 + 3 * s] = jw[s].y; of[17 + 3 * s] = jw[s].z; }
+                } else if (kFk == 2) {
+                    float* of = sh.out_fk + lane * 12;
+#pragma unroll
+                    for (int s = 0; s < 4; ++s) { of[3 * s] = jw[s].x; of[3 * s + 1] = jw[s].y; of[3 * s + 2] = jw[s].z; }
+                }
+            }
+            if (j >= nv) break;
+            // ================= replay lane j through the serial solver (the frame body of hostsim run_carried) =================
+            // state before frame j: the previous lane's (or the pass's starting state), angles from the accumulated series
+            float qsa[4], qca[4], qsb[4], qcb[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                qsa[s] = __shfl_sync(full, Tsa[s], (j + 31) & 31); qca[s] = __shfl_sync(full, Tca[s], (j + 31) & 31);
+                qsb[s] = __shfl_sync(full, Tsb[s], (j + 31) & 31); qcb[s] = __shfl_sync(full, Tcb[s], (j + 31) & 31);
+                if (j == j0) { qsa[s] = sh.P[s][0]; qca[s] = sh.P[s][1]; qsb[s] = sh.P[s][2]; qcb[s] = sh.P[s][3]; }
+            }
+            if (lane == j) {
+                Mat3<float> A = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
+                Vec3<float> piv = {0.f, 0.f, 0.f};
+                float* oa = sh.out_ang + lane * 7;
+                float* of = sh.out_fk + lane * FKF;
+                const bool warm_ok = t_abs0 + lane > 0 || warm_given;
+#pragma unroll 1
+                for (int s = 0; s < 4; ++s) {
+                    const float* K = sh.kc[s];
+                    StageSolve<float> S;
+                    S.set_problem(s == 0 ? KIND_XY : KIND_ZY, K[KC_L], s == 3 ? 0.f : 1.f, K[KC_NSQ], (s == 0) ? 4 : (s == 1) ? 6 : (s == 2) ? 8 : 9,
+                                  stage_mode(a.gn_mask, s));
+                    S.sl0 = K[KC_SL0]; S.cl0 = K[KC_CL0]; S.su0 = K[KC_SU0]; S.cu0 = K[KC_CU0];
+                    S.have_bt = K[KC_LB0] > -inf && K[KC_UB0] < inf;
+                    S.x0 = (s < 3) ? sh.acc_x[s < 3 ? s : 0][lane] : 0.f; S.x1 = sh.acc_x[3 + s][lane];
+                    S.sa = (s == 0) ? qsa[0] : (s == 1) ? qsa[1] : (s == 2) ? qsa[2] : qsa[3];
+                    S.ca = (s == 0) ? qca[0] : (s == 1) ? qca[1] : (s == 2) ? qca[2] : qca[3];
+                    S.sb = (s == 0) ? qsb[0] : (s == 1) ? qsb[1] : (s == 2) ? qsb[2] : qsb[3];
+                    S.cb = (s == 0) ? qcb[0] : (s == 1) ? qcb[1] : (s == 2) ? qcb[2] : qcb[3];
+                    const Vec3<float> kt = map.apply({kp[3 * s + 3], kp[3 * s + 4], kp[3 * s + 5]}, s + 1);
+                    const Vec3<float> rel = {(kt.x - o.x) - piv.x, (kt.y - o.y) - piv.y, (kt.z - o.z) - piv.z};
+                    const Vec3<float> q3 = mulT(A, rel);
+                    S.restart(q3, K[KC_LB0], K[KC_UB0], K[KC_LB1], K[KC_UB1], false, warm_ok);
+                    for (;;) {
+                        while (!S.done()) S.trip();
+                        if (!(esc && S.escape())) break;
+                    }
+                    const float xa = S.x0, xb = S.angle_b();
+                    if (s == 0) { oa[0] = xa; oa[1] = xb; nf[0] += (uint32_t)S.nfev; }
+                    else if (s == 1) { oa[2] = xa; oa[3] = xb; nf[1] += (uint32_t)S.nfev; }
+                    else if (s == 2) { oa[4] = xa; oa[5] = xb; nf[2] += (uint32_t)S.nfev; }
+                    else { oa[6] = xb; nf[3] += (uint32_t)S.nfev; }
+                    worst = (S.status == ST_MAXFEV && worst > ST_MAXFEV) ? ST_MAXFEV : worst;
+                    worst = (S.status == ST_NONFINITE) ? ST_NONFINITE : worst;
+                    const Vec3<float> Af = mul(A, S.res());
+                    const Vec3<float> np_ = {(piv.x + rel.x) + Af.x, (piv.y + rel.y) + Af.y, (piv.z + rel.z) + Af.z};
+                    const Vec3<float> w = {np_.x + o.x, np_.y + o.y, np_.z + o.z};
+                    if (kFk == 1) {
+                        of[3 * s] = o.x; of[3 * s + 1] = o.y; of[3 * s + 2] = o.z;
+                        of[15 + 3 * s] = w.x; of[16 + 3 * s] = w.y; of[17 + 3 * s] = w.z;
+                        if (s == 0) { of[12] = w.x; of[13] = w.y; of[14] = w.z; }
+                    } else if (kFk == 2) { of[3 * s] = w.x; of[3 * s + 1] = w.y; of[3 * s + 2] = w.z; }
+                    A = rotate_frame_sel(A, s == 0 ? KIND_XY : KIND_ZY, S.sa, S.ca, S.sin_b(), S.cos_b());
+                    piv = np_;
+                    // hand the final state on: the next pass starts from it
+                    sh.P[s][0] = S.sa; sh.P[s][1] = S.ca; sh.P[s][2] = S.sb; sh.P[s][3] = S.cb;
+                    if (s < 3) sh.acc_x[s < 3 ? s : 0][lane + 1] = place1(S.x0, K[KC_LB0], K[KC_UB0]);
+                    sh.acc_x[3 + s][lane + 1] = place1(S.x1, K[KC_LB1S], K[KC_UB1S]);
+                }
+            }
+            __syncwarp(full);
+            j0 = j + 1;
+            if (j0 >= nv) break;
+        }
+        // ---- carry the angles to the next block in the caller's terms (xa = x0, xb = x1 + shift)
+        __syncwarp(full);
+        if (is_ser) xcar = sh.acc_x[lane][nv] + ser_shift;
+        // ---- results of the block leave: two bulk stores (or plain coalesced stores when sizes / addresses do not allow them)
+        const bool bulk_store = bulk_out && (nv & 3) == 0;
+        if (bulk_store) {
+            fence_async_smem();
+            __syncwarp(full);
+            if (lane == 0) {
+                tma_store_1d_nocommit(ang + (int64_t)t_abs0 * 7, sh.out_ang, (uint32_t)nv * 28u);
+                if (kFk) tma_store_1d_nocommit(fk + (int64_t)t_abs0 * FKF, sh.out_fk, (uint32_t)nv * (FKF * 4u));
+                tma_commit();
+            }
+        } else {
+            __syncwarp(full);
+            float* da = ang + (int64_t)t_abs0 * a.ang_fs;
+            for (int i = lane; i < nv * 7; i += BLK) da[(int64_t)(i / 7) * a.ang_fs + i % 7] = sh.out_ang[i];
+            if (kFk) {
+                float* df = fk + (int64_t)t_abs0 * a.fk_fs;
+                for (int i = lane; i < nv * FKF; i += BLK) df[(int64_t)(i / FKF) * a.fk_fs + i % FKF] = sh.out_fk[i];
+            }
+            __syncwarp(full);
+        }
+    }
+    if (lane == 0) tma_store_wait_read<0>();
+    // per-chain statistics
+#pragma unroll
+    for (int s = 0; s < 4; ++s) nf[s] = __reduce_add_sync(full, nf[s]);
+    const int w_all = __reduce_min_sync(full, worst);
+    if (lane == 0) {
+        if (a.nfev) { uint32_t* p = a.nfev + c * 4; p[0] = nf[0]; p[1] = nf[1]; p[2] = nf[2]; p[3] = nf[3]; }
+        if (a.status) a.status[c] = w_all == ST_NONFINITE ? -1 : w_all;
+    }
+}
+
+// Launch of schedule 3.  One CTA (= one warp) per chain; the hardware block scheduler deals chains to SMs as warps
+// retire.  Chains cost about the same, so the batch runs in "waves" of (resident warps per SM) x (SMs) chains and the
+// time is ~ ceil(n_chain / (R n_sm)) * R: R is chosen to minimise that (a last wave that is nearly empty costs a full
+// wave's latency; config 4's 7 500-chain shard: R = 13 -> 4 full waves instead of 3.2 at R = 16) and imposed through the
+// dynamic shared memory size.  `forced` (1..32): tuning / tests.
+template <int kFk>
+static int launch_block_kernel(const LegArgs& a, int bulk_in, int bulk_out, int forced, cudaStream_t st) {
+    static thread_local int cached_dev = -1;
+    static thread_local int n_sm = 148, r_max = 16, static_smem = 0, smem_sm = 227 * 1024;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != cached_dev) {
+        cudaFuncAttributes at;
+        if (cudaFuncGetAttributes(&at, leg_solve_block_kernel<kFk>) != cudaSuccess) return seqik_check_launch("seqik_leg_solve_f32 (attributes)");
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+        cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+        static_smem = (int)at.sharedSizeBytes;
+        int regs_sm = 65536;
+        cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
+        const int by_regs = regs_sm / (((at.numRegs + 7) / 8 * 8) * BLK);            // registers are allocated per warp in units of 256
+        const int by_smem = smem_sm / (static_smem + 1024);                            // 1 KB per CTA is reserved by the system
+        r_max = by_regs < by_smem ? by_regs : by_smem;
+        if (r_max > 32) r_max = 32;                                                    // CTAs per SM
+        if (r_max < 1) r_max = 1;
+        cudaFuncSetAttribute(leg_solve_block_kernel<kFk>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sm - static_smem - 1024);
+        cudaFuncSetAttribute(leg_solve_block_kernel<kFk>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cached_dev = dev;
+    }
+    int r = r_max;
+    if (forced) r = forced < r_max ? forced : r_max;
+    else {
+        const int r_min = r_max * 5 / 8 > 1 ? r_max * 5 / 8 : 1;                      // fewer resident warps hide less latency
+        int64_t best = -1;
+        for (int k = r_max; k >= r_min; --k) {
+            const int64_t waves = (a.n_chain + (int64_t)k * n_sm - 1) / ((int64_t)k * n_sm);
+            const int64_t cost = waves * k;
+            if (best < 0 || cost < best) { best = cost; r = k; }
+        }
+    }
+    // shared memory per CTA such that exactly r CTAs fit one SM
+    int dyn = smem_sm / r - 1024 - static_smem;
+    dyn = dyn < 0 ? 0 : dyn & ~127;
+    if (r == r_max && !forced) dyn = 0;
+    leg_solve_block_kernel<kFk><<<(unsigned)a.n_chain, BLK, (size_t)dyn, st>>>(a, bulk_in, bulk_out);
+    return SEQIK_OK;
+}
+static int launch_block_schedule(const LegArgs& a, bool want_fk, bool fk_joints, int forced, cudaStream_t st) {
+    const int fkf = fk_joints ? 12 : 27;
+    const bool al_in = (((uintptr_t)a.pose) & 15) == 0 && (a.pose_cs & 3) == 0 && a.pose_fs == 15;
+    const bool al_out = (((uintptr_t)a.angles) & 15) == 0 && (a.ang_cs & 3) == 0 && a.ang_fs == 7
+                        && (!want_fk || ((((uintptr_t)a.fk) & 15) == 0 && (a.fk_cs & 3) == 0 && a.fk_fs == fkf));
+    if (!want_fk) return launch_block_kernel<0>(a, al_in, al_out, forced, st);
+    return fk_joints ? launch_block_kernel<2>(a, al_in, al_out, forced, st) : launch_block_kernel<1>(a, al_in, al_out, forced, st);
+}
+
+// ---------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------
 extern "C" int seqik_leg_solve_f32(const float* pose, int64_t pose_chain_stride, int64_t pose_frame_stride,
@@ -318,9 +694,13 @@ extern "C" int seqik_leg_solve_f32(const float* pose, int64_t pose_chain_stride,
         return seqik_fail(SEQIK_EINVAL, "seqik_leg_solve_f32: frame stride smaller than the innermost block");
     if (n_frame > 2147483647LL) return seqik_fail(SEQIK_EINVAL, "seqik_leg_solve_f32: too many frames");
     uint32_t sched = (flags & SEQIK_FLAG_SCHED_MASK) >> SEQIK_FLAG_SCHED_SHIFT;
-    if (sched > 2) return seqik_fail(SEQIK_EINVAL, "seqik_leg_solve_f32: unknown schedule");
-    // automatic: the stage pipeline (measured faster than one lane per chain from 600 to 60 000 chains)
-    if (sched == 0) sched = 2;
+    if (sched > 3) return seqik_fail(SEQIK_EINVAL, "seqik_leg_solve_f32: unknown schedule");
+    // automatic: frame-parallel blocks when every stage is solved with the closed-form warm step (the default flags) --
+    // the schedule speculates on it; otherwise the stage pipeline (faster than one lane per chain at every size)
+    const bool block_ok = stage_mask == 0xF && (flags & 0x8Fu) == 0x8Fu;
+    if (sched == 3 && !block_ok)
+        return seqik_fail(SEQIK_EINVAL, "seqik_leg_solve_f32: schedule 3 needs all four stages and SEQIK_FLAG_CLOSED_FORM with Gauss-Newton mode in every stage");
+    if (sched == 0) sched = block_ok ? 3 : 2;
     LegArgs a;
     a.pose = pose; a.pose_cs = pose_chain_stride; a.pose_fs = pose_frame_stride;
     a.affine = affine; a.params = params;
@@ -330,7 +710,11 @@ extern "C" int seqik_leg_solve_f32(const float* pose, int64_t pose_chain_stride,
     a.status = status; a.nfev = nfev; a.n_chain = n_chain; a.n_frame = n_frame;
     a.fk_joints = fk_joints ? 1 : 0;
     a.stage_mask = (int)stage_mask; a.gn_mask = (int)(flags & 0xFF);   // bits 0-3 Gauss-Newton mode per stage, 4 escape, 5 skip-confirm, 6 Newton, 7 closed-form warm step
-    if (sched == 1) {
+    if (sched == 3) {
+        if (n_chain > 2147483647LL) return seqik_fail(SEQIK_EINVAL, "seqik_leg_solve_f32: too many chains");
+        const int rc = launch_block_schedule(a, fk != nullptr, fk_joints, (flags >> SEQIK_FLAG_CPW_SHIFT) & 0x3F, (cudaStream_t)stream);
+        if (rc != SEQIK_OK) return rc;
+    } else if (sched == 1) {
         const int64_t grid = (n_chain + 31) / 32;
         leg_solve_lane_kernel<<<(unsigned)grid, 32, 0, (cudaStream_t)stream>>>(a);
     } else {

@@ -18,7 +18,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    deps = [SRC, CSRC / "seqik_core.cuh", CSRC / "seqik_generic.cuh"]
+    deps = [SRC, CSRC / "seqik_core.cuh", CSRC / "seqik_generic.cuh", CSRC / "seqik_block.cuh"]
     if not OUT.exists() or any(d.stat().st_mtime > OUT.stat().st_mtime for d in deps):
         # -ffp-contract=off: no FMA contraction, so the f64 build tracks the Python model closely
         cmd = ["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-std=c++17", "-x", "c++", str(SRC),
@@ -83,6 +83,28 @@ def run_carried_f32(pose, prm, gn_mask=0xFF):
     fn.restype = None
     fn(pose.ctypes.data, n, prm.ctypes.data, angles.ctypes.data, fk.ctypes.data, nfev.ctypes.data, gn_mask)
     return angles, fk, nfev
+
+
+def run_block_f32(pose, prm, gn_mask=0xFF, warm=None):
+    """The frame-parallel block schedule (csrc/seqik_block.cuh; leg_solve_block_kernel) emulated lane by lane on the host
+    build: pose (N,5,3), prm (32,) -> angles (N,7), fk (N,9,3), nfev (N,4), stats (blocks, passes, serial frames, of which
+    first frames, of which not admitted).  Must equal run_carried_f32 bit for bit."""
+    lib = load()
+    pose = np.ascontiguousarray(pose, dtype=np.float32)
+    prm = np.ascontiguousarray(prm, dtype=np.float32)
+    n = pose.shape[0]
+    angles = np.zeros((n, 7), dtype=np.float32)
+    fk = np.zeros((n, 9, 3), dtype=np.float32)
+    nfev = np.zeros((n, 4), dtype=np.int32)
+    stats = np.zeros(8, dtype=np.int64)
+    w = None if warm is None else np.ascontiguousarray(warm, dtype=np.float32)
+    P = ctypes.c_void_p
+    fn = lib.hostsim_block_f32
+    fn.argtypes = [P, ctypes.c_int64, P, P, P, P, P, ctypes.c_int, P]
+    fn.restype = None
+    fn(pose.ctypes.data, n, prm.ctypes.data, None if w is None else w.ctypes.data, angles.ctypes.data, fk.ctypes.data,
+       nfev.ctypes.data, gn_mask, stats.ctypes.data)
+    return angles, fk, nfev, stats
 
 
 def solve_generic(pose2, prm, teacher=None, dtype=np.float32, want_fk=True):

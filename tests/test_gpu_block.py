@@ -1,0 +1,130 @@
+"""Schedule 3 (frame-parallel blocks: a warp per chain, 32 frames per pass, csrc/seqik_block.cuh) against schedule 2 (the
+stage pipeline): the two run the same per-frame arithmetic, so every output must agree BIT FOR BIT -- on the synthetic
+workload, on the bundled grooming trial (iterating solves, pitch angles parked on their limits, the singular episodes), with
+ragged frame counts, warm-started frame ranges, the alignment map applied on load, every FK layout and NaN key points."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+    from seqikpy_b200 import _native as N, data as D, engine, synthetic as S
+    from seqikpy_b200.batch import chain_param_table
+    from seqikpy_b200.kinematic_chain import KinematicChainSeq
+    N.load_library()
+    size, bounds, init = S.chain_constants()
+    chain = KinematicChainSeq(bounds, list(S.LEGS), size)
+
+    class E:
+        pass
+    e = E()
+    e.torch, e.N, e.D, e.engine, e.S = torch, N, D, engine, S
+    e.pose = S.to_chains(torch.from_numpy(S.make_trials(range(8), 1000)).cuda())            # 48 chains x 1000 frames
+    e.params = torch.from_numpy(chain_param_table(chain, init, S.LEGS, 8)).cuda()
+    return e
+
+
+def both(env, pose, params, **kw):
+    out = []
+    for sched in (2, 3):
+        ang, fk, st, nf = env.engine.leg_solve(pose, params, schedule=sched, **kw)
+        env.torch.cuda.synchronize()
+        out.append((ang.cpu().numpy(), None if fk is None else fk.cpu().numpy(), st.cpu().numpy(), nf.cpu().numpy()))
+    return out
+
+
+def assert_same(a, b):
+    for x, y, name in zip(a, b, ("angles", "fk", "status", "nfev")):
+        if x is None:
+            assert y is None
+            continue
+        assert x.shape == y.shape, name
+        bad = np.argwhere(x != y)
+        assert len(bad) == 0, (name, len(bad), bad[:5])
+
+
+def test_block_schedule_is_the_default(env):
+    """Automatic schedule = 3 for the default flags and all stages; 2 where schedule 3 does not apply."""
+    pose = env.pose[:6, :96].contiguous()
+    a0, f0, _, _ = env.engine.leg_solve(pose, env.params[:6])
+    a3, f3, _, _ = env.engine.leg_solve(pose, env.params[:6], schedule=3)
+    assert env.torch.equal(a0, a3) and env.torch.equal(f0, f3)
+    with pytest.raises(Exception):
+        env.engine.leg_solve(pose, env.params[:6], schedule=3, flags=env.N.FLAG_REFERENCE_ITERATES)
+
+
+@pytest.mark.parametrize("n_frame", [1000, 999, 33, 32, 31, 5, 4, 1])
+def test_synthetic_bitwise(env, n_frame):
+    pose = env.pose[:, :n_frame].contiguous()
+    a, b = both(env, pose, env.params)
+    assert_same(a, b)
+    assert (a[2] == 1).all()
+
+
+@pytest.mark.parametrize("layout", ["full", "joints", None])
+def test_fk_layouts_bitwise(env, layout):
+    kw = dict(want_fk=layout is not None)
+    if layout:
+        kw["fk_layout"] = layout
+    a, b = both(env, env.pose[:12, :200].contiguous(), env.params[:12], **kw)
+    assert_same(a, b)
+
+
+def test_resident_warps_do_not_change_results(env):
+    ref = both(env, env.pose[:, :256].contiguous(), env.params)[1]
+    for r in (1, 5, 13):
+        ang, fk, st, nf = env.engine.leg_solve(env.pose[:, :256].contiguous(), env.params, schedule=3, chains_per_warp=r)
+        assert np.array_equal(ang.cpu().numpy(), ref[0]) and np.array_equal(fk.cpu().numpy(), ref[1])
+
+
+def test_warm_started_frame_ranges_bitwise(env):
+    """Frame ranges solved in place, each warm-started from the frame before it: equal to one launch on the 32-frame grid."""
+    torch = env.torch
+    one = env.engine.leg_solve(env.pose, env.params, schedule=3)
+    ang = torch.zeros_like(one[0]); fk = torch.zeros_like(one[1])
+    for t0, t1 in ((0, 128), (128, 480), (480, 1000)):
+        env.engine.leg_solve(env.pose, env.params, angles=ang, fk=fk, schedule=3, frames=(t0, t1))
+    assert torch.equal(ang, one[0]) and torch.equal(fk, one[1])
+    # an unaligned range (plain loads/stores instead of bulk copies; not on the 32-frame grid: equal to schedule 2 on the same range)
+    for sched in (2, 3):
+        a2 = one[0].clone(); f2 = one[1].clone()
+        env.engine.leg_solve(env.pose, env.params, angles=a2, fk=f2, schedule=sched, frames=(333, 777))
+        if sched == 2:
+            ra, rf = a2, f2
+    assert torch.equal(a2, ra) and torch.equal(f2, rf)
+
+
+def test_alignment_map_on_load_bitwise(env):
+    torch = env.torch
+    n = 12
+    aff = torch.tensor([[0.1, -0.2, 0.3, 1.05, 0.0, 0.0, 0.0, 0.0]], device="cuda").repeat(n, 1)
+    aff[:, 4:7] = env.pose[:n, 0, 0]                                      # template coxa = the pose's own (constant) origin
+    raw = (env.pose[:n, :300] - env.pose[:n, :1, :1]) / 1.05 + env.pose[:n, :1, :1] + 0.0
+    a, b = both(env, raw.contiguous(), env.params[:n], affine=aff)
+    assert_same(a, b)
+
+
+def test_grooming_trial_bitwise(env, grooming_leg):
+    """6000 frames x 2 legs of real data: ~3-4 % of the frames replay through the serial solver (iterating solves, pitch
+    angles parked on a limit, the CTr_pitch = 0 episodes)."""
+    from seqikpy_b200.kinematic_chain import KinematicChainSeq
+    torch = env.torch
+    chain = KinematicChainSeq(env.D.BOUNDS, ["RF", "LF"], None)
+    params = torch.from_numpy(np.stack([chain.pack_chain_params(leg, env.D.INITIAL_ANGLES[leg]) for leg in ("RF", "LF")]).astype(np.float32)).cuda()
+    pose = torch.from_numpy(np.ascontiguousarray(grooming_leg["pose"], dtype=np.float32)).cuda()
+    a, b = both(env, pose, params)
+    assert_same(a, b)
+    assert (a[3] > 6000).any()                                             # some solves did iterate
+
+
+def test_non_finite_key_points_bitwise(env):
+    pose = env.pose[:6, :100].clone()
+    pose[1, 40, 2, 1] = float("nan")
+    pose[4, 0, 1, 0] = float("inf")
+    a, b = both(env, pose, env.params[:6])
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y, equal_nan=True)
+    assert a[2][1] == -1 and a[2][4] == -1 and a[2][0] == 1

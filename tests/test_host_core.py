@@ -333,3 +333,45 @@ def test_newton_step_is_the_newton_step():
         fn(L, x.ctypes.data, q.ctypes.data, lbub.ctypes.data, 1, 200, end_g.ctypes.data)
         assert np.abs(end_n[:2] - end_g[:2]).max() < 2e-5 and end_n[3] <= end_g[3]
     assert n_newton > 150, n_newton
+
+
+def test_block_schedule_equals_the_serial_carried_solves(grooming_leg, locomotion):
+    """The frame-parallel block schedule (csrc/seqik_block.cuh: speculate the closed-form warm step for 32 frames at once,
+    accumulate the angle increments in frame order, verify warm_step's admission tests with the exact angles, replay the first
+    frame that fails through the serial solver), emulated lane by lane on the host build, gives BIT-IDENTICAL angles, forward
+    kinematics and evaluation counts to the serial carried solves -- on synthetic chains (limits active on the mid and hind
+    legs), on both legs of the grooming trial (iterating solves, pitch angles parked on a limit, the singular episodes), on
+    the locomotion recording (a fifth of its frames iterate), with ragged lengths and for a warm-started tail."""
+    from seqikpy_b200 import data as D, synthetic as S
+    from seqikpy_b200.kinematic_chain import KinematicChainSeq
+    from seqikpy_b200.utils import calculate_body_size
+
+    def same(pose, row, warm=None, carried=None):
+        a1, f1, n1 = carried if carried is not None else H.run_carried_f32(pose, row, GN)
+        a2, f2, n2, st = H.run_block_f32(pose, row, GN, warm=warm)
+        assert np.array_equal(a1, a2) and np.array_equal(f1, f2) and np.array_equal(n1, n2)
+        return (a1, f1, n1), st
+
+    size, bounds, init = S.chain_constants()
+    chain = KinematicChainSeq(bounds, list(S.LEGS), size)
+    replays = frames = 0
+    for tr in range(2):
+        pose = S.make_trial(tr, 1000)
+        for li, leg in enumerate(S.LEGS):
+            _, st = same(pose[:, li], chain.pack_chain_params(leg, init[leg]))
+            replays += int(st[2]); frames += 1000
+    assert replays < 0.01 * frames                       # the schedule's premise on the benchmark workload: < 1 % of the frames replay
+    for n in (1, 31, 32, 33, 100):
+        same(S.make_trial(5, 128)[:n, 2], chain.pack_chain_params("RH", init["RH"]))
+    chain_g = KinematicChainSeq(D.BOUNDS, ["RF", "LF"], None)
+    for li, leg in enumerate(("RF", "LF")):
+        row = chain_g.pack_chain_params(leg, D.INITIAL_ANGLES[leg])
+        (a1, f1, n1), st = same(grooming_leg["pose"][li], row)
+        assert st[2] < 0.06 * 6000
+        # a frame range warm-started from the frame before it (on the 32-frame grid) continues the recording bit for bit
+        a3, f3, n3, _ = H.run_block_f32(grooming_leg["pose"][li][3200:], row, GN, warm=a1[3199])
+        assert np.array_equal(a3, a1[3200:]) and np.array_equal(f3, f1[3200:]) and np.array_equal(n3, n1[3200:])
+    legs = list(locomotion["legs"])
+    chain_l = KinematicChainSeq(D.BOUNDS_LOCOMOTION, legs, calculate_body_size(D.TEMPLATE_NMF_LOCOMOTION, legs))
+    for i, leg in enumerate(legs):
+        same(locomotion["aligned"][i], chain_l.pack_chain_params(leg, D.INITIAL_ANGLES_LOCOMOTION[leg]))
