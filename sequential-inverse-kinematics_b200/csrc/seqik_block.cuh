@@ -37,14 +37,8 @@ template <typename R> SK_HD R place1(R x, R lb, R ub) {
     return x;
 }
 
-// asin for |s| < 0.25 (StageSolve::asin_small)
-template <typename R> SK_HD R asin_small_(R s) {
-    typedef Num<R> N;
-    const R z = s * s;
-    R p = N::fma_(z, R(0.030381944444444444), R(0.044642857142857144));
-    p = N::fma_(p, z, R(0.075)); p = N::fma_(p, z, R(0.16666666666666666));
-    return N::fma_(p * z, s, s);
-}
+template <typename R> SK_HD R asin_small_(R s) { return StageSolve<R>::asin_small(s); }
+template <typename R> SK_HD R ws_hs_max_() { return StageSolve<R>::ws_hs_max(); }
 
 // ---- warm_step(), piece 1: the interior candidate -- the point of the sphere nearest to the target q (already mapped into
 // the Rz Ry form), on the branch `sgn` of the warm start.  (sa, ca): the warm start's first-angle trigonometry, used by the
@@ -74,7 +68,7 @@ template <typename R> SK_HD WarmMove<R> warm_move(R n_sa, R n_ca, R n_sb, R n_cb
     const R sdb = N::fma_(n_sb, cb, -(n_cb * sb)), cdb = N::fma_(n_cb, cb, n_sb * sb);
     const R hsa = sda * N::rsqrt_(R(2) + R(2) * cda), hsb = sdb * N::rsqrt_(R(2) + R(2) * cdb);
     m.dA = R(2) * asin_small_(hsa); m.dB = R(2) * asin_small_(hsb);
-    m.small_a = (N::abs_(hsa) < R(0.25)) & (cda > R(0)); m.small_b = (N::abs_(hsb) < R(0.25)) & (cdb > R(0));
+    m.small_a = (N::abs_(hsa) < ws_hs_max_<R>()) & (cda > R(0)); m.small_b = (N::abs_(hsb) < ws_hs_max_<R>()) & (cdb > R(0));
     return m;
 }
 
@@ -99,7 +93,7 @@ template <typename R> SK_HD void warm_limit_move(R c_sb, R c_cb, R sb, R cb, R& 
     const R sdb2 = N::fma_(c_sb, cb, -(c_cb * sb)), cdb2 = N::fma_(c_cb, cb, c_sb * sb);
     const R hsb2 = sdb2 * N::rsqrt_(R(2) + R(2) * cdb2);
     dB2 = R(2) * asin_small_(hsb2);
-    small_b2 = (N::abs_(hsb2) < R(0.25)) & (cdb2 > R(0));
+    small_b2 = (N::abs_(hsb2) < ws_hs_max_<R>()) & (cdb2 > R(0));
 }
 
 // ---- speculation of the case from the candidate's direction alone: 1 / 2 when it lies just outside the lower / upper
@@ -109,7 +103,7 @@ template <typename R> SK_HD int warm_guess(R n_sa, R n_ca, R sl0, R cl0, R su0, 
     typedef Num<R> N;
     const R s_lo = N::fma_(n_sa, cl0, -(n_ca * sl0)), c_lo = N::fma_(n_ca, cl0, n_sa * sl0);   // sin / cos (a - lb)
     const R s_hi = N::fma_(su0, n_ca, -(cu0 * n_sa)), c_hi = N::fma_(cu0, n_ca, su0 * n_sa);   // sin / cos (ub - a)
-    const bool below = (c_lo > R(0.8)) & (s_lo <= R(1e-5)), above = (c_hi > R(0.8)) & (s_hi <= R(1e-5));
+    const bool below = (c_lo > R(0.5)) & (s_lo <= R(1e-5)), above = (c_hi > R(0.5)) & (s_hi <= R(1e-5));
     return (below == above) ? WC_INTERIOR : below ? WC_LO : WC_HI;
 }
 
@@ -133,7 +127,7 @@ SK_HD int warm_case(bool enable, bool have_bt, bool one_var, R xp0, R xp1, const
     if (guess != (lo ? WC_LO : WC_HI)) return WC_NONE;
     const R b_x0 = lo ? lb0 : ub0;
     const R cx1 = xp1 + dB2;
-    const bool ok_b = (N::abs_(b_x0 - xp0) < R(0.5)) & small_b2 & lim_ok_q & (cx1 - lb1s > m) & (ub1s - cx1 > m);
+    const bool ok_b = (N::abs_(b_x0 - xp0) < StageSolve<R>::ws_move_max()) & small_b2 & lim_ok_q & (cx1 - lb1s > m) & (ub1s - cx1 > m);
     x0 = b_x0; x1 = cx1;
     return ok_b ? (lo ? WC_LO : WC_HI) : WC_NONE;
 }

@@ -289,13 +289,18 @@ struct StageSolve {
     // (least_squares prologue without the trigonometry).  Callers pass fresh = true every SEQIK_RESYNC frames so that the
     // carried sin/cos cannot drift from the angle (float32 random walk, ~1e-6 rad over 32 frames).  One code path for
     // both, so that lanes of a warp that re-derive and lanes that carry run the same instructions but the trigonometry.
-    // asin for |s| < 0.25 (truncation < 1e-8)
+    // asin for |s| <= WS_HS_MAX (series through s^15: truncation < 3e-8 at 0.44)
     static SK_HD R asin_small(R s) {
         const R z = s * s;
-        R p = N::fma_(z, R(0.030381944444444444), R(0.044642857142857144));
+        R p = N::fma_(z, R(0.013964843750000000), R(0.017352764423076924));
+        p = N::fma_(p, z, R(0.022372159090909092)); p = N::fma_(p, z, R(0.030381944444444444));
+        p = N::fma_(p, z, R(0.044642857142857144));
         p = N::fma_(p, z, R(0.075)); p = N::fma_(p, z, R(0.16666666666666666));
         return N::fma_(p * z, s, s);
     }
+    // largest half-angle sine of a closed-form move: both rotations of a warm step stay below 2 asin(0.44) = 0.91 rad
+    static SK_HD R ws_hs_max() { return R(0.44); }
+    static SK_HD R ws_move_max() { return R(0.91); }
 
     // Optional (SEQIK_FLAG_CLOSED_FORM): the closed-form warm step.  A stage points a segment of fixed length at its
     // target: without the box, the minimiser of |w(a, b) - q|^2 is the point of the sphere |w| = L nearest to q, i.e.
@@ -326,7 +331,7 @@ struct StageSolve {
         const R m = R(1e-5);
         // (bitwise &: every test is evaluated, no short-circuit branches in this block)
         const bool in_a = (nx0 - lb0 > m) & (ub0 - nx0 > m), in_b = (nx1 - lb1 > m) & (ub1 - nx1 > m);
-        const bool small_a = (N::abs_(hsa) < R(0.25)) & (cda > R(0)), small_b = (N::abs_(hsb) < R(0.25)) & (cdb > R(0));
+        const bool small_a = (N::abs_(hsa) < ws_hs_max()) & (cda > R(0)), small_b = (N::abs_(hsb) < ws_hs_max()) & (cdb > R(0));
         const bool ok = enable & small_a & small_b & (one_var | (rho2 > R(0.01) * qn2)) & (qn2 > R(0.25) * L * L) & (qn2 < N::inf())
                         & in_a & in_b;
         // residual there: w = L q / |q| (in the rotation's plane for one variable), f = w - q
@@ -353,8 +358,8 @@ struct StageSolve {
             const R cx1 = x1 + R(2) * asin_small(hsb2);
             const R ga = c_sb * N::fma_(b_ca, q.y, -(b_sa * q.x));      // sign of d cost / d a at the candidate (times L > 0)
             const bool kkt = lo ? (ga > R(0)) : (ga < R(0));
-            const bool ok_b = (N::abs_(b_x0 - x0) < R(0.5))
-                              & (N::abs_(hsb2) < R(0.25)) & (cdb2 > R(0)) & (c_sb * sgn > R(0.1)) & (pn2 > R(0.25) * L * L) & (pn2 < N::inf())
+            const bool ok_b = (N::abs_(b_x0 - x0) < ws_move_max())
+                              & (N::abs_(hsb2) < ws_hs_max()) & (cdb2 > R(0)) & (c_sb * sgn > R(0.1)) & (pn2 > R(0.25) * L * L) & (pn2 < N::inf())
                               & (cx1 - lb1 > m) & (ub1 - cx1 > m) & kkt;
             if (ok_b) {
                 x0 = b_x0; x1 = cx1; sa = b_sa; ca = b_ca; sb = c_sb; cb = c_cb;

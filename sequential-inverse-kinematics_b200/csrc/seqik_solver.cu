@@ -309,12 +309,12 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, 
 // memory so that the chains of a batch run in whole waves (seqik_leg_solve_f32).
 constexpr int BLK = 32;
 enum : int { KC_L, KC_LB0, KC_UB0, KC_LB1S, KC_UB1S, KC_SL0, KC_CL0, KC_SU0, KC_CU0, KC_LB0P, KC_UB0P, KC_NSQ, KC_LB1, KC_UB1, KC_N = 16 };
-struct BlockShared {
+struct __align__(16) BlockShared {
     float pose[2][BLK * 15];           // key points of the current / next block (bulk-copy destination)
     float out_ang[BLK * 7];            // staged results (bulk-store source)
     float out_fk[BLK * 27];
-    float2 acc_vk[7][BLK + 1];         // per angle series and frame: (v, k) of x <- k x + v   (+1: bank padding)
-    float acc_x[7][BLK + 1];           // [l][t]: placed angle BEFORE frame t of series l; [l][t + 1] after it
+    float2 acc_vk[7][BLK + 2];         // per angle series and frame: (v, k) of x <- k x + v   (+2: 16-byte rows, bank spread)
+    float acc_x[7][BLK + 2];           // [l][t + 1]: placed angle BEFORE frame t of series l; [l][t + 2] after it ([0] unused)
     float kc[4][KC_N];                 // per-stage constants of the chain
     float P[4][4];                     // sin/cos (sa, ca, sb, cb) per stage of the state before the first lane of a pass
     uint64_t bar[2];
@@ -393,7 +393,7 @@ __global__ void __launch_bounds__(BLK) leg_solve_block_kernel(LegArgs a, int bul
             const float x = place1(xcar - ser_shift, ser_lb, ser_ub);
             float es, ec, v_;
             Num<float>::sincosv_(x, &es, &ec, &v_);
-            sh.acc_x[lane][0] = x;
+            sh.acc_x[lane][1] = x;
             if (is_a) { sh.P[sl_][0] = es; sh.P[sl_][1] = ec; } else { sh.P[sl_][2] = es; sh.P[sl_][3] = ec; }
             if (lane == 6) { sh.P[3][0] = 0.f; sh.P[3][1] = 1.f; }            // one-variable stage: first angle fixed at 0
         }
@@ -463,13 +463,17 @@ __global__ void __launch_bounds__(BLK) leg_solve_block_kernel(LegArgs a, int bul
             }
             __syncwarp(full);
             // ================= accumulate (frame order, one series per lane) =================
+            // always from frame 0 (a replayed frame has left (its placed angle, 0) behind): one straight-line block
             if (is_ser) {
-                float x = sh.acc_x[lane][j0];
-#pragma unroll 4
-                for (int t = j0; t < nv; ++t) {
-                    const float2 vk = sh.acc_vk[lane][t];
-                    x = fmaf(vk.y, x, vk.x);
-                    sh.acc_x[lane][t + 1] = x;
+                float x = sh.acc_x[lane][1];
+                const float4* vk = reinterpret_cast<const float4*>(sh.acc_vk[lane]);
+                float2* xo = reinterpret_cast<float2*>(sh.acc_x[lane] + 2);
+#pragma unroll
+                for (int t = 0; t < BLK; t += 2) {
+                    const float4 p = vk[t >> 1];
+                    const float x1 = fmaf(p.y, x, p.x);
+                    x = fmaf(p.w, x1, p.z);
+                    xo[t >> 1] = make_float2(x1, x);
                 }
             }
             __syncwarp(full);
@@ -483,7 +487,7 @@ __global__ void __launch_bounds__(BLK) leg_solve_block_kernel(LegArgs a, int bul
                     const float* K = sh.kc[s];
                     const uint32_t bs = bits >> (8 * s);
                     const int g = (int)((bs >> 5) & 3u);
-                    const float xp0 = (s < 3) ? sh.acc_x[s < 3 ? s : 0][lane] : 0.f, xp1 = sh.acc_x[3 + s][lane];
+                    const float xp0 = (s < 3) ? sh.acc_x[s < 3 ? s : 0][lane + 1] : 0.f, xp1 = sh.acc_x[3 + s][lane + 1];
                     WarmMove<float> mv; mv.dA = dA[s]; mv.dB = dB[s]; mv.small_a = bs & 1u; mv.small_b = bs & 2u;
                     const int wc = warm_case(enable_t, s < 3 && K[KC_CL0] * K[KC_CL0] + K[KC_SL0] * K[KC_SL0] > 0.f, s == 3, xp0, xp1, mv,
                                              (bs & 8u) != 0u, K[KC_LB0], K[KC_UB0], K[KC_LB1S], K[KC_UB1S], g, dB2[s], (bs & 4u) != 0u,
@@ -540,7 +544,7 @@ __global__ void __launch_bounds__(BLK) leg_solve_block_kernel(LegArgs a, int bul
                                   stage_mode(a.gn_mask, s));
                     S.sl0 = K[KC_SL0]; S.cl0 = K[KC_CL0]; S.su0 = K[KC_SU0]; S.cu0 = K[KC_CU0];
                     S.have_bt = K[KC_LB0] > -inf && K[KC_UB0] < inf;
-                    S.x0 = (s < 3) ? sh.acc_x[s < 3 ? s : 0][lane] : 0.f; S.x1 = sh.acc_x[3 + s][lane];
+                    S.x0 = (s < 3) ? sh.acc_x[s < 3 ? s : 0][lane + 1] : 0.f; S.x1 = sh.acc_x[3 + s][lane + 1];
                     S.sa = (s == 0) ? qsa[0] : (s == 1) ? qsa[1] : (s == 2) ? qsa[2] : qsa[3];
                     S.ca = (s == 0) ? qca[0] : (s == 1) ? qca[1] : (s == 2) ? qca[2] : qca[3];
                     S.sb = (s == 0) ? qsb[0] : (s == 1) ? qsb[1] : (s == 2) ? qsb[2] : qsb[3];
@@ -572,8 +576,9 @@ __global__ void __launch_bounds__(BLK) leg_solve_block_kernel(LegArgs a, int bul
                     piv = np_;
                     // hand the final state on: the next pass starts from it
                     sh.P[s][0] = S.sa; sh.P[s][1] = S.ca; sh.P[s][2] = S.sb; sh.P[s][3] = S.cb;
-                    if (s < 3) sh.acc_x[s < 3 ? s : 0][lane + 1] = place1(S.x0, K[KC_LB0], K[KC_UB0]);
-                    sh.acc_x[3 + s][lane + 1] = place1(S.x1, K[KC_LB1S], K[KC_UB1S]);
+                    // ... and the angles, as a reset of their series: x <- 0 x + (placed angle)
+                    if (s < 3) sh.acc_vk[s < 3 ? s : 0][lane] = make_float2(place1(S.x0, K[KC_LB0], K[KC_UB0]), 0.f);
+                    sh.acc_vk[3 + s][lane] = make_float2(place1(S.x1, K[KC_LB1S], K[KC_UB1S]), 0.f);
                 }
             }
             __syncwarp(full);
@@ -582,7 +587,15 @@ __global__ void __launch_bounds__(BLK) leg_solve_block_kernel(LegArgs a, int bul
         }
         // ---- carry the angles to the next block in the caller's terms (xa = x0, xb = x1 + shift)
         __syncwarp(full);
-        if (is_ser) xcar = sh.acc_x[lane][nv] + ser_shift;
+        if (j0 >= nv && nv > 0) {                                  // the block ended with a replay: run the series over its reset
+            if (is_ser) {
+                float x = sh.acc_x[lane][1];
+                for (int t = 0; t < nv; ++t) { const float2 p = sh.acc_vk[lane][t]; x = fmaf(p.y, x, p.x); }
+                sh.acc_x[lane][nv + 1] = x;
+            }
+            __syncwarp(full);
+        }
+        if (is_ser) xcar = sh.acc_x[lane][nv + 1] + ser_shift;
         // ---- results of the block leave: two bulk stores (or plain coalesced stores when sizes / addresses do not allow them)
         const bool bulk_store = bulk_out && (nv & 3) == 0;
         if (bulk_store) {

@@ -265,7 +265,18 @@ static void run_block(const float* pose, int64_t n_frame, const float* prm, cons
                     WarmMove<R> mv; mv.dA = dA[s][t]; mv.dB = dB[s][t]; mv.small_a = sm_a[s][t]; mv.small_b = sm_b[s][t];
                     const int wc = warm_case(enable, k.have_bt, k.one_var, xp0, xp1, mv, cond[s][t], k.lb0, k.ub0, k.lb1s, k.ub1s,
                                              guess[s][t], dB2[s][t], sm_b2[s][t], limq[s][t], outx0[s][t], outx1[s][t]);
-                    if (wc != guess[s][t]) { fail = t; break; }
+                    if (wc != guess[s][t]) {
+                        fail = t;
+                        if (getenv("HOSTSIM_BLOCK_LOG") && enable_t) {
+                            const R nx0 = xp0 + dA[s][t], nx1 = xp1 + dB[s][t];
+                            fprintf(stderr, "verify-fail frame %lld stage %d guess %d wc %d small_a %d small_b %d cond %d in_a %d in_b %d dA %.4g dB %.4g nx0 %.6g [%.6g %.6g] nx1 %.6g [%.6g %.6g] limq %d sm_b2 %d\n",
+                                    (long long)(t0 + t), s, guess[s][t], wc, (int)sm_a[s][t], (int)sm_b[s][t], (int)cond[s][t],
+                                    (int)((nx0 - k.lb0 > 1e-5f) & (k.ub0 - nx0 > 1e-5f)), (int)((nx1 - k.lb1s > 1e-5f) & (k.ub1s - nx1 > 1e-5f)),
+                                    (double)dA[s][t], (double)dB[s][t], (double)nx0, (double)k.lb0, (double)k.ub0, (double)nx1, (double)k.lb1s, (double)k.ub1s,
+                                    (int)limq[s][t], (int)sm_b2[s][t]);
+                        }
+                        break;
+                    }
                 }
             }
             // ---- commit lanes j0 .. fail-1
