@@ -308,6 +308,38 @@ __global__ void __launch_bounds__(32) leg_solve_pipe_kernel(LegArgs a, int cpw, 
 // A CTA is one warp (no block-level barrier); the launch shapes the number of resident warps per SM with dynamic shared
 // memory so that the chains of a batch run in whole waves (seqik_leg_solve_f32).
 constexpr int BLK = 32;
+// One stage of one frame through the serial solver, exactly as hostsim run_carried / leg_solve_pipe_kernel run it for a carried
+// solve: the iterate (x0, x1: placed angles; sa..cb: their sin/cos) meets the target kt in the frame (A, piv) the earlier
+// stages of this frame built.  On return the iterate is the solve's final one, (A, piv) are those of the next stage, w is the
+// joint position.  Shared by the replay path of the block kernel and by the first-frame kernel.
+struct StageK { float L, lb0, ub0, lb1, ub1, sl0, cl0, su0, cu0, nsq; };
+__device__ __forceinline__ void serial_stage(int s, const StageK& k, int gn_mask, bool esc, bool warm_ok, const Vec3<float>& kt,
+                                             const Vec3<float>& o, Mat3<float>& A, Vec3<float>& piv, float& x0, float& x1,
+                                             float& sa, float& ca, float& sb, float& cb, float& xb_out, Vec3<float>& w,
+                                             uint32_t& nfev, int& worst) {
+    const float inf = Num<float>::inf();
+    StageSolve<float> S;
+    S.set_problem(s == 0 ? KIND_XY : KIND_ZY, k.L, s == 3 ? 0.f : 1.f, k.nsq, (s == 0) ? 4 : (s == 1) ? 6 : (s == 2) ? 8 : 9, stage_mode(gn_mask, s));
+    S.sl0 = k.sl0; S.cl0 = k.cl0; S.su0 = k.su0; S.cu0 = k.cu0;
+    S.have_bt = k.lb0 > -inf && k.ub0 < inf;
+    S.x0 = x0; S.x1 = x1; S.sa = sa; S.ca = ca; S.sb = sb; S.cb = cb;
+    const Vec3<float> rel = {(kt.x - o.x) - piv.x, (kt.y - o.y) - piv.y, (kt.z - o.z) - piv.z};
+    const Vec3<float> q3 = mulT(A, rel);
+    S.restart(q3, k.lb0, k.ub0, k.lb1, k.ub1, false, warm_ok);
+    for (;;) {
+        while (!S.done()) S.trip();
+        if (!(esc && S.escape())) break;
+    }
+    nfev += (uint32_t)S.nfev;
+    worst = (S.status == ST_MAXFEV && worst > ST_MAXFEV) ? ST_MAXFEV : worst;
+    worst = (S.status == ST_NONFINITE) ? ST_NONFINITE : worst;
+    const Vec3<float> Af = mul(A, S.res());
+    const Vec3<float> np_ = {(piv.x + rel.x) + Af.x, (piv.y + rel.y) + Af.y, (piv.z + rel.z) + Af.z};
+    w = {np_.x + o.x, np_.y + o.y, np_.z + o.z};
+    A = rotate_frame_sel(A, s == 0 ? KIND_XY : KIND_ZY, S.sa, S.ca, S.sin_b(), S.cos_b());
+    piv = np_;
+    x0 = S.x0; x1 = S.x1; sa = S.sa; ca = S.ca; sb = S.sb; cb = S.cb; xb_out = S.angle_b();
+}
 enum : int { KC_L, KC_LB0, KC_UB0, KC_LB1S, KC_UB1S, KC_SL0, KC_CL0, KC_SU0, KC_CU0, KC_LB0P, KC_UB0P, KC_NSQ, KC_LB1, KC_UB1, KC_N = 16 };
 struct __align__(16) BlockShared {
     float pose[2][BLK * 15];           // key points of the current / next block (bulk-copy destination)
@@ -320,8 +352,66 @@ struct __align__(16) BlockShared {
     uint64_t bar[2];
 };
 
+// The first frame of a recording is solved from the seed (never by the closed form): ~17 evaluations, 10 000 instructions that
+// the block kernel would execute with ONE active lane per chain.  This kernel runs them for 32 chains per warp (lane = chain)
+// before the block kernel starts and leaves, per chain, frame 0's results in the outputs and a record of the final state in the
+// chain's angle rows 1..4 (they are overwritten with their own results later): 16 sin/cos, 7 placed angles, 4 evaluation
+// counts, the status.  Same arithmetic as the replay path (serial_stage), so results do not depend on which of the two ran.
+constexpr int FF_REC = 28;
+template <int kFk>
+__global__ void __launch_bounds__(BLK) leg_first_frame_kernel(LegArgs a) {
+    const int64_t c = (int64_t)blockIdx.x * BLK + threadIdx.x;
+    if (c >= a.n_chain) return;
+    const float* prm = a.params + c * SEQIK_CHAIN_PARAM_FLOATS;
+    const float* kp = a.pose + c * a.pose_cs;
+    float* ang = a.angles + c * a.ang_cs;
+    float* fk = kFk ? a.fk + c * a.fk_cs : nullptr;
+    const float inf = Num<float>::inf();
+    const float half_pi = 1.57079632679489661923f;
+    LoadMap map; map.init(a.affine, c);
+    const bool esc = (a.gn_mask >> 4) & 1;
+    const Vec3<float> o = map.apply({__ldg(kp), __ldg(kp + 1), __ldg(kp + 2)}, 0);
+    Mat3<float> A = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
+    Vec3<float> piv = {0.f, 0.f, 0.f};
+    int worst = ST_GTOL;
+#pragma unroll 1
+    for (int s = 0; s < 4; ++s) {
+        const int ia = 2 * s, ib = (s == 3) ? 6 : 2 * s + 1;
+        const float shift = (s == 0) ? half_pi : 0.f;
+        StageK k;
+        k.L = __ldg(prm + s); k.nsq = __ldg(prm + 25 + s);
+        k.lb0 = (s == 3) ? -inf : __ldg(prm + 4 + ia); k.ub0 = (s == 3) ? inf : __ldg(prm + 11 + ia);
+        k.lb1 = __ldg(prm + 4 + ib); k.ub1 = __ldg(prm + 11 + ib);
+        k.sl0 = k.cl0 = k.su0 = k.cu0 = 0.f;
+        float v_;
+        if (k.lb0 > -inf && k.ub0 < inf) { Num<float>::sincosv_(k.lb0, &k.sl0, &k.cl0, &v_); Num<float>::sincosv_(k.ub0, &k.su0, &k.cu0, &v_); }
+        // the seed enters like a carried angle: set_iterate + place, sin/cos derived from the placed value
+        float x0 = (s == 3) ? 0.f : place1(__ldg(prm + 18 + ia), k.lb0, k.ub0);
+        float x1 = place1(__ldg(prm + 18 + ib) - shift, k.lb1 - shift, k.ub1 - shift);
+        float sa = 0.f, ca = 1.f, sb, cb;
+        if (s < 3) Num<float>::sincosv_(x0, &sa, &ca, &v_);
+        Num<float>::sincosv_(x1, &sb, &cb, &v_);
+        const Vec3<float> kt = map.apply({__ldg(kp + 3 * s + 3), __ldg(kp + 3 * s + 4), __ldg(kp + 3 * s + 5)}, s + 1);
+        float xb; Vec3<float> w; uint32_t ne = 0u;
+        serial_stage(s, k, a.gn_mask, esc, false, kt, o, A, piv, x0, x1, sa, ca, sb, cb, xb, w, ne, worst);
+        if (s < 3) ang[ia] = x0;
+        ang[ib] = xb;
+        if (kFk == 1) {
+            fk[3 * s] = o.x; fk[3 * s + 1] = o.y; fk[3 * s + 2] = o.z;
+            fk[15 + 3 * s] = w.x; fk[16 + 3 * s] = w.y; fk[17 + 3 * s] = w.z;
+            if (s == 0) { fk[12] = w.x; fk[13] = w.y; fk[14] = w.z; }
+        } else if (kFk == 2) { fk[3 * s] = w.x; fk[3 * s + 1] = w.y; fk[3 * s + 2] = w.z; }
+        auto rec = [&](int i) -> float& { return ang[(int64_t)(1 + i / 7) * a.ang_fs + i % 7]; };
+        rec(4 * s) = sa; rec(4 * s + 1) = ca; rec(4 * s + 2) = sb; rec(4 * s + 3) = cb;
+        if (s < 3) rec(16 + s) = place1(x0, k.lb0, k.ub0);
+        rec(19 + s) = place1(x1, k.lb1 - shift, k.ub1 - shift);
+        rec(23 + s) = __int_as_float((int)ne);
+    }
+    ang[(int64_t)4 * a.ang_fs + 6] = __int_as_float(worst);                  // record slot 27
+}
+
 template <int kFk>                     // 0: no forward kinematics, 1: nine rows, 2: the four joint rows only
-__global__ void __launch_bounds__(BLK) leg_solve_block_kernel(LegArgs a, int bulk_in, int bulk_out) {
+__global__ void __launch_bounds__(BLK) leg_solve_block_kernel(LegArgs a, int bulk_in, int bulk_out, int first_done) {
     __shared__ __align__(128) BlockShared sh;
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x;
@@ -400,7 +490,25 @@ __global__ void __launch_bounds__(BLK) leg_solve_block_kernel(LegArgs a, int bul
         __syncwarp(full);
         bool staged = false;
         int j0 = 0;
-        for (;;) {
+        if (first_done && b == 0) {
+            // frame 0 was solved by leg_first_frame_kernel: its record (final sin/cos, placed angles, counters) waits in the
+            // chain's angle rows 1..4, its results in row 0 of the outputs; the block starts at lane 1 from that state
+            float rec = 0.f;
+            if (lane < FF_REC) rec = ang[(int64_t)(1 + lane / 7) * a.ang_fs + lane % 7];
+            if (lane < 16) sh.P[lane >> 2][lane & 3] = rec;
+            const float vx = __shfl_sync(full, rec, 16 + (lane < 7 ? lane : 0));
+            if (is_ser) sh.acc_vk[lane][0] = make_float2(vx, 0.f);
+#pragma unroll
+            for (int s = 0; s < 4; ++s) { const uint32_t n = (uint32_t)__float_as_int(__shfl_sync(full, rec, 23 + s)); if (lane == 0) nf[s] += n; }
+            const int w0 = __float_as_int(__shfl_sync(full, rec, 27));
+            if (lane == 0) worst = w0;
+            if (lane < 7) sh.out_ang[lane] = ang[lane];
+            if (kFk && lane < FKF) sh.out_fk[lane] = fk[lane];
+            staged = true;                                                     // (first block: no earlier bulk store to wait for)
+            j0 = 1;
+            __syncwarp(full);
+        }
+        for (; j0 < nv;) {
             const bool act = lane >= j0 && lane < nv;
             // ================= pass =================
             float Tsa[4], Tca[4], Tsb[4], Tcb[4];                  // this lane's final sin/cos per stage (speculated)
@@ -539,46 +647,29 @@ __global__ void __launch_bounds__(BLK) leg_solve_block_kernel(LegArgs a, int bul
 #pragma unroll 1
                 for (int s = 0; s < 4; ++s) {
                     const float* K = sh.kc[s];
-                    StageSolve<float> S;
-                    S.set_problem(s == 0 ? KIND_XY : KIND_ZY, K[KC_L], s == 3 ? 0.f : 1.f, K[KC_NSQ], (s == 0) ? 4 : (s == 1) ? 6 : (s == 2) ? 8 : 9,
-                                  stage_mode(a.gn_mask, s));
-                    S.sl0 = K[KC_SL0]; S.cl0 = K[KC_CL0]; S.su0 = K[KC_SU0]; S.cu0 = K[KC_CU0];
-                    S.have_bt = K[KC_LB0] > -inf && K[KC_UB0] < inf;
-                    S.x0 = (s < 3) ? sh.acc_x[s < 3 ? s : 0][lane + 1] : 0.f; S.x1 = sh.acc_x[3 + s][lane + 1];
-                    S.sa = (s == 0) ? qsa[0] : (s == 1) ? qsa[1] : (s == 2) ? qsa[2] : qsa[3];
-                    S.ca = (s == 0) ? qca[0] : (s == 1) ? qca[1] : (s == 2) ? qca[2] : qca[3];
-                    S.sb = (s == 0) ? qsb[0] : (s == 1) ? qsb[1] : (s == 2) ? qsb[2] : qsb[3];
-                    S.cb = (s == 0) ? qcb[0] : (s == 1) ? qcb[1] : (s == 2) ? qcb[2] : qcb[3];
+                    const StageK k = {K[KC_L], K[KC_LB0], K[KC_UB0], K[KC_LB1], K[KC_UB1], K[KC_SL0], K[KC_CL0], K[KC_SU0], K[KC_CU0], K[KC_NSQ]};
+                    float x0 = (s < 3) ? sh.acc_x[s < 3 ? s : 0][lane + 1] : 0.f, x1 = sh.acc_x[3 + s][lane + 1];
+                    float sa = (s == 0) ? qsa[0] : (s == 1) ? qsa[1] : (s == 2) ? qsa[2] : qsa[3];
+                    float ca = (s == 0) ? qca[0] : (s == 1) ? qca[1] : (s == 2) ? qca[2] : qca[3];
+                    float sb = (s == 0) ? qsb[0] : (s == 1) ? qsb[1] : (s == 2) ? qsb[2] : qsb[3];
+                    float cb = (s == 0) ? qcb[0] : (s == 1) ? qcb[1] : (s == 2) ? qcb[2] : qcb[3];
                     const Vec3<float> kt = map.apply({kp[3 * s + 3], kp[3 * s + 4], kp[3 * s + 5]}, s + 1);
-                    const Vec3<float> rel = {(kt.x - o.x) - piv.x, (kt.y - o.y) - piv.y, (kt.z - o.z) - piv.z};
-                    const Vec3<float> q3 = mulT(A, rel);
-                    S.restart(q3, K[KC_LB0], K[KC_UB0], K[KC_LB1], K[KC_UB1], false, warm_ok);
-                    for (;;) {
-                        while (!S.done()) S.trip();
-                        if (!(esc && S.escape())) break;
-                    }
-                    const float xa = S.x0, xb = S.angle_b();
-                    if (s == 0) { oa[0] = xa; oa[1] = xb; nf[0] += (uint32_t)S.nfev; }
-                    else if (s == 1) { oa[2] = xa; oa[3] = xb; nf[1] += (uint32_t)S.nfev; }
-                    else if (s == 2) { oa[4] = xa; oa[5] = xb; nf[2] += (uint32_t)S.nfev; }
-                    else { oa[6] = xb; nf[3] += (uint32_t)S.nfev; }
-                    worst = (S.status == ST_MAXFEV && worst > ST_MAXFEV) ? ST_MAXFEV : worst;
-                    worst = (S.status == ST_NONFINITE) ? ST_NONFINITE : worst;
-                    const Vec3<float> Af = mul(A, S.res());
-                    const Vec3<float> np_ = {(piv.x + rel.x) + Af.x, (piv.y + rel.y) + Af.y, (piv.z + rel.z) + Af.z};
-                    const Vec3<float> w = {np_.x + o.x, np_.y + o.y, np_.z + o.z};
+                    float xb; Vec3<float> w; uint32_t ne = 0u;
+                    serial_stage(s, k, a.gn_mask, esc, warm_ok, kt, o, A, piv, x0, x1, sa, ca, sb, cb, xb, w, ne, worst);
+                    if (s == 0) { oa[0] = x0; oa[1] = xb; nf[0] += ne; }
+                    else if (s == 1) { oa[2] = x0; oa[3] = xb; nf[1] += ne; }
+                    else if (s == 2) { oa[4] = x0; oa[5] = xb; nf[2] += ne; }
+                    else { oa[6] = xb; nf[3] += ne; }
                     if (kFk == 1) {
                         of[3 * s] = o.x; of[3 * s + 1] = o.y; of[3 * s + 2] = o.z;
                         of[15 + 3 * s] = w.x; of[16 + 3 * s] = w.y; of[17 + 3 * s] = w.z;
                         if (s == 0) { of[12] = w.x; of[13] = w.y; of[14] = w.z; }
                     } else if (kFk == 2) { of[3 * s] = w.x; of[3 * s + 1] = w.y; of[3 * s + 2] = w.z; }
-                    A = rotate_frame_sel(A, s == 0 ? KIND_XY : KIND_ZY, S.sa, S.ca, S.sin_b(), S.cos_b());
-                    piv = np_;
                     // hand the final state on: the next pass starts from it
-                    sh.P[s][0] = S.sa; sh.P[s][1] = S.ca; sh.P[s][2] = S.sb; sh.P[s][3] = S.cb;
+                    sh.P[s][0] = sa; sh.P[s][1] = ca; sh.P[s][2] = sb; sh.P[s][3] = cb;
                     // ... and the angles, as a reset of their series: x <- 0 x + (placed angle)
-                    if (s < 3) sh.acc_vk[s < 3 ? s : 0][lane] = make_float2(place1(S.x0, K[KC_LB0], K[KC_UB0]), 0.f);
-                    sh.acc_vk[3 + s][lane] = make_float2(place1(S.x1, K[KC_LB1S], K[KC_UB1S]), 0.f);
+                    if (s < 3) sh.acc_vk[s < 3 ? s : 0][lane] = make_float2(place1(x0, K[KC_LB0], K[KC_UB0]), 0.f);
+                    sh.acc_vk[3 + s][lane] = make_float2(place1(x1, K[KC_LB1S], K[KC_UB1S]), 0.f);
                 }
             }
             __syncwarp(full);
@@ -656,22 +747,17 @@ static int launch_block_kernel(const LegArgs& a, int bulk_in, int bulk_out, int 
         cudaFuncSetAttribute(leg_solve_block_kernel<kFk>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cached_dev = dev;
     }
+    // resident warps per SM: as many as registers and shared memory allow -- measured faster than any "whole waves" choice
+    // of fewer (latency hiding outweighs a partly filled last wave; profiles/r02_block_resident_sweep.jsonl)
     int r = r_max;
     if (forced) r = forced < r_max ? forced : r_max;
-    else {
-        const int r_min = r_max * 5 / 8 > 1 ? r_max * 5 / 8 : 1;                      // fewer resident warps hide less latency
-        int64_t best = -1;
-        for (int k = r_max; k >= r_min; --k) {
-            const int64_t waves = (a.n_chain + (int64_t)k * n_sm - 1) / ((int64_t)k * n_sm);
-            const int64_t cost = waves * k;
-            if (best < 0 || cost < best) { best = cost; r = k; }
-        }
-    }
     // shared memory per CTA such that exactly r CTAs fit one SM
     int dyn = smem_sm / r - 1024 - static_smem;
     dyn = dyn < 0 ? 0 : dyn & ~127;
     if (r == r_max && !forced) dyn = 0;
-    leg_solve_block_kernel<kFk><<<(unsigned)a.n_chain, BLK, (size_t)dyn, st>>>(a, bulk_in, bulk_out);
+    const int first_done = (a.warm == nullptr && a.n_frame >= 5) ? 1 : 0;
+    if (first_done) leg_first_frame_kernel<kFk><<<(unsigned)((a.n_chain + BLK - 1) / BLK), BLK, 0, st>>>(a);
+    leg_solve_block_kernel<kFk><<<(unsigned)a.n_chain, BLK, (size_t)dyn, st>>>(a, bulk_in, bulk_out, first_done);
     return SEQIK_OK;
 }
 static int launch_block_schedule(const LegArgs& a, bool want_fk, bool fk_joints, int forced, cudaStream_t st) {
