@@ -3,7 +3,11 @@ import sys, json
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
+import os
 import numpy as np, torch
+from seqikpy_b200 import _native as _N
+if os.environ.get("SEQIK_LIB"):
+    _N.LIB_PATH = Path(os.environ["SEQIK_LIB"]).resolve()
 from seqikpy_b200 import synthetic as S, engine
 from seqikpy_b200.batch import chain_param_table
 from seqikpy_b200.kinematic_chain import KinematicChainSeq
@@ -39,9 +43,12 @@ if __name__ == "__main__":
         for n_trial in (100, 1000, 1250, 10000):
             run(n_trial, 1000, 2)
             run(n_trial, 1000, 3)
+    elif mode == "s3":
+        for n_trial in (100, 1000, 1250, 10000):
+            run(n_trial, 1000, 3)
     elif mode == "r":
         for n_trial in (1000, 1250, 10000):
-            for r in (6, 8, 10, 11, 12, 13, 14, 15, 16, 18, 20):
+            for r in (10, 12, 13, 14, 15, 16, 17, 18):
                 run(n_trial, 1000, 3, r)
     elif mode == "one":
         run(int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4]), int(sys.argv[5]) if len(sys.argv) > 5 else 0, reps=2)

@@ -410,8 +410,11 @@ __global__ void __launch_bounds__(BLK) leg_first_frame_kernel(LegArgs a) {
     ang[(int64_t)4 * a.ang_fs + 6] = __int_as_float(worst);                  // record slot 27
 }
 
+#ifndef SEQIK_BLOCK_MIN_CTAS
+#define SEQIK_BLOCK_MIN_CTAS 18        // resident one-warp CTAs per SM the register allocation must allow (measured)
+#endif
 template <int kFk>                     // 0: no forward kinematics, 1: nine rows, 2: the four joint rows only
-__global__ void __launch_bounds__(BLK) leg_solve_block_kernel(LegArgs a, int bulk_in, int bulk_out, int first_done) {
+__global__ void __launch_bounds__(BLK, SEQIK_BLOCK_MIN_CTAS) leg_solve_block_kernel(LegArgs a, int bulk_in, int bulk_out, int first_done) {
     __shared__ __align__(128) BlockShared sh;
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x;
@@ -572,16 +575,23 @@ __global__ void __launch_bounds__(BLK) leg_solve_block_kernel(LegArgs a, int bul
             __syncwarp(full);
             // ================= accumulate (frame order, one series per lane) =================
             // always from frame 0 (a replayed frame has left (its placed angle, 0) behind): one straight-line block
+            // (the loads of the next group of 8 frames are in flight while the current group's dependent multiply-adds run)
             if (is_ser) {
                 float x = sh.acc_x[lane][1];
-                const float4* vk = reinterpret_cast<const float4*>(sh.acc_vk[lane]);
-                float2* xo = reinterpret_cast<float2*>(sh.acc_x[lane] + 2);
+                const float4* __restrict__ vk = reinterpret_cast<const float4*>(sh.acc_vk[lane]);
+                float2* __restrict__ xo = reinterpret_cast<float2*>(sh.acc_x[lane] + 2);
+                float4 p0 = vk[0], p1 = vk[1], p2 = vk[2], p3 = vk[3];
 #pragma unroll
-                for (int t = 0; t < BLK; t += 2) {
-                    const float4 p = vk[t >> 1];
-                    const float x1 = fmaf(p.y, x, p.x);
-                    x = fmaf(p.w, x1, p.z);
-                    xo[t >> 1] = make_float2(x1, x);
+                for (int g = 0; g < 4; ++g) {
+                    float4 n0 = p0, n1 = p1, n2 = p2, n3 = p3;
+                    if (g < 3) { n0 = vk[4 * g + 4]; n1 = vk[4 * g + 5]; n2 = vk[4 * g + 6]; n3 = vk[4 * g + 7]; }
+                    const float a0 = fmaf(p0.y, x, p0.x), a1 = fmaf(p0.w, a0, p0.z);
+                    const float a2 = fmaf(p1.y, a1, p1.x), a3 = fmaf(p1.w, a2, p1.z);
+                    const float a4 = fmaf(p2.y, a3, p2.x), a5 = fmaf(p2.w, a4, p2.z);
+                    const float a6 = fmaf(p3.y, a5, p3.x), a7 = fmaf(p3.w, a6, p3.z);
+                    xo[4 * g] = make_float2(a0, a1); xo[4 * g + 1] = make_float2(a2, a3);
+                    xo[4 * g + 2] = make_float2(a4, a5); xo[4 * g + 3] = make_float2(a6, a7);
+                    x = a7; p0 = n0; p1 = n1; p2 = n2; p3 = n3;
                 }
             }
             __syncwarp(full);
