@@ -128,3 +128,58 @@ def test_non_finite_key_points_bitwise(env):
     for x, y in zip(a, b):
         assert np.array_equal(x, y, equal_nan=True)
     assert a[2][1] == -1 and a[2][4] == -1 and a[2][0] == 1
+
+
+def test_config5_depth_windows_vs_oracle(env):
+    """BASELINE config 5 is 100 000 serially warm-started frames.  Two synthetic chains are run to that depth on the GPU and the
+    CPU oracle (memoryless between frames but for x0 = previous frame's angles, leg_inverse_kinematics.py:272) is run on
+    three windows -- start, middle (across a 32-frame re-derivation boundary), end -- seeded with the GPU's own angles of the
+    frame before each window: angles within 1e-3 rad, FK residual per joint not worse by more than 1e-4 mm."""
+    from helpers import ANGLE_TOL, FK_TOL, F32_FK_NOISE, fk_residual
+    from oracle import seqik_oracle as O
+    from seqikpy_b200.kinematic_chain import DOF_ORDER, STAGE_ACTIVE_DOFS, STAGE_ACTIVE_SLOTS, KinematicChainSeq
+    torch, S = env.torch, env.S
+    n_frame = 100_000
+    legs = ("RF", "RM")
+    size, bounds, init = S.chain_constants()
+    chain = KinematicChainSeq(bounds, list(S.LEGS), size)
+    pose64 = S.make_trial(11, n_frame)                                                   # (F, 6, 5, 3) float64
+    li = [S.LEGS.index(l) for l in legs]
+    pose = torch.from_numpy(np.ascontiguousarray(pose64[:, li].transpose(1, 0, 2, 3), dtype=np.float32)).cuda()
+    params = torch.from_numpy(np.stack([chain.pack_chain_params(l, init[l]) for l in legs]).astype(np.float32)).cuda()
+    ang, fk, st, nf = env.engine.leg_solve(pose, params)
+    ang, fk = ang.cpu().numpy().astype(np.float64), fk.cpu().numpy().astype(np.float64)
+    assert (st.cpu().numpy() == 1).all()
+    assert nf.cpu().numpy().sum() < 1.05 * 2 * 4 * n_frame                               # the depth run stays on the closed form
+    for (t0, t1) in ((0, 300), (49_984, 50_300), (99_700, 100_000)):
+        for ci, leg in enumerate(legs):
+            seeds = {k: np.array(v, dtype=float) for k, v in init[leg].items()}
+            if t0 > 0:
+                for stage in (1, 2, 3, 4):
+                    for slot, dof in zip(STAGE_ACTIVE_SLOTS[stage], STAGE_ACTIVE_DOFS[stage]):
+                        seeds[f"stage_{stage}"][slot] = ang[ci, t0 - 1, DOF_ORDER.index(dof)]
+            p = pose[ci, t0:t1].cpu().numpy().astype(np.float64)
+            ref, ref_fk = O.run_ik_and_fk({f"{leg}_leg": p}, size, bounds, {leg: seeds})
+            ref7 = np.stack([ref[f"Angle_{leg}_{d}"] for d in DOF_ORDER], 1)
+            assert np.abs(ang[ci, t0:t1] - ref7).max() < ANGLE_TOL, (leg, t0, np.abs(ang[ci, t0:t1] - ref7).max())
+            worse = fk_residual(fk[ci, t0:t1], p) - fk_residual(ref_fk[f"{leg}_leg"], p)
+            assert worse.max() < FK_TOL + F32_FK_NOISE, (leg, t0, worse.max())
+
+
+@pytest.mark.parametrize("flags_name", ["FLAG_DEFAULT", "FLAG_REFERENCE_ITERATES"])
+def test_large_batch_on_the_automatic_schedule_is_bit_identical(env, flags_name):
+    """19 200 chains (the 8 golden trials tiled 400 times) on the AUTOMATIC schedule -- schedule 3 for the default flags;
+    schedule 2 with its large-batch packing and phase period (chains per warp 6, period 3 beyond ~16 000 chains) for the
+    reference-iterates set -- give, chain for chain, the bits of the 48-chain run."""
+    torch = env.torch
+    flags = getattr(env.N, flags_name)
+    n_frame, tiles = 512, 400
+    pose = env.pose[:, :n_frame].contiguous()
+    a0, f0, s0, n0 = env.engine.leg_solve(pose, env.params, flags=flags)
+    big_pose = pose.repeat(tiles, 1, 1, 1)
+    big_params = env.params.repeat(tiles, 1)
+    a1, f1, s1, n1 = env.engine.leg_solve(big_pose, big_params, flags=flags)
+    torch.cuda.synchronize()
+    assert torch.equal(a1.view(tiles, 48, n_frame, 7), a0.expand(tiles, -1, -1, -1))
+    assert torch.equal(f1.view(tiles, 48, n_frame, 9, 3), f0.expand(tiles, -1, -1, -1, -1))
+    assert torch.equal(n1.view(tiles, 48, 4), n0.expand(tiles, -1, -1)) and torch.equal(s1.view(tiles, 48), s0.expand(tiles, -1))
