@@ -5,13 +5,18 @@
 
 One "step" = one pass of the hot path (stages 1-4 + 9-row FK) over T trials x 6 legs x F frames per GPU
 (default T = 1000, F = 1000: BASELINE.json config "synthetic 1k trials x 1000 frames x 6 legs on 1 B200").
-Under torchrun every rank owns its own T trials (weak scaling; no collective on the data path) -- N = 8 with
---trials 1250 is exactly the 10k-trial configuration sharded over 8 GPUs.
+Under torchrun every rank owns its own T trials (weak scaling; no collective on the data path).
 
 Prints ONE JSON line (rank 0).  `value` times the kernel with the pose already resident in HBM; `e2e` times
 the public batched call with HOST pinned buffers (H2D of the pose, solve, D2H of angles + FK in the timed
 region).  `roofline` describes the solver kernel; `cpu_baseline` is the CPU oracle (the reference's
 algorithm: restated ikpy glue + scipy TRF) timed on this box's host cores on a bounded sample.
+The same line carries
+  config4      BASELINE.json config 4: the FIXED 10 000-trial x 1000-frame x 6-leg workload, trials sharded over the
+               N ranks (10000 / N per rank; all 60 000 chains on one GPU at N = 1) -- kernel and end-to-end figures, so
+               that dividing config4 at N = 8 by config4 at N = 1 is the strong-scaling factor of north_star;
+  secondary    driver-timed records of config 5 (fused long sequence), the HBM-bound stream kernels and config 2
+               through the dict API with its parity counts against the reference's shipped angles (rank 0).
 
 --impl reference times that CPU implementation alone, with every host core, on bounded samples of the same
 workload (the reference's own per-frame chain rebuild needs ikpy/sympy, which is not
@@ -40,14 +45,21 @@ ALG_FLOP_PER_LEG_FRAME = 14.5e3                   # nominal full-chain model of 
 
 # --------------------------------------------------------------------------------------------- CPU oracle legs
 def _oracle_job(job):
-    """One (trial, leg) chain through the CPU oracle; returns leg-frames solved."""
+    """One (trial, leg) chain through the CPU oracle over frames [f0, f0 + n); returns leg-frames solved.  f0 > 0: the
+    warm start of frame f0 is the synthetic ground truth of frame f0 - 1 (steady-state frames: no cold first solve)."""
     from oracle import seqik_oracle as O
     from seqikpy_b200 import synthetic as S
-    trial, li, n_frame = job
+    from seqikpy_b200.kinematic_chain import DOF_ORDER, STAGE_ACTIVE_DOFS, STAGE_ACTIVE_SLOTS
+    trial, li, f0, n_frame = job
     size, bounds, init = S.chain_constants()
     leg = S.LEGS[li]
-    pose = S.make_trial(trial, 1000)[:n_frame, li]
-    O.run_ik_and_fk({f"{leg}_leg": pose}, size, bounds, init)
+    pose, truth = S.make_trial(trial, 1000, return_truth=True)
+    seeds = {k: np.array(v, dtype=float) for k, v in init[leg].items()}
+    if f0 > 0:
+        for stage in (1, 2, 3, 4):
+            for slot, dof in zip(STAGE_ACTIVE_SLOTS[stage], STAGE_ACTIVE_DOFS[stage]):
+                seeds[f"stage_{stage}"][slot] = truth[f0 - 1, li, DOF_ORDER.index(dof)]
+    O.run_ik_and_fk({f"{leg}_leg": pose[f0:f0 + n_frame, li]}, size, bounds, {leg: seeds})
     return n_frame
 
 
@@ -55,10 +67,10 @@ def oracle_throughput(n_trial, n_frame, procs, repeats=1):
     """leg-frames/s of the CPU oracle over n_trial x 6 chains with `procs` worker processes
     (process-level parallelism over legs like examples/example_leg_inv_kinematics_parallel.py:186-189)."""
     from multiprocessing import get_context
-    jobs = [(tr, li, n_frame) for tr in range(n_trial) for li in range(6)]
+    jobs = [(tr, li, 0, n_frame) for tr in range(n_trial) for li in range(6)]
     ctx = get_context("fork")
     with ctx.Pool(procs) as pool:
-        pool.map(_oracle_job, [(0, 0, 2)] * procs)          # import + first-call costs out of the timed region
+        pool.map(_oracle_job, [(0, 0, 0, 2)] * procs)       # import + first-call costs out of the timed region
         times = []
         for _ in range(repeats):
             t0 = time.perf_counter()
@@ -84,9 +96,10 @@ def run_reference(args):
     n_frame = args.ref_frames
     per_step = n_trial * 6 * n_frame
     from multiprocessing import get_context
-    jobs = [(tr, li, n_frame) for tr in range(n_trial) for li in range(6)]
+    f0 = 100                                                # steady-state frames: warm-started, no cold first solve
+    jobs = [(tr, li, f0, n_frame) for tr in range(n_trial) for li in range(6)]
     with get_context("fork").Pool(procs) as pool:
-        pool.map(_oracle_job, [(0, 0, 2)] * procs)
+        pool.map(_oracle_job, [(0, 0, 0, 2)] * procs)
         for _ in range(args.warmup):
             pool.map(_oracle_job, jobs, chunksize=1)
         t0 = time.perf_counter()
@@ -94,7 +107,8 @@ def run_reference(args):
             pool.map(_oracle_job, jobs, chunksize=1)
         dt = time.perf_counter() - t0
     value = per_step * args.steps / dt
-    sample = f"{n_trial} trial(s) x 6 legs x first {n_frame} frames per step, {procs} worker processes (one chain each)"
+    sample = (f"{n_trial} trial(s) x 6 legs x frames {f0}..{f0 + n_frame} (steady state, warm-started) per step, "
+              f"{procs} worker processes (one chain each)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -273,6 +287,7 @@ def run_ours(args):
     for _ in range(2):
         sess.solve_host(host_pose, n_chunks=args.chunks)
     ms_e2e = timed(lambda: sess.solve_host(host_pose, synchronize=False, n_chunks=args.chunks), args.steps) / args.steps
+    e2e_launches = sess.launches_per_call + 1                     # one solve per frame chunk + the first-frame kernel of chunk 0
     clocks = sampler.stop() if sampler else None
     # ---- the same call with the joints-only FK layout (rows 5..8: the rows that carry information); a secondary figure,
     #      the headline `e2e` above keeps the reference's 9-row layout
@@ -284,12 +299,12 @@ def run_ours(args):
         ms_e2e_joints = timed(lambda: sess_j.solve_host(host_pose, synchronize=False, n_chunks=args.chunks), args.steps) / args.steps
         del sess_j
 
-    # ---- the same kernel walking the reference's own iterates (SEQIK_FLAG_REFERENCE_ITERATES: no Newton steps, no
-    #      closed-form warm step): a secondary figure that shows what the default flags save
+    # ---- the same kernel family walking the reference's own iterates (SEQIK_FLAG_REFERENCE_ITERATES: no Newton steps, no
+    #      closed-form warm step; runs on the stage-pipeline schedule): a secondary figure that shows what the default flags save
     sess.flags = _native.FLAG_REFERENCE_ITERATES
     for _ in range(3):
         sess.solve_device()
-    ms_ref_it = timed(lambda: sess.solve_device(want_stats=False), args.steps) / args.steps
+    ms_ref_it = timed(lambda: sess.solve_device(want_stats=False), max(3, args.steps // 2)) / max(3, args.steps // 2)
     sess.solve_device()
     torch.cuda.synchronize()
     nfev_ref_it = sess.nfev.to(torch.float64).sum(0)
@@ -306,6 +321,80 @@ def run_ours(args):
     leg_frames = leg_frames_rank * world
     nfev_per_lf = (nfev / leg_frames).tolist()
 
+    # ---- BASELINE config 4: the FIXED 10 000-trial workload, trials sharded over the ranks (strong scaling).  The device
+    #      pose is tiled from this rank's unique trials (the kernel's cost does not depend on the values repeating); the
+    #      end-to-end leg moves every byte of the shard through the 1000-trial session's pinned buffers, sub-batch by sub-batch
+    config4 = None
+    if not args.no_config4:
+        from seqikpy_b200.batch import shard_range
+        T4_total = args.config4_trials
+        lo4, hi4 = shard_range(T4_total, rank, world)
+        T4 = hi4 - lo4
+        sess4 = BatchedLegIK(chain, init, S.LEGS, T4, F, device=dev, schedule=args.schedule, chains_per_warp=args.cpw, host_buffers=False)
+        reps4 = (T4 + T - 1) // T
+        sess4.d_pose.copy_(sess.d_pose.view(T, 6, F, 5, 3).repeat(reps4, 1, 1, 1, 1)[:T4].reshape(sess4.n_chain, F, 5, 3))
+        for _ in range(3):
+            sess4.solve_device(want_stats=False)
+        steps4 = max(3, args.steps // 2)
+        ms4 = timed(lambda: sess4.solve_device(want_stats=False), steps4) / steps4
+        sess4.solve_device()
+        torch.cuda.synchronize()
+        ok4 = (sess4.status == 1).sum().to(torch.float64).reshape(1)
+        err4 = torch.tensor([sess4.mean_fk_error() * T4], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ok4); dist.all_reduce(err4)
+        del sess4
+        torch.cuda.empty_cache()
+        # end to end: full sub-batches through `sess`, the remainder through a smaller session
+        n_full, rem = divmod(T4, T)
+        sess_rem = host_rem = None
+        if rem:
+            sess_rem = BatchedLegIK(chain, init, S.LEGS, rem, F, device=dev, schedule=args.schedule, chains_per_warp=args.cpw)
+            host_rem = host_pose[:rem].contiguous().pin_memory()
+
+        def e2e4():
+            for _ in range(n_full):
+                sess.solve_host(host_pose, synchronize=False, n_chunks=args.chunks)
+            if sess_rem is not None:
+                sess_rem.solve_host(host_rem, synchronize=False, n_chunks=args.chunks)
+        e2e4(); torch.cuda.synchronize()
+        steps4e = max(2, args.steps // 4)
+        ms4_e2e = timed(e2e4, steps4e) / steps4e
+        lf4 = T4_total * 6 * F
+        config4 = {
+            "workload": f"synthetic {T4_total} trials x {F} frames x 6 legs IN TOTAL (BASELINE.json config 4), trials sharded over "
+                        f"{world} GPU(s) in contiguous shards, no collective; strong scaling: divide by the same object at N = 1",
+            "trials_total": T4_total, "trials_this_rank": T4, "chains_this_rank": T4 * 6, "scaling": "strong",
+            "value": lf4 / (ms4 * 1e-3), "unit": UNIT, "ms_per_step": ms4, "steps": steps4, "timing": "CUDA events, max over ranks, pose resident in HBM",
+            "e2e": {"value": lf4 / (ms4_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms4_e2e, "steps": steps4e,
+                    "h2d_bytes_per_step": T4 * 6 * F * 60, "d2h_bytes_per_step": T4 * 6 * F * 136, "bytes_are": "per GPU",
+                    "how": f"{n_full} sub-batch(es) of {T} trials" + (f" + one of {rem}" if rem else "") + " through BatchedLegIK.solve_host "
+                           "(pinned host pose in, pinned host angles + 9-row FK out; the sub-batches reuse the same pinned buffers)"},
+            "chains_converged": int(ok4.item()), "chains": T4_total * 6, "mean_fk_error_mm": float(err4.item()) / T4_total,
+            "data": f"device-tiled from each rank's {T} unique synthetic trials",
+        }
+        del sess_rem, host_rem
+
+    # ---- secondary, driver-timed records (rank 0; the other ranks wait at the barrier below)
+    secondary = {}
+    if rank == 0 and not args.no_secondary:
+        sys.path.insert(0, str(ROOT / "scripts"))
+        import bench_secondary as B2
+        peaks_ = {}
+        try:
+            peaks_ = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        except Exception:
+            pass
+        for name, fn in (("config2_dict_api", B2.config2_dict_api), ("stream_kernels", lambda: B2.stream_kernels(float(peaks_.get("hbm_gbs", 6650.0)))),
+                         ("config5_fused", lambda: B2.config5_fused(args.config5_trials, args.config5_frames))):
+            try:
+                t_s = time.perf_counter()
+                secondary[name] = fn()
+                secondary[name]["record_wall_s"] = time.perf_counter() - t_s
+            except Exception as exc:                                  # never lose the headline to a secondary record
+                secondary[name] = {"error": repr(exc)[:300]}
+            torch.cuda.empty_cache()
+
     if rank == 0:
         peaks = {}
         try:
@@ -317,40 +406,58 @@ def run_ours(args):
         fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12           # TFLOP/s at max clock
         ach_gbs = leg_frames_rank * ALG_BYTES_PER_LEG_FRAME / (ms_step * 1e-3) / 1e9
         ach_tf = leg_frames_rank * ALG_FLOP_PER_LEG_FRAME / (ms_step * 1e-3) / 1e12
+        # static ncu counters of the committed capture (profiles/solver_traffic.json): quoted only for the configuration they
+        # were captured on and only while this run's kernel time agrees with the capture's within 5 %
         traffic = ncu_flop = ncu_issue = None
+        capture = None
         try:
             prof = json.loads((ROOT / "profiles" / "solver_traffic.json").read_text())
-            ncu_issue = prof.get("issue_active_per_smsp")
-            if args.trials == 1000 and args.frames == 1000:          # the capture is of the default configuration
+            cap_ms = 1e3 * float(prof["duration_s_under_ncu"])
+            agrees = abs(ms_step - cap_ms) <= 0.05 * cap_ms
+            capture = {"file": "profiles/solver_traffic.json", "source": prof.get("source"), "commit": prof.get("commit"),
+                       "kernel": prof.get("kernel"), "duration_ms": cap_ms, "this_run_ms": ms_step, "agrees_within_5pct": bool(agrees),
+                       "what": "STATIC counters of one committed ncu --set full capture (default configuration), not measured in this run"}
+            if agrees and args.trials == 1000 and args.frames == 1000:
                 traffic = prof.get("dram_bytes_per_launch")
-            ncu_flop = prof.get("fp32_flop_per_launch", 0) / 6e6     # measured FP32 FLOP per leg-frame (ffma x2 + fmul + fadd)
+                ncu_flop = prof.get("fp32_flop_per_launch", 0) / 6e6  # measured FP32 FLOP per leg-frame (ffma x2 + fmul + fadd)
+                ncu_issue = prof.get("issue_active_per_smsp")
         except Exception:
             pass
+        c2 = secondary.get("config2_dict_api", {})
         line = {
             "metric": METRIC, "value": leg_frames / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
             "e2e": {"value": leg_frames / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": leg_frames_rank * 60, "d2h_bytes_per_step": leg_frames_rank * (28 + 108),
-                    "bytes_are": "per GPU", "frame_chunks": args.chunks, "gpu_launches": args.steps * sess.launches_per_call},
+                    "bytes_are": "per GPU", "frame_chunks": args.chunks, "gpu_launches": args.steps * e2e_launches},
             "e2e_joints_only": None if ms_e2e_joints is None else {
                 "value": leg_frames / (ms_e2e_joints * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_joints,
                 "h2d_bytes_per_step": leg_frames_rank * 60, "d2h_bytes_per_step": leg_frames_rank * (28 + 48),
                 "note": "fk_layout='joints': FK rows 5..8 only (rows 0-3 of the reference layout repeat the input origin, row 4 repeats row 5)"},
-            "gpu_launches": args.steps,
+            "gpu_launches": args.steps * 2,                           # per step: leg_first_frame_kernel + leg_solve_block_kernel
+            "kernels": "leg_first_frame_kernel (frame 0 of every chain, lane per chain) + leg_solve_block_kernel (schedule 3: a warp per "
+                       "chain, 32 frames per pass, bulk-copy staged)",
+            "config4": config4,
+            "parity_extras": {k: c2[k] for k in c2 if k.startswith(("rf_", "lf_", "head_"))} or None,
+            "secondary": secondary or None,
             "solver_flags": {"value": "SEQIK_FLAG_DEFAULT (0xFF): Gauss-Newton mode, escape, skip-confirm, Newton steps, closed-form warm step",
-                             "reference_iterates": {"flags": "SEQIK_FLAG_REFERENCE_ITERATES (0x3F)", "ms_per_step": ms_ref_it,
+                             "reference_iterates": {"flags": "SEQIK_FLAG_REFERENCE_ITERATES (0x3F), stage-pipeline schedule", "ms_per_step": ms_ref_it,
                                                     "value": leg_frames / (ms_ref_it * 1e-3), "unit": UNIT,
                                                     "nfev_per_leg_frame_by_stage": (nfev_ref_it / leg_frames).tolist()}},
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                         "traffic": traffic, "kernel": "leg_solve", "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback",
-                         "note": "the solver is bound by dependent-issue latency, neither by HBM nor by the FP32 pipe; see fp32 and DESIGN.md 5.1",
+                         "traffic": traffic, "kernel": "leg_solve_block_kernel (+ leg_first_frame_kernel, ~5 % of the step)",
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback",
+                         "algorithmic_bytes_per_leg_frame": ALG_BYTES_PER_LEG_FRAME, "ncu_capture": capture,
+                         "note": "achieved = 196 B x leg-frames per step / the step's CUDA-event time (both kernels of the step); the rest "
+                                 "of the gap to the copy peak is instruction issue: ~40 warp-instructions per leg-frame at ~0.7 issue slots "
+                                 "per cycle per scheduler (DESIGN.md 5.1)",
                          "fp32": {"achieved": ach_tf, "peak": fp32_peak, "unit": "TFLOP/s", "frac": ach_tf / fp32_peak,
                                   "flop_model": "nominal 14.5 kFLOP per leg-frame = the REFERENCE's work (SURVEY.md 8d: full-chain, "
                                                 "finite-difference evaluations x its iteration counts).  The kernel does not do "
-                                                "that work (two-variable closed forms, ~1.1 evaluations per solve), so `achieved`/"
-                                                "`frac` here say how fast the reference's work is retired, NOT how busy the FP32 "
-                                                "pipe is: that is ncu_frac",
+                                                "that work (two-variable closed forms, one evaluation per solve), so `achieved`/"
+                                                "`frac` here say how fast the reference's work is retired and can exceed 1; how busy "
+                                                "the FP32 pipe is: ncu_frac",
                                   "ncu_flop_per_leg_frame": ncu_flop,
                                   "ncu_achieved": None if not ncu_flop else leg_frames_rank * ncu_flop / (ms_step * 1e-3) / 1e12,
                                   "ncu_frac": None if not ncu_flop else leg_frames_rank * ncu_flop / (ms_step * 1e-3) / 1e12 / fp32_peak,
@@ -384,13 +491,18 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin each rank to its GPU's local CPUs")
     ap.add_argument("--no-joints-e2e", action="store_true", help="skip the secondary end-to-end figure with the joints-only FK layout")
+    ap.add_argument("--no-config4", action="store_true", help="skip the config-4 (fixed 10 000-trial, sharded) record")
+    ap.add_argument("--config4-trials", type=int, default=10000, help="total trials of the config-4 record")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary records (config 2 dict API, stream kernels, config 5)")
+    ap.add_argument("--config5-trials", type=int, default=100)
+    ap.add_argument("--config5-frames", type=int, default=100000)
     ap.add_argument("--cpu-baseline-only", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--cpu-procs", type=int, default=6, help=argparse.SUPPRESS)
     args = ap.parse_args()
     if args.cpu_baseline_only:
         done, times = oracle_throughput(1, args.cpu_frames, args.cpu_procs)
         t0 = time.perf_counter()
-        one = _oracle_job((0, 0, min(args.cpu_frames, 100)))          # one chain, one process: the per-core rate
+        one = _oracle_job((0, 0, 0, min(args.cpu_frames, 100)))       # one chain, one process: the per-core rate
         t_one = time.perf_counter() - t0
         print(json.dumps({"leg_frames": done, "seconds": times[0], "one_core_leg_frames": one, "one_core_seconds": t_one}))
         return
