@@ -113,16 +113,23 @@ class BatchedLegIK:
                                                         want_stats=want_stats, fk_layout=self.fk_layout)
         return self.d_angles, self.d_fk
 
-    def solve_host(self, pose_host, synchronize: bool = True, n_chunks: Optional[int] = None):
+    def solve_host(self, pose_host, synchronize: bool = True, n_chunks: Optional[int] = None, out=None):
         """Host (pinned) pose (n_trial, n_leg, n_frame, 5, 3) float32 -> pinned host (angles, fk).
+        ``out``: optional (angles, fk) pinned host tensors of this session's shapes to receive the results instead of the
+        session's own buffers (``MultiGpuLegIK`` passes each device its slice of ONE result tensor).
 
         The frames are cut into ``n_chunks`` ranges.  While range k is solved (warm-started from the last frame of
         range k-1: bit-identical to one launch over all frames), range k+1 is copied host->device and the results of
         range k-1 device->host on two copy streams, so PCIe traffic in both directions overlaps the kernel.
         """
         torch, lib = self.torch, N.load_library()
-        if self.h_angles is None:
-            raise RuntimeError("session was created with host_buffers=False")
+        h_angles, h_fk = (self.h_angles, self.h_fk) if out is None else out
+        if h_angles is None:
+            raise RuntimeError("session was created with host_buffers=False: pass out=(angles, fk)")
+        if h_angles.numel() != self.n_chain * self.n_frame * 7 or not h_angles.is_contiguous() or h_angles.dtype != torch.float32:
+            raise ValueError("out angles must be a contiguous float32 tensor of (n_trial, n_leg, n_frame, 7)")
+        if self.d_fk is not None and (h_fk is None or h_fk.numel() != self.n_chain * self.n_frame * 3 * self.fk_rows or not h_fk.is_contiguous()):
+            raise ValueError(f"out fk must be a contiguous float32 tensor of (n_trial, n_leg, n_frame, {self.fk_rows}, 3)")
         src = pose_host if isinstance(pose_host, torch.Tensor) else torch.from_numpy(pose_host)
         if src.dtype != torch.float32 or not src.is_contiguous() or src.numel() != self.n_chain * self.n_frame * 15:
             raise ValueError("pose_host must be a contiguous float32 array of (n_trial, n_leg, n_frame, 5, 3)")
@@ -160,14 +167,14 @@ class BatchedLegIK:
                 ev_k = torch.cuda.Event()
                 ev_k.record(main)
                 s_out.wait_event(ev_k)
-                copy2d(self.h_angles, self.d_angles, 7, t0, t1, 2, s_out)
-                if self.h_fk is not None:
-                    copy2d(self.h_fk, self.d_fk, 3 * self.fk_rows, t0, t1, 2, s_out)
+                copy2d(h_angles, self.d_angles, 7, t0, t1, 2, s_out)
+                if self.d_fk is not None:
+                    copy2d(h_fk, self.d_fk, 3 * self.fk_rows, t0, t1, 2, s_out)
             main.wait_stream(s_out)
         self.launches_per_call = len(bounds) - 1
         if synchronize:
             main.synchronize()
-        return self.h_angles, self.h_fk
+        return h_angles, h_fk
 
     def mean_fk_error(self, pose=None) -> float:
         """Mean over chains, frames and the 4 distal joints of |fk[5..8] - pose[1..4]| in mm.
@@ -176,6 +183,73 @@ class BatchedLegIK:
         joints = self.d_fk if self.fk_layout == "joints" else self.d_fk[:, :, 5:9, :]
         d = joints - pose[:, :, 1:5, :]
         return float(d.square().sum(-1).sqrt().mean())
+
+
+class MultiGpuLegIK:
+    """The hot path over every visible GPU of one host, in one process: contiguous trial shards (``shard_range``), one
+    ``BatchedLegIK`` session + stream set + issuing thread per device, NO collective -- chains never exchange data -- and
+    the results of all devices land in ONE pinned host tensor, gathered once.  The multi-GPU analogue of the reference's
+    only parallel driver, ``multiprocessing.Pool(6).starmap`` over legs followed by ``dict.update``
+    (examples/example_leg_inv_kinematics_parallel.py:143-160,186-193): split, run, merge once.
+
+    Results are bit-identical to a single-device ``BatchedLegIK`` over the same trials (chains are independent; tested).
+    """
+
+    def __init__(self, kinematic_chain_class, initial_angles, legs: Sequence[str], n_trial: int, n_frame: int,
+                 devices: Optional[Sequence] = None, want_fk: bool = True, fk_layout: str = "full", flags: int = N.FLAG_DEFAULT):
+        torch = N.require_cuda()
+        N.load_library()
+        self.torch = torch
+        if devices is None:
+            devices = [f"cuda:{i}" for i in range(torch.cuda.device_count())]
+        self.devices = [torch.device(d) for d in devices]
+        if not self.devices:
+            raise N.SeqIKNativeError("MultiGpuLegIK needs at least one CUDA device")
+        self.n_trial, self.n_leg, self.n_frame = int(n_trial), len(list(legs)), int(n_frame)
+        self.fk_rows = 9 if fk_layout == "full" else 4
+        world = len(self.devices)
+        self.shards = [shard_range(self.n_trial, r, world) for r in range(world)]
+        self.sessions = [None if hi == lo else
+                         BatchedLegIK(kinematic_chain_class, initial_angles, legs, hi - lo, n_frame, device=d, want_fk=want_fk,
+                                      host_buffers=False, fk_layout=fk_layout, flags=flags)
+                         for d, (lo, hi) in zip(self.devices, self.shards)]
+        self.h_angles = torch.empty((self.n_trial, self.n_leg, self.n_frame, 7), dtype=torch.float32, pin_memory=True)
+        self.h_fk = (torch.empty((self.n_trial, self.n_leg, self.n_frame, self.fk_rows, 3), dtype=torch.float32, pin_memory=True)
+                     if want_fk else None)
+        self.status = None
+
+    @property
+    def leg_frames(self) -> int:
+        return self.n_trial * self.n_leg * self.n_frame
+
+    def solve_host(self, pose_host, n_chunks: Optional[int] = None):
+        """Pinned host pose (n_trial, n_leg, n_frame, 5, 3) float32 -> pinned host (angles, fk) of all trials.  Each device
+        runs the chunked copy/solve/copy pipeline of ``BatchedLegIK.solve_host`` on its shard, issued by its own thread
+        (ctypes and the CUDA runtime release the GIL); returns when every device is done."""
+        import threading
+        torch = self.torch
+        src = pose_host if isinstance(pose_host, torch.Tensor) else torch.from_numpy(pose_host)
+        if src.dtype != torch.float32 or not src.is_contiguous() or src.numel() != self.leg_frames * 15:
+            raise ValueError("pose_host must be a contiguous float32 array of (n_trial, n_leg, n_frame, 5, 3)")
+        src = src.view(self.n_trial, self.n_leg, self.n_frame, 5, 3)
+        errors = []
+
+        def work(sess, dev, lo, hi):
+            try:
+                with torch.cuda.device(dev):
+                    sess.solve_host(src[lo:hi], synchronize=True, n_chunks=n_chunks,
+                                    out=(self.h_angles[lo:hi], None if self.h_fk is None else self.h_fk[lo:hi]))
+            except Exception as exc:            # re-raised in the caller's thread
+                errors.append(exc)
+        threads = [threading.Thread(target=work, args=(s_, d, lo, hi))
+                   for s_, d, (lo, hi) in zip(self.sessions, self.devices, self.shards) if s_ is not None]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+        return self.h_angles, self.h_fk
 
 
 class FusedPipeline:

@@ -183,3 +183,26 @@ def test_large_batch_on_the_automatic_schedule_is_bit_identical(env, flags_name)
     assert torch.equal(a1.view(tiles, 48, n_frame, 7), a0.expand(tiles, -1, -1, -1))
     assert torch.equal(f1.view(tiles, 48, n_frame, 9, 3), f0.expand(tiles, -1, -1, -1, -1))
     assert torch.equal(n1.view(tiles, 48, 4), n0.expand(tiles, -1, -1)) and torch.equal(s1.view(tiles, 48), s0.expand(tiles, -1))
+
+
+def test_multi_gpu_driver_equals_one_device(env):
+    """batch.MultiGpuLegIK: trial shards over every visible device, results in one pinned host tensor, bit-identical to a
+    single-device session over the same trials.  With one visible device the driver still runs (one shard); with two or more
+    (gpurun --gpus N) the shards really sit on different devices."""
+    from seqikpy_b200.batch import BatchedLegIK, MultiGpuLegIK
+    from seqikpy_b200.kinematic_chain import KinematicChainSeq
+    torch, S = env.torch, env.S
+    size, bounds, init = S.chain_constants()
+    chain = KinematicChainSeq(bounds, list(S.LEGS), size)
+    n_trial, n_frame = 8, 256
+    host = env.pose.view(8, 6, 1000, 5, 3)[:, :, :n_frame].contiguous().cpu().pin_memory()
+    one = BatchedLegIK(chain, init, S.LEGS, n_trial, n_frame, device="cuda:0")
+    a1, f1 = one.solve_host(host)
+    multi = MultiGpuLegIK(chain, init, S.LEGS, n_trial, n_frame)
+    assert len(multi.devices) == torch.cuda.device_count() and sum(hi - lo for lo, hi in multi.shards) == n_trial
+    a2, f2 = multi.solve_host(host)
+    assert torch.equal(a1.view_as(a2), a2) and torch.equal(f1.view_as(f2), f2)
+    # fewer trials than devices / uneven shards
+    m3 = MultiGpuLegIK(chain, init, S.LEGS, 3, n_frame, devices=[f"cuda:{i}" for i in range(torch.cuda.device_count())] * 2)
+    a3, f3 = m3.solve_host(host[:3].contiguous().pin_memory())
+    assert torch.equal(a3, a2[:3]) and torch.equal(f3, f2[:3])
