@@ -25,6 +25,11 @@ Fixtures
                      the free-running angles (2,500,9) with status/nfev/cost, and -- because that problem is under-determined and
                      its free-running answer depends on rounding noise -- the SAME solves repeated with the target
                      perturbed by 1e-12 mm from the same seeds (the oracle's own reproducibility, frame by frame)
+  loader.npz         the reference's OWN raw-format converters (seqikpy.alignment.convert_from_anipose_to_dict / _df3d_to_dict /
+                     _df3dpp_to_dict, imported from /root/reference) run on small inputs in the three formats: an anipose table
+                     rebuilt from the bundled converted_dict.pkl with data.PTS2ALIGN's key-point names (40 frames), a
+                     DeepFly3D array (30 frames x 38 key points) and the bundled df3dPP dictionary (frames 300:330) --
+                     inputs and converter outputs, for the batched loader's key-order semantics
   synthetic_long.npz trial 5, legs RM and LH, 2000 frames: oracle angles (float32) -- a long warm-start chain that spans
                      many of the kernel's 64-frame resync periods
 """
@@ -256,5 +261,55 @@ def main():
         print(f.name, f.stat().st_size // 1024, "KiB")
 
 
+def make_loader_fixture():
+    """Inputs in the three raw formats + what the reference's converters make of them."""
+    from seqikpy import alignment as RA                       # the reference's module (imports without ikpy)
+    from seqikpy.data import PTS2ALIGN as REF_PTS
+    out = {}
+    # anipose: a table rebuilt from the bundled converted dictionary
+    conv = load(GROOM / "converted_dict.pkl")
+    n = 40
+    table = {}
+    for seg, kps in REF_PTS.items():
+        if seg not in conv:
+            continue
+        for i, kp in enumerate(kps):
+            for a, ax in enumerate("xyz"):
+                table[f"{kp}_{ax}"] = np.asarray(conv[seg][:n, i, a], dtype=np.float64)
+    pts = {seg: kps for seg, kps in REF_PTS.items() if seg in conv}
+    ref = RA.convert_from_anipose_to_dict(table, pts)
+    out["anipose_columns"] = np.array(sorted(table.keys()))
+    out["anipose_table"] = np.stack([table[k] for k in sorted(table.keys())])
+    out["anipose_segments"] = np.array(list(pts.keys()))
+    for seg in pts:
+        out[f"anipose_ref_{seg}"] = ref[seg]
+        out[f"anipose_kps_{seg}"] = np.array(pts[seg])
+        assert np.array_equal(ref[seg], conv[seg][:n])
+    # df3d: an array of 38 key points and the index map of the reference's docstring (alignment.py:172-179)
+    rng = np.random.default_rng(7)
+    arr = rng.normal(size=(30, 38, 3))
+    idx = {"RF_leg": np.arange(0, 5), "RM_leg": np.arange(5, 10), "RH_leg": np.arange(10, 15),
+           "LF_leg": np.arange(19, 24), "LM_leg": np.arange(24, 29), "LH_leg": np.arange(29, 34)}
+    ref = RA.convert_from_df3d_to_dict(arr, idx)
+    out["df3d_array"] = arr
+    for seg, ix in idx.items():
+        out[f"df3d_idx_{seg}"] = ix
+        out[f"df3d_ref_{seg}"] = ref[seg]
+    # df3dPP: the bundled dictionary
+    pp = load(LOCO / "pose_result__210902_PR_Fly1_aligned.pkl")
+    segs = [f"{leg}_leg" for leg in LOCO_LEGS]
+    cut = {seg: {kp: {"raw_pos_aligned": np.asarray(pp[seg][kp]["raw_pos_aligned"])[300:330]} for kp in ("Coxa", "Femur", "Tibia", "Tarsus", "Claw")}
+           for seg in segs}
+    ref = RA.convert_from_df3dpp_to_dict(cut, segs)
+    for seg in segs:
+        out[f"df3dpp_raw_{seg}"] = np.stack([cut[seg][kp]["raw_pos_aligned"] for kp in ("Coxa", "Femur", "Tibia", "Tarsus", "Claw")])
+        out[f"df3dpp_ref_{seg}"] = ref[seg]
+    np.savez_compressed(GOLD / "loader.npz", **out)
+    print("loader.npz", {k: v.shape for k, v in out.items() if k.endswith(("_table", "_array")) or "_ref_RF" in k})
+
+
 if __name__ == "__main__":
-    main()
+    if "--loader-only" in sys.argv:
+        make_loader_fixture()
+    else:
+        main()

@@ -206,3 +206,42 @@ def test_multi_gpu_driver_equals_one_device(env):
     m3 = MultiGpuLegIK(chain, init, S.LEGS, 3, n_frame, devices=[f"cuda:{i}" for i in range(torch.cuda.device_count())] * 2)
     a3, f3 = m3.solve_host(host[:3].contiguous().pin_memory())
     assert torch.equal(a3, a2[:3]) and torch.equal(f3, f2[:3])
+
+
+def test_batched_loader_feeds_the_device_paths(env):
+    """loader.BatchedPoseLoader (raw anipose tables -> one pinned (n_trial, n_leg, n_frame, 5, 3) tensor) -> FusedPipeline
+    (alignment statistics + align-on-load solve) against the dict API (AlignPose -> LegInvKinSeq) on the same recordings."""
+    import conftest
+    from seqikpy_b200.alignment import AlignPose
+    from seqikpy_b200.batch import FusedPipeline
+    from seqikpy_b200.kinematic_chain import DOF_ORDER, KinematicChainSeq
+    from seqikpy_b200.leg_inverse_kinematics import LegInvKinSeq
+    from seqikpy_b200.loader import BatchedPoseLoader, to_pose_dicts
+    from seqikpy_b200.utils import calculate_body_size
+    torch, D = env.torch, env.D
+    ga = dict(np.load(conftest.GOLDEN / "grooming_align.npz"))
+    legs = ["RF", "LF"]
+    pts = {"RF_leg": [f"rf{i}" for i in range(5)], "LF_leg": [f"lf{i}" for i in range(5)]}
+
+    def table(lo, hi):                                   # an anipose-style table cut from the bundled raw key points
+        t = {}
+        for seg, arr in (("RF_leg", ga["raw_full_RF"]), ("LF_leg", ga["raw_full_LF"])):
+            for i, kp in enumerate(pts[seg]):
+                for a, ax in enumerate("xyz"):
+                    t[f"{kp}_{ax}"] = arr[lo:hi, i, a]
+        return t
+    batch = BatchedPoseLoader(legs, fmt="anipose", pts2align=pts).load([table(0, 640), table(2000, 2640), table(4000, 4640)])
+    assert batch["legs"].is_pinned() and tuple(batch["legs"].shape) == (3, 2, 640, 5, 3)
+    size = calculate_body_size(D.NMF_TEMPLATE, legs)
+    chain = KinematicChainSeq(D.BOUNDS, legs, size)
+    pipe = FusedPipeline(chain, D.INITIAL_ANGLES, legs, D.NMF_TEMPLATE, size, 3, 640, with_head=False)
+    out = pipe.run(batch["legs"].cuda(non_blocking=True))
+    torch.cuda.synchronize()
+    for tr, raw in enumerate(to_pose_dicts(batch, legs)):
+        al = AlignPose(raw, legs_list=legs, include_claw=False, body_template=D.NMF_TEMPLATE, log_level="ERROR").align_pose()
+        ang, fk = LegInvKinSeq(al, chain, D.INITIAL_ANGLES, log_level="ERROR").run_ik_and_fk()
+        for li, leg in enumerate(legs):
+            ref = np.stack([ang[f"Angle_{leg}_{d}"] for d in DOF_ORDER], 1)
+            ours = out["angles"][tr, li].cpu().numpy()
+            close = np.abs(ours - ref).max(axis=1) < 2e-4                    # float32 pose rounding; singular episodes may differ
+            assert close.mean() > 0.99, (tr, leg, close.mean())
