@@ -221,3 +221,57 @@ def test_leg_ik_class_exposes_the_solver_mode():
     assert LegInvKinSeq(pose, ch, D.INITIAL_ANGLES, log_level="ERROR").flags == N.FLAG_DEFAULT
     assert LegInvKinSeq(pose, ch, D.INITIAL_ANGLES, log_level="ERROR", reference_iterates=True).flags == N.FLAG_REFERENCE_ITERATES
     assert LegInvKinSeq(pose, ch, D.INITIAL_ANGLES, log_level="ERROR", flags=0x7F).flags == 0x7F
+
+
+def test_reference_visualization_loader_reads_our_pickles(tmp_path, grooming_leg, grooming_head):
+    """the reference's plotting code consumes the pickles through visualization.load_grid_plot_data
+    (visualization.py:191-213).  The REFERENCE's own function (imported from /root/reference with matplotlib stubbed out --
+    it is not installed here and the loader does not use it) reads the files our writers produce, under the reference's file
+    names, and finds the keys and shapes its consumers index.  Skipped where the reference checkout is absent (GPU box)."""
+    import sys
+    import types
+    from pathlib import Path
+    ref_root = Path("/root/reference")
+    if not (ref_root / "seqikpy" / "visualization.py").exists():
+        pytest.skip("reference checkout not available")
+    class _Stub(types.ModuleType):                                  # any attribute (plt.Axes in annotations, GridSpec, ...) is a dummy class
+        def __getattr__(self, name):
+            if name.startswith("__"):
+                raise AttributeError(name)
+            return type(name, (), {})
+    stubs = {}
+    for name in ("matplotlib", "matplotlib.animation", "matplotlib.gridspec", "matplotlib.pyplot", "matplotlib.backends",
+                 "matplotlib.backends.backend_agg"):
+        if name not in sys.modules:
+            stubs[name] = _Stub(name)
+    for name, mod in stubs.items():                                 # `import a.b as c` resolves b as an attribute of a
+        if "." in name and name.rsplit(".", 1)[0] in stubs:
+            setattr(stubs[name.rsplit(".", 1)[0]], name.rsplit(".", 1)[1], mod)
+    sys.modules.update(stubs)
+    sys.path.insert(0, str(ref_root))
+    try:
+        try:
+            from seqikpy import visualization as RV
+        except Exception as exc:                                   # e.g. cv2 missing
+            pytest.skip(f"reference visualization module not importable: {exc!r}")
+        # files exactly as our classes write them (export_path=): plain dicts of float64 arrays under the reference's names
+        leg = {str(k): grooming_leg["ref_angles"][i // 7][:, i % 7].astype(np.float64) for i, k in enumerate(grooming_leg["angle_keys"])}
+        head = {str(k): grooming_head["ref_angles"][i].astype(np.float64) for i, k in enumerate(grooming_head["keys"])}
+        aligned = {"RF_leg": grooming_leg["pose"][0], "LF_leg": grooming_leg["pose"][1], "R_head": grooming_head["r_head"],
+                   "L_head": grooming_head["l_head"], "Neck": grooming_head["neck"]}
+        save_file(tmp_path / "leg_joint_angles.pkl", leg)
+        save_file(tmp_path / "head_joint_angles.pkl", head)
+        save_file(tmp_path / "pose3d_aligned.pkl", aligned)
+        ja, pose = RV.load_grid_plot_data(tmp_path)                # head + leg files merged
+        assert list(ja.keys()) == list(head.keys()) + list(leg.keys()) and len(ja) == 21
+        assert pose["RF_leg"].shape == (6000, 5, 3) and pose["Neck"].shape == (1, 1, 3)
+        save_file(tmp_path / "body_joint_angles.pkl", {**head, **leg})
+        ja2, _ = RV.load_grid_plot_data(tmp_path)                  # the merged file takes precedence
+        assert list(ja2.keys()) == list(ja.keys()) and all(np.array_equal(ja2[k], ja[k]) for k in ja)
+        assert all(k.startswith("Angle_") and v.shape == (6000,) and v.dtype == np.float64 for k, v in ja2.items())
+    finally:
+        sys.path.remove(str(ref_root))
+        for name in stubs:
+            sys.modules.pop(name, None)
+        for name in [m for m in sys.modules if m == "seqikpy" or m.startswith("seqikpy.")]:
+            sys.modules.pop(name, None)
