@@ -291,13 +291,20 @@ def run_ours(args):
     clocks = sampler.stop() if sampler else None
     # ---- the same call with the joints-only FK layout (rows 5..8: the rows that carry information); a secondary figure,
     #      the headline `e2e` above keeps the reference's 9-row layout
-    ms_e2e_joints = None
+    ms_e2e_joints = ms_e2e_wire = expand_threads = None
     if not args.no_joints_e2e:
         sess_j = BatchedLegIK(chain, init, S.LEGS, T, F, device=dev, schedule=args.schedule, chains_per_warp=args.cpw, fk_layout="joints")
         for _ in range(2):
             sess_j.solve_host(host_pose, n_chunks=args.chunks)
         ms_e2e_joints = timed(lambda: sess_j.solve_host(host_pose, synchronize=False, n_chunks=args.chunks), args.steps) / args.steps
         del sess_j
+        # ... and as a WIRE format only: joints-only over the host link, the reference's 9-row layout rebuilt in host memory
+        sess_w = BatchedLegIK(chain, init, S.LEGS, T, F, device=dev, schedule=args.schedule, chains_per_warp=args.cpw, wire="joints")
+        for _ in range(2):
+            sess_w.solve_host(host_pose, n_chunks=args.chunks)
+        ms_e2e_wire = timed(lambda: sess_w.solve_host(host_pose, synchronize=False, n_chunks=args.chunks), args.steps) / args.steps
+        expand_threads = sess_w.expand_threads
+        del sess_w
 
     # ---- the same kernel family walking the reference's own iterates (SEQIK_FLAG_REFERENCE_ITERATES: no Newton steps, no
     #      closed-form warm step; runs on the stage-pipeline schedule): a secondary figure that shows what the default flags save
@@ -435,6 +442,12 @@ def run_ours(args):
                 "value": leg_frames / (ms_e2e_joints * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_joints,
                 "h2d_bytes_per_step": leg_frames_rank * 60, "d2h_bytes_per_step": leg_frames_rank * (28 + 48),
                 "note": "fk_layout='joints': FK rows 5..8 only (rows 0-3 of the reference layout repeat the input origin, row 4 repeats row 5)"},
+            "e2e_joints_wire": None if ms_e2e_wire is None else {
+                "value": leg_frames / (ms_e2e_wire * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_wire,
+                "h2d_bytes_per_step": leg_frames_rank * 60, "d2h_bytes_per_step": leg_frames_rank * (28 + 48), "host_threads": expand_threads,
+                "note": "BatchedLegIK(wire='joints'): the caller still receives the reference's (..., 9, 3) FK; only rows 5..8 cross the "
+                        "host link, rows 0-4 are rebuilt in host memory from the host-resident pose by host threads "
+                        "(seqik_fk_expand_host_f32), chunk by chunk behind the copies; bit-identical to `e2e`"},
             "gpu_launches": args.steps * 2,                           # per step: leg_first_frame_kernel + leg_solve_block_kernel
             "kernels": "leg_first_frame_kernel (frame 0 of every chain, lane per chain) + leg_solve_block_kernel (schedule 3: a warp per "
                        "chain, 32 frames per pass, bulk-copy staged)",

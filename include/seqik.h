@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SEQIK_ABI_VERSION 5   /* 5: solver flag bits 6-7 (Newton steps, closed-form warm step), phase periods in bits 21-27 */
+#define SEQIK_ABI_VERSION 6   /* 6: schedule 3 (frame-parallel blocks), seqik_fk_expand_host_f32; 5: solver flag bits 6-7, phase periods in bits 21-27 */
 #define SEQIK_OK 0
 #define SEQIK_EINVAL (-1)
 #define SEQIK_ECUDA (-3)
@@ -263,6 +263,15 @@ int seqik_pchip_resample_f64(const double* in, double* out, int64_t n_block, int
  * chain-major array is a 2-D block); a thin wrapper over cudaMemcpy2DAsync so that callers need no CUDA binding. */
 int seqik_memcpy2d_async(void* dst, int64_t dst_pitch_bytes, const void* src, int64_t src_pitch_bytes,
                          int64_t width_bytes, int64_t height, int direction, void* stream);
+
+/* HOST-side helper of the joints-only wire format (SEQIK_FLAG_FK_JOINTS over the host link, the reference's layout in host
+ * memory): rebuilds fk [n_chain][n_frame][9][3] (leg_inverse_kinematics.py:71-77: rows 0-3 = origin, 4-5 = Coxa-Femur joint,
+ * 6-8 = the other joints) for frames [t0, t1) from joints [n_chain][n_frame][4][3] and row 0 of the HOST pose.  All pointers
+ * are HOST pointers here; strides in floats; chains are split over n_threads host threads; synchronous. */
+int seqik_fk_expand_host_f32(const float* joints, int64_t j_chain_stride, int64_t j_frame_stride,
+                             const float* pose, int64_t p_chain_stride, int64_t p_frame_stride,
+                             float* fk, int64_t f_chain_stride, int64_t f_frame_stride,
+                             int64_t n_chain, int64_t t0, int64_t t1, int n_threads);
 
 #ifdef __cplusplus
 }

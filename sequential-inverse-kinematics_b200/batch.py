@@ -66,8 +66,13 @@ class BatchedLegIK:
 
     def __init__(self, kinematic_chain_class, initial_angles, legs: Sequence[str], n_trial: int, n_frame: int,
                  device="cuda", want_fk: bool = True, schedule: int = N.SCHED_AUTO, host_buffers: bool = True,
-                 chains_per_warp: int = 0, fk_layout: str = "full", flags: int = N.FLAG_DEFAULT):
+                 chains_per_warp: int = 0, fk_layout: str = "full", flags: int = N.FLAG_DEFAULT, wire: str = "same",
+                 expand_threads: int = 0):
         """``flags``: solver flags (include/seqik.h; ``N.FLAG_REFERENCE_ITERATES`` walks the reference's own iterates).
+        ``wire="joints"`` (with ``fk_layout="full"``): ``solve_host`` still returns the reference's 9-row FK, but only the
+        four joint rows cross the host link (76 instead of 136 result bytes per leg-frame); rows 0-3 are rebuilt on the host
+        from the origin row of the host-resident pose and row 4 from row 5 by ``expand_threads`` host threads
+        (``seqik_fk_expand_host_f32``), chunk by chunk while later chunks are still in flight.  Bit-identical results.
         ``fk_layout``: "full" = the reference's 9 rows per leg-frame; "joints" = only the four rows that carry
         information (rows 5..8: rows 0-3 of the full layout repeat the input origin, row 4 repeats row 5), which cuts
         the device->host result from 136 to 76 bytes per leg-frame -- the end-to-end call is bound by that copy."""
@@ -87,13 +92,23 @@ class BatchedLegIK:
         self.d_angles = torch.empty((self.n_chain, self.n_frame, 7), **f32)
         if fk_layout not in ("full", "joints"):
             raise ValueError(f"fk_layout must be 'full' or 'joints', got {fk_layout!r}")
+        if wire not in ("same", "joints"):
+            raise ValueError(f"wire must be 'same' or 'joints', got {wire!r}")
+        self.wire_joints = wire == "joints" and fk_layout == "full" and want_fk
+        self.out_rows = 9 if fk_layout == "full" else 4               # rows of the fk the caller receives
+        if self.wire_joints:
+            fk_layout = "joints"                                       # what the device computes and the link carries
         self.fk_layout = fk_layout
         self.fk_rows = 9 if fk_layout == "full" else 4
         self.d_fk = torch.empty((self.n_chain, self.n_frame, self.fk_rows, 3), **f32) if want_fk else None
-        self.h_angles = self.h_fk = None
+        self.h_angles = self.h_fk = self.h_wire = None
+        import os
+        self.expand_threads = int(expand_threads) if expand_threads else max(1, min(16, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
         if host_buffers:
             self.h_angles = torch.empty((self.n_chain, self.n_frame, 7), dtype=torch.float32, pin_memory=True)
-            self.h_fk = torch.empty((self.n_chain, self.n_frame, self.fk_rows, 3), dtype=torch.float32, pin_memory=True) if want_fk else None
+            self.h_fk = torch.empty((self.n_chain, self.n_frame, self.out_rows, 3), dtype=torch.float32, pin_memory=True) if want_fk else None
+        if self.wire_joints:
+            self.h_wire = torch.empty((self.n_chain, self.n_frame, 4, 3), dtype=torch.float32, pin_memory=True)
         self.status = self.nfev = None
         self._copy_streams = None
         self.default_chunks = 8
@@ -128,8 +143,8 @@ class BatchedLegIK:
             raise RuntimeError("session was created with host_buffers=False: pass out=(angles, fk)")
         if h_angles.numel() != self.n_chain * self.n_frame * 7 or not h_angles.is_contiguous() or h_angles.dtype != torch.float32:
             raise ValueError("out angles must be a contiguous float32 tensor of (n_trial, n_leg, n_frame, 7)")
-        if self.d_fk is not None and (h_fk is None or h_fk.numel() != self.n_chain * self.n_frame * 3 * self.fk_rows or not h_fk.is_contiguous()):
-            raise ValueError(f"out fk must be a contiguous float32 tensor of (n_trial, n_leg, n_frame, {self.fk_rows}, 3)")
+        if self.d_fk is not None and (h_fk is None or h_fk.numel() != self.n_chain * self.n_frame * 3 * self.out_rows or not h_fk.is_contiguous()):
+            raise ValueError(f"out fk must be a contiguous float32 tensor of (n_trial, n_leg, n_frame, {self.out_rows}, 3)")
         src = pose_host if isinstance(pose_host, torch.Tensor) else torch.from_numpy(pose_host)
         if src.dtype != torch.float32 or not src.is_contiguous() or src.numel() != self.n_chain * self.n_frame * 15:
             raise ValueError("pose_host must be a contiguous float32 array of (n_trial, n_leg, n_frame, 5, 3)")
@@ -146,6 +161,8 @@ class BatchedLegIK:
         # chunk starts on multiples of 32 frames (the kernel's resync period): then chunking is bit-identical
         # to one launch over all frames
         bounds = sorted({0, F} | {min(F, RESYNC_FRAMES * round(F * k / n_chunks / RESYNC_FRAMES)) for k in range(1, n_chunks)})
+
+        arrived = []
 
         def copy2d(dst, src_, row_floats, t0, t1, direction, stream):
             off = 4 * row_floats * t0
@@ -169,9 +186,19 @@ class BatchedLegIK:
                 s_out.wait_event(ev_k)
                 copy2d(h_angles, self.d_angles, 7, t0, t1, 2, s_out)
                 if self.d_fk is not None:
-                    copy2d(h_fk, self.d_fk, 3 * self.fk_rows, t0, t1, 2, s_out)
+                    copy2d(self.h_wire if self.wire_joints else h_fk, self.d_fk, 3 * self.fk_rows, t0, t1, 2, s_out)
+                if self.wire_joints:
+                    ev_o = torch.cuda.Event()
+                    ev_o.record(s_out)
+                    arrived.append((ev_o, t0, t1))
             main.wait_stream(s_out)
         self.launches_per_call = len(bounds) - 1
+        # joints-only wire format: the 9-row layout is rebuilt on the host, chunk by chunk as the copies land (later chunks
+        # are still being solved / copied meanwhile); this part of the call is synchronous by nature
+        for ev_o, t0, t1 in arrived:
+            ev_o.synchronize()
+            N.check(lib.seqik_fk_expand_host_f32(self.h_wire.data_ptr(), F * 12, 12, src.data_ptr(), F * 15, 15, h_fk.data_ptr(), F * 27, 27,
+                                                 self.n_chain, t0, t1, self.expand_threads), "seqik_fk_expand_host_f32")
         if synchronize:
             main.synchronize()
         return h_angles, h_fk
@@ -180,7 +207,7 @@ class BatchedLegIK:
         """Mean over chains, frames and the 4 distal joints of |fk[5..8] - pose[1..4]| in mm.
         Reduction of RESULTS for reporting (torch ops on the device tensors), not part of the solve."""
         pose = self.d_pose if pose is None else pose.reshape(self.n_chain, self.n_frame, 5, 3)
-        joints = self.d_fk if self.fk_layout == "joints" else self.d_fk[:, :, 5:9, :]
+        joints = self.d_fk if self.fk_layout == "joints" else self.d_fk[:, :, 5:9, :]      # (wire="joints": the device holds joints)
         d = joints - pose[:, :, 1:5, :]
         return float(d.square().sum(-1).sqrt().mean())
 

@@ -11,6 +11,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <thread>
+#include <vector>
 
 #include "../../include/seqik.h"
 #include "seqik_common.h"
@@ -54,6 +56,40 @@ extern "C" int seqik_memcpy2d_async(void* dst, int64_t dst_pitch_bytes, const vo
     return SEQIK_OK;
 }
 extern "C" const char* seqik_last_error(void) { return g_err; }
+
+// Host side of the joints-only wire format: the reference's nine-row FK layout rebuilt in HOST memory from the four joint rows
+// that crossed the link and the origin row of the host-resident pose (rows 0-3 = origin, row 4 = row 5 = first joint).
+// A memory-bound copy; chains are split over `n_threads` host threads.
+extern "C" int seqik_fk_expand_host_f32(const float* joints, int64_t j_chain_stride, int64_t j_frame_stride,
+                                        const float* pose, int64_t p_chain_stride, int64_t p_frame_stride,
+                                        float* fk, int64_t f_chain_stride, int64_t f_frame_stride,
+                                        int64_t n_chain, int64_t t0, int64_t t1, int n_threads) {
+    if (n_chain < 0 || t0 < 0 || t1 < t0) return fail(SEQIK_EINVAL, "seqik_fk_expand_host_f32: bad range");
+    if (n_chain == 0 || t1 == t0) return SEQIK_OK;
+    if (!joints || !pose || !fk) return fail(SEQIK_EINVAL, "seqik_fk_expand_host_f32: NULL pointer");
+    if (j_frame_stride < 12 || p_frame_stride < 3 || f_frame_stride < 27) return fail(SEQIK_EINVAL, "seqik_fk_expand_host_f32: frame stride too small");
+    if (n_threads < 1) n_threads = 1;
+    if ((int64_t)n_threads > n_chain) n_threads = (int)n_chain;
+    auto work = [=](int64_t c0, int64_t c1) {
+        for (int64_t c = c0; c < c1; ++c) {
+            const float* j = joints + c * j_chain_stride + t0 * j_frame_stride;
+            const float* p = pose + c * p_chain_stride + t0 * p_frame_stride;
+            float* o = fk + c * f_chain_stride + t0 * f_frame_stride;
+            for (int64_t t = t0; t < t1; ++t, j += j_frame_stride, p += p_frame_stride, o += f_frame_stride) {
+                const float x = p[0], y = p[1], z = p[2];
+                for (int r = 0; r < 4; ++r) { o[3 * r] = x; o[3 * r + 1] = y; o[3 * r + 2] = z; }
+                o[12] = j[0]; o[13] = j[1]; o[14] = j[2];
+                memcpy(o + 15, j, 12 * sizeof(float));
+            }
+        }
+    };
+    if (n_threads == 1) { work(0, n_chain); return SEQIK_OK; }
+    std::vector<std::thread> pool;
+    pool.reserve(n_threads);
+    for (int k = 0; k < n_threads; ++k) pool.emplace_back(work, n_chain * k / n_threads, n_chain * (k + 1) / n_threads);
+    for (auto& th : pool) th.join();
+    return SEQIK_OK;
+}
 
 // ---------------------------------------------------------------------------------------------
 // forward kinematics (streaming)

@@ -648,6 +648,7 @@ __global__ void __launch_bounds__(BLK, SEQIK_BLOCK_MIN_CTAS) leg_solve_block_ker
                 qsb[s] = __shfl_sync(full, Tsb[s], (j + 31) & 31); qcb[s] = __shfl_sync(full, Tcb[s], (j + 31) & 31);
                 if (j == j0) { qsa[s] = sh.P[s][0]; qca[s] = sh.P[s][1]; qsb[s] = sh.P[s][2]; qcb[s] = sh.P[s][3]; }
             }
+            __syncwarp(full);        // every lane has read sh.P before the replaying lane overwrites it
             if (lane == j) {
                 Mat3<float> A = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
                 Vec3<float> piv = {0.f, 0.f, 0.f};

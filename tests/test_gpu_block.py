@@ -245,3 +245,22 @@ def test_batched_loader_feeds_the_device_paths(env):
             ours = out["angles"][tr, li].cpu().numpy()
             close = np.abs(ours - ref).max(axis=1) < 2e-4                    # float32 pose rounding; singular episodes may differ
             assert close.mean() > 0.99, (tr, leg, close.mean())
+
+
+def test_joints_wire_format_returns_the_reference_layout(env):
+    """BatchedLegIK(wire="joints"): only the four joint rows cross the host link; the 9-row FK the caller receives (rows 0-3
+    rebuilt from the host pose, row 4 from row 5, seqik_fk_expand_host_f32) is bit-identical to the plain call's."""
+    from seqikpy_b200.batch import BatchedLegIK
+    from seqikpy_b200.kinematic_chain import KinematicChainSeq
+    torch, S = env.torch, env.S
+    size, bounds, init = S.chain_constants()
+    chain = KinematicChainSeq(bounds, list(S.LEGS), size)
+    n_trial, n_frame = 8, 300
+    host = env.pose.view(8, 6, 1000, 5, 3)[:, :, :n_frame].contiguous().cpu().pin_memory()
+    a1, f1 = BatchedLegIK(chain, init, S.LEGS, n_trial, n_frame).solve_host(host)
+    for threads in (1, 5):
+        w = BatchedLegIK(chain, init, S.LEGS, n_trial, n_frame, wire="joints", expand_threads=threads)
+        a2, f2 = w.solve_host(host, n_chunks=4)
+        assert tuple(f2.shape) == (48, n_frame, 9, 3)
+        assert torch.equal(a1, a2) and torch.equal(f1, f2)
+        assert abs(w.mean_fk_error() - 0.0264) < 2e-3
