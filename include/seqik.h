@@ -76,6 +76,8 @@ extern "C" {
                                                 of the full layout repeat the input origin and row 4 repeats row 5; leaving them out
                                                 cuts the result from 136 to 76 bytes per leg-frame, which is what an end-to-end
                                                 call over PCIe is bound by */
+#define SEQIK_FLAG_BLOCK_VARIANT_SHIFT 28    /* bits 28..29: kernel variant of schedule 3, 0 = automatic (by batch size), 1 = lean (large batches),
+                                                2 = robust (replay-heavy recordings: stage-granular replays).  Scheduling only */
 #define SEQIK_FLAG_CPW_SHIFT 12              /* bits 12..17: chains per warp of schedule 2 (1..8) / resident warps per SM of schedule 3
                                                 (1..32), 0 = automatic */
 

@@ -98,7 +98,7 @@ template <typename R> SK_HD void warm_limit_move(R c_sb, R c_cb, R sb, R cb, R& 
 
 // ---- speculation of the case from the candidate's direction alone: 1 / 2 when it lies just outside the lower / upper
 // limit of the first angle, else 0 (interior).  Only a guess -- warm_case() below decides with the exact angles.
-enum : int { WC_INTERIOR = 0, WC_LO = 1, WC_HI = 2, WC_NONE = -1 };
+enum : int { WC_INTERIOR = 0, WC_LO = 1, WC_HI = 2, WC_STAYS = 3, WC_NONE = -1 };   // WC_STAYS: one-variable stage parked on a limit (block kernel)
 template <typename R> SK_HD int warm_guess(R n_sa, R n_ca, R sl0, R cl0, R su0, R cu0) {
     typedef Num<R> N;
     const R s_lo = N::fma_(n_sa, cl0, -(n_ca * sl0)), c_lo = N::fma_(n_ca, cl0, n_sa * sl0);   // sin / cos (a - lb)

@@ -340,6 +340,14 @@ __device__ __forceinline__ void serial_stage(int s, const StageK& k, int gn_mask
     piv = np_;
     x0 = S.x0; x1 = S.x1; sa = S.sa; ca = S.ca; sb = S.sb; cb = S.cb; xb_out = S.angle_b();
 }
+// The same as a real call (robust block kernel): the ~75 registers of the serial solver are then the callee's business and what
+// the kernel keeps across it is saved at the -- cold -- call site instead of being spilled where it is defined, in the hot pass.
+__device__ __noinline__ void serial_stage_call(int s, const StageK& k, int gn_mask, bool esc, bool warm_ok, const Vec3<float>& kt,
+                                               const Vec3<float>& o, Mat3<float>& A, Vec3<float>& piv, float& x0, float& x1,
+                                               float& sa, float& ca, float& sb, float& cb, float& xb_out, Vec3<float>& w,
+                                               uint32_t& nfev, int& worst) {
+    serial_stage(s, k, gn_mask, esc, warm_ok, kt, o, A, piv, x0, x1, sa, ca, sb, cb, xb_out, w, nfev, worst);
+}
 enum : int { KC_L, KC_LB0, KC_UB0, KC_LB1S, KC_UB1S, KC_SL0, KC_CL0, KC_SU0, KC_CU0, KC_LB0P, KC_UB0P, KC_NSQ, KC_LB1, KC_UB1, KC_N = 16 };
 struct __align__(16) BlockShared {
     float pose[2][BLK * 15];           // key points of the current / next block (bulk-copy destination)
@@ -349,6 +357,8 @@ struct __align__(16) BlockShared {
     float acc_x[7][BLK + 2];           // [l][t + 1]: placed angle BEFORE frame t of series l; [l][t + 2] after it ([0] unused)
     float kc[4][KC_N];                 // per-stage constants of the chain
     float P[4][4];                     // sin/cos (sa, ca, sb, cb) per stage of the state before the first lane of a pass
+    float mapc[8];                     // alignment map applied on load (fixed xyz, scale, template xyz, on/off): rarely used, kept out of registers
+    uint32_t nfx[4];                   // evaluations of replayed solves per stage (committed lanes count one each)
     uint64_t bar[2];
 };
 
@@ -410,36 +420,59 @@ __global__ void __launch_bounds__(BLK) leg_first_frame_kernel(LegArgs a) {
     ang[(int64_t)4 * a.ang_fs + 6] = __int_as_float(worst);                  // record slot 27
 }
 
+// Two instantiations of the same source.  kRobust = false: the lean kernel for large batches -- a replay reruns the whole
+// frame serially and the lanes after it are recomputed from stage 1; 96 registers, 18 resident warps per SM.  kRobust = true:
+// for recordings that replay often (joint limits active, fast motion: 3-4 % of the frames of the bundled grooming trial) --
+// a replay starts at the first failing stage, the lanes after it keep their earlier stages, and the one-variable stage
+// sitting on its limit is decided exactly in the pass; 128 registers, 16 resident warps per SM.  Same results, bit for bit.
 #ifndef SEQIK_BLOCK_MIN_CTAS
-#define SEQIK_BLOCK_MIN_CTAS 18        // resident one-warp CTAs per SM the register allocation must allow (measured)
+#define SEQIK_BLOCK_MIN_CTAS 16        // resident one-warp CTAs per SM the register allocation must allow: 128 registers, no spills (measured: 96 registers spill in the pass)
 #endif
-template <int kFk>                     // 0: no forward kinematics, 1: nine rows, 2: the four joint rows only
-__global__ void __launch_bounds__(BLK, SEQIK_BLOCK_MIN_CTAS) leg_solve_block_kernel(LegArgs a, int bulk_in, int bulk_out, int first_done) {
+#ifndef SEQIK_BLOCK_MIN_CTAS_ROBUST
+#define SEQIK_BLOCK_MIN_CTAS_ROBUST 16
+#endif
+template <int kFk, bool kRobust>       // kFk 0: no forward kinematics, 1: nine rows, 2: the four joint rows only
+__global__ void __launch_bounds__(BLK, kRobust ? SEQIK_BLOCK_MIN_CTAS_ROBUST : SEQIK_BLOCK_MIN_CTAS)
+leg_solve_block_kernel(LegArgs a, int bulk_in, int bulk_out, int first_done) {
     __shared__ __align__(128) BlockShared sh;
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x;
     const int64_t c = blockIdx.x;
-    const float* prm = a.params + c * SEQIK_CHAIN_PARAM_FLOATS;
-    const float* pose = a.pose + c * a.pose_cs;
-    float* ang = a.angles + c * a.ang_cs;
-    float* fk = kFk ? a.fk + c * a.fk_cs : nullptr;
+    // (global pointers are rebuilt from the kernel arguments where they are used: a handful of places, and registers are scarce)
+#define BLK_PRM (a.params + c * SEQIK_CHAIN_PARAM_FLOATS)
+#define BLK_POSE (a.pose + c * a.pose_cs)
+#define BLK_ANG (a.angles + c * a.ang_cs)
+#define BLK_FK (a.fk + c * a.fk_cs)
     constexpr int FKF = kFk == 1 ? 27 : 12;                        // floats per leg-frame of the fk layout
     const int n_frame = (int)a.n_frame;
     const float inf = Num<float>::inf();
     const float half_pi = 1.57079632679489661923f;
-    LoadMap map; map.init(a.affine, c);
     const bool esc = (a.gn_mask >> 4) & 1;
     const bool warm_given = a.warm != nullptr;
     const bool cf_all = (a.gn_mask & 0x8F) == 0x8F;                // closed-form warm step enabled in all four stages
+    if (lane < 8) {
+        float v = (lane == 3) ? 1.f : 0.f;
+        if (a.affine != nullptr) v = (lane == 7) ? 1.f : __ldg(a.affine + c * 8 + lane);
+        sh.mapc[lane] = v;
+        if (lane < 4) sh.nfx[lane] = 0u;
+    }
+    auto map_apply = [&](Vec3<float> v, int row) -> Vec3<float> {  // AlignPose.align_leg on load (LoadMap), constants in shared memory
+        if (sh.mapc[7] != 0.f) {
+            const float sc = sh.mapc[3];
+            if (row == 0) v = {sh.mapc[4], sh.mapc[5], sh.mapc[6]};
+            else v = {(v.x - sh.mapc[0]) * sc + sh.mapc[4], (v.y - sh.mapc[1]) * sc + sh.mapc[5], (v.z - sh.mapc[2]) * sc + sh.mapc[6]};
+        }
+        return v;
+    };
 
     if (lane < 4) {                                                // per-(chain, stage) constants
         const int s = lane, ia = 2 * s, ib = (s == 3) ? 6 : 2 * s + 1;
         const float shift = (s == 0) ? half_pi : 0.f;
-        const float lb0 = (s == 3) ? -inf : __ldg(prm + 4 + ia), ub0 = (s == 3) ? inf : __ldg(prm + 11 + ia);
-        const float lb1 = __ldg(prm + 4 + ib), ub1 = __ldg(prm + 11 + ib);
+        const float lb0 = (s == 3) ? -inf : __ldg(BLK_PRM + 4 + ia), ub0 = (s == 3) ? inf : __ldg(BLK_PRM + 11 + ia);
+        const float lb1 = __ldg(BLK_PRM + 4 + ib), ub1 = __ldg(BLK_PRM + 11 + ib);
         float* K = sh.kc[s];
-        K[KC_L] = __ldg(prm + s); K[KC_LB0] = lb0; K[KC_UB0] = ub0; K[KC_LB1S] = lb1 - shift; K[KC_UB1S] = ub1 - shift;
-        K[KC_LB1] = lb1; K[KC_UB1] = ub1; K[KC_NSQ] = __ldg(prm + 25 + s);
+        K[KC_L] = __ldg(BLK_PRM + s); K[KC_LB0] = lb0; K[KC_UB0] = ub0; K[KC_LB1S] = lb1 - shift; K[KC_UB1S] = ub1 - shift;
+        K[KC_LB1] = lb1; K[KC_UB1] = ub1; K[KC_NSQ] = __ldg(BLK_PRM + 25 + s);
         float sl = 0.f, cl = 0.f, su = 0.f, cu = 0.f, v_;
         if (lb0 > -inf && ub0 < inf) { Num<float>::sincosv_(lb0, &sl, &cl, &v_); Num<float>::sincosv_(ub0, &su, &cu, &v_); }
         K[KC_SL0] = sl; K[KC_CL0] = cl; K[KC_SU0] = su; K[KC_CU0] = cu;           // all zero: no limit case (warm_guess says interior)
@@ -457,17 +490,17 @@ __global__ void __launch_bounds__(BLK, SEQIK_BLOCK_MIN_CTAS) leg_solve_block_ker
     const float ser_shift = (lane == 3) ? half_pi : 0.f;
     float xcar = 0.f;                                              // carried angle of this lane's series, caller's terms
     {
-        const float* seed = warm_given ? a.warm + c * a.warm_cs : prm + 18;
+        const float* seed = warm_given ? a.warm + c * a.warm_cs : BLK_PRM + 18;
         if (is_ser) xcar = seed[is_a ? 2 * sl_ : (sl_ == 3 ? 6 : 2 * sl_ + 1)];
     }
-    uint32_t nf[4] = {0u, 0u, 0u, 0u}; int worst = ST_GTOL;
+    uint32_t n_commit = 0u; int worst = ST_GTOL;   // frames this lane committed from the pass (one evaluation per stage each)
     const int n_blk = (n_frame + BLK - 1) / BLK;
     auto frames_of = [&](int b) { const int r = n_frame - b * BLK; return r < BLK ? r : BLK; };
     auto bulk_load_ok = [&](int b) { return bulk_in && (frames_of(b) & 3) == 0; };
     auto issue_load = [&](int b) {                                 // lane 0
         const uint32_t bytes = (uint32_t)frames_of(b) * 60u;
         mbar_expect_tx(&sh.bar[b & 1], bytes);
-        tma_load_1d(sh.pose[b & 1], pose + (int64_t)b * (BLK * 15), bytes, &sh.bar[b & 1]);
+        tma_load_1d(sh.pose[b & 1], BLK_POSE + (int64_t)b * (BLK * 15), bytes, &sh.bar[b & 1]);
     };
     if (lane == 0 && bulk_load_ok(0)) issue_load(0);
 
@@ -476,7 +509,7 @@ __global__ void __launch_bounds__(BLK, SEQIK_BLOCK_MIN_CTAS) leg_solve_block_ker
         const float* kp = sh.pose[cur] + lane * 15;
         if (bulk_load_ok(b)) mbar_wait(&sh.bar[cur], (uint32_t)(b >> 1) & 1u);
         else {
-            const float* src = pose + (int64_t)t_abs0 * a.pose_fs;
+            const float* src = BLK_POSE + (int64_t)t_abs0 * a.pose_fs;
             for (int i = lane; i < nv * 15; i += BLK) sh.pose[cur][i] = __ldg(src + (int64_t)(i / 15) * a.pose_fs + i % 15);
         }
         __syncwarp(full);
@@ -492,43 +525,59 @@ __global__ void __launch_bounds__(BLK, SEQIK_BLOCK_MIN_CTAS) leg_solve_block_ker
         }
         __syncwarp(full);
         bool staged = false;
-        int j0 = 0;
+        int j0 = 0, s_start = 0;         // the pass covers lanes j0.. and stages s_start.. (earlier stages of those lanes stand)
         if (first_done && b == 0) {
             // frame 0 was solved by leg_first_frame_kernel: its record (final sin/cos, placed angles, counters) waits in the
             // chain's angle rows 1..4, its results in row 0 of the outputs; the block starts at lane 1 from that state
             float rec = 0.f;
-            if (lane < FF_REC) rec = ang[(int64_t)(1 + lane / 7) * a.ang_fs + lane % 7];
+            if (lane < FF_REC) rec = BLK_ANG[(int64_t)(1 + lane / 7) * a.ang_fs + lane % 7];
             if (lane < 16) sh.P[lane >> 2][lane & 3] = rec;
             const float vx = __shfl_sync(full, rec, 16 + (lane < 7 ? lane : 0));
             if (is_ser) sh.acc_vk[lane][0] = make_float2(vx, 0.f);
 #pragma unroll
-            for (int s = 0; s < 4; ++s) { const uint32_t n = (uint32_t)__float_as_int(__shfl_sync(full, rec, 23 + s)); if (lane == 0) nf[s] += n; }
+            if (lane >= 23 && lane < 27) sh.nfx[lane - 23] = (uint32_t)__float_as_int(rec);
             const int w0 = __float_as_int(__shfl_sync(full, rec, 27));
             if (lane == 0) worst = w0;
-            if (lane < 7) sh.out_ang[lane] = ang[lane];
-            if (kFk && lane < FKF) sh.out_fk[lane] = fk[lane];
+            if (lane < 7) sh.out_ang[lane] = BLK_ANG[lane];
+            if (kFk && lane < FKF) sh.out_fk[lane] = BLK_FK[lane];
             staged = true;                                                     // (first block: no earlier bulk store to wait for)
             j0 = 1;
             __syncwarp(full);
         }
+        const Vec3<float> o = map_apply({kp[0], kp[1], kp[2]}, 0);
+        const bool enable_t = cf_all && (t_abs0 + lane > 0 || warm_given);
+        // A replay that starts at stage sf leaves the stages before it valid for the lanes after it: those lanes park their
+        // results of stages 0..2 in their own -- not yet committed -- rows of the staging area across the replay (31 floats)
+        // and the next pass picks them up, so that the first pass of a block, the hot one, carries nothing over.
+        float* const stash_f = sh.out_fk + lane * 27;
+        float* const stash_a = sh.out_ang + lane * 7;
         for (; j0 < nv;) {
             const bool act = lane >= j0 && lane < nv;
-            // ================= pass =================
-            float Tsa[4], Tca[4], Tsb[4], Tcb[4];                  // this lane's final sin/cos per stage (speculated)
+            // results of the pass per lane and stage
+            float Tsa[4], Tca[4], Tsb[4], Tcb[4];                  // final sin/cos per stage (speculated)
             float dA[4], dB[4], dB2[4]; uint32_t bits = 0u;        // per stage: bit 0 small_a, 1 small_b, 2 small_b2, 3 cond, 4 lim ok_q, 5-6 guess
-            Vec3<float> jw[4];
-            const Vec3<float> o = map.apply({kp[0], kp[1], kp[2]}, 0);
+            Vec3<float> npv[4];                                    // end point of each stage relative to the origin
+            // ================= pass =================
             {
                 Mat3<float> A = {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}, {0.f, 0.f, 1.f}};
                 Vec3<float> piv = {0.f, 0.f, 0.f};
 #pragma unroll
                 for (int s = 0; s < 4; ++s) {
                     const bool xy = s == 0, one_var = s == 3;
+                    if (kRobust && s < s_start) {                  // (rare, warp-uniform) this stage's results of the previous pass stand
+                        Tsa[s] = stash_f[9 * s]; Tca[s] = stash_f[9 * s + 1]; Tsb[s] = stash_f[9 * s + 2]; Tcb[s] = stash_f[9 * s + 3];
+                        npv[s].x = stash_f[9 * s + 7]; npv[s].y = stash_f[9 * s + 8]; npv[s].z = stash_a[s < 3 ? s : 0];
+                        if (s < 3) {
+                            A = rotate_frame(A, xy ? KIND_XY : KIND_ZY, Tsa[s], Tca[s], xy ? Tcb[s] : Tsb[s], xy ? -Tsb[s] : Tcb[s]);
+                            piv = npv[s];
+                        }
+                        continue;
+                    }
                     const float* K = sh.kc[s];
                     const float L = K[KC_L];
                     const float Psa = sh.P[s][0], Pca = sh.P[s][1], Psb = sh.P[s][2], Pcb = sh.P[s][3];
                     const float sgn = (Psb < 0.f) ? -1.f : 1.f;
-                    const Vec3<float> kt = map.apply({kp[3 * s + 3], kp[3 * s + 4], kp[3 * s + 5]}, s + 1);
+                    const Vec3<float> kt = map_apply({kp[3 * s + 3], kp[3 * s + 4], kp[3 * s + 5]}, s + 1);
                     const Vec3<float> rel = {(kt.x - o.x) - piv.x, (kt.y - o.y) - piv.y, (kt.z - o.z) - piv.z};
                     const Vec3<float> q3 = mulT(A, rel);
                     const Vec3<float> q = xy ? Vec3<float>{-q3.z, q3.y, q3.x} : q3;
@@ -545,6 +594,32 @@ __global__ void __launch_bounds__(BLK, SEQIK_BLOCK_MIN_CTAS) leg_solve_block_ker
                         const WarmLimit<float> lc = warm_limit(q, L, lo, tsa, tca, sgn);
                         tsb = lc.c_sb; tcb = lc.c_cb; f = lc.f; limq = lc.ok_q;
                     }
+                    if (kRobust && one_var) {
+                        // The one-variable stage sitting ON a limit (TiTa_pitch = 0 for long stretches of a real recording): while
+                        // the target keeps pushing it outward the serial solver's first evaluation meets a vanishing scaled
+                        // gradient and the iterate stays where it is (status 1, one evaluation).  The lanes that follow the pass's
+                        // starting state without a gap inherit that state unchanged, so the test is exact here -- no speculation.
+                        const float xP = (j0 == 0) ? sh.acc_x[6][1] : sh.acc_vk[6][j0 - 1].x;          // placed angle before lane j0
+                        float dl1 = xP - K[KC_LB1S], du1 = K[KC_UB1S] - xP;
+                        if (dl1 <= 0.f) { dl1 = 1e-10f * fmaxf(1.f, fabsf(K[KC_LB1S])); du1 = (K[KC_UB1S] - K[KC_LB1S]) - dl1; }
+                        if (du1 <= 0.f) { du1 = 1e-10f * fmaxf(1.f, fabsf(K[KC_UB1S])); dl1 = (K[KC_UB1S] - K[KC_LB1S]) - du1; }
+                        if (fminf(dl1, du1) < 1e-6f) {             // (warp-uniform)
+                            const WarmMove<float> mp = warm_move(cd.n_sa, cd.n_ca, cd.n_sb, cd.n_cb, Psa, Pca, Psb, Pcb);
+                            const float nx1 = xP + mp.dB;
+                            const bool in_b = (nx1 - K[KC_LB1S] > 1e-5f) & (K[KC_UB1S] - nx1 > 1e-5f);
+                            const bool okP = enable_t & mp.small_a & mp.small_b & cd.cond & in_b;
+                            const float Lsb = L * Psb, Lcb = L * Pcb;
+                            const Vec3<float> fP = {-Lsb * Pca - q.x, -Lsb * Psa - q.y, -Lcb - q.z};
+                            const float cost = 0.5f * dot(fP, fP);
+                            const float g0 = 0.f * Lsb * fmaf(Psa, fP.x, -(Pca * fP.y));
+                            const float g1 = fmaf(Lsb, fP.z, -(Lcb * fmaf(Pca, fP.x, Psa * fP.y)));
+                            const float v1 = (g1 < 0.f && du1 < inf) ? du1 : (g1 > 0.f && dl1 < inf) ? dl1 : 1.f;
+                            const bool stays = !okP && cost < inf && fmaxf(fabsf(g0), fabsf(g1 * v1)) < 1e-8f;
+                            const unsigned run = __ballot_sync(full, act && stays) >> j0;            // bit k: lane j0 + k stays
+                            const int n_stay = (run == 0xffffffffu) ? 32 : __ffs((int)~run) - 1;     // length of the run that starts at j0
+                            if (act && lane < j0 + n_stay) { tsa = Psa; tca = Pca; tsb = Psb; tcb = Pcb; f = fP; g = WC_STAYS; }
+                        }
+                    }
                     Tsa[s] = tsa; Tca[s] = tca; Tsb[s] = tsb; Tcb[s] = tcb;
                     // the previous lane's state (the first lane of the pass: the state the pass starts from)
                     float psa = __shfl_up_sync(full, tsa, 1), pca = __shfl_up_sync(full, tca, 1);
@@ -554,18 +629,19 @@ __global__ void __launch_bounds__(BLK, SEQIK_BLOCK_MIN_CTAS) leg_solve_block_ker
                     float d2 = 0.f; bool sm2 = false;
                     if (any_lim && g != WC_INTERIOR) warm_limit_move(tsb, tcb, psb, pcb, d2, sm2);
                     dA[s] = mv.dA; dB[s] = mv.dB; dB2[s] = d2;
-                    bits |= ((mv.small_a ? 1u : 0u) | (mv.small_b ? 2u : 0u) | (sm2 ? 4u : 0u) | (cd.cond ? 8u : 0u) | (limq ? 16u : 0u)
-                             | ((uint32_t)g << 5)) << (8 * s);
+                    bits = (bits & ~(0xffu << (8 * s)))
+                           | (((mv.small_a ? 1u : 0u) | (mv.small_b ? 2u : 0u) | (sm2 ? 4u : 0u) | (cd.cond ? 8u : 0u) | (limq ? 16u : 0u)
+                               | ((uint32_t)g << 5)) << (8 * s));
                     if (act) {
-                        const bool lim = g != WC_INTERIOR;
+                        const bool lim = g == WC_LO || g == WC_HI;
                         if (!one_var) sh.acc_vk[s][lane] = make_float2(lim ? (g == WC_LO ? K[KC_LB0P] : K[KC_UB0P]) : mv.dA, lim ? 0.f : 1.f);
-                        sh.acc_vk[3 + s][lane] = make_float2(lim ? d2 : mv.dB, 1.f);
+                        sh.acc_vk[3 + s][lane] = make_float2(g == WC_STAYS ? 0.f : lim ? d2 : mv.dB, 1.f);
                     }
                     // end point, joint position, frame of the next stage
                     const Vec3<float> res = xy ? Vec3<float>{f.z, f.y, -f.x} : f;
                     const Vec3<float> Af = mul(A, res);
                     const Vec3<float> np_ = {(piv.x + rel.x) + Af.x, (piv.y + rel.y) + Af.y, (piv.z + rel.z) + Af.z};
-                    jw[s] = {np_.x + o.x, np_.y + o.y, np_.z + o.z};
+                    npv[s] = np_;
                     if (s < 3) {
                         A = rotate_frame(A, xy ? KIND_XY : KIND_ZY, tsa, tca, xy ? tcb : tsb, xy ? -tsb : tcb);
                         piv = np_;
@@ -596,24 +672,29 @@ __global__ void __launch_bounds__(BLK, SEQIK_BLOCK_MIN_CTAS) leg_solve_block_ker
             }
             __syncwarp(full);
             // ================= verify =================
-            float ox0[4], ox1[4];
-            bool pass_ok = true;
-            {
-                const bool enable_t = cf_all && (t_abs0 + lane > 0 || warm_given);
+            if (kRobust && s_start > 0) {                                     // (rare) the stages that stood: their verification data
 #pragma unroll
-                for (int s = 0; s < 4; ++s) {
-                    const float* K = sh.kc[s];
-                    const uint32_t bs = bits >> (8 * s);
-                    const int g = (int)((bs >> 5) & 3u);
-                    const float xp0 = (s < 3) ? sh.acc_x[s < 3 ? s : 0][lane + 1] : 0.f, xp1 = sh.acc_x[3 + s][lane + 1];
-                    WarmMove<float> mv; mv.dA = dA[s]; mv.dB = dB[s]; mv.small_a = bs & 1u; mv.small_b = bs & 2u;
-                    const int wc = warm_case(enable_t, s < 3 && K[KC_CL0] * K[KC_CL0] + K[KC_SL0] * K[KC_SL0] > 0.f, s == 3, xp0, xp1, mv,
-                                             (bs & 8u) != 0u, K[KC_LB0], K[KC_UB0], K[KC_LB1S], K[KC_UB1S], g, dB2[s], (bs & 4u) != 0u,
-                                             (bs & 16u) != 0u, ox0[s], ox1[s]);
-                    pass_ok = pass_ok && wc == g;
-                }
+                for (int s = 0; s < 3; ++s)
+                    if (s < s_start) { dA[s] = stash_f[9 * s + 4]; dB[s] = stash_f[9 * s + 5]; dB2[s] = stash_f[9 * s + 6]; }
+                const uint32_t keep = 0xffffffffu << (8 * s_start);          // bytes of the stages this pass recomputed
+                bits = (bits & keep) | (__float_as_uint(stash_a[3]) & ~keep);
             }
-            const unsigned failed = __ballot_sync(full, act && !pass_ok);
+            float ox0[4], ox1[4];
+            int fs = 4;                                                       // first stage of this lane whose speculation does not hold
+#pragma unroll
+            for (int s = 3; s >= 0; --s) {
+                const float* K = sh.kc[s];
+                const uint32_t bs = bits >> (8 * s);
+                const int g = (int)((bs >> 5) & 3u);
+                const float xp0 = (s < 3) ? sh.acc_x[s < 3 ? s : 0][lane + 1] : 0.f, xp1 = sh.acc_x[3 + s][lane + 1];
+                WarmMove<float> mv; mv.dA = dA[s]; mv.dB = dB[s]; mv.small_a = bs & 1u; mv.small_b = bs & 2u;
+                int wc = warm_case(enable_t, s < 3 && K[KC_CL0] * K[KC_CL0] + K[KC_SL0] * K[KC_SL0] > 0.f, s == 3, xp0, xp1, mv,
+                                   (bs & 8u) != 0u, K[KC_LB0], K[KC_UB0], K[KC_LB1S], K[KC_UB1S], g, dB2[s], (bs & 4u) != 0u,
+                                   (bs & 16u) != 0u, ox0[s], ox1[s]);
+                if (s == 3 && g == WC_STAYS) { wc = WC_STAYS; ox0[s] = 0.f; ox1[s] = xp1; }      // decided exactly in the pass
+                fs = (wc != g) ? s : fs;
+            }
+            const unsigned failed = __ballot_sync(full, act && fs < 4);
             const int j = failed ? __ffs((int)failed) - 1 : nv;              // first lane whose speculation does not hold
             // ================= commit lanes j0 .. j-1 =================
             if (!staged) {                                                     // the previous block's bulk stores have read the staging area
@@ -624,29 +705,39 @@ __global__ void __launch_bounds__(BLK, SEQIK_BLOCK_MIN_CTAS) leg_solve_block_ker
             if (act && lane < j) {
                 float* oa = sh.out_ang + lane * 7;
                 oa[0] = ox0[0]; oa[1] = ox1[0] + half_pi; oa[2] = ox0[1]; oa[3] = ox1[1]; oa[4] = ox0[2]; oa[5] = ox1[2]; oa[6] = ox1[3];
-                nf[0] += 1u; nf[1] += 1u; nf[2] += 1u; nf[3] += 1u;
+                n_commit += 1u;
                 if (kFk == 1) {
                     float* of = sh.out_fk + lane * 27;
 #pragma unroll
                     for (int r = 0; r < 4; ++r) { of[3 * r] = o.x; of[3 * r + 1] = o.y; of[3 * r + 2] = o.z; }
-                    of[12] = jw[0].x; of[13] = jw[0].y; of[14] = jw[0].z;
+                    of[12] = npv[0].x + o.x; of[13] = npv[0].y + o.y; of[14] = npv[0].z + o.z;
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) { of[15 + 3 * s] = jw[s].x; of[16 + 3 * s] = jw[s].y; of[17 + 3 * s] = jw[s].z; }
+                    for (int s = 0; s < 4; ++s) { of[15 + 3 * s] = npv[s].x + o.x; of[16 + 3 * s] = npv[s].y + o.y; of[17 + 3 * s] = npv[s].z + o.z; }
                 } else if (kFk == 2) {
                     float* of = sh.out_fk + lane * 12;
 #pragma unroll
-                    for (int s = 0; s < 4; ++s) { of[3 * s] = jw[s].x; of[3 * s + 1] = jw[s].y; of[3 * s + 2] = jw[s].z; }
+                    for (int s = 0; s < 4; ++s) { of[3 * s] = npv[s].x + o.x; of[3 * s + 1] = npv[s].y + o.y; of[3 * s + 2] = npv[s].z + o.z; }
                 }
             }
             if (j >= nv) break;
-            // ================= replay lane j through the serial solver (the frame body of hostsim run_carried) =================
+            // ================= replay lane j through the serial solver, from its first failing stage =================
             // state before frame j: the previous lane's (or the pass's starting state), angles from the accumulated series
+            const int sf = kRobust ? __shfl_sync(full, fs, j) : 0;           // (lean kernel: the whole frame)
             float qsa[4], qca[4], qsb[4], qcb[4];
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
                 qsa[s] = __shfl_sync(full, Tsa[s], (j + 31) & 31); qca[s] = __shfl_sync(full, Tca[s], (j + 31) & 31);
                 qsb[s] = __shfl_sync(full, Tsb[s], (j + 31) & 31); qcb[s] = __shfl_sync(full, Tcb[s], (j + 31) & 31);
                 if (j == j0) { qsa[s] = sh.P[s][0]; qca[s] = sh.P[s][1]; qsb[s] = sh.P[s][2]; qcb[s] = sh.P[s][3]; }
+            }
+            if (kRobust && act && lane > j && sf > 0) {                       // park stages 0..2 across the replay (see above)
+#pragma unroll
+                for (int s = 0; s < 3; ++s) {
+                    stash_f[9 * s] = Tsa[s]; stash_f[9 * s + 1] = Tca[s]; stash_f[9 * s + 2] = Tsb[s]; stash_f[9 * s + 3] = Tcb[s];
+                    stash_f[9 * s + 4] = dA[s]; stash_f[9 * s + 5] = dB[s]; stash_f[9 * s + 6] = dB2[s];
+                    stash_f[9 * s + 7] = npv[s].x; stash_f[9 * s + 8] = npv[s].y; stash_a[s] = npv[s].z;
+                }
+                stash_a[3] = __uint_as_float(bits);
             }
             __syncwarp(full);        // every lane has read sh.P before the replaying lane overwrites it
             if (lane == j) {
@@ -655,8 +746,25 @@ __global__ void __launch_bounds__(BLK, SEQIK_BLOCK_MIN_CTAS) leg_solve_block_ker
                 float* oa = sh.out_ang + lane * 7;
                 float* of = sh.out_fk + lane * FKF;
                 const bool warm_ok = t_abs0 + lane > 0 || warm_given;
+                // the stages before the failing one stand as the pass left them: results out, frame rebuilt, state handed on
+#pragma unroll
+                for (int s = 0; s < 3; ++s) {
+                    if (kRobust && s < sf) {
+                        const bool xy = s == 0;
+                        oa[2 * s] = ox0[s]; oa[2 * s + 1] = xy ? ox1[s] + half_pi : ox1[s]; sh.nfx[s] += 1u;
+                        const Vec3<float> w = {npv[s].x + o.x, npv[s].y + o.y, npv[s].z + o.z};
+                        if (kFk == 1) {
+                            of[3 * s] = o.x; of[3 * s + 1] = o.y; of[3 * s + 2] = o.z;
+                            of[15 + 3 * s] = w.x; of[16 + 3 * s] = w.y; of[17 + 3 * s] = w.z;
+                            if (s == 0) { of[12] = w.x; of[13] = w.y; of[14] = w.z; }
+                        } else if (kFk == 2) { of[3 * s] = w.x; of[3 * s + 1] = w.y; of[3 * s + 2] = w.z; }
+                        A = rotate_frame(A, xy ? KIND_XY : KIND_ZY, Tsa[s], Tca[s], xy ? Tcb[s] : Tsb[s], xy ? -Tsb[s] : Tcb[s]);
+                        piv = npv[s];
+                        sh.P[s][0] = Tsa[s]; sh.P[s][1] = Tca[s]; sh.P[s][2] = Tsb[s]; sh.P[s][3] = Tcb[s];
+                    }
+                }
 #pragma unroll 1
-                for (int s = 0; s < 4; ++s) {
+                for (int s = sf; s < 4; ++s) {
                     const float* K = sh.kc[s];
                     const StageK k = {K[KC_L], K[KC_LB0], K[KC_UB0], K[KC_LB1], K[KC_UB1], K[KC_SL0], K[KC_CL0], K[KC_SU0], K[KC_CU0], K[KC_NSQ]};
                     float x0 = (s < 3) ? sh.acc_x[s < 3 ? s : 0][lane + 1] : 0.f, x1 = sh.acc_x[3 + s][lane + 1];
@@ -664,13 +772,12 @@ __global__ void __launch_bounds__(BLK, SEQIK_BLOCK_MIN_CTAS) leg_solve_block_ker
                     float ca = (s == 0) ? qca[0] : (s == 1) ? qca[1] : (s == 2) ? qca[2] : qca[3];
                     float sb = (s == 0) ? qsb[0] : (s == 1) ? qsb[1] : (s == 2) ? qsb[2] : qsb[3];
                     float cb = (s == 0) ? qcb[0] : (s == 1) ? qcb[1] : (s == 2) ? qcb[2] : qcb[3];
-                    const Vec3<float> kt = map.apply({kp[3 * s + 3], kp[3 * s + 4], kp[3 * s + 5]}, s + 1);
+                    const Vec3<float> kt = map_apply({kp[3 * s + 3], kp[3 * s + 4], kp[3 * s + 5]}, s + 1);
                     float xb; Vec3<float> w; uint32_t ne = 0u;
-                    serial_stage(s, k, a.gn_mask, esc, warm_ok, kt, o, A, piv, x0, x1, sa, ca, sb, cb, xb, w, ne, worst);
-                    if (s == 0) { oa[0] = x0; oa[1] = xb; nf[0] += ne; }
-                    else if (s == 1) { oa[2] = x0; oa[3] = xb; nf[1] += ne; }
-                    else if (s == 2) { oa[4] = x0; oa[5] = xb; nf[2] += ne; }
-                    else { oa[6] = xb; nf[3] += ne; }
+                    if (kRobust) serial_stage_call(s, k, a.gn_mask, esc, warm_ok, kt, o, A, piv, x0, x1, sa, ca, sb, cb, xb, w, ne, worst);
+                    else serial_stage(s, k, a.gn_mask, esc, warm_ok, kt, o, A, piv, x0, x1, sa, ca, sb, cb, xb, w, ne, worst);
+                    if (s < 3) { oa[2 * s] = x0; oa[2 * s + 1] = xb; } else oa[6] = xb;
+                    sh.nfx[s] += ne;
                     if (kFk == 1) {
                         of[3 * s] = o.x; of[3 * s + 1] = o.y; of[3 * s + 2] = o.z;
                         of[15 + 3 * s] = w.x; of[16 + 3 * s] = w.y; of[17 + 3 * s] = w.z;
@@ -685,6 +792,7 @@ __global__ void __launch_bounds__(BLK, SEQIK_BLOCK_MIN_CTAS) leg_solve_block_ker
             }
             __syncwarp(full);
             j0 = j + 1;
+            s_start = sf;            // the lanes after j keep their stages before sf: nothing those depend on has changed
             if (j0 >= nv) break;
         }
         // ---- carry the angles to the next block in the caller's terms (xa = x0, xb = x1 + shift)
@@ -704,16 +812,16 @@ __global__ void __launch_bounds__(BLK, SEQIK_BLOCK_MIN_CTAS) leg_solve_block_ker
             fence_async_smem();
             __syncwarp(full);
             if (lane == 0) {
-                tma_store_1d_nocommit(ang + (int64_t)t_abs0 * 7, sh.out_ang, (uint32_t)nv * 28u);
-                if (kFk) tma_store_1d_nocommit(fk + (int64_t)t_abs0 * FKF, sh.out_fk, (uint32_t)nv * (FKF * 4u));
+                tma_store_1d_nocommit(BLK_ANG + (int64_t)t_abs0 * 7, sh.out_ang, (uint32_t)nv * 28u);
+                if (kFk) tma_store_1d_nocommit(BLK_FK + (int64_t)t_abs0 * FKF, sh.out_fk, (uint32_t)nv * (FKF * 4u));
                 tma_commit();
             }
         } else {
             __syncwarp(full);
-            float* da = ang + (int64_t)t_abs0 * a.ang_fs;
+            float* da = BLK_ANG + (int64_t)t_abs0 * a.ang_fs;
             for (int i = lane; i < nv * 7; i += BLK) da[(int64_t)(i / 7) * a.ang_fs + i % 7] = sh.out_ang[i];
             if (kFk) {
-                float* df = fk + (int64_t)t_abs0 * a.fk_fs;
+                float* df = BLK_FK + (int64_t)t_abs0 * a.fk_fs;
                 for (int i = lane; i < nv * FKF; i += BLK) df[(int64_t)(i / FKF) * a.fk_fs + i % FKF] = sh.out_fk[i];
             }
             __syncwarp(full);
@@ -721,21 +829,26 @@ __global__ void __launch_bounds__(BLK, SEQIK_BLOCK_MIN_CTAS) leg_solve_block_ker
     }
     if (lane == 0) tma_store_wait_read<0>();
     // per-chain statistics
-#pragma unroll
-    for (int s = 0; s < 4; ++s) nf[s] = __reduce_add_sync(full, nf[s]);
+    n_commit = __reduce_add_sync(full, n_commit);
     const int w_all = __reduce_min_sync(full, worst);
+    __syncwarp(full);
     if (lane == 0) {
-        if (a.nfev) { uint32_t* p = a.nfev + c * 4; p[0] = nf[0]; p[1] = nf[1]; p[2] = nf[2]; p[3] = nf[3]; }
+        if (a.nfev) { uint32_t* p = a.nfev + c * 4; for (int s = 0; s < 4; ++s) p[s] = n_commit + sh.nfx[s]; }
         if (a.status) a.status[c] = w_all == ST_NONFINITE ? -1 : w_all;
     }
 }
+
+#undef BLK_PRM
+#undef BLK_POSE
+#undef BLK_ANG
+#undef BLK_FK
 
 // Launch of schedule 3.  One CTA (= one warp) per chain; the hardware block scheduler deals chains to SMs as warps
 // retire.  Chains cost about the same, so the batch runs in "waves" of (resident warps per SM) x (SMs) chains and the
 // time is ~ ceil(n_chain / (R n_sm)) * R: R is chosen to minimise that (a last wave that is nearly empty costs a full
 // wave's latency; config 4's 7 500-chain shard: R = 13 -> 4 full waves instead of 3.2 at R = 16) and imposed through the
 // dynamic shared memory size.  `forced` (1..32): tuning / tests.
-template <int kFk>
+template <int kFk, bool kRobust>
 static int launch_block_kernel(const LegArgs& a, int bulk_in, int bulk_out, int forced, cudaStream_t st) {
     static thread_local int cached_dev = -1;
     static thread_local int n_sm = 148, r_max = 16, static_smem = 0, smem_sm = 227 * 1024;
@@ -743,7 +856,7 @@ static int launch_block_kernel(const LegArgs& a, int bulk_in, int bulk_out, int 
     cudaGetDevice(&dev);
     if (dev != cached_dev) {
         cudaFuncAttributes at;
-        if (cudaFuncGetAttributes(&at, leg_solve_block_kernel<kFk>) != cudaSuccess) return seqik_check_launch("seqik_leg_solve_f32 (attributes)");
+        if (cudaFuncGetAttributes(&at, leg_solve_block_kernel<kFk, kRobust>) != cudaSuccess) return seqik_check_launch("seqik_leg_solve_f32 (attributes)");
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
         static_smem = (int)at.sharedSizeBytes;
@@ -754,8 +867,8 @@ static int launch_block_kernel(const LegArgs& a, int bulk_in, int bulk_out, int 
         r_max = by_regs < by_smem ? by_regs : by_smem;
         if (r_max > 32) r_max = 32;                                                    // CTAs per SM
         if (r_max < 1) r_max = 1;
-        cudaFuncSetAttribute(leg_solve_block_kernel<kFk>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sm - static_smem - 1024);
-        cudaFuncSetAttribute(leg_solve_block_kernel<kFk>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(leg_solve_block_kernel<kFk, kRobust>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_sm - static_smem - 1024);
+        cudaFuncSetAttribute(leg_solve_block_kernel<kFk, kRobust>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         cached_dev = dev;
     }
     // resident warps per SM: as many as registers and shared memory allow -- measured faster than any "whole waves" choice
@@ -768,16 +881,27 @@ static int launch_block_kernel(const LegArgs& a, int bulk_in, int bulk_out, int 
     if (r == r_max && !forced) dyn = 0;
     const int first_done = (a.warm == nullptr && a.n_frame >= 5) ? 1 : 0;
     if (first_done) leg_first_frame_kernel<kFk><<<(unsigned)((a.n_chain + BLK - 1) / BLK), BLK, 0, st>>>(a);
-    leg_solve_block_kernel<kFk><<<(unsigned)a.n_chain, BLK, (size_t)dyn, st>>>(a, bulk_in, bulk_out, first_done);
+    leg_solve_block_kernel<kFk, kRobust><<<(unsigned)a.n_chain, BLK, (size_t)dyn, st>>>(a, bulk_in, bulk_out, first_done);
     return SEQIK_OK;
 }
-static int launch_block_schedule(const LegArgs& a, bool want_fk, bool fk_joints, int forced, cudaStream_t st) {
+static int launch_block_schedule(const LegArgs& a, bool want_fk, bool fk_joints, int forced, int variant, cudaStream_t st) {
     const int fkf = fk_joints ? 12 : 27;
     const bool al_in = (((uintptr_t)a.pose) & 15) == 0 && (a.pose_cs & 3) == 0 && a.pose_fs == 15;
     const bool al_out = (((uintptr_t)a.angles) & 15) == 0 && (a.ang_cs & 3) == 0 && a.ang_fs == 7
                         && (!want_fk || ((((uintptr_t)a.fk) & 15) == 0 && (a.fk_cs & 3) == 0 && a.fk_fs == fkf));
-    if (!want_fk) return launch_block_kernel<0>(a, al_in, al_out, forced, st);
-    return fk_joints ? launch_block_kernel<2>(a, al_in, al_out, forced, st) : launch_block_kernel<1>(a, al_in, al_out, forced, st);
+    // variant: 1 lean, 2 robust, 0 automatic -- robust while the batch does not fill the robust kernel's resident warps anyway
+    // (its lower occupancy then costs nothing and replay-heavy recordings, which typically come as a few long chains, gain
+    // up to 2.5x); lean beyond (throughput regime; config 3: 0.335 against 0.372 ms)
+    int n_sm = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    const bool robust = variant == 2 || (variant == 0 && a.n_chain <= (int64_t)SEQIK_BLOCK_MIN_CTAS_ROBUST * n_sm);
+    if (robust) {
+        if (!want_fk) return launch_block_kernel<0, true>(a, al_in, al_out, forced, st);
+        return fk_joints ? launch_block_kernel<2, true>(a, al_in, al_out, forced, st) : launch_block_kernel<1, true>(a, al_in, al_out, forced, st);
+    }
+    if (!want_fk) return launch_block_kernel<0, false>(a, al_in, al_out, forced, st);
+    return fk_joints ? launch_block_kernel<2, false>(a, al_in, al_out, forced, st) : launch_block_kernel<1, false>(a, al_in, al_out, forced, st);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -822,7 +946,8 @@ extern "C" int seqik_leg_solve_f32(const float* pose, int64_t pose_chain_stride,
     a.stage_mask = (int)stage_mask; a.gn_mask = (int)(flags & 0xFF);   // bits 0-3 Gauss-Newton mode per stage, 4 escape, 5 skip-confirm, 6 Newton, 7 closed-form warm step
     if (sched == 3) {
         if (n_chain > 2147483647LL) return seqik_fail(SEQIK_EINVAL, "seqik_leg_solve_f32: too many chains");
-        const int rc = launch_block_schedule(a, fk != nullptr, fk_joints, (flags >> SEQIK_FLAG_CPW_SHIFT) & 0x3F, (cudaStream_t)stream);
+        const int rc = launch_block_schedule(a, fk != nullptr, fk_joints, (flags >> SEQIK_FLAG_CPW_SHIFT) & 0x3F,
+                                             (int)((flags >> SEQIK_FLAG_BLOCK_VARIANT_SHIFT) & 0x3u), (cudaStream_t)stream);
         if (rc != SEQIK_OK) return rc;
     } else if (sched == 1) {
         const int64_t grid = (n_chain + 31) / 32;

@@ -44,7 +44,8 @@ def stages_to_mask(stages: Sequence[int]) -> int:
 
 def leg_solve(pose, params, affine=None, stages: Sequence[int] = (1, 2, 3, 4), want_fk: bool = True,
               angles=None, fk=None, flags: int = N.FLAG_DEFAULT, schedule: int = N.SCHED_AUTO,
-              want_stats: bool = True, chains_per_warp: int = 0, frames=None, gate: int = 0, fk_layout: str = "full", trip_period: int = 0):
+              want_stats: bool = True, chains_per_warp: int = 0, frames=None, gate: int = 0, fk_layout: str = "full", trip_period: int = 0,
+              block_variant: int = 0):
     """4-stage sequential IK (+FK) of every chain.  Returns (angles, fk|None, status|None, nfev|None).
 
     ``angles`` must be given (and is updated in place) when ``stages`` does not start at 1:
@@ -54,6 +55,7 @@ def leg_solve(pose, params, affine=None, stages: Sequence[int] = (1, 2, 3, 4), w
     from frame t0-1 of ``angles`` (t0 > 0).  Chunked calls over consecutive ranges are bit-identical to one call over
     all frames when every t0 is a multiple of 32 (the kernel re-derives sin/cos from the angles every 32 frames and at
     the first frame of a call); otherwise they agree to float32 rounding.
+    ``block_variant`` (schedule 3): 0 automatic, 1 lean kernel, 2 robust kernel (replay-heavy recordings); same results.
     ``fk_layout="joints"``: ``fk`` is (n_chain, n_frame, 4, 3), the joint rows 5..8 of the full layout only (rows 0-3
     repeat the origin, row 4 repeats row 5) -- 76 instead of 136 result bytes per leg-frame.
     """
@@ -107,7 +109,7 @@ def leg_solve(pose, params, affine=None, stages: Sequence[int] = (1, 2, 3, 4), w
             warm, n_frame * 7,
             N.ptr(status), N.ptr(nfev), n_chain, t1 - t0, mask,
             (flags & 0xFF) | ((schedule & 0xF) << N.FLAG_SCHED_SHIFT) | ((chains_per_warp & 0x3F) << 12) | ((gate & 0xF) << 21) | ((trip_period & 7) << 25)
-            | (N.FLAG_FK_JOINTS if fk_layout == "joints" else 0),
+            | (N.FLAG_FK_JOINTS if fk_layout == "joints" else 0) | ((block_variant & 3) << 28),
             N.stream_ptr(torch, dev))
     N.check(rc, "seqik_leg_solve_f32")
     return angles, fk, status, nfev

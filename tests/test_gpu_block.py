@@ -28,12 +28,16 @@ def env():
 
 
 def both(env, pose, params, **kw):
+    """Schedule 2, then schedule 3 with the lean and with the robust kernel (which must agree with each other bit for bit:
+    asserted here); returns (schedule 2, schedule 3)."""
     out = []
-    for sched in (2, 3):
-        ang, fk, st, nf = env.engine.leg_solve(pose, params, schedule=sched, **kw)
+    for sched, variant in ((2, 0), (3, 1), (3, 2)):
+        ang, fk, st, nf = env.engine.leg_solve(pose, params, schedule=sched, block_variant=variant, **kw)
         env.torch.cuda.synchronize()
         out.append((ang.cpu().numpy(), None if fk is None else fk.cpu().numpy(), st.cpu().numpy(), nf.cpu().numpy()))
-    return out
+    for x, y in zip(out[1], out[2]):
+        assert (x is None and y is None) or np.array_equal(x, y, equal_nan=True)
+    return out[:2]
 
 
 def assert_same(a, b):
