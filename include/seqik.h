@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SEQIK_ABI_VERSION 6   /* 6: schedule 3 (frame-parallel blocks), seqik_fk_expand_host_f32; 5: solver flag bits 6-7, phase periods in bits 21-27 */
+#define SEQIK_ABI_VERSION 7   /* 7: seqik_leg_affine_from_pose_f32; 6: schedule 3 (frame-parallel blocks), seqik_fk_expand_host_f32; 5: solver flag bits 6-7, phase periods in bits 21-27 */
 #define SEQIK_OK 0
 #define SEQIK_EINVAL (-1)
 #define SEQIK_ECUDA (-3)
@@ -218,6 +218,15 @@ int seqik_leg_series_f32(const float* pose, int64_t pose_chain_stride, int64_t p
  *   affine [n_chain][8] out = (fixed_coxa xyz, scale, template xyz, 0) */
 int seqik_leg_affine_f32(const float* stats, const float* consts, int include_claw, float* affine,
                          int64_t n_chain, void* stream);
+
+/* The three calls above in one (AlignPose.get_fixed_pos / get_mean_length / find_scale_leg, alignment.py:392-423, and the
+ * affine row of align_leg, :465-485): key points [n_chain][n_frame][5][3] -> affine [n_chain][8].  Recordings of up to 1024
+ * frames run ONE fused kernel -- a CTA per chain streams the key points through shared memory once (60 B per leg-frame, the
+ * only DRAM traffic), seven warps select the seven mid-quantiles -- and need no scratch (NULL); longer recordings run the
+ * series / select / affine kernels with scratch = n_chain * 7 * (n_frame + 1) floats.  Same results as the separate calls. */
+int seqik_leg_affine_from_pose_f32(const float* pose, int64_t pose_chain_stride, int64_t pose_frame_stride,
+                                   const float* consts, int include_claw, float* scratch, float* affine,
+                                   int64_t n_chain, int64_t n_frame, void* stream);
 
 /* The affine map of AlignPose.align_leg (alignment.py:471-485) as a standalone elementwise pass:
  * out[:,0] = template, out[:,i] = (pose[:,i] - fixed) * scale + template.   affine [n_chain][8] as above. */

@@ -1,11 +1,6 @@
 mkdir -p gpurun_out
-# A: 96-register lean block kernel, resident warps 16..18, against the 128-register build
-SEQIK_LIB=build_variants/libseqik_r96.so timeout 600 python scripts/block_bench.py r > gpurun_out/x1_block_r96.jsonl 2>&1
-tail -3 gpurun_out/x1_block_r96.jsonl
-# B: generic solver, chains per warp
-GEN_CPW=0,1,2,3,4,6,8 GEN_DTYPES=float32 timeout 600 python scripts/generic_bench.py 100 6000 60000 > gpurun_out/x1_generic_cpw_f32.jsonl 2>&1
-GEN_CPW=0,1,2,3,4,6,8 GEN_DTYPES=float64 timeout 900 python scripts/generic_bench.py 100 6000 > gpurun_out/x1_generic_cpw_f64.jsonl 2>&1
-tail -2 gpurun_out/x1_generic_cpw_f64.jsonl
-# C: full captures of the cold stream kernels
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'mid_quantile|leg_series|pchip' -c 12 -f -o gpurun_out/x1_prof_stream python scripts/stream_bench.py > gpurun_out/x1_ncu_stream.log 2>&1
-ls -la gpurun_out/
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/x4_tests.log 2>&1; tail -3 gpurun_out/x4_tests.log
+timeout 300 python scripts/stream_bench.py > gpurun_out/x4_stream.jsonl 2>&1
+grep -E "leg_affine|pchip" gpurun_out/x4_stream.jsonl | cut -c1-160
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:leg_affine_fused -s 4 -c 1 -f -o gpurun_out/x4_prof_affine python scripts/stream_bench.py > gpurun_out/x4_ncu_affine.log 2>&1
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/x4_launches_c5.csv python scripts/c5_bench.py > gpurun_out/x4_c5.log 2>&1

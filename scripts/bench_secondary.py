@@ -98,19 +98,27 @@ def stream_kernels(hbm_peak, n_trial=1000, n_frame=1000):
     rest = torch.zeros((n_trial, 2), device="cuda")
     haff = torch.rand((n_trial, 8), device="cuda", generator=g) + 0.5
     x = torch.empty(1 << 28, device="cuda"); y = torch.empty_like(x)
+    # key points as a recording has them (the synthetic workload's trials, tiled): every series lives in a narrow range
+    base = S.to_chains(torch.from_numpy(S.make_trials(range(32), n_frame)).cuda())
+    rec = base.repeat((n_chain + base.shape[0] - 1) // base.shape[0], 1, 1, 1)[:n_chain].contiguous()
     cases = [
         ("fk", lambda: engine.forward_kinematics(angles, origin, params), lf * (28 + 12 + 108)),
         ("align_apply", lambda: engine.align_apply(pose, aff), lf * 120),
-        ("alignment_statistics (series + radix select + affine)", lambda: engine.leg_affine(pose, consts), lf * (60 + 28 + 28)),
+        ("alignment_statistics (fused: key points -> affine rows)", lambda: engine.leg_affine(rec, consts), lf * 60 + n_chain * 32),
+        ("alignment_statistics, normal-random key points (wide-range series: two radix passes)", lambda: engine.leg_affine(pose, consts), lf * 60 + n_chain * 32),
+        ("alignment_statistics, three-kernel path (series written and re-read)", lambda: engine.leg_affine_unfused(rec, consts), lf * (60 + 28 + 28)),
         ("head_angles", lambda: engine.head_angles(r, l, neck, rest), nf * (48 + 28)),
         ("head_apply", lambda: engine.head_apply(r, haff), nf * 48),
+        ("pchip_resample float32 (x10 upsampling of the angles tensor)", lambda: engine.pchip_resample(angles, 0.01, 0.001), lf * 7 * 4 * 11),
         ("torch copy_ of 1 GiB (reference point)", lambda: y.copy_(x), 2 * x.numel() * 4),
     ]
     out = {}
     for name, fn, nbytes in cases:
         ms = _timeit(torch, fn, 10, warm=3)
         out[name] = {"ms": ms, "GB/s": nbytes / ms / 1e6, "frac_of_measured_hbm": nbytes / ms / 1e6 / hbm_peak, "algorithmic_bytes": nbytes}
-    out["units"] = f"{n_chain} chains x {n_frame} frames; algorithmic bytes per unit in DESIGN.md 5.3; peak = {hbm_peak} GB/s (MEASURED_PEAKS.json)"
+    out["units"] = (f"{n_chain} chains x {n_frame} frames; algorithmic bytes per unit in DESIGN.md 5.3 (alignment statistics: 60 B per "
+                    f"leg-frame in, one 32-byte row per chain out; the three-kernel path also moves its series, 28 B out + 28 B in); "
+                    f"peak = {hbm_peak} GB/s (MEASURED_PEAKS.json)")
     return out
 
 

@@ -49,7 +49,12 @@ pose = torch.randn((n_chain, n_frame, 5, 3), device="cuda", generator=g)
 aff = torch.rand((n_chain, 8), device="cuda", generator=g) + 0.5
 report("align_apply_kernel", timeit(lambda: engine.align_apply(pose, aff)), lf * 120, lf, "leg-frames")
 consts = torch.rand((n_chain, 4), device="cuda", generator=g) + 1.0
-report("leg_affine (series + 4x4-pass radix select + affine)", timeit(lambda: engine.leg_affine(pose, consts)), lf * (60 + 28 + 28), lf, "leg-frames")
+base = S.to_chains(torch.from_numpy(S.make_trials(range(32), n_frame)).cuda())
+rec = base.repeat((n_chain + base.shape[0] - 1) // base.shape[0], 1, 1, 1)[:n_chain].contiguous()       # key points as a recording has them
+report("leg_affine fused, recording-like key points", timeit(lambda: engine.leg_affine(rec, consts)), lf * 60 + n_chain * 32, lf, "leg-frames")
+report("leg_affine fused, normal-random key points (wide-range series)", timeit(lambda: engine.leg_affine(pose, consts)), lf * 60 + n_chain * 32, lf, "leg-frames")
+report("leg_affine three-kernel path (series + select + affine), recording-like", timeit(lambda: engine.leg_affine_unfused(rec, consts)), lf * (60 + 28 + 28), lf, "leg-frames")
+del base
 nf = n_trial * n_frame * 6
 r = torch.randn((n_trial, 6 * n_frame, 2, 3), device="cuda", generator=g); l = torch.randn((n_trial, 6 * n_frame, 2, 3), device="cuda", generator=g)
 neck = torch.randn((n_trial, 3), device="cuda", generator=g); rest = torch.zeros((n_trial, 2), device="cuda")

@@ -346,6 +346,7 @@ struct GenericSolve {
         if (alpha == R(0)) alpha = R(0.001) * a_up;
         bool brk = false;
         R p[GEN_DOF], dp[GEN_DOF];
+#pragma unroll 1
         for (int it = 0; it < 10; ++it) {
             if (!brk) {
                 if (alpha < a_lo || alpha > a_up) alpha = N::max_(R(0.001) * a_up, N::sqrt_(a_lo * a_up));

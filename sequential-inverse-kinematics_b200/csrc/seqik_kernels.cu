@@ -394,6 +394,7 @@ extern "C" int seqik_head_angles_f32(const float* r_head, const float* l_head, c
 
 // ---------------------------------------------------------------------------------------------
 // AlignPose: series, mid-quantiles, affine maps
+
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) leg_series_kernel(const float* __restrict__ pose, int64_t cs, int64_t fs,
                                                          float* __restrict__ series, int64_t n_chain, int64_t n_frame) {
@@ -516,15 +517,180 @@ __global__ void __launch_bounds__(SEL_BLOCK) mid_quantile_kernel(const float* __
     }
 }
 
-// Short series (n <= WQ_N, e.g. the 1000-frame trials of the benchmark configurations): ONE WARP per series.  Same 4-pass
-// radix select, but the histograms are private to the warp, so there is no block barrier and no idle thread: 8 warps
-// x ~600 instructions per series become 1 warp x ~1000 (measured 0.52 -> see profiles/r01_stream_kernels.jsonl).
+// Short series (n <= WQ_N, e.g. the 1000-frame trials of the benchmark configurations): ONE WARP per series, no block
+// barrier.  warp_mid_quantile() is shared with the fused per-chain kernel below.  Against a plain 4-pass radix select
+// (5 700 warp instructions per 1000-sample series, profiles/r02_stream_ncu.txt) it
+//   * starts at the first bit in which the series' keys differ (one min/max sweep): the leading passes, in which every key
+//     fell into the same bin -- 32-way conflicts on one shared-memory counter -- no longer exist, and the first digit is spread
+//     over its 256 bins;
+//   * aggregates equal digits of a warp instruction before the atomic (match.any), so that what conflicts remain cost one add;
+//   * after a pass, compacts the keys that still share a prefix with one of the four ranks to the front of the cache (a few
+//     per rank): the next pass sweeps those only, and with 32 or fewer left the ranks are read off directly (each lane counts
+//     the keys below its own);
+//   * packs the four histograms into 256 words of two 16-bit pairs (counts <= 1024): 2 KB per warp.
+// Bit-compatible with np.quantile(..., method="linear") on float32 input, like the kernel it replaces.
 constexpr int WQ_N = 1024, WQ_WARPS = 4;
+__device__ __forceinline__ uint32_t low_mask(int nb) { return nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u); }
+
+// key[0..n): order keys of the series in shared memory, 16-byte aligned (overwritten); m: the m smallest take part;
+// hist: 2 x 256 words of this warp
+__device__ float warp_mid_quantile(uint32_t* __restrict__ key, int n, int64_t m, unsigned int (*hist)[256], int lane) {
+    const unsigned full = 0xffffffffu;
+    const unsigned lt = (1u << lane) - 1u;
+    int64_t lo45, lo55; float f45, f55;
+    quantile_pos(0.45, m, lo45, f45); quantile_pos(0.55, m, lo55, f55);
+    unsigned int rank[4]; uint32_t prefix[4], val[4];               // warp-uniform
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const int64_t r = (k < 2 ? lo45 : lo55) + (k & 1); rank[k] = (unsigned int)(r > m - 1 ? m - 1 : r); }
+    const uint4* key4 = reinterpret_cast<const uint4*>(key);
+    const int n4 = n >> 2;
+    uint32_t kmin = 0xffffffffu, kmax = 0u;
+    for (int i = lane; i < n4; i += 32) {
+        const uint4 k = key4[i];
+        kmin = min(min(kmin, k.x), min(min(k.y, k.z), k.w)); kmax = max(max(kmax, k.x), max(max(k.y, k.z), k.w));
+    }
+    if (4 * n4 + lane < n) { const uint32_t k = key[4 * n4 + lane]; kmin = min(kmin, k); kmax = max(kmax, k); }
+    kmin = __reduce_min_sync(full, kmin); kmax = __reduce_max_sync(full, kmax);
+    int hi = 32 - __clz((int)(kmin ^ kmax));                        // bits [0, hi) differ within the series (0: a constant series)
+    uint32_t mask = ~low_mask(hi);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) prefix[k] = kmin & mask;
+    int cnt = n;                                                    // keys still in play: key[0..cnt)
+    const uint32_t* fin = key;                                      // where the candidates of the direct finish sit
+    bool direct = false;
+#pragma unroll 1
+    while (hi > 0) {
+        const int lo = hi > 8 ? hi - 8 : 0;
+        const uint32_t dm = (1u << (hi - lo)) - 1u;
+        // ranks that still share a prefix share a histogram (h is non-decreasing: equal prefixes are adjacent)
+        int h[4];
+        h[0] = 0; h[1] = (prefix[1] == prefix[0]) ? 0 : 1;
+        h[2] = (prefix[2] == prefix[1]) ? h[1] : h[1] + 1;
+        h[3] = (prefix[3] == prefix[2]) ? h[2] : h[2] + 1;
+        const bool one = h[3] == 0 && cnt == n;                     // every key shares the one prefix: the first pass
+        {
+            uint4* z = reinterpret_cast<uint4*>(&hist[0][0]);
+            const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+            for (int k = lane; k < (one ? 256 : 512) / 4; k += 32) z[k] = zero;
+        }
+        __syncwarp(full);
+        if (one) {
+            // no prefix test, 128 keys per step (few conflicts: the digit starts at the first bit that varies)
+            for (int i = lane; i < n4; i += 32) {
+                const uint4 k = key4[i];
+                atomicAdd(&hist[0][(k.x >> lo) & dm], 1u); atomicAdd(&hist[0][(k.y >> lo) & dm], 1u);
+                atomicAdd(&hist[0][(k.z >> lo) & dm], 1u); atomicAdd(&hist[0][(k.w >> lo) & dm], 1u);
+            }
+            if (4 * n4 + lane < n) atomicAdd(&hist[0][(key[4 * n4 + lane] >> lo) & dm], 1u);
+        } else {
+            for (int i0 = 0; i0 < cnt; i0 += 32) {
+                const int i = i0 + lane;
+                const uint32_t k = i < cnt ? key[i] : 0u;
+                const uint32_t km = k & mask, d = (k >> lo) & dm;
+                int hh = -1;                                        // histogram this key counts in
+                if (i < cnt) hh = (km == prefix[0]) ? 0 : (km == prefix[1]) ? h[1] : (km == prefix[2]) ? h[2] : (km == prefix[3]) ? h[3] : -1;
+                if (hh >= 0) atomicAdd(&hist[hh >> 1][d], 1u << (16 * (hh & 1)));
+            }
+        }
+        __syncwarp(full);
+        unsigned int own = 0, incl = 0, in_bins = 0;                // in_bins: keys in the (distinct) bins the ranks fall into
+        int bins[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            // the bin of rank[k] in its histogram: each lane sums 8 bins, a warp scan finds the lane whose cumulative count first
+            // exceeds the rank, that lane walks its 8 bins and broadcasts (bin, count below, count in the bin)
+            const unsigned int* hrow = &hist[h[k] >> 1][8 * lane];
+            const int sh16 = 16 * (h[k] & 1);
+            if (k == 0 || h[k] != h[k - 1]) {
+                own = 0;
+#pragma unroll
+                for (int d = 0; d < 8; ++d) own += (hrow[d] >> sh16) & 0xffffu;
+                incl = own;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) { const unsigned int t = __shfl_up_sync(full, incl, off); if (lane >= off) incl += t; }
+            }
+            const unsigned int hit = __ballot_sync(full, incl > rank[k]);
+            const int sel = hit ? __ffs(hit) - 1 : 31;
+            unsigned int acc = incl - own, hv = 0; int d = 0;
+            for (; d < 8; ++d) { hv = (hrow[d] >> sh16) & 0xffffu; if (acc + hv > rank[k]) break; acc += hv; }
+            if (d > 7) d = 7;
+            bins[k] = __shfl_sync(full, 8 * lane + d, sel);
+            const unsigned int below = __shfl_sync(full, acc, sel);
+            const unsigned int inbin = __shfl_sync(full, hv, sel);
+            if (k == 0 || h[k] != h[k - 1] || bins[k] != bins[k - 1]) in_bins += inbin;
+            prefix[k] |= ((uint32_t)bins[k] << lo); rank[k] -= below;
+        }
+        mask |= dm << lo;
+        hi = lo;
+        if (hi == 0) break;
+        if (one && in_bins <= 64u) {
+            // the usual end: a handful of keys share a bin with one of the ranks.  They are gathered (in any order) into the
+            // unused half of the histogram storage and the ranks are read off directly
+            uint32_t* list = hist[1];
+            unsigned int* cursor = &hist[0][0];                     // (the first histogram has been read: its first word counts)
+            __syncwarp(full);
+            if (lane == 0) *cursor = 0u;
+            __syncwarp(full);
+            const int b0 = bins[0], b1 = bins[1], b2 = bins[2], b3 = bins[3];
+            auto take = [&](uint32_t k) {
+                const int d = (int)((k >> lo) & dm);
+                if (d == b0 || d == b1 || d == b2 || d == b3) list[atomicAdd(cursor, 1u)] = k;
+            };
+            for (int i = lane; i < n4; i += 32) { const uint4 k = key4[i]; take(k.x); take(k.y); take(k.z); take(k.w); }
+            if (4 * n4 + lane < n) take(key[4 * n4 + lane]);
+            __syncwarp(full);
+            cnt = (int)in_bins; fin = list; direct = true;
+            break;
+        }
+        // compaction: the keys that still match one of the four prefixes move to the front (pos <= i, and every lane has read
+        // its key of this step before any lane writes: in-place is safe)
+        int out = 0;
+        for (int i0 = 0; i0 < cnt; i0 += 32) {
+            const int i = i0 + lane;
+            const uint32_t k = i < cnt ? key[i] : 0u;
+            const uint32_t km = k & mask;
+            const bool keep = i < cnt && (km == prefix[0] || km == prefix[1] || km == prefix[2] || km == prefix[3]);
+            const unsigned b = __ballot_sync(full, keep);
+            if (keep) key[out + __popc(b & lt)] = k;
+            out += __popc(b);
+            __syncwarp(full);
+        }
+        cnt = out;
+        if (cnt <= 64) { direct = true; break; }
+    }
+    if (direct) {
+        // each lane holds up to two candidates and counts the candidates of the same prefix group that sort before each of
+        // them (ties by position): their ranks within the group
+        const bool va = lane < cnt, vb = lane + 32 < cnt;
+        const uint32_t ka = va ? fin[lane] : 0u, kb = vb ? fin[lane + 32] : 0u;
+        const uint32_t ga = ka & mask, gb = kb & mask;
+        unsigned int ra = 0, rb = 0;
+        for (int j = 0; j < cnt; ++j) {
+            const uint32_t kj = fin[j], gj = kj & mask;
+            ra += (gj == ga && (kj < ka || (kj == ka && j < lane))) ? 1u : 0u;
+            rb += (gj == gb && (kj < kb || (kj == kb && j < lane + 32))) ? 1u : 0u;
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const unsigned int hit_a = __ballot_sync(full, va && ga == prefix[t] && ra == rank[t]);
+            const unsigned int hit_b = __ballot_sync(full, vb && gb == prefix[t] && rb == rank[t]);
+            const uint32_t from_a = __shfl_sync(full, ka, hit_a ? __ffs(hit_a) - 1 : 0);
+            const uint32_t from_b = __shfl_sync(full, kb, hit_b ? __ffs(hit_b) - 1 : 0);
+            val[t] = hit_a ? from_a : from_b;
+        }
+    } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) val[t] = prefix[t];
+    }
+    const float a0 = key_value(val[0]), a1 = key_value(val[1]), b0 = key_value(val[2]), b1 = key_value(val[3]);
+    const float q0 = a0 + (a1 - a0) * f45, q1 = b0 + (b1 - b0) * f55;
+    return 0.5f * (q0 + q1);
+}
+
 __global__ void __launch_bounds__(32 * WQ_WARPS) mid_quantile_warp_kernel(const float* __restrict__ series, const int32_t* __restrict__ counts,
                                                                           int64_t n_series, int n, float* __restrict__ out) {
-    __shared__ uint32_t cache[WQ_WARPS][WQ_N];
-    __shared__ unsigned int hist[WQ_WARPS][4][256];
-    const unsigned full = 0xffffffffu;
+    __shared__ __align__(16) uint32_t cache[WQ_WARPS][WQ_N];
+    __shared__ __align__(16) unsigned int hist[WQ_WARPS][2][256];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t sidx = (int64_t)blockIdx.x * WQ_WARPS + w;
     if (sidx >= n_series) return;                                 // whole warps leave: no block-level barrier below
@@ -533,58 +699,62 @@ __global__ void __launch_bounds__(32 * WQ_WARPS) mid_quantile_warp_kernel(const 
     if (m <= 0) { if (lane == 0) out[sidx] = __int_as_float(0x7fc00000); return; }
     uint32_t* key = cache[w];
     for (int i = lane; i < n; i += 32) key[i] = order_key(__ldg(v + i));
-    int64_t lo45, lo55; float f45, f55;
-    quantile_pos(0.45, m, lo45, f45); quantile_pos(0.55, m, lo55, f55);
-    unsigned int rank[4]; uint32_t prefix[4] = {0u, 0u, 0u, 0u};   // warp-uniform
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { const int64_t r = (k < 2 ? lo45 : lo55) + (k & 1); rank[k] = (unsigned int)(r > m - 1 ? m - 1 : r); }
-    uint32_t mask = 0;
-#pragma unroll 1
-    for (int pass = 3; pass >= 0; --pass) {
-        const int shift = 8 * pass;
-        // ranks that still share a prefix share a histogram
-        int h[4];
-        h[0] = 0; h[1] = (prefix[1] == prefix[0]) ? 0 : 1;
-        h[2] = (prefix[2] == prefix[0]) ? 0 : (prefix[2] == prefix[1]) ? 1 : 2;
-        h[3] = (prefix[3] == prefix[0]) ? 0 : (prefix[3] == prefix[1]) ? 1 : (prefix[3] == prefix[2]) ? 2 : 3;
-        for (int k = lane; k < 4 * 256; k += 32) (&hist[w][0][0])[k] = 0;
-        __syncwarp(full);
-        for (int i = lane; i < n; i += 32) {
-            const uint32_t k = key[i];
-            const uint32_t km = k & mask, d = (k >> shift) & 0xFF;
-            if (km == prefix[0]) atomicAdd(&hist[w][0][d], 1u);
-            if (h[1] == 1 && km == prefix[1]) atomicAdd(&hist[w][1][d], 1u);
-            if (h[2] == 2 && km == prefix[2]) atomicAdd(&hist[w][2][d], 1u);
-            if (h[3] == 3 && km == prefix[3]) atomicAdd(&hist[w][3][d], 1u);
+    __syncwarp(0xffffffffu);
+    const float q = warp_mid_quantile(key, n, m, hist[w], lane);
+    if (lane == 0) out[sidx] = q;
+}
+
+// AlignPose.align_leg statistics of one chain in ONE kernel (recordings of up to LA_N frames): a CTA of seven warps streams
+// the chain's key points through shared memory once (60 B per leg-frame: the only DRAM traffic), builds the order keys of
+// the seven series -- coxa x, y, z and the four segment lengths, alignment.py:392-415 -- in shared memory, each warp
+// selects the mid-quantile of one series, and thread 0 writes the affine row (find_scale_leg + align_leg,
+// alignment.py:417-423, 465-485).  The series never exist in global memory (the three-kernel path below wrote and re-read
+// 56 B per leg-frame).
+constexpr int LA_WARPS = 7, LA_THREADS = 32 * LA_WARPS, LA_N = 1024, LA_TILE = LA_THREADS;
+__global__ void __launch_bounds__(LA_THREADS) leg_affine_fused_kernel(const float* __restrict__ pose, int64_t cs, int64_t fs,
+                                                                      const float* __restrict__ consts, int include_claw,
+                                                                      float* __restrict__ affine, int n_frame) {
+    __shared__ __align__(16) uint32_t key[LA_WARPS][LA_N];
+    __shared__ __align__(16) union { float stage[LA_TILE * 15]; unsigned int hist[LA_WARPS][2][256]; } u;
+    __shared__ float stat[8];
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int64_t c = blockIdx.x;
+    const float* src = pose + c * cs;
+    const bool vec = fs == 15 && ((((uintptr_t)src) & 15) == 0);
+    for (int f0 = 0; f0 < n_frame; f0 += LA_TILE) {
+        const int nf = min(LA_TILE, n_frame - f0);
+        const float* tsrc = src + (int64_t)f0 * fs;               // (f0 * 60 B is a multiple of 16)
+        if (vec) {
+            const int n4 = nf * 15 / 4;
+            const float4* s4 = reinterpret_cast<const float4*>(tsrc);
+            float4* d4 = reinterpret_cast<float4*>(u.stage);
+            for (int i = tid; i < n4; i += LA_THREADS) d4[i] = __ldg(s4 + i);
+            for (int i = 4 * n4 + tid; i < nf * 15; i += LA_THREADS) u.stage[i] = __ldg(tsrc + i);
+        } else {
+            for (int i = tid; i < nf * 15; i += LA_THREADS) u.stage[i] = __ldg(tsrc + (int64_t)(i / 15) * fs + i % 15);
         }
-        __syncwarp(full);
+        __syncthreads();
+        if (tid < nf) {
+            const float* k = u.stage + tid * 15;                   // stride 15 words: conflict-free
+            key[0][f0 + tid] = order_key(k[0]); key[1][f0 + tid] = order_key(k[1]); key[2][f0 + tid] = order_key(k[2]);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            // the bin of rank[k] in hist[h[k]]: each lane sums 8 bins, a warp scan finds the lane whose cumulative count first
-            // exceeds the rank, that lane walks its 8 bins and broadcasts (bin, count below)
-            const unsigned int* hrow = &hist[w][h[k]][8 * lane];
-            unsigned int own = 0;
-#pragma unroll
-            for (int d = 0; d < 8; ++d) own += hrow[d];
-            unsigned int incl = own;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) { const unsigned int t = __shfl_up_sync(full, incl, off); if (lane >= off) incl += t; }
-            const unsigned int hit = __ballot_sync(full, incl > rank[k]);
-            const int sel = hit ? __ffs(hit) - 1 : 31;
-            unsigned int acc = incl - own; int d = 0;
-            for (; d < 8; ++d) { if (acc + hrow[d] > rank[k]) break; acc += hrow[d]; }
-            if (d > 7) d = 7;
-            const int bin = __shfl_sync(full, 8 * lane + d, sel);
-            const unsigned int below = __shfl_sync(full, acc, sel);
-            prefix[k] |= ((uint32_t)bin << shift); rank[k] -= below;
+            for (int j = 0; j < 4; ++j) {
+                const float dx = k[3 * j + 3] - k[3 * j], dy = k[3 * j + 4] - k[3 * j + 1], dz = k[3 * j + 5] - k[3 * j + 2];
+                key[3 + j][f0 + tid] = order_key(sqrtf(dx * dx + dy * dy + dz * dz));
+            }
         }
-        mask |= 0xFFu << shift;
-        __syncwarp(full);
+        __syncthreads();
     }
-    if (lane == 0) {
-        const float a0 = key_value(prefix[0]), a1 = key_value(prefix[1]), b0 = key_value(prefix[2]), b1 = key_value(prefix[3]);
-        const float q0 = a0 + (a1 - a0) * f45, q1 = b0 + (b1 - b0) * f55;
-        out[sidx] = 0.5f * (q0 + q1);
+    const float q = warp_mid_quantile(key[w], n_frame, n_frame, u.hist[w], lane);
+    if (lane == 0) stat[w] = q;
+    __syncthreads();
+    if (tid == 0) {
+        const float* k = consts + c * 4;
+        float len = stat[3] + stat[4] + stat[5];
+        if (include_claw) len += stat[6];
+        float* a = affine + c * 8;
+        a[0] = stat[0]; a[1] = stat[1]; a[2] = stat[2]; a[3] = k[3] / len;
+        a[4] = k[0]; a[5] = k[1]; a[6] = k[2]; a[7] = 0.f;
     }
 }
 
@@ -622,6 +792,33 @@ extern "C" int seqik_leg_affine_f32(const float* stats, const float* consts, int
     if (!stats || !consts || !affine) return fail(SEQIK_EINVAL, "seqik_leg_affine_f32: NULL pointer");
     leg_affine_kernel<<<(unsigned)((n_chain + 127) / 128), 128, 0, (cudaStream_t)stream>>>(stats, consts, include_claw, affine, n_chain);
     return check_launch("seqik_leg_affine_f32");
+}
+
+// The whole statistics step of AlignPose.align_leg behind one call: key points -> affine rows.  Recordings of up to LA_N frames
+// run the fused per-chain kernel (no scratch needed); longer ones the series / select / affine kernels with the series in
+// `scratch` (n_chain * 7 * (n_frame + 1) floats).
+extern "C" int seqik_leg_affine_from_pose_f32(const float* pose, int64_t pose_chain_stride, int64_t pose_frame_stride,
+                                              const float* consts, int include_claw, float* scratch, float* affine,
+                                              int64_t n_chain, int64_t n_frame, void* stream) {
+    if (n_chain < 0 || n_frame < 0) return fail(SEQIK_EINVAL, "seqik_leg_affine_from_pose_f32: negative size");
+    if (n_chain == 0) return SEQIK_OK;
+    if (n_frame == 0) return fail(SEQIK_EINVAL, "seqik_leg_affine_from_pose_f32: empty recording");
+    if (!pose || !consts || !affine) return fail(SEQIK_EINVAL, "seqik_leg_affine_from_pose_f32: NULL pointer");
+    if (pose_frame_stride < 15) return fail(SEQIK_EINVAL, "seqik_leg_affine_from_pose_f32: frame stride smaller than the innermost block");
+    if (n_chain > 2147483647LL) return fail(SEQIK_EINVAL, "seqik_leg_affine_from_pose_f32: too many chains");
+    if (n_frame <= LA_N) {
+        leg_affine_fused_kernel<<<(unsigned)n_chain, LA_THREADS, 0, (cudaStream_t)stream>>>(pose, pose_chain_stride, pose_frame_stride, consts,
+                                                                                          include_claw, affine, (int)n_frame);
+        return check_launch("seqik_leg_affine_from_pose_f32");
+    }
+    if (!scratch) return fail(SEQIK_EINVAL, "seqik_leg_affine_from_pose_f32: recordings of more than 1024 frames need the scratch buffer");
+    float* series = scratch;
+    float* stats = scratch + n_chain * 7 * n_frame;
+    int rc = seqik_leg_series_f32(pose, pose_chain_stride, pose_frame_stride, series, n_chain, n_frame, stream);
+    if (rc != SEQIK_OK) return rc;
+    rc = seqik_mid_quantile_f32(series, nullptr, nullptr, stats, n_chain * 7, n_frame, stream);
+    if (rc != SEQIK_OK) return rc;
+    return seqik_leg_affine_f32(stats, consts, include_claw, affine, n_chain, stream);
 }
 
 __global__ void __launch_bounds__(256) align_apply_kernel(const float* __restrict__ pose, int64_t cs, int64_t fs,
@@ -913,13 +1110,29 @@ __global__ void __launch_bounds__(256) pchip_kernel(const T* __restrict__ in, T*
             const T t_ = (d0 + d1 - T(2) * slope) * rh;
             const T c0 = t_ * rh, c1 = (slope - d0) * rh - t_;
             T* o = (staged ? stage : dst) + (u_lo - first) * width + j;
-            for (int u = u_lo; u < u_hi; ++u, o += width) {
-                const T s = (T)((double)u * new_ts - xk);
-                T res = y0, z = s;
-                res += d0 * z; z *= s;
-                res += c1 * z; z *= s;
-                res += c0 * z;
-                *o = res;
+            if (sizeof(T) == 4) {
+                // float32: the offset of the first sample from the knot in float64, then one float32 multiply-add per sample
+                // (s is rounded to float32 anyway; the error of the increment stays below half an ulp of the interval
+                // length) -- four FP64-pipe instructions per output sample were the largest item of this kernel's issue budget
+                const float s0 = (float)((double)u_lo * new_ts - xk), dt = (float)new_ts;
+                float ur = 0.f;
+                for (int u = u_lo; u < u_hi; ++u, o += width, ur += 1.f) {
+                    const T s = (T)fmaf(ur, dt, s0);
+                    T res = y0, z = s;
+                    res += d0 * z; z *= s;
+                    res += c1 * z; z *= s;
+                    res += c0 * z;
+                    *o = res;
+                }
+            } else {
+                for (int u = u_lo; u < u_hi; ++u, o += width) {
+                    const T s = (T)((double)u * new_ts - xk);
+                    T res = y0, z = s;
+                    res += d0 * z; z *= s;
+                    res += c1 * z; z *= s;
+                    res += c0 * z;
+                    *o = res;
+                }
             }
         }
         if (staged) {

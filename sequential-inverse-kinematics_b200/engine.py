@@ -236,6 +236,27 @@ def leg_affine(pose, consts, include_claw: bool = False):
     n_chain, n_frame = int(pose.shape[0]), int(pose.shape[1])
     consts = _check(consts, "consts", (4,))
     dev = pose.device
+    if consts.shape[0] != n_chain:
+        raise ValueError("consts must have one row per chain")
+    affine = torch.empty((n_chain, 8), dtype=torch.float32, device=dev)
+    # recordings of up to 1024 frames: one fused kernel, the series never exist in global memory; longer ones need them
+    scratch = None if n_frame <= 1024 else torch.empty((n_chain * 7 * (n_frame + 1),), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        N.check(lib.seqik_leg_affine_from_pose_f32(N.ptr(pose), n_frame * 15, 15, N.ptr(consts), int(bool(include_claw)),
+                                                   N.ptr(scratch), N.ptr(affine), n_chain, n_frame, N.stream_ptr(torch, dev)),
+                "seqik_leg_affine_from_pose_f32")
+    return affine
+
+
+def leg_affine_unfused(pose, consts, include_claw: bool = False):
+    """The same through the three separate entry points (series, mid-quantiles, affine rows): the path of recordings longer
+    than 1024 frames, kept callable at any length for tests and measurements."""
+    torch = N.require_cuda()
+    lib = N.load_library()
+    pose = _check(pose, "pose", (5, 3))
+    n_chain, n_frame = int(pose.shape[0]), int(pose.shape[1])
+    consts = _check(consts, "consts", (4,))
+    dev = pose.device
     series = torch.empty((n_chain * 7, n_frame), dtype=torch.float32, device=dev)
     affine = torch.empty((n_chain, 8), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
@@ -330,8 +351,9 @@ def pchip_resample(series, original_ts: float, new_ts: float):
     if not (original_ts > 0 and new_ts > 0):
         raise ValueError("time steps must be positive")
     m = int(np.ceil((n * original_ts) / new_ts))                # length of np.arange(0, n * original_ts, new_ts)
-    finite = torch.isfinite(x)
-    if not bool(finite.all()):
+    lo_hi = torch.stack(torch.aminmax(x))                      # one read-only pass; NaN propagates, +-inf shows up as an extreme
+    if not bool(torch.isfinite(lo_hi).all()):
+        finite = torch.isfinite(x)
         if bool(torch.isnan(x).any()):
             raise ValueError("`y` must contain only finite values.")
         x = torch.where(finite, x, torch.zeros_like(x))

@@ -491,6 +491,59 @@ def test_mid_quantile_matches_numpy(api):
         api.engine.mid_quantile(t.zeros((3, 0), device="cuda"))
 
 
+def test_mid_quantile_narrow_ranges_ties_and_counts(api):
+    """The warp select starts at the first bit in which the keys of a series differ and compacts the candidates after every
+    pass: series that live in a sliver of an octave (segment lengths with 1e-3 noise), constants, two-valued series, series
+    that straddle zero, +inf padding with `counts` (the head series), lengths around the 32-key direct finish."""
+    t = api.torch
+    rng = np.random.default_rng(11)
+    for n in (1, 2, 31, 32, 33, 64, 65, 500, 1000, 1023, 1024):
+        rows = [0.7312 + 1e-3 * rng.normal(size=n), np.full(n, -3.25), rng.choice([1.5, 1.5000001], size=n),
+                1e-3 * rng.normal(size=n), np.where(rng.random(n) < 0.5, 0.0, -0.0), 1e30 * rng.normal(size=n),
+                np.sort(rng.normal(size=n)), 0.4 + 1e-6 * rng.integers(0, 4, size=n)]
+        x = np.stack(rows).astype(np.float32)
+        got = api.engine.mid_quantile(t.from_numpy(x).cuda()).cpu().numpy()
+        ref = 0.5 * (np.quantile(x.astype(np.float64), 0.45, axis=1) + np.quantile(x.astype(np.float64), 0.55, axis=1))
+        scale = np.abs(x).max(axis=1).astype(np.float64)               # float32 interpolation between two order statistics
+        assert (np.abs(got - ref) <= 3e-7 * scale).all(), (n, got, ref)
+        # only the m smallest take part (the rest is +inf padding)
+        m = rng.integers(1, n + 1, size=x.shape[0]).astype(np.int32)
+        y = x.copy()
+        for r in range(y.shape[0]):
+            y[r] = np.sort(y[r])
+            y[r, m[r]:] = np.inf
+            y[r] = rng.permutation(y[r])
+        got = api.engine.mid_quantile(t.from_numpy(y).cuda(), t.from_numpy(m).cuda()).cpu().numpy()
+        ref = np.array([0.5 * (np.quantile(np.sort(y[r].astype(np.float64))[:m[r]], 0.45) + np.quantile(np.sort(y[r].astype(np.float64))[:m[r]], 0.55))
+                        for r in range(y.shape[0])])
+        assert (np.abs(got - ref) <= 3e-7 * scale).all(), (n, "counts", got, ref)
+
+
+@pytest.mark.parametrize("n_frame", [1, 7, 224, 225, 1000, 1024, 1025, 3000])
+def test_fused_leg_affine_equals_the_three_kernels(api, n_frame):
+    """seqik_leg_affine_from_pose_f32 (one kernel per chain up to 1024 frames, series never written) against the series /
+    select / affine kernels, bit for bit, and against numpy on the same key points; contiguous and strided input."""
+    t = api.torch
+    rng = np.random.default_rng(n_frame)
+    n_chain = 13
+    pose = (rng.normal(size=(n_chain, 1, 5, 3)) + 0.02 * rng.normal(size=(n_chain, n_frame, 5, 3))).astype(np.float32)
+    consts = (1.0 + rng.random((n_chain, 4))).astype(np.float32)
+    d_pose, d_consts = t.from_numpy(pose).cuda(), t.from_numpy(consts).cuda()
+    for claw in (False, True):
+        fused = api.engine.leg_affine(d_pose, d_consts, include_claw=claw)
+        three = api.engine.leg_affine_unfused(d_pose, d_consts, include_claw=claw)
+        assert t.equal(fused, three)
+    p64 = pose.astype(np.float64)
+    mid = lambda a: 0.5 * (np.quantile(a, 0.45, axis=1) + np.quantile(a, 0.55, axis=1))
+    seg = np.linalg.norm(np.diff(pose, axis=2).astype(np.float32), axis=-1)          # (chain, frame, 4)
+    ref_len = mid(seg.astype(np.float64))[:, :3].sum(1)
+    got = fused.cpu().numpy() if not claw else api.engine.leg_affine(d_pose, d_consts).cpu().numpy()
+    got = api.engine.leg_affine(d_pose, d_consts).cpu().numpy()
+    assert np.allclose(got[:, :3], mid(p64[:, :, 0]), rtol=1e-6, atol=1e-7)
+    assert np.allclose(got[:, 3], consts[:, 3] / ref_len, rtol=2e-6)
+    assert np.array_equal(got[:, 4:7], consts[:, :3]) and (got[:, 7] == 0).all()
+
+
 # ------------------------------------------------------------------------------------------ edge cases and errors
 def test_edge_cases(api):
     chain = api.Chain(api.data.BOUNDS, ["RF", "LF"])
