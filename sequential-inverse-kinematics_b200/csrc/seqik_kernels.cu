@@ -448,12 +448,14 @@ __device__ __forceinline__ void quantile_pos(double q, int64_t n, int64_t& lo, f
 // One block per series: the four order statistics (two neighbours of each of the 0.45 / 0.55 quantile positions)
 // are found together by a 4-pass MSB radix select -- per pass one sweep over the series (from shared memory when it
 // fits, else re-read from global/L2) feeding four 256-bin histograms -- and combined into the mid-quantile.
+constexpr uint32_t MQ_RETRY = 0x7fc00001u;   // NaN payload a fast kernel leaves in `out` for the series it hands to the general one
 __global__ void __launch_bounds__(SEL_BLOCK) mid_quantile_kernel(const float* __restrict__ series, const int32_t* __restrict__ counts,
-                                                                 int64_t n, float* __restrict__ out) {
+                                                                 int64_t n, float* __restrict__ out, int only_flagged) {
     __shared__ unsigned int hist[4][256];
     __shared__ uint32_t s_prefix[4]; __shared__ unsigned long long s_rank[4]; __shared__ int s_hist[4];
     __shared__ uint32_t cache[SEL_CACHE];
     const int64_t sidx = blockIdx.x;
+    if (only_flagged && __float_as_uint(out[sidx]) != MQ_RETRY) return;       // (block-uniform)
     const float* v = series + sidx * n;
     const int64_t m = counts ? (int64_t)counts[sidx] : n;             // values that take part (the m smallest)
     if (m <= 0) { if (threadIdx.x == 0) out[sidx] = __int_as_float(0x7fc00000); return; }
@@ -532,16 +534,15 @@ __global__ void __launch_bounds__(SEL_BLOCK) mid_quantile_kernel(const float* __
 constexpr int WQ_N = 1024, WQ_WARPS = 4;
 __device__ __forceinline__ uint32_t low_mask(int nb) { return nb >= 32 ? 0xffffffffu : ((1u << nb) - 1u); }
 
-// key[0..n): order keys of the series in shared memory, 16-byte aligned (overwritten); m: the m smallest take part;
-// hist: 2 x 256 words of this warp
-__device__ float warp_mid_quantile(uint32_t* __restrict__ key, int n, int64_t m, unsigned int (*hist)[256], int lane) {
+// The four keys of ranks rank[0] <= rank[1] <= rank[2] <= rank[3] (0-based, in sorted order) of key[0..n) -> val[0..3], by ONE
+// warp.  key: shared memory, 16-byte aligned, overwritten; hist: 2 x 256 words of this warp.  n <= 4096 (16-bit counters
+// once the ranks have separated).  Keys are handled as offsets from the smallest one, so that the digits of every pass --
+// 8 bits starting at the top bit of the SPAN max - min -- are spread whatever the exponent the series lives in (a segment
+// length that wanders around 0.5 differs from its neighbours in bit 24 of the raw keys and in nothing else).
+__device__ void warp_select4(uint32_t* __restrict__ key, int n, unsigned int* rank, unsigned int (*hist)[256], int lane, uint32_t* val) {
     const unsigned full = 0xffffffffu;
     const unsigned lt = (1u << lane) - 1u;
-    int64_t lo45, lo55; float f45, f55;
-    quantile_pos(0.45, m, lo45, f45); quantile_pos(0.55, m, lo55, f55);
-    unsigned int rank[4]; uint32_t prefix[4], val[4];               // warp-uniform
-#pragma unroll
-    for (int k = 0; k < 4; ++k) { const int64_t r = (k < 2 ? lo45 : lo55) + (k & 1); rank[k] = (unsigned int)(r > m - 1 ? m - 1 : r); }
+    uint32_t prefix[4];                                             // warp-uniform
     const uint4* key4 = reinterpret_cast<const uint4*>(key);
     const int n4 = n >> 2;
     uint32_t kmin = 0xffffffffu, kmax = 0u;
@@ -551,12 +552,13 @@ __device__ float warp_mid_quantile(uint32_t* __restrict__ key, int n, int64_t m,
     }
     if (4 * n4 + lane < n) { const uint32_t k = key[4 * n4 + lane]; kmin = min(kmin, k); kmax = max(kmax, k); }
     kmin = __reduce_min_sync(full, kmin); kmax = __reduce_max_sync(full, kmax);
-    int hi = 32 - __clz((int)(kmin ^ kmax));                        // bits [0, hi) differ within the series (0: a constant series)
+    int hi = 32 - __clz((int)(kmax - kmin));                        // offsets need the bits [0, hi) (0: a constant series)
     uint32_t mask = ~low_mask(hi);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) prefix[k] = kmin & mask;
+    for (int k = 0; k < 4; ++k) prefix[k] = 0u;
+    uint32_t sub = kmin;                                            // key[] holds raw keys until the first compaction, offsets after it
     int cnt = n;                                                    // keys still in play: key[0..cnt)
-    const uint32_t* fin = key;                                      // where the candidates of the direct finish sit
+    const uint32_t* fin = key;                                      // where the candidates of the direct finish sit (as offsets)
     bool direct = false;
 #pragma unroll 1
     while (hi > 0) {
@@ -575,17 +577,17 @@ __device__ float warp_mid_quantile(uint32_t* __restrict__ key, int n, int64_t m,
         }
         __syncwarp(full);
         if (one) {
-            // no prefix test, 128 keys per step (few conflicts: the digit starts at the first bit that varies)
+            // no prefix test, 128 keys per step, 32-bit counters
             for (int i = lane; i < n4; i += 32) {
                 const uint4 k = key4[i];
-                atomicAdd(&hist[0][(k.x >> lo) & dm], 1u); atomicAdd(&hist[0][(k.y >> lo) & dm], 1u);
-                atomicAdd(&hist[0][(k.z >> lo) & dm], 1u); atomicAdd(&hist[0][(k.w >> lo) & dm], 1u);
+                atomicAdd(&hist[0][((k.x - sub) >> lo) & dm], 1u); atomicAdd(&hist[0][((k.y - sub) >> lo) & dm], 1u);
+                atomicAdd(&hist[0][((k.z - sub) >> lo) & dm], 1u); atomicAdd(&hist[0][((k.w - sub) >> lo) & dm], 1u);
             }
-            if (4 * n4 + lane < n) atomicAdd(&hist[0][(key[4 * n4 + lane] >> lo) & dm], 1u);
+            if (4 * n4 + lane < n) atomicAdd(&hist[0][((key[4 * n4 + lane] - sub) >> lo) & dm], 1u);
         } else {
             for (int i0 = 0; i0 < cnt; i0 += 32) {
                 const int i = i0 + lane;
-                const uint32_t k = i < cnt ? key[i] : 0u;
+                const uint32_t k = i < cnt ? key[i] - sub : 0u;
                 const uint32_t km = k & mask, d = (k >> lo) & dm;
                 int hh = -1;                                        // histogram this key counts in
                 if (i < cnt) hh = (km == prefix[0]) ? 0 : (km == prefix[1]) ? h[1] : (km == prefix[2]) ? h[2] : (km == prefix[3]) ? h[3] : -1;
@@ -594,6 +596,7 @@ __device__ float warp_mid_quantile(uint32_t* __restrict__ key, int n, int64_t m,
         }
         __syncwarp(full);
         unsigned int own = 0, incl = 0, in_bins = 0;                // in_bins: keys in the (distinct) bins the ranks fall into
+        const unsigned int cmask = one ? 0xffffffffu : 0xffffu;
         int bins[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -604,7 +607,7 @@ __device__ float warp_mid_quantile(uint32_t* __restrict__ key, int n, int64_t m,
             if (k == 0 || h[k] != h[k - 1]) {
                 own = 0;
 #pragma unroll
-                for (int d = 0; d < 8; ++d) own += (hrow[d] >> sh16) & 0xffffu;
+                for (int d = 0; d < 8; ++d) own += (hrow[d] >> sh16) & cmask;
                 incl = own;
 #pragma unroll
                 for (int off = 1; off < 32; off <<= 1) { const unsigned int t = __shfl_up_sync(full, incl, off); if (lane >= off) incl += t; }
@@ -612,7 +615,7 @@ __device__ float warp_mid_quantile(uint32_t* __restrict__ key, int n, int64_t m,
             const unsigned int hit = __ballot_sync(full, incl > rank[k]);
             const int sel = hit ? __ffs(hit) - 1 : 31;
             unsigned int acc = incl - own, hv = 0; int d = 0;
-            for (; d < 8; ++d) { hv = (hrow[d] >> sh16) & 0xffffu; if (acc + hv > rank[k]) break; acc += hv; }
+            for (; d < 8; ++d) { hv = (hrow[d] >> sh16) & cmask; if (acc + hv > rank[k]) break; acc += hv; }
             if (d > 7) d = 7;
             bins[k] = __shfl_sync(full, 8 * lane + d, sel);
             const unsigned int below = __shfl_sync(full, acc, sel);
@@ -633,6 +636,7 @@ __device__ float warp_mid_quantile(uint32_t* __restrict__ key, int n, int64_t m,
             __syncwarp(full);
             const int b0 = bins[0], b1 = bins[1], b2 = bins[2], b3 = bins[3];
             auto take = [&](uint32_t k) {
+                k -= sub;
                 const int d = (int)((k >> lo) & dm);
                 if (d == b0 || d == b1 || d == b2 || d == b3) list[atomicAdd(cursor, 1u)] = k;
             };
@@ -642,12 +646,12 @@ __device__ float warp_mid_quantile(uint32_t* __restrict__ key, int n, int64_t m,
             cnt = (int)in_bins; fin = list; direct = true;
             break;
         }
-        // compaction: the keys that still match one of the four prefixes move to the front (pos <= i, and every lane has read
-        // its key of this step before any lane writes: in-place is safe)
+        // compaction: the keys that still match one of the four prefixes move to the front, as offsets (pos <= i, and every lane
+        // has read its key of this step before any lane writes: in-place is safe)
         int out = 0;
         for (int i0 = 0; i0 < cnt; i0 += 32) {
             const int i = i0 + lane;
-            const uint32_t k = i < cnt ? key[i] : 0u;
+            const uint32_t k = i < cnt ? key[i] - sub : 0u;
             const uint32_t km = k & mask;
             const bool keep = i < cnt && (km == prefix[0] || km == prefix[1] || km == prefix[2] || km == prefix[3]);
             const unsigned b = __ballot_sync(full, keep);
@@ -655,7 +659,7 @@ __device__ float warp_mid_quantile(uint32_t* __restrict__ key, int n, int64_t m,
             out += __popc(b);
             __syncwarp(full);
         }
-        cnt = out;
+        cnt = out; sub = 0u;
         if (cnt <= 64) { direct = true; break; }
     }
     if (direct) {
@@ -676,15 +680,32 @@ __device__ float warp_mid_quantile(uint32_t* __restrict__ key, int n, int64_t m,
             const unsigned int hit_b = __ballot_sync(full, vb && gb == prefix[t] && rb == rank[t]);
             const uint32_t from_a = __shfl_sync(full, ka, hit_a ? __ffs(hit_a) - 1 : 0);
             const uint32_t from_b = __shfl_sync(full, kb, hit_b ? __ffs(hit_b) - 1 : 0);
-            val[t] = hit_a ? from_a : from_b;
+            val[t] = (hit_a ? from_a : from_b) + kmin;
         }
     } else {
 #pragma unroll
-        for (int t = 0; t < 4; ++t) val[t] = prefix[t];
+        for (int t = 0; t < 4; ++t) val[t] = prefix[t] + kmin;
     }
+}
+
+// the four ranks of the mid-quantile of the m smallest keys, and the interpolation weights (numpy "linear")
+__device__ __forceinline__ void mid_quantile_ranks(int64_t m, unsigned int* rank, float& f45, float& f55) {
+    int64_t lo45, lo55;
+    quantile_pos(0.45, m, lo45, f45); quantile_pos(0.55, m, lo55, f55);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const int64_t r = (k < 2 ? lo45 : lo55) + (k & 1); rank[k] = (unsigned int)(r > m - 1 ? m - 1 : r); }
+}
+__device__ __forceinline__ float mid_quantile_value(const uint32_t* val, float f45, float f55) {
     const float a0 = key_value(val[0]), a1 = key_value(val[1]), b0 = key_value(val[2]), b1 = key_value(val[3]);
     const float q0 = a0 + (a1 - a0) * f45, q1 = b0 + (b1 - b0) * f55;
     return 0.5f * (q0 + q1);
+}
+// key[0..n): order keys of the series (shared memory, 16-byte aligned, overwritten); m: the m smallest take part
+__device__ float warp_mid_quantile(uint32_t* __restrict__ key, int n, int64_t m, unsigned int (*hist)[256], int lane) {
+    unsigned int rank[4]; uint32_t val[4]; float f45, f55;
+    mid_quantile_ranks(m, rank, f45, f55);
+    warp_select4(key, n, rank, hist, lane, val);
+    return mid_quantile_value(val, f45, f55);
 }
 
 __global__ void __launch_bounds__(32 * WQ_WARPS) mid_quantile_warp_kernel(const float* __restrict__ series, const int32_t* __restrict__ counts,
@@ -758,6 +779,156 @@ __global__ void __launch_bounds__(LA_THREADS) leg_affine_fused_kernel(const floa
     }
 }
 
+// Long series (recordings of more than WQ_N frames; BASELINE config 5 has 100 000): one block per series, TWO sweeps over
+// global memory instead of four, and hardly any conflicting atomics.  A strided sample of 2048 keys gives the range the
+// bulk of the series lives in; sweep 1 bins every key of that range by the top 12 bits of its offset from the sample's
+// minimum (4096 bins: the bins of the four ranks hold n / 4096-ish keys each) and counts the keys below the range;
+// sweep 2 gathers the keys of those bins (a few hundred) into shared memory, where one warp finishes with warp_select4.
+// A series the sample does not describe -- a rank outside its range, more than LQ_CAND candidates (heavy ties) -- is left to
+// the general kernel (MQ_RETRY in `out`).  Series of up to LQ_CAND samples skip the sweeps: keys to shared memory, one warp.
+constexpr int LQ_BLOCK = 256, LQ_BINS = 4096, LQ_CAND = 4096, LQ_SAMPLE = 2048;
+constexpr uint32_t KEY_INF = 0xff800000u;     // order_key(+inf): padding of the head series, never part of the range
+__global__ void __launch_bounds__(LQ_BLOCK) mid_quantile_long_kernel(const float* __restrict__ series, const int32_t* __restrict__ counts,
+                                                                     int64_t n, float* __restrict__ out) {
+    __shared__ __align__(16) unsigned int hist[LQ_BINS];           // (the first 512 words serve warp_select4 afterwards)
+    __shared__ __align__(16) uint32_t cand[LQ_CAND];
+    __shared__ uint32_t s_min, s_max;
+    __shared__ unsigned int s_below, s_cnt, s_warp_tot[LQ_BLOCK / 32];
+    __shared__ int s_bin[4]; __shared__ unsigned int s_binbelow[4], s_bincount[4];
+    const unsigned full = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int64_t sidx = blockIdx.x;
+    const float* v = series + sidx * n;
+    const int64_t m = counts ? (int64_t)counts[sidx] : n;
+    if (m <= 0) { if (tid == 0) out[sidx] = __int_as_float(0x7fc00000); return; }
+    unsigned int rank[4]; uint32_t val[4]; float f45, f55;
+    mid_quantile_ranks(m, rank, f45, f55);
+    if (n <= LQ_CAND) {
+        for (int i = tid; i < (int)n; i += LQ_BLOCK) cand[i] = order_key(__ldg(v + i));
+        __syncthreads();
+        if (w == 0) {
+            warp_select4(cand, (int)n, rank, reinterpret_cast<unsigned int (*)[256]>(hist), lane, val);
+            if (lane == 0) out[sidx] = mid_quantile_value(val, f45, f55);
+        }
+        return;
+    }
+    // ---- the range of a strided sample (+inf padding left out)
+    if (tid == 0) { s_min = 0xffffffffu; s_max = 0u; s_below = 0u; s_cnt = 0u; }
+    for (int k = tid; k < LQ_BINS; k += LQ_BLOCK) hist[k] = 0u;
+    __syncthreads();
+    {
+        const int64_t stride = n / LQ_SAMPLE;
+        uint32_t lo = 0xffffffffu, hi = 0u;
+        for (int j = tid; j < LQ_SAMPLE; j += LQ_BLOCK) {
+            const uint32_t k = order_key(__ldg(v + (int64_t)j * stride));
+            if (k < KEY_INF) { lo = min(lo, k); hi = max(hi, k); }
+        }
+        lo = __reduce_min_sync(full, lo); hi = __reduce_max_sync(full, hi);
+        if (lane == 0) { atomicMin(&s_min, lo); atomicMax(&s_max, hi); }
+    }
+    __syncthreads();
+    const uint32_t smin = s_min, smax = s_max;
+    if (smin > smax) { if (tid == 0) out[sidx] = __uint_as_float(MQ_RETRY); return; }       // nothing finite in the sample
+    const int nb = 32 - __clz((int)(smax - smin));
+    const int shift = nb > 12 ? nb - 12 : 0;
+    // ---- sweep 1
+    {
+        unsigned int below = 0;
+        auto count = [&](float x) {
+            const uint32_t k = order_key(x);
+            if (k < smin) ++below;
+            else if (k <= smax) atomicAdd(&hist[(k - smin) >> shift], 1u);
+        };
+        if ((((uintptr_t)v) & 15) == 0) {
+            const float4* v4 = reinterpret_cast<const float4*>(v);
+            const int64_t n4 = n >> 2;
+            for (int64_t i = tid; i < n4; i += LQ_BLOCK) { const float4 x = __ldg(v4 + i); count(x.x); count(x.y); count(x.z); count(x.w); }
+            for (int64_t i = 4 * n4 + tid; i < n; i += LQ_BLOCK) count(__ldg(v + i));
+        } else {
+            for (int64_t i = tid; i < n; i += LQ_BLOCK) count(__ldg(v + i));
+        }
+        below = __reduce_add_sync(full, below);
+        if (lane == 0 && below) atomicAdd(&s_below, below);
+    }
+    __syncthreads();
+    // ---- the bins of the four ranks: every thread owns 16 bins, block-wide exclusive scan of the per-thread sums
+    unsigned int own = 0;
+#pragma unroll
+    for (int d = 0; d < 16; ++d) own += hist[16 * tid + d];
+    unsigned int incl = own;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const unsigned int t = __shfl_up_sync(full, incl, off); if (lane >= off) incl += t; }
+    if (lane == 31) s_warp_tot[w] = incl;
+    if (tid < 4) s_bin[tid] = -1;
+    __syncthreads();
+    unsigned int base = 0, n_in = 0;
+#pragma unroll
+    for (int k = 0; k < LQ_BLOCK / 32; ++k) { if (k < w) base += s_warp_tot[k]; n_in += s_warp_tot[k]; }
+    const unsigned int excl = base + incl - own;
+    const unsigned int below_all = s_below;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        if (rank[t] >= below_all && rank[t] - below_all < n_in) {
+            const unsigned int r = rank[t] - below_all;
+            if (r >= excl && r < excl + own) {                      // exactly one thread
+                unsigned int acc = excl; int d = 0;
+                for (; d < 16; ++d) { const unsigned int hv = hist[16 * tid + d]; if (acc + hv > r) break; acc += hv; }
+                if (d > 15) d = 15;
+                s_bin[t] = 16 * tid + d; s_binbelow[t] = acc; s_bincount[t] = hist[16 * tid + d];
+            }
+        }
+    }
+    __syncthreads();
+    const int b0 = s_bin[0], b1 = s_bin[1], b2 = s_bin[2], b3 = s_bin[3];
+    // candidates = the keys of the distinct bins (b0 <= b1 <= b2 <= b3); rank of each target within their sorted list
+    unsigned int c = 0, lrank[4];
+    {
+        const int bb[4] = {b0, b1, b2, b3};
+        unsigned int before = 0;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            if (t > 0 && bb[t] != bb[t - 1]) before += s_bincount[t - 1];
+            lrank[t] = before + (rank[t] - below_all - s_binbelow[t]);
+        }
+        c = before + s_bincount[3];
+    }
+    if (b0 < 0 || b1 < 0 || b2 < 0 || b3 < 0 || (shift > 0 && c > (unsigned int)LQ_CAND)) {
+        if (tid == 0) out[sidx] = __uint_as_float(MQ_RETRY);
+        return;
+    }
+    if (shift == 0) {
+        // the range spans fewer than 4096 distinct keys (a constant or few-valued series): a bin IS a key value
+        if (tid == 0) {
+            val[0] = smin + (uint32_t)b0; val[1] = smin + (uint32_t)b1; val[2] = smin + (uint32_t)b2; val[3] = smin + (uint32_t)b3;
+            out[sidx] = mid_quantile_value(val, f45, f55);
+        }
+        return;
+    }
+    // ---- sweep 2
+    {
+        auto take = [&](float x) {
+            const uint32_t k = order_key(x);
+            if (k >= smin && k <= smax) {
+                const int d = (int)((k - smin) >> shift);
+                if (d == b0 || d == b1 || d == b2 || d == b3) cand[atomicAdd(&s_cnt, 1u)] = k;
+            }
+        };
+        if ((((uintptr_t)v) & 15) == 0) {
+            const float4* v4 = reinterpret_cast<const float4*>(v);
+            const int64_t n4 = n >> 2;
+            for (int64_t i = tid; i < n4; i += LQ_BLOCK) { const float4 x = __ldg(v4 + i); take(x.x); take(x.y); take(x.z); take(x.w); }
+            for (int64_t i = 4 * n4 + tid; i < n; i += LQ_BLOCK) take(__ldg(v + i));
+        } else {
+            for (int64_t i = tid; i < n; i += LQ_BLOCK) take(__ldg(v + i));
+        }
+    }
+    __syncthreads();
+    if (w == 0) {
+        warp_select4(cand, (int)c, lrank, reinterpret_cast<unsigned int (*)[256]>(hist), lane, val);
+        if (lane == 0) out[sidx] = mid_quantile_value(val, f45, f55);
+    }
+}
+
 extern "C" int seqik_mid_quantile_f32(const float* series, const int32_t* counts, float* scratch, float* out,
                                       int64_t n_series, int64_t n, void* stream) {
     (void)scratch;   // kept in the signature (ABI): the single-kernel select needs no scratch
@@ -766,10 +937,13 @@ extern "C" int seqik_mid_quantile_f32(const float* series, const int32_t* counts
     if (n == 0) return fail(SEQIK_EINVAL, "seqik_mid_quantile_f32: empty series");
     if (!series || !out) return fail(SEQIK_EINVAL, "seqik_mid_quantile_f32: NULL pointer");
     if (n_series > 2147483647LL) return fail(SEQIK_EINVAL, "seqik_mid_quantile_f32: too many series");
-    if (n <= WQ_N)
+    if (n <= WQ_N) {
         mid_quantile_warp_kernel<<<(unsigned)((n_series + WQ_WARPS - 1) / WQ_WARPS), 32 * WQ_WARPS, 0, (cudaStream_t)stream>>>(series, counts, n_series, (int)n, out);
-    else
-        mid_quantile_kernel<<<(unsigned)n_series, SEL_BLOCK, 0, (cudaStream_t)stream>>>(series, counts, n, out);
+    } else {
+        // two sweeps from a sampled range; the series it could not settle that way (MQ_RETRY) go through the general kernel
+        mid_quantile_long_kernel<<<(unsigned)n_series, LQ_BLOCK, 0, (cudaStream_t)stream>>>(series, counts, n, out);
+        mid_quantile_kernel<<<(unsigned)n_series, SEL_BLOCK, 0, (cudaStream_t)stream>>>(series, counts, n, out, 1);
+    }
     return check_launch("seqik_mid_quantile_f32");
 }
 

@@ -497,10 +497,13 @@ def test_mid_quantile_narrow_ranges_ties_and_counts(api):
     that straddle zero, +inf padding with `counts` (the head series), lengths around the 32-key direct finish."""
     t = api.torch
     rng = np.random.default_rng(11)
-    for n in (1, 2, 31, 32, 33, 64, 65, 500, 1000, 1023, 1024):
+    for n in (1, 2, 31, 32, 33, 64, 65, 500, 1000, 1023, 1024, 1025, 4096, 4097, 20000, 100003):
+        # (beyond 1024 samples: the sampled-range two-sweep kernel; the two-valued and the four-valued series have more
+        #  candidates than it keeps and go through the general kernel, the drifting one has its ranks inside the sample's range)
         rows = [0.7312 + 1e-3 * rng.normal(size=n), np.full(n, -3.25), rng.choice([1.5, 1.5000001], size=n),
                 1e-3 * rng.normal(size=n), np.where(rng.random(n) < 0.5, 0.0, -0.0), 1e30 * rng.normal(size=n),
-                np.sort(rng.normal(size=n)), 0.4 + 1e-6 * rng.integers(0, 4, size=n)]
+                np.sort(rng.normal(size=n)), 0.4 + 1e-6 * rng.integers(0, 4, size=n),
+                0.5 + 2e-3 * rng.normal(size=n), np.linspace(-1.0, 3.0, n) + 0.05 * rng.normal(size=n)]
         x = np.stack(rows).astype(np.float32)
         got = api.engine.mid_quantile(t.from_numpy(x).cuda()).cpu().numpy()
         ref = 0.5 * (np.quantile(x.astype(np.float64), 0.45, axis=1) + np.quantile(x.astype(np.float64), 0.55, axis=1))
