@@ -153,7 +153,10 @@ int seqik_leg_solve_f32(const float* pose, int64_t pose_chain_stride, int64_t po
  *   angles  [n_chain][n_frame][7] out;  fk NULL, or [n_chain][n_frame][9][3] out (rows 0-3 origin, 4-5 Coxa-Femur
  *           joint, 6 Femur-Tibia, 7 Tibia-Tarsus, 8 Claw);  warm / status / nfev ([n_chain], evaluations summed over
  *           frames) as in seqik_leg_solve_f32
- *   flags   bits SEQIK_FLAG_CPW_SHIFT..+5: chains per warp (1..32), 0 = automatic; other bits must be 0
+ *   flags   bits SEQIK_FLAG_CPW_SHIFT..+5: chains per warp (1..32), 0 = automatic; bits SEQIK_FLAG_SCHED_SHIFT..+3: 0 automatic
+ *           (2 while the batch is resident at once, else 1), 1 one lane per chain, 2 eight lanes per chain (a joint per lane,
+ *           sums over the joints by butterfly shuffles; up to 4 chains per warp).  Same iteration, different summation
+ *           order; other bits must be 0
  *
  * The reference's generic solve is under-determined (3 equations, 7 unknowns) and its answer depends on rounding noise
  * (DESIGN.md 5.4): this entry point restates the same iteration, reproduces the reference solve by solve from the same

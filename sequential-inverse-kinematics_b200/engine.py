@@ -116,13 +116,16 @@ def leg_solve(pose, params, affine=None, stages: Sequence[int] = (1, 2, 3, 4), w
 
 
 def leg_solve_generic(pose, params, target_row: int = -1, want_fk: bool = True, warm=None, want_stats: bool = True,
-                      chains_per_warp: int = 0):
+                      chains_per_warp: int = 0, schedule: int = 0):
     """Generic single-target leg IK (LegInvKinGeneric): pose (n_chain, n_frame, k, 3) with the ThC at row 0 and the end
     effector at ``target_row`` (default: the last row, like the reference); params (n_chain, 32) from
     ``KinematicChainGeneric.pack_chain_params``.  float32 tensors run the FP32 kernel, float64 tensors the FP64 one
     (data and device arithmetic; see include/seqik.h).  Returns (angles (n_chain, n_frame, 7) in GENERIC chain order --
     ThC_roll, ThC_yaw, ThC_pitch, CTr_pitch, CTr_roll, FTi_pitch, TiTa_pitch --, fk (n_chain, n_frame, 9, 3) | None,
-    status | None, nfev | None).  ``warm`` (n_chain, 7) replaces the seeds of ``params``."""
+    status | None, nfev | None).  ``warm`` (n_chain, 7) replaces the seeds of ``params``.
+    ``schedule``: 0 automatic (2 while the batch is resident at once, else 1), 1 one lane per chain (the host-buildable form), 2 eight lanes per chain (a joint per
+    lane, sums by butterfly shuffles: same iteration, different summation order).  ``chains_per_warp``: tuning / tests
+    (1..32 for schedule 1, capped at 4 for schedule 2); results do not depend on it."""
     torch = N.require_cuda()
     lib = N.load_library()
     if not isinstance(pose, torch.Tensor) or pose.dim() != 4 or pose.shape[-1] != 3:
@@ -152,7 +155,7 @@ def leg_solve_generic(pose, params, target_row: int = -1, want_fk: bool = True, 
     with torch.cuda.device(dev):
         rc = fn(pose.data_ptr(), n_frame * k * 3, k * 3, row, N.ptr(params),
                 angles.data_ptr(), n_frame * 7, 7, N.ptr(fk), n_frame * 27, 27,
-                N.ptr(warm), 7, N.ptr(status), N.ptr(nfev), n_chain, n_frame, (chains_per_warp & 0x3F) << 12,
+                N.ptr(warm), 7, N.ptr(status), N.ptr(nfev), n_chain, n_frame, ((chains_per_warp & 0x3F) << 12) | ((schedule & 0xF) << N.FLAG_SCHED_SHIFT),
                 N.stream_ptr(torch, dev))
     N.check(rc, "seqik_leg_solve_generic")
     return angles, fk, status, nfev

@@ -32,9 +32,11 @@ def api():
     return a
 
 
+@pytest.mark.parametrize("schedule", [2, 1])
 @pytest.mark.parametrize("dtype,min_frac,med", [("float64", 0.96, 1e-7), ("float32", 0.84, 1e-5)])
-def test_teacher_forced_single_solves(api, generic_gold, grooming_leg, dtype, min_frac, med):
-    """Every solve of the fixture as its own one-frame chain, seeded with the oracle's previous answer."""
+def test_teacher_forced_single_solves(api, generic_gold, grooming_leg, dtype, min_frac, med, schedule):
+    """Every solve of the fixture as its own one-frame chain, seeded with the oracle's previous answer; with the chain
+    spread over eight lanes (schedule 2, the default) and with one lane per chain (schedule 1)."""
     torch = api.torch
     td = getattr(torch, dtype)
     n = int(generic_gold["n_frame"])
@@ -44,7 +46,7 @@ def test_teacher_forced_single_solves(api, generic_gold, grooming_leg, dtype, mi
         teacher = teacher_of(generic_gold, li, seed)
         rows = np.stack([params_row(seg, lb, ub, teacher[t]) for t in range(n)])
         d_pose = torch.tensor(pose[:, None], dtype=td, device="cuda")                 # (n chains, 1 frame, 5, 3)
-        ang, fk, status, nfev = api.engine.leg_solve_generic(d_pose, torch.tensor(rows, dtype=td, device="cuda"))
+        ang, fk, status, nfev = api.engine.leg_solve_generic(d_pose, torch.tensor(rows, dtype=td, device="cuda"), schedule=schedule)
         ang, fk = ang.cpu().numpy()[:, 0].astype(float), fk.cpu().numpy()[:, 0].astype(float)
         dev = np.abs(ang - generic_gold["oracle_angles"][li][:, 1:8]).max(axis=1)
         assert (dev <= ANGLE_TOL).mean() >= min_frac, (leg, (dev <= ANGLE_TOL).mean())
@@ -112,10 +114,17 @@ def test_generic_schedule_invariance_and_errors(api, grooming_leg):
     pose = np.stack([grooming_leg["pose"][0][50 * k:50 * k + 60] for k in range(40)])      # 40 chains x 60 frames
     d_pose = torch.tensor(pose, dtype=torch.float32, device="cuda")
     d_rows = torch.tensor(rows, dtype=torch.float32, device="cuda")
-    ref = api.engine.leg_solve_generic(d_pose, d_rows)
-    for cpw in (1, 7, 32):
-        out = api.engine.leg_solve_generic(d_pose, d_rows, chains_per_warp=cpw)
-        assert torch.equal(out[0], ref[0]) and torch.equal(out[1], ref[1]) and torch.equal(out[3], ref[3])
+    for schedule in (1, 2):
+        ref = api.engine.leg_solve_generic(d_pose, d_rows, schedule=schedule)
+        for cpw in (1, 3, 7, 32):
+            out = api.engine.leg_solve_generic(d_pose, d_rows, chains_per_warp=cpw, schedule=schedule)
+            assert torch.equal(out[0], ref[0]) and torch.equal(out[1], ref[1]) and torch.equal(out[3], ref[3])
+    # the two mappings run the same iteration with different summation orders: same claw, same limits, nearly always the
+    # same angles (the problem is under-determined: a few solves may settle on another point of the self-motion manifold)
+    one = api.engine.leg_solve_generic(d_pose, d_rows, schedule=1)
+    resid = lambda o: (o[1][:, :, 8] - d_pose[:, :, 4]).norm(dim=-1).max().item()
+    assert resid(ref) < 1e-4 and resid(one) < 1e-4
+    assert abs(float(ref[3].double().mean()) - float(one[3].double().mean())) < 0.1 * float(one[3].double().mean())
     # warm start replaces the seeds: continuing from frame 29 reproduces frames 30..59
     tail = api.engine.leg_solve_generic(d_pose[:, 30:].contiguous(), d_rows, warm=ref[0][:, 29].contiguous())
     assert torch.equal(tail[0], ref[0][:, 30:])
