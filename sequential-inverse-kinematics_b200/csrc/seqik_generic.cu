@@ -204,7 +204,8 @@ static int launch_generic(const char* me, const R* pose, int64_t pose_chain_stri
         if (warps_sm > 32) warps_sm = 32;
         if (warps_sm < 4) warps_sm = 4;
     }
-    const bool group = sched == 2 || (sched == 0 && n_chain <= 4LL * warps_sm * n_sm);
+    // (float64: the one-lane kernel spills and holds 8 warps per SM, so the groups still win at 1.3 waves: 6 000 chains)
+    const bool group = sched == 2 || (sched == 0 && n_chain <= (sizeof(R) == 8 ? 6LL : 4LL) * warps_sm * n_sm);
     if (group) {
         // fill the warps early: fewer warps at different places of the (long) evaluation code run faster than more
         int gpw = (int)((n_chain + 4LL * n_sm - 1) / (4LL * n_sm));
