@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SEQIK_ABI_VERSION 7   /* 7: seqik_leg_affine_from_pose_f32; 6: schedule 3 (frame-parallel blocks), seqik_fk_expand_host_f32; 5: solver flag bits 6-7, phase periods in bits 21-27 */
+#define SEQIK_ABI_VERSION 8   /* 8: seqik_origin_rows_f32; 7: seqik_leg_affine_from_pose_f32; 6: schedule 3 (frame-parallel blocks), seqik_fk_expand_host_f32; 5: solver flag bits 6-7, phase periods in bits 21-27 */
 #define SEQIK_OK 0
 #define SEQIK_EINVAL (-1)
 #define SEQIK_ECUDA (-3)
@@ -286,6 +286,13 @@ int seqik_fk_expand_host_f32(const float* joints, int64_t j_chain_stride, int64_
                              const float* pose, int64_t p_chain_stride, int64_t p_frame_stride,
                              float* fk, int64_t f_chain_stride, int64_t f_frame_stride,
                              int64_t n_chain, int64_t t0, int64_t t1, int n_threads);
+
+/* DEVICE side of the same wire format: out [n_chain][..][3] (chain stride out_chain_stride floats, frame stride 3) receives
+ * key point 0 of frames [t0, t1) of pose [n_chain][..][>= 3].  Shipped next to the joint rows it lets the host rebuild rows
+ * 0-3 from 12 contiguous bytes per leg-frame (pass it to seqik_fk_expand_host_f32 as `pose` with p_frame_stride = 3) instead
+ * of walking the 60-byte-per-frame host pose: 88 instead of 136 result bytes per leg-frame on the link. */
+int seqik_origin_rows_f32(const float* pose, int64_t pose_chain_stride, int64_t pose_frame_stride, float* out,
+                          int64_t out_chain_stride, int64_t n_chain, int64_t t0, int64_t t1, void* stream);
 
 #ifdef __cplusplus
 }

@@ -12,7 +12,7 @@ import numpy as np
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "csrc" / "libseqik_sm100.so"
 
-ABI_VERSION = 7
+ABI_VERSION = 8
 CHAIN_PARAM_FLOATS = 32
 FLAG_ESCAPE = 1 << 4
 FLAG_SKIP_CONFIRM = 1 << 5
@@ -47,6 +47,7 @@ _SIGNATURES = {
     "seqik_mid_quantile_f32": (_int, [_vp, _vp, _vp, _vp, _i64, _i64, _vp]),
     "seqik_leg_series_f32": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _vp]),
     "seqik_leg_affine_f32": (_int, [_vp, _vp, _int, _vp, _i64, _vp]),
+    "seqik_origin_rows_f32": (_int, [_vp, _i64, _i64, _vp, _i64, _i64, _i64, _i64, _vp]),
     "seqik_leg_affine_from_pose_f32": (_int, [_vp, _i64, _i64, _vp, _int, _vp, _vp, _i64, _i64, _vp]),
     "seqik_align_apply_f32": (_int, [_vp, _i64, _i64, _vp, _vp, _i64, _i64, _vp]),
     "seqik_head_series_f32": (_int, [_vp, _vp, _i64, _f32, _vp, _vp, _i64, _i64, _vp]),

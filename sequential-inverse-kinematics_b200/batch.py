@@ -107,8 +107,13 @@ class BatchedLegIK:
         if host_buffers:
             self.h_angles = torch.empty((self.n_chain, self.n_frame, 7), dtype=torch.float32, pin_memory=True)
             self.h_fk = torch.empty((self.n_chain, self.n_frame, self.out_rows, 3), dtype=torch.float32, pin_memory=True) if want_fk else None
+        self.h_origin = self.d_origin = None
         if self.wire_joints:
             self.h_wire = torch.empty((self.n_chain, self.n_frame, 4, 3), dtype=torch.float32, pin_memory=True)
+            # the origin rows travel compact next to the joint rows (12 B per leg-frame): the host then rebuilds rows 0-3 from
+            # contiguous memory instead of walking its 60-byte-per-frame pose
+            self.d_origin = torch.empty((self.n_chain, self.n_frame, 3), **f32)
+            self.h_origin = torch.empty((self.n_chain, self.n_frame, 3), dtype=torch.float32, pin_memory=True)
         self.status = self.nfev = None
         self._copy_streams = None
         self.default_chunks = 8
@@ -181,23 +186,28 @@ class BatchedLegIK:
                 engine.leg_solve(self.d_pose, self.params, angles=self.d_angles, fk=self.d_fk, want_fk=self.d_fk is not None,
                                  schedule=self.schedule, chains_per_warp=self.chains_per_warp, want_stats=False, frames=(t0, t1),
                                  fk_layout=self.fk_layout, flags=self.flags)
+                if self.wire_joints:
+                    N.check(lib.seqik_origin_rows_f32(self.d_pose.data_ptr(), F * 15, 15, self.d_origin.data_ptr(), F * 3, self.n_chain,
+                                                      t0, t1, main.cuda_stream), "seqik_origin_rows_f32")
                 ev_k = torch.cuda.Event()
                 ev_k.record(main)
                 s_out.wait_event(ev_k)
-                copy2d(h_angles, self.d_angles, 7, t0, t1, 2, s_out)
-                if self.d_fk is not None:
-                    copy2d(self.h_wire if self.wire_joints else h_fk, self.d_fk, 3 * self.fk_rows, t0, t1, 2, s_out)
-                if self.wire_joints:
+                if self.wire_joints:                                   # what the host expansion needs first
+                    copy2d(self.h_wire, self.d_fk, 12, t0, t1, 2, s_out)
+                    copy2d(self.h_origin, self.d_origin, 3, t0, t1, 2, s_out)
                     ev_o = torch.cuda.Event()
                     ev_o.record(s_out)
                     arrived.append((ev_o, t0, t1))
+                elif self.d_fk is not None:
+                    copy2d(h_fk, self.d_fk, 3 * self.fk_rows, t0, t1, 2, s_out)
+                copy2d(h_angles, self.d_angles, 7, t0, t1, 2, s_out)
             main.wait_stream(s_out)
         self.launches_per_call = len(bounds) - 1
         # joints-only wire format: the 9-row layout is rebuilt on the host, chunk by chunk as the copies land (later chunks
         # are still being solved / copied meanwhile); this part of the call is synchronous by nature
         for ev_o, t0, t1 in arrived:
             ev_o.synchronize()
-            N.check(lib.seqik_fk_expand_host_f32(self.h_wire.data_ptr(), F * 12, 12, src.data_ptr(), F * 15, 15, h_fk.data_ptr(), F * 27, 27,
+            N.check(lib.seqik_fk_expand_host_f32(self.h_wire.data_ptr(), F * 12, 12, self.h_origin.data_ptr(), F * 3, 3, h_fk.data_ptr(), F * 27, 27,
                                                  self.n_chain, t0, t1, self.expand_threads), "seqik_fk_expand_host_f32")
         if synchronize:
             main.synchronize()

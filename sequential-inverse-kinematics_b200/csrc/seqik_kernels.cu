@@ -13,6 +13,9 @@
 #include <string.h>
 #include <thread>
 #include <vector>
+#if defined(__SSE2__)
+#include <immintrin.h>
+#endif
 
 #include "../../include/seqik.h"
 #include "seqik_common.h"
@@ -57,6 +60,28 @@ extern "C" int seqik_memcpy2d_async(void* dst, int64_t dst_pitch_bytes, const vo
 }
 extern "C" const char* seqik_last_error(void) { return g_err; }
 
+// Device side of the joints-only wire format: the origin rows (key point 0) of frames [t0, t1) of every chain, compact
+// ([n_chain][n_frame][3]), so that the host rebuilds rows 0-3 from 12 contiguous bytes per leg-frame instead of touching
+// every cache line of its 60-byte-per-frame pose.
+__global__ void __launch_bounds__(256) origin_rows_kernel(const float* __restrict__ pose, int64_t cs, int64_t fs, float* __restrict__ out,
+                                                          int64_t out_cs, int64_t n_chain, int64_t t0, int64_t nt) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;          // one float of one origin row
+    if (i >= n_chain * nt * 3) return;
+    const int64_t c = i / (nt * 3), r = i - c * (nt * 3), t = r / 3, k = r - 3 * t;
+    out[c * out_cs + (t0 + t) * 3 + k] = __ldg(pose + c * cs + (t0 + t) * fs + k);
+}
+extern "C" int seqik_origin_rows_f32(const float* pose, int64_t pose_chain_stride, int64_t pose_frame_stride, float* out,
+                                     int64_t out_chain_stride, int64_t n_chain, int64_t t0, int64_t t1, void* stream) {
+    if (n_chain < 0 || t0 < 0 || t1 < t0) return fail(SEQIK_EINVAL, "seqik_origin_rows_f32: bad range");
+    if (n_chain == 0 || t1 == t0) return SEQIK_OK;
+    if (!pose || !out) return fail(SEQIK_EINVAL, "seqik_origin_rows_f32: NULL pointer");
+    if (pose_frame_stride < 3) return fail(SEQIK_EINVAL, "seqik_origin_rows_f32: frame stride too small");
+    const int64_t total = n_chain * (t1 - t0) * 3;
+    origin_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pose, pose_chain_stride, pose_frame_stride, out,
+                                                                                         out_chain_stride, n_chain, t0, t1 - t0);
+    return check_launch("seqik_origin_rows_f32");
+}
+
 // Host side of the joints-only wire format: the reference's nine-row FK layout rebuilt in HOST memory from the four joint rows
 // that crossed the link and the origin row of the host-resident pose (rows 0-3 = origin, row 4 = row 5 = first joint).
 // A memory-bound copy; chains are split over `n_threads` host threads.
@@ -75,7 +100,26 @@ extern "C" int seqik_fk_expand_host_f32(const float* joints, int64_t j_chain_str
             const float* j = joints + c * j_chain_stride + t0 * j_frame_stride;
             const float* p = pose + c * p_chain_stride + t0 * p_frame_stride;
             float* o = fk + c * f_chain_stride + t0 * f_frame_stride;
-            for (int64_t t = t0; t < t1; ++t, j += j_frame_stride, p += p_frame_stride, o += f_frame_stride) {
+            int64_t t = t0;
+#if defined(__SSE2__)
+            // four frames = 108 floats = 27 x 16 bytes: assembled in registers / L1 and written with streaming stores, so that
+            // the 648 MB of rows of a config-3 step are not first READ into the cache (write-allocate) before being overwritten
+            if (f_frame_stride == 27 && ((((uintptr_t)o) & 15) == 0)) {
+                alignas(16) float buf[108];
+                for (; t + 4 <= t1; t += 4, o += 108) {
+                    for (int f = 0; f < 4; ++f, j += j_frame_stride, p += p_frame_stride) {
+                        float* b = buf + 27 * f;
+                        const float x = p[0], y = p[1], z = p[2];
+                        for (int r = 0; r < 4; ++r) { b[3 * r] = x; b[3 * r + 1] = y; b[3 * r + 2] = z; }
+                        b[12] = j[0]; b[13] = j[1]; b[14] = j[2];
+                        memcpy(b + 15, j, 12 * sizeof(float));
+                    }
+                    for (int k = 0; k < 27; ++k) _mm_stream_ps(o + 4 * k, _mm_load_ps(buf + 4 * k));
+                }
+                _mm_sfence();
+            }
+#endif
+            for (; t < t1; ++t, j += j_frame_stride, p += p_frame_stride, o += f_frame_stride) {
                 const float x = p[0], y = p[1], z = p[2];
                 for (int r = 0; r < 4; ++r) { o[3 * r] = x; o[3 * r + 1] = y; o[3 * r + 2] = z; }
                 o[12] = j[0]; o[13] = j[1]; o[14] = j[2];
@@ -655,6 +699,7 @@ __device__ void warp_select4(uint32_t* __restrict__ key, int n, unsigned int* ra
             const uint32_t km = k & mask;
             const bool keep = i < cnt && (km == prefix[0] || km == prefix[1] || km == prefix[2] || km == prefix[3]);
             const unsigned b = __ballot_sync(full, keep);
+            __syncwarp(full);                                       // (every lane holds its key: the ballot already implies it)
             if (keep) key[out + __popc(b & lt)] = k;
             out += __popc(b);
             __syncwarp(full);
@@ -742,32 +787,55 @@ __global__ void __launch_bounds__(LA_THREADS) leg_affine_fused_kernel(const floa
     const int64_t c = blockIdx.x;
     const float* src = pose + c * cs;
     const bool vec = fs == 15 && ((((uintptr_t)src) & 15) == 0);
+    // tile t + 1 is in flight (four 128-bit loads per thread, held in registers) while the keys of tile t are built
+    float4 pre[4];
+    auto prefetch = [&](int f0) {
+        const int nf = min(LA_TILE, n_frame - f0);
+        const int n4 = nf * 15 / 4;
+        const float4* s4 = reinterpret_cast<const float4*>(src + (int64_t)f0 * 15);      // (f0 * 60 B is a multiple of 16)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const int i = tid + k * LA_THREADS; if (i < n4) pre[k] = __ldg(s4 + i); }
+    };
+    if (vec) prefetch(0);
     for (int f0 = 0; f0 < n_frame; f0 += LA_TILE) {
         const int nf = min(LA_TILE, n_frame - f0);
-        const float* tsrc = src + (int64_t)f0 * fs;               // (f0 * 60 B is a multiple of 16)
+        const float* tsrc = src + (int64_t)f0 * fs;
         if (vec) {
             const int n4 = nf * 15 / 4;
-            const float4* s4 = reinterpret_cast<const float4*>(tsrc);
             float4* d4 = reinterpret_cast<float4*>(u.stage);
-            for (int i = tid; i < n4; i += LA_THREADS) d4[i] = __ldg(s4 + i);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const int i = tid + k * LA_THREADS; if (i < n4) d4[i] = pre[k]; }
             for (int i = 4 * n4 + tid; i < nf * 15; i += LA_THREADS) u.stage[i] = __ldg(tsrc + i);
         } else {
             for (int i = tid; i < nf * 15; i += LA_THREADS) u.stage[i] = __ldg(tsrc + (int64_t)(i / 15) * fs + i % 15);
         }
         __syncthreads();
+        if (vec && f0 + LA_TILE < n_frame) prefetch(f0 + LA_TILE);
         if (tid < nf) {
             const float* k = u.stage + tid * 15;                   // stride 15 words: conflict-free
             key[0][f0 + tid] = order_key(k[0]); key[1][f0 + tid] = order_key(k[1]); key[2][f0 + tid] = order_key(k[2]);
+            // the SQUARED segment lengths are selected (the square root is monotone: the order statistics of the lengths are
+            // the roots of the order statistics of the squares, bit for bit); the root is taken of the four selected values only
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float dx = k[3 * j + 3] - k[3 * j], dy = k[3 * j + 4] - k[3 * j + 1], dz = k[3 * j + 5] - k[3 * j + 2];
-                key[3 + j][f0 + tid] = order_key(sqrtf(dx * dx + dy * dy + dz * dz));
+                key[3 + j][f0 + tid] = order_key(dx * dx + dy * dy + dz * dz);
             }
         }
         __syncthreads();
     }
-    const float q = warp_mid_quantile(key[w], n_frame, n_frame, u.hist[w], lane);
-    if (lane == 0) stat[w] = q;
+    {
+        unsigned int rank[4]; uint32_t val[4]; float f45, f55;
+        mid_quantile_ranks(n_frame, rank, f45, f55);
+        warp_select4(key[w], n_frame, rank, u.hist[w], lane, val);
+        if (lane == 0) {
+            float v4[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) { v4[t] = key_value(val[t]); if (w >= 3) v4[t] = sqrtf(v4[t]); }
+            const float q0 = v4[0] + (v4[1] - v4[0]) * f45, q1 = v4[2] + (v4[3] - v4[2]) * f55;
+            stat[w] = 0.5f * (q0 + q1);
+        }
+    }
     __syncthreads();
     if (tid == 0) {
         const float* k = consts + c * 4;
@@ -840,9 +908,17 @@ __global__ void __launch_bounds__(LQ_BLOCK) mid_quantile_long_kernel(const float
             else if (k <= smax) atomicAdd(&hist[(k - smin) >> shift], 1u);
         };
         if ((((uintptr_t)v) & 15) == 0) {
+            // four independent 128-bit loads in flight per thread (the sweep is bound by load latency, not by the counting)
             const float4* v4 = reinterpret_cast<const float4*>(v);
             const int64_t n4 = n >> 2;
-            for (int64_t i = tid; i < n4; i += LQ_BLOCK) { const float4 x = __ldg(v4 + i); count(x.x); count(x.y); count(x.z); count(x.w); }
+            const float4 none = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000), __int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
+            for (int64_t i = tid; i < n4; i += 4 * LQ_BLOCK) {
+                float4 x[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) x[k] = (i + k * LQ_BLOCK < n4) ? __ldg(v4 + i + k * LQ_BLOCK) : none;      // (NaN: above every range)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { count(x[k].x); count(x[k].y); count(x[k].z); count(x[k].w); }
+            }
             for (int64_t i = 4 * n4 + tid; i < n; i += LQ_BLOCK) count(__ldg(v + i));
         } else {
             for (int64_t i = tid; i < n; i += LQ_BLOCK) count(__ldg(v + i));
@@ -916,7 +992,14 @@ __global__ void __launch_bounds__(LQ_BLOCK) mid_quantile_long_kernel(const float
         if ((((uintptr_t)v) & 15) == 0) {
             const float4* v4 = reinterpret_cast<const float4*>(v);
             const int64_t n4 = n >> 2;
-            for (int64_t i = tid; i < n4; i += LQ_BLOCK) { const float4 x = __ldg(v4 + i); take(x.x); take(x.y); take(x.z); take(x.w); }
+            const float4 none = make_float4(__int_as_float(0x7fc00000), __int_as_float(0x7fc00000), __int_as_float(0x7fc00000), __int_as_float(0x7fc00000));
+            for (int64_t i = tid; i < n4; i += 4 * LQ_BLOCK) {
+                float4 x[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) x[k] = (i + k * LQ_BLOCK < n4) ? __ldg(v4 + i + k * LQ_BLOCK) : none;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { take(x[k].x); take(x[k].y); take(x[k].z); take(x[k].w); }
+            }
             for (int64_t i = 4 * n4 + tid; i < n; i += LQ_BLOCK) take(__ldg(v + i));
         } else {
             for (int64_t i = tid; i < n; i += LQ_BLOCK) take(__ldg(v + i));
@@ -1290,13 +1373,10 @@ __global__ void __launch_bounds__(256) pchip_kernel(const T* __restrict__ in, T*
                 // length) -- four FP64-pipe instructions per output sample were the largest item of this kernel's issue budget
                 const float s0 = (float)((double)u_lo * new_ts - xk), dt = (float)new_ts;
                 float ur = 0.f;
+                const float k0 = (float)y0, k1 = (float)d0, k2 = (float)c1, k3 = (float)c0;
                 for (int u = u_lo; u < u_hi; ++u, o += width, ur += 1.f) {
-                    const T s = (T)fmaf(ur, dt, s0);
-                    T res = y0, z = s;
-                    res += d0 * z; z *= s;
-                    res += c1 * z; z *= s;
-                    res += c0 * z;
-                    *o = res;
+                    const float s = fmaf(ur, dt, s0);
+                    *o = (T)fmaf(fmaf(fmaf(k3, s, k2), s, k1), s, k0);      // Horner, three multiply-adds (float32 bound: 2e-6 relative)
                 }
             } else {
                 for (int u = u_lo; u < u_hi; ++u, o += width) {
