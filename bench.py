@@ -444,10 +444,10 @@ def run_ours(args):
                 "note": "fk_layout='joints': FK rows 5..8 only (rows 0-3 of the reference layout repeat the input origin, row 4 repeats row 5)"},
             "e2e_joints_wire": None if ms_e2e_wire is None else {
                 "value": leg_frames / (ms_e2e_wire * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_wire,
-                "h2d_bytes_per_step": leg_frames_rank * 60, "d2h_bytes_per_step": leg_frames_rank * (28 + 48), "host_threads": expand_threads,
-                "note": "BatchedLegIK(wire='joints'): the caller still receives the reference's (..., 9, 3) FK; only rows 5..8 cross the "
-                        "host link, rows 0-4 are rebuilt in host memory from the host-resident pose by host threads "
-                        "(seqik_fk_expand_host_f32), chunk by chunk behind the copies; bit-identical to `e2e`"},
+                "h2d_bytes_per_step": leg_frames_rank * 60, "d2h_bytes_per_step": leg_frames_rank * (28 + 48 + 12), "host_threads": expand_threads,
+                "note": "BatchedLegIK(wire='joints'): the caller still receives the reference's (..., 9, 3) FK; only rows 5..8 and a compact "
+                        "copy of the origin row (seqik_origin_rows_f32) cross the host link, rows 0-4 are rebuilt in host memory by host "
+                        "threads with streaming stores (seqik_fk_expand_host_f32), chunk by chunk behind the copies; bit-identical to `e2e`"},
             "gpu_launches": args.steps * 2,                           # per step: leg_first_frame_kernel + leg_solve_block_kernel
             "kernels": "leg_first_frame_kernel (frame 0 of every chain, lane per chain) + leg_solve_block_kernel (schedule 3: a warp per "
                        "chain, 32 frames per pass, bulk-copy staged)",

@@ -525,7 +525,7 @@ def test_mid_quantile_narrow_ranges_ties_and_counts(api):
 @pytest.mark.parametrize("n_frame", [1, 7, 224, 225, 1000, 1024, 1025, 3000])
 def test_fused_leg_affine_equals_the_three_kernels(api, n_frame):
     """seqik_leg_affine_from_pose_f32 (one kernel per chain up to 1024 frames, series never written) against the series /
-    select / affine kernels, bit for bit, and against numpy on the same key points; contiguous and strided input."""
+    select / affine kernels, bit for bit, and against numpy on the same key points."""
     t = api.torch
     rng = np.random.default_rng(n_frame)
     n_chain = 13
