@@ -354,8 +354,8 @@ def pchip_resample(series, original_ts: float, new_ts: float):
     if not (original_ts > 0 and new_ts > 0):
         raise ValueError("time steps must be positive")
     m = int(np.ceil((n * original_ts) / new_ts))                # length of np.arange(0, n * original_ts, new_ts)
-    lo_hi = torch.stack(torch.aminmax(x))                      # one read-only pass; NaN propagates, +-inf shows up as an extreme
-    if not bool(torch.isfinite(lo_hi).all()):
+    # one read-only pass; NaN propagates, +-inf shows up as an extreme (an empty batch has nothing to check)
+    if x.numel() and not bool(torch.isfinite(torch.stack(torch.aminmax(x))).all()):
         finite = torch.isfinite(x)
         if bool(torch.isnan(x).any()):
             raise ValueError("`y` must contain only finite values.")
