@@ -348,7 +348,7 @@ __device__ __noinline__ void serial_stage_call(int s, const StageK& k, int gn_ma
                                                uint32_t& nfev, int& worst) {
     serial_stage(s, k, gn_mask, esc, warm_ok, kt, o, A, piv, x0, x1, sa, ca, sb, cb, xb_out, w, nfev, worst);
 }
-enum : int { KC_L, KC_LB0, KC_UB0, KC_LB1S, KC_UB1S, KC_SL0, KC_CL0, KC_SU0, KC_CU0, KC_LB0P, KC_UB0P, KC_NSQ, KC_LB1, KC_UB1, KC_N = 16 };
+enum : int { KC_L, KC_LB0, KC_UB0, KC_LB1S, KC_UB1S, KC_SL0, KC_CL0, KC_SU0, KC_CU0, KC_LB0P, KC_UB0P, KC_NSQ, KC_LB1, KC_UB1, KC_HAVE_BT, KC_N = 16 };
 struct __align__(16) BlockShared {
     float pose[2][BLK * 15];           // key points of the current / next block (bulk-copy destination)
     float out_ang[BLK * 7];            // staged results (bulk-store source)
@@ -456,8 +456,9 @@ leg_solve_block_kernel(LegArgs a, int bulk_in, int bulk_out, int first_done) {
         sh.mapc[lane] = v;
         if (lane < 4) sh.nfx[lane] = 0u;
     }
+    const bool mapped = a.affine != nullptr;                       // (kernel argument: uniform, no shared-memory test per key point)
     auto map_apply = [&](Vec3<float> v, int row) -> Vec3<float> {  // AlignPose.align_leg on load (LoadMap), constants in shared memory
-        if (sh.mapc[7] != 0.f) {
+        if (mapped) {
             const float sc = sh.mapc[3];
             if (row == 0) v = {sh.mapc[4], sh.mapc[5], sh.mapc[6]};
             else v = {(v.x - sh.mapc[0]) * sc + sh.mapc[4], (v.y - sh.mapc[1]) * sc + sh.mapc[5], (v.z - sh.mapc[2]) * sc + sh.mapc[6]};
@@ -477,6 +478,7 @@ leg_solve_block_kernel(LegArgs a, int bulk_in, int bulk_out, int first_done) {
         if (lb0 > -inf && ub0 < inf) { Num<float>::sincosv_(lb0, &sl, &cl, &v_); Num<float>::sincosv_(ub0, &su, &cu, &v_); }
         K[KC_SL0] = sl; K[KC_CL0] = cl; K[KC_SU0] = su; K[KC_CU0] = cu;           // all zero: no limit case (warm_guess says interior)
         K[KC_LB0P] = place1(lb0, lb0, ub0); K[KC_UB0P] = place1(ub0, lb0, ub0);
+        K[KC_HAVE_BT] = (s < 3 && cl * cl + sl * sl > 0.f) ? 1.f : 0.f;            // (the verification's have_bt, once per chain)
     }
     if (lane == 0) {
         mbar_init(&sh.bar[0], 1); mbar_init(&sh.bar[1], 1);
@@ -633,9 +635,13 @@ leg_solve_block_kernel(LegArgs a, int bulk_in, int bulk_out, int first_done) {
                            | (((mv.small_a ? 1u : 0u) | (mv.small_b ? 2u : 0u) | (sm2 ? 4u : 0u) | (cd.cond ? 8u : 0u) | (limq ? 16u : 0u)
                                | ((uint32_t)g << 5)) << (8 * s));
                     if (act) {
-                        const bool lim = g == WC_LO || g == WC_HI;
-                        if (!one_var) sh.acc_vk[s][lane] = make_float2(lim ? (g == WC_LO ? K[KC_LB0P] : K[KC_UB0P]) : mv.dA, lim ? 0.f : 1.f);
-                        sh.acc_vk[3 + s][lane] = make_float2(g == WC_STAYS ? 0.f : lim ? d2 : mv.dB, 1.f);
+                        float2 va = make_float2(mv.dA, 1.f), vb = make_float2(mv.dB, 1.f);
+                        if (any_lim && (g == WC_LO || g == WC_HI)) {         // (rare: behind the warp-uniform test)
+                            va = make_float2(g == WC_LO ? K[KC_LB0P] : K[KC_UB0P], 0.f); vb.x = d2;
+                        }
+                        if (kRobust && g == WC_STAYS) vb.x = 0.f;
+                        if (!one_var) sh.acc_vk[s][lane] = va;
+                        sh.acc_vk[3 + s][lane] = vb;
                     }
                     // end point, joint position, frame of the next stage
                     const Vec3<float> res = xy ? Vec3<float>{f.z, f.y, -f.x} : f;
@@ -688,7 +694,7 @@ leg_solve_block_kernel(LegArgs a, int bulk_in, int bulk_out, int first_done) {
                 const int g = (int)((bs >> 5) & 3u);
                 const float xp0 = (s < 3) ? sh.acc_x[s < 3 ? s : 0][lane + 1] : 0.f, xp1 = sh.acc_x[3 + s][lane + 1];
                 WarmMove<float> mv; mv.dA = dA[s]; mv.dB = dB[s]; mv.small_a = bs & 1u; mv.small_b = bs & 2u;
-                int wc = warm_case(enable_t, s < 3 && K[KC_CL0] * K[KC_CL0] + K[KC_SL0] * K[KC_SL0] > 0.f, s == 3, xp0, xp1, mv,
+                int wc = warm_case(enable_t, s < 3 && K[KC_HAVE_BT] != 0.f, s == 3, xp0, xp1, mv,
                                    (bs & 8u) != 0u, K[KC_LB0], K[KC_UB0], K[KC_LB1S], K[KC_UB1S], g, dB2[s], (bs & 4u) != 0u,
                                    (bs & 16u) != 0u, ox0[s], ox1[s]);
                 if (s == 3 && g == WC_STAYS) { wc = WC_STAYS; ox0[s] = 0.f; ox1[s] = xp1; }      // decided exactly in the pass
