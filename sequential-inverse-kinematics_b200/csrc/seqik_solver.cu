@@ -732,7 +732,7 @@ leg_solve_block_kernel(LegArgs a, int bulk_in, int bulk_out, int first_done) {
             if (j >= nv) break;
             // ================= replay lane j through the serial solver, from its first failing stage =================
             // state before frame j: the previous lane's (or the pass's starting state), angles from the accumulated series
-            const int sf = kRobust ? __shfl_sync(full, fs, j) : 0;           // (lean kernel: the whole frame)
+            const int sf = __shfl_sync(full, fs, j);                         // (both kernels: the replaying lane keeps its verified stages)
             float qsa[4], qca[4], qsb[4], qcb[4];
 #pragma unroll
             for (int s = 0; s < 4; ++s) {
@@ -759,7 +759,7 @@ leg_solve_block_kernel(LegArgs a, int bulk_in, int bulk_out, int first_done) {
                 // the stages before the failing one stand as the pass left them: results out, frame rebuilt, state handed on
 #pragma unroll
                 for (int s = 0; s < 3; ++s) {
-                    if (kRobust && s < sf) {
+                    if (s < sf) {
                         const bool xy = s == 0;
                         oa[2 * s] = ox0[s]; oa[2 * s + 1] = xy ? ox1[s] + half_pi : ox1[s]; sh.nfx[s] += 1u;
                         const Vec3<float> w = {npv[s].x + o.x, npv[s].y + o.y, npv[s].z + o.z};
@@ -802,7 +802,7 @@ leg_solve_block_kernel(LegArgs a, int bulk_in, int bulk_out, int first_done) {
             }
             __syncwarp(full);
             j0 = j + 1;
-            s_start = sf;            // the lanes after j keep their stages before sf: nothing those depend on has changed
+            s_start = kRobust ? sf : 0;    // robust: the lanes after j keep their stages before sf (nothing those depend on has changed); lean: recomputed
             if (j0 >= nv) break;
         }
         // ---- carry the angles to the next block in the caller's terms (xa = x0, xb = x1 + shift)
