@@ -557,7 +557,7 @@ leg_solve_block_kernel(LegArgs a, int bulk_in, int bulk_out, int first_done) {
             const bool act = lane >= j0 && lane < nv;
             // results of the pass per lane and stage
             float Tsa[4], Tca[4], Tsb[4], Tcb[4];                  // final sin/cos per stage (speculated)
-            float dA[4], dB[4], dB2[4]; uint32_t bits = 0u;        // per stage: bit 0 small_a, 1 small_b, 2 small_b2, 3 cond, 4 lim ok_q, 5-6 guess
+            float dA[4], dB[4], dB2[4]; uint32_t bits = 0u;        // per stage: bit 0 small_a, 1 small_a & small_b & cond, 2 small_b2 & lim ok_q, 5-6 guess
             Vec3<float> npv[4];                                    // end point of each stage relative to the origin
             // ================= pass =================
             {
@@ -635,8 +635,10 @@ leg_solve_block_kernel(LegArgs a, int bulk_in, int bulk_out, int first_done) {
                     float d2 = 0.f; bool sm2 = false;
                     if (any_lim && g != WC_INTERIOR) warm_limit_move(tsb, tcb, psb, pcb, d2, sm2);
                     dA[s] = mv.dA; dB[s] = mv.dB; dB2[s] = d2;
+                    // (what the verification needs of the tests that depend on the target alone: small_a on its own, the
+                    //  conjunction small_a & small_b & cond of the interior case, the conjunction small_b2 & ok_q of the limit case)
                     bits = (bits & ~(0xffu << (8 * s)))
-                           | (((mv.small_a ? 1u : 0u) | (mv.small_b ? 2u : 0u) | (sm2 ? 4u : 0u) | (cd.cond ? 8u : 0u) | (limq ? 16u : 0u)
+                           | (((mv.small_a ? 1u : 0u) | ((mv.small_a & mv.small_b & cd.cond) ? 2u : 0u) | ((sm2 & limq) ? 4u : 0u)
                                | ((uint32_t)g << 5)) << (8 * s));
                     if (act) {
                         float2 va = make_float2(mv.dA, 1.f), vb = make_float2(mv.dB, 1.f);
@@ -699,8 +701,8 @@ leg_solve_block_kernel(LegArgs a, int bulk_in, int bulk_out, int first_done) {
                 const float xp0 = (s < 3) ? sh.acc_x[s < 3 ? s : 0][lane + 1] : 0.f, xp1 = sh.acc_x[3 + s][lane + 1];
                 WarmMove<float> mv; mv.dA = (s < 3 || kRobust) ? dA[s] : 0.f; mv.dB = dB[s]; mv.small_a = bs & 1u; mv.small_b = bs & 2u;
                 int wc = warm_case(enable_t, s < 3 && K[KC_HAVE_BT] != 0.f, s == 3, xp0, xp1, mv,
-                                   (bs & 8u) != 0u, (s < 3 || kRobust) ? K[KC_LB0] : -inf, (s < 3 || kRobust) ? K[KC_UB0] : inf, K[KC_LB1S], K[KC_UB1S], g, dB2[s],
-                                   (bs & 4u) != 0u, (bs & 16u) != 0u, ox0[s], ox1[s]);
+                                   true, (s < 3 || kRobust) ? K[KC_LB0] : -inf, (s < 3 || kRobust) ? K[KC_UB0] : inf, K[KC_LB1S], K[KC_UB1S], g, dB2[s],
+                                   (bs & 4u) != 0u, true, ox0[s], ox1[s]);
                 if (s == 3 && g == WC_STAYS) { wc = WC_STAYS; ox0[s] = 0.f; ox1[s] = xp1; }      // decided exactly in the pass
                 fs = (wc != g) ? s : fs;
             }
