@@ -15,8 +15,9 @@ The same line carries
   config4      BASELINE.json config 4: the FIXED 10 000-trial x 1000-frame x 6-leg workload, trials sharded over the
                N ranks (10000 / N per rank; all 60 000 chains on one GPU at N = 1) -- kernel and end-to-end figures, so
                that dividing config4 at N = 8 by config4 at N = 1 is the strong-scaling factor of north_star;
-  secondary    driver-timed records of config 5 (fused long sequence), the HBM-bound stream kernels and config 2
-               through the dict API with its parity counts against the reference's shipped angles (rank 0).
+  secondary    driver-timed records of config 5 (fused long sequence), the HBM-bound stream kernels, config 1 (bundled
+               locomotion recording) and config 2 (bundled grooming trial) through the dict API with their parity figures
+               against the oracle / the reference's shipped angles (rank 0).
 
 --impl reference times that CPU implementation alone, with every host core, on bounded samples of the same
 workload (the reference's own per-frame chain rebuild needs ikpy/sympy, which is not
@@ -392,7 +393,7 @@ def run_ours(args):
             peaks_ = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
         except Exception:
             pass
-        for name, fn in (("config2_dict_api", B2.config2_dict_api), ("stream_kernels", lambda: B2.stream_kernels(float(peaks_.get("hbm_gbs", 6650.0)))),
+        for name, fn in (("config1_dict_api", B2.config1_dict_api), ("config2_dict_api", B2.config2_dict_api), ("stream_kernels", lambda: B2.stream_kernels(float(peaks_.get("hbm_gbs", 6650.0)))),
                          ("config5_fused", lambda: B2.config5_fused(args.config5_trials, args.config5_frames))):
             try:
                 t_s = time.perf_counter()

@@ -126,6 +126,50 @@ def _fk_residual(fk9, pose5):
     return np.linalg.norm(np.asarray(fk9)[:, [5, 6, 7, 8]] - np.asarray(pose5)[:, 1:5], axis=2)
 
 
+def config1_dict_api(reps=5):
+    """BASELINE config 1 on the bundled df3d locomotion recording (6 legs x 100 frames): AlignPose -> LegInvKinSeq with the
+    NeuroMechFly locomotion chain through the reference's class API (numpy dicts in, float64 dicts out).  Wall-clock per
+    pipeline run and parity of the run against the CPU oracle's angles / FK residuals for the same input (tests/golden/
+    locomotion.npz; the reference ships no outputs for this recording)."""
+    import torch
+    from seqikpy_b200 import data as D
+    from seqikpy_b200.alignment import AlignPose
+    from seqikpy_b200.kinematic_chain import DOF_ORDER, KinematicChainSeq
+    from seqikpy_b200.leg_inverse_kinematics import LegInvKinSeq
+    from seqikpy_b200.utils import calculate_body_size
+    g = dict(np.load(ROOT / "tests" / "golden" / "locomotion.npz"))
+    legs = [str(l) for l in g["legs"]]
+    raw = {f"{leg}_leg": g["raw"][i] for i, leg in enumerate(legs)}
+    chain = KinematicChainSeq(D.BOUNDS_LOCOMOTION, legs, calculate_body_size(D.TEMPLATE_NMF_LOCOMOTION, legs))
+
+    def run():
+        aligned = AlignPose(raw, legs_list=legs, include_claw=False, body_template=D.TEMPLATE_NMF_LOCOMOTION, log_level="ERROR").align_pose()
+        angles, fk = LegInvKinSeq(aligned, chain, D.INITIAL_ANGLES_LOCOMOTION, log_level="ERROR").run_ik_and_fk(hide_progress_bar=True)
+        return aligned, angles, fk
+    run()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        aligned, angles, fk = run()
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / reps
+    n = int(g["raw"].shape[1])
+    worst_angle, worst_fk, err = 0.0, -1.0, []
+    for i, leg in enumerate(legs):
+        ours = np.stack([angles[f"Angle_{leg}_{d}"] for d in DOF_ORDER], 1)
+        worst_angle = max(worst_angle, float(np.abs(ours - g["oracle_angles"][i]).max()))
+        r_ours = _fk_residual(fk[f"{leg}_leg"], aligned[f"{leg}_leg"])
+        r_ref = _fk_residual(g["oracle_fk"][i], g["aligned"][i])
+        worst_fk = max(worst_fk, float((r_ours - r_ref).max()))
+        err.append(float(r_ours.mean()))
+    return {"workload": "bundled df3d_pose_result__210902_PR_Fly1 locomotion recording: AlignPose + LegInvKinSeq (6 legs x 100 frames, "
+                        "NeuroMechFly locomotion chain) through the dict API, raw key points -> float64 dicts",
+            "wall_ms_per_pipeline": wall * 1e3, "leg_frames_per_s": len(legs) * n / wall,
+            "max_abs_angle_diff_vs_oracle_rad": worst_angle, "max_fk_residual_excess_vs_oracle_mm": worst_fk,
+            "mean_fk_error_mm_by_leg": dict(zip(legs, err)),
+            "aligned_max_abs_diff_vs_reference_class": float(max(np.abs(aligned[f"{leg}_leg"] - g["aligned"][i]).max() for i, leg in enumerate(legs)))}
+
+
 def config2_dict_api(reps=3):
     """BASELINE config 2 on the bundled grooming trial (2 legs x 6000 frames + head): AlignPose -> HeadInverseKinematics ->
     LegInvKinSeq through the reference's class API (numpy dicts in, numpy dicts out; cf. the reference's
