@@ -309,14 +309,16 @@ def run_ours(args):
 
     # ---- the same kernel family walking the reference's own iterates (SEQIK_FLAG_REFERENCE_ITERATES: no Newton steps, no
     #      closed-form warm step; runs on the stage-pipeline schedule): a secondary figure that shows what the default flags save
-    sess.flags = _native.FLAG_REFERENCE_ITERATES
-    for _ in range(3):
+    ms_ref_it, nfev_ref_it = None, torch.zeros(4, dtype=torch.float64, device=dev)
+    if not args.no_ref_iterates:
+        sess.flags = _native.FLAG_REFERENCE_ITERATES
+        for _ in range(3):
+            sess.solve_device()
+        ms_ref_it = timed(lambda: sess.solve_device(want_stats=False), max(3, args.steps // 2)) / max(3, args.steps // 2)
         sess.solve_device()
-    ms_ref_it = timed(lambda: sess.solve_device(want_stats=False), max(3, args.steps // 2)) / max(3, args.steps // 2)
-    sess.solve_device()
-    torch.cuda.synchronize()
-    nfev_ref_it = sess.nfev.to(torch.float64).sum(0)
-    sess.flags = _native.FLAG_DEFAULT
+        torch.cuda.synchronize()
+        nfev_ref_it = sess.nfev.to(torch.float64).sum(0)
+        sess.flags = _native.FLAG_DEFAULT
 
     sess.solve_device()
     torch.cuda.synchronize()
@@ -456,9 +458,10 @@ def run_ours(args):
             "parity_extras": {k: c2[k] for k in c2 if k.startswith(("rf_", "lf_", "head_"))} or None,
             "secondary": secondary or None,
             "solver_flags": {"value": "SEQIK_FLAG_DEFAULT (0xFF): Gauss-Newton mode, escape, skip-confirm, Newton steps, closed-form warm step",
-                             "reference_iterates": {"flags": "SEQIK_FLAG_REFERENCE_ITERATES (0x3F), stage-pipeline schedule", "ms_per_step": ms_ref_it,
-                                                    "value": leg_frames / (ms_ref_it * 1e-3), "unit": UNIT,
-                                                    "nfev_per_leg_frame_by_stage": (nfev_ref_it / leg_frames).tolist()}},
+                             "reference_iterates": None if ms_ref_it is None else {
+                                 "flags": "SEQIK_FLAG_REFERENCE_ITERATES (0x3F), stage-pipeline schedule", "ms_per_step": ms_ref_it,
+                                 "value": leg_frames / (ms_ref_it * 1e-3), "unit": UNIT,
+                                 "nfev_per_leg_frame_by_stage": (nfev_ref_it / leg_frames).tolist()}},
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                          "traffic": traffic, "kernel": "leg_solve_block_kernel (+ leg_first_frame_kernel, ~5 % of the step)",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback",
@@ -505,6 +508,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true", help="do not pin each rank to its GPU's local CPUs")
     ap.add_argument("--no-joints-e2e", action="store_true", help="skip the secondary end-to-end figure with the joints-only FK layout")
+    ap.add_argument("--no-ref-iterates", action="store_true", help="skip the secondary figure with SEQIK_FLAG_REFERENCE_ITERATES (stage-pipeline kernel)")
     ap.add_argument("--no-config4", action="store_true", help="skip the config-4 (fixed 10 000-trial, sharded) record")
     ap.add_argument("--config4-trials", type=int, default=10000, help="total trials of the config-4 record")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary records (config 2 dict API, stream kernels, config 5)")

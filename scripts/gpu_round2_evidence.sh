@@ -9,7 +9,7 @@ tail -3 gpurun_out/${TAG}_gputests.log
 timeout 900 python bench.py > gpurun_out/${TAG}_bench_1gpu.json 2> gpurun_out/${TAG}_bench_1gpu.err
 cut -c1-600 gpurun_out/${TAG}_bench_1gpu.json
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${TAG}_bench_reference_arm.json 2> gpurun_out/${TAG}_bench_ref.err
-LIGHT="--no-cpu-baseline --no-secondary --no-config4 --no-joints-e2e"
+LIGHT="--no-cpu-baseline --no-secondary --no-config4 --no-joints-e2e --no-ref-iterates"   # the headline step only: first-frame + block kernel, and the end-to-end call
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/${TAG}_launches_bench.csv \
     python bench.py --steps 2 --warmup 3 $LIGHT > gpurun_out/${TAG}_ncu_bench.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:leg_solve_block -s 3 -c 1 -f -o gpurun_out/${TAG}_prof_block \
